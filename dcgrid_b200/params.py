@@ -1,0 +1,78 @@
+"""Host-side mirror of the reference's ``struct SimParams`` (src/data/sim_params.h:14-47).
+
+Layout-identical ctypes structure (100 bytes) used on both sides of the C ABI
+(``include/dcgrid_b200.h``).  ``default_params`` follows ``SimParams::defaultParams``
+(src/data/sim_params.cpp:4-34) and ``scene_params`` the presets of src/data/scenes.h:13-32;
+``rdx`` is set here the way src/main.cpp:17 does it (``rdx = 1.f / dx``).
+"""
+import ctypes
+
+import numpy as np
+
+
+class Float3(ctypes.Structure):
+    _fields_ = [("x", ctypes.c_float), ("y", ctypes.c_float), ("z", ctypes.c_float)]
+
+
+class SimParams(ctypes.Structure):
+    _fields_ = [
+        ("dt", ctypes.c_float),
+        ("gx", ctypes.c_int),
+        ("gy", ctypes.c_int),
+        ("gz", ctypes.c_int),
+        ("dx", ctypes.c_float),
+        ("rdx", ctypes.c_float),
+        ("velocity_emission_rate", ctypes.c_float),
+        ("density_emission_rate", ctypes.c_float),
+        ("emission_radius", ctypes.c_float),
+        ("enable_additional_solids", ctypes.c_bool),
+        ("render_solids", ctypes.c_bool),
+        ("render_shadows", ctypes.c_bool),
+        ("render_precise", ctypes.c_bool),
+        ("render_channel", ctypes.c_int32),
+        ("aa_samples", ctypes.c_float),
+        ("ambient", ctypes.c_float),
+        ("background_color", Float3),
+        ("floor_color", Float3),
+        ("smoke_color", Float3),
+        ("scene_color", Float3),
+    ]
+
+
+assert ctypes.sizeof(SimParams) == 100
+
+
+def default_params() -> SimParams:
+    """SimParams::defaultParams() + rdx (src/data/sim_params.cpp:4-34, src/main.cpp:17)."""
+    p = SimParams()
+    p.gx = p.gy = p.gz = 128
+    p.dx = np.float32(10000.0) / np.float32(128)
+    p.dt = 3.0
+    p.velocity_emission_rate = 150.0
+    p.density_emission_rate = 0.002
+    p.emission_radius = 750.0
+    p.enable_additional_solids = False
+    p.render_solids = True
+    p.render_shadows = True
+    p.render_precise = True
+    p.render_channel = 4  # RenderChannel::Resolution
+    p.aa_samples = 1.0
+    p.ambient = 0.3
+    p.background_color = Float3(0.0, 0.0, 0.0)
+    p.floor_color = Float3(*(np.float32([178.0, 158.0, 135.0]) / np.float32(255.0)))
+    p.smoke_color = Float3(0.9, 0.9, 0.9)
+    p.scene_color = Float3(*(np.float32([107.0, 163.0, 204.0]) / np.float32(255.0)))
+    p.rdx = np.float32(1.0) / np.float32(p.dx)
+    return p
+
+
+def scene_params(gx: int, gy: int = None, gz: int = None, solids: bool = False) -> SimParams:
+    """Scene preset in the style of src/data/scenes.h: dx = 10000/gx, rdx = 1/dx."""
+    p = default_params()
+    p.gx = gx
+    p.gy = gx if gy is None else gy
+    p.gz = gx if gz is None else gz
+    p.dx = np.float32(10000.0) / np.float32(gx)
+    p.rdx = np.float32(1.0) / np.float32(p.dx)
+    p.enable_additional_solids = solids
+    return p

@@ -1,0 +1,193 @@
+/*
+ * dcgrid_b200 — C ABI of the B200-native per-timestep fluid solve.
+ *
+ * This is the drop-in boundary for the reference's solver interface
+ *   class FluidSimulation            (reference src/fluid_simulation.h:4-27)
+ * and its two implementations
+ *   FluidSimulationUniform           (src/uniformgrid/fluid_simulation_uniform.h:5-39)
+ *   FluidSimulationDCGrid            (src/dcgrid/fluid_simulation_dcgrid.h:5-61)
+ * One opaque handle == one FluidSimulation instance.  Every reference virtual has
+ * one entry point here; `dcg_step` is the 4-call sequence the reference's UI layer
+ * issues once per frame (src/simulation.cpp:104-111).  All calls return a status
+ * (the reference prints and exit()s instead, include/cuda/helper_cuda.h:771-781).
+ *
+ * No torch types, plain pointers and sizes only.  A maintainer binds this from the
+ * reference tree with the adapter class in dcgrid_b200/csrc/fluid_simulation_b200.h
+ * (see INTEGRATION.md).
+ */
+#ifndef DCGRID_B200_H
+#define DCGRID_B200_H
+
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DCG_API __attribute__((visibility("default")))
+
+/* ---- status codes ------------------------------------------------------ */
+enum {
+  DCG_OK = 0,
+  DCG_ERR_INVALID = 1,   /* bad argument / null handle                               */
+  DCG_ERR_CUDA = 2,      /* a CUDA runtime call failed; see dcg_last_error           */
+  DCG_ERR_POOL = 3,      /* block pool cannot fill the coarsest level / reach level 0
+                            (reference: printf + exit(1),
+                            src/dcgrid/fluid_simulation_dcgrid.cu:35-39,50-53)       */
+  DCG_ERR_UNSUPPORTED = 4,
+  DCG_ERR_NO_DEVICE = 5  /* no CUDA device: there is NO CPU fallback                 */
+};
+
+/* ---- SimParams ---------------------------------------------------------
+ * Layout-identical (field order, types, 100 bytes) to the reference's
+ * `struct SimParams` (src/data/sim_params.h:14-47), so a caller can pass its own
+ * struct by pointer.  Only the first ten fields influence the solve; the render
+ * fields are carried for layout compatibility (rendering is out of scope).
+ * NOTE: as in the reference, `rdx` is NOT derived from `dx` (src/main.cpp:17 sets
+ * it); dcg_default_params() sets both.                                            */
+typedef struct dcg_float3 { float x, y, z; } dcg_float3;
+
+typedef struct dcg_sim_params {
+  float dt;                       /* timestep                                        */
+  int gx, gy, gz;                 /* effective (level-0) grid size                   */
+  float dx;                       /* cell size                                       */
+  float rdx;                      /* 1/dx, set by the caller                         */
+  float velocity_emission_rate;   /* inlet velocity                                  */
+  float density_emission_rate;    /* inlet density                                   */
+  float emission_radius;          /* inlet disc radius (world units)                 */
+  bool enable_additional_solids;  /* sphere SDF obstacle (src/sdf.cuh:8-20)          */
+  bool render_solids, render_shadows, render_precise;
+  int32_t render_channel;         /* enum class RenderChannel                        */
+  float aa_samples;
+  float ambient;
+  dcg_float3 background_color, floor_color, smoke_color, scene_color;
+} dcg_sim_params;
+
+typedef struct dcg_sim dcg_sim;   /* opaque: one FluidSimulation instance            */
+
+/* ---- field / layout selectors for the accessors ------------------------- */
+enum {
+  DCG_FIELD_DENSITY = 0,   /* 1 float / cell                                         */
+  DCG_FIELD_VELOCITY = 1,  /* 3 floats / cell (x,y,z interleaved, like float3[])     */
+  DCG_FIELD_FLUIDITY = 2,  /* 1 float / cell (uniform: level-0 part of the pyramid)  */
+  DCG_FIELD_PRESSURE = 3,  /* 1 float / cell; valid between project() and the next
+                              advectVelocity() (buffers alias in the reference,
+                              src/dcgrid/dcgrid_structure.cu:94-102)                 */
+  DCG_FIELD_DIVERGENCE = 4,/* same validity window as pressure                       */
+  DCG_FIELD_T_PRESSURE = 5 /* the penultimate Jacobi iterate                         */
+};
+enum {
+  DCG_LAYOUT_NATIVE = 0,   /* reference memory order: uniform idx=(z*gy+y)*gx+x
+                              (src/utils/grid_math.cuh:10); DCGrid cell id =
+                              64*slot + in-block bits (src/dcgrid/dcgrid_utils.cuh:31-81),
+                              numCells = 64*maxNumBlocks entries                     */
+  DCG_LAYOUT_DENSE_L0 = 1  /* DCGrid only: finest covering cell resampled onto the
+                              gx*gy*gz level-0 grid, uniform memory order            */
+};
+
+/* ---- lifetime ----------------------------------------------------------- */
+/* SimParams::defaultParams() (src/data/sim_params.cpp:4-34) plus rdx = 1/dx. */
+DCG_API int dcg_default_params(dcg_sim_params *out);
+
+/* new FluidSimulationUniform(size): allocates and reset()s
+ * (src/uniformgrid/fluid_simulation_uniform.cu:6-57).  `device` = CUDA ordinal. */
+DCG_API int dcg_create_uniform(const dcg_sim_params *params, int device, dcg_sim **out);
+
+/* new FluidSimulationDCGrid(size, maxNumBlocks): level/pool sizing, allocation,
+ * reset() incl. its 5 adaptTopology passes
+ * (src/dcgrid/fluid_simulation_dcgrid.cu:9-140,190-261).                          */
+DCG_API int dcg_create_dcgrid(const dcg_sim_params *params, uint64_t max_num_blocks,
+                              int device, dcg_sim **out);
+
+DCG_API int dcg_destroy(dcg_sim *sim);
+
+/* copySimParamsToDevice (src/utils/sim_utils.cu:7-9); per-instance here. */
+DCG_API int dcg_set_params(dcg_sim *sim, const dcg_sim_params *params);
+DCG_API int dcg_get_params(const dcg_sim *sim, dcg_sim_params *out);
+
+/* ---- the 9 virtuals of FluidSimulation (render is a stub) --------------- */
+DCG_API int dcg_init(dcg_sim *sim);             /* fluid_simulation.h:9   */
+DCG_API int dcg_reset(dcg_sim *sim);            /* fluid_simulation.h:10  */
+DCG_API int dcg_adapt_topology(dcg_sim *sim);   /* fluid_simulation.h:11  */
+DCG_API int dcg_advect_velocity(dcg_sim *sim);  /* fluid_simulation.h:13  */
+DCG_API int dcg_project(dcg_sim *sim);          /* fluid_simulation.h:14  */
+DCG_API int dcg_project_local(dcg_sim *sim);    /* fluid_simulation.h:15  */
+DCG_API int dcg_advect_density(dcg_sim *sim);   /* fluid_simulation.h:16  */
+DCG_API int dcg_render(dcg_sim *sim);           /* fluid_simulation.h:18-20: out of
+                                                   scope, returns DCG_ERR_UNSUPPORTED */
+/* debugStats (fluid_simulation.h:22): uniform = sum(density*fluidity)
+ * (uniformgrid_structure.cu:33-43, fluid_simulation_uniform.cu:160-176); DCGrid = L1
+ * pressure residual over leaf cells (dcgrid_structure.cu:224-251,
+ * fluid_simulation_dcgrid.cu:517-528).  Same summation order as the reference.    */
+DCG_API int dcg_debug_stats(dcg_sim *sim, float *out);
+
+/* ---- additions the reference lacks -------------------------------------- */
+/* n x { advectVelocity; adaptTopology; project; advectDensity }
+ * (src/simulation.cpp:104-111).  Asynchronous; dcg_synchronize() waits.          */
+DCG_API int dcg_step(dcg_sim *sim, int n);
+DCG_API int dcg_synchronize(dcg_sim *sim);
+
+/* Jacobi schedule (pairs = jacobi + jacobi_inv).  Defaults are the reference's
+ * compile-time constants: uniform project 2 coarsest + 1/level, projectLocal 5
+ * (fluid_simulation_uniform.cu:103-121,129-132); DCGrid project 5/level,
+ * projectLocal 10/level (fluid_simulation_dcgrid.cu:274-289,300-307).            */
+DCG_API int dcg_set_jacobi_schedule(dcg_sim *sim, int project_coarsest_pairs,
+                                    int project_level_pairs, int local_pairs);
+
+/* sum over all cells of density*fluidity reduced on the device (8 bytes D2H). */
+DCG_API int dcg_total_density(dcg_sim *sim, double *out);
+
+/* ---- observable state ---------------------------------------------------- */
+DCG_API int dcg_is_dcgrid(const dcg_sim *sim);
+DCG_API uint64_t dcg_num_cells(const dcg_sim *sim);        /* N or 64*maxNumBlocks   */
+DCG_API uint64_t dcg_max_num_blocks(const dcg_sim *sim);   /* 0 for uniform          */
+DCG_API int dcg_num_levels(const dcg_sim *sim);            /* mipmapLevels / levels  */
+DCG_API int dcg_sparse_levels(const dcg_sim *sim);
+
+/* Copies a field to HOST memory; `count` = number of floats `dst` can hold. */
+DCG_API int dcg_get_field(dcg_sim *sim, int field, int layout, float *dst, uint64_t count);
+
+/* Per-level tables, each `levels` entries (any pointer may be NULL):
+ * maxNumBlocksLevel, fullBlocksLevel, blockLoads, levelOffsets
+ * (fluid_simulation_dcgrid.cu:24-58,232-241).                                     */
+DCG_API int dcg_get_level_table(dcg_sim *sim, uint64_t *max_blocks, uint64_t *full_blocks,
+                                uint64_t *block_loads, uint64_t *level_offsets);
+
+/* Block pool in the reference's own types/meaning (struct DCGrid, dcgrid.h:5-43);
+ * any pointer may be NULL.  positions: 3*M ints; levels: M (0xFF = free slot);
+ * parent: M (8*parentSlot+subblock, UINT64_MAX = none); children: 8*M;
+ * apron: 216*M cell ids (z fastest).                                               */
+DCG_API int dcg_get_topology(dcg_sim *sim, int32_t *positions, uint8_t *levels,
+                             uint64_t *parent, uint64_t *children, uint64_t *apron);
+
+/* Finest block covering a level-0 cell: getBlockIndexDeep(pos, 0)
+ * (dcgrid_utils.cuh:201-233), evaluated for `n` positions (3*n ints) on the
+ * device.  out_slot[i] = pool slot, out_level[i] = its level.                     */
+DCG_API int dcg_lookup_blocks(dcg_sim *sim, const int32_t *positions, uint64_t n,
+                              uint64_t *out_slot, uint8_t *out_level);
+
+/* Counters: [0] adaptTopology calls, [1] calls that changed the topology,
+ * [2] blocks moved, [3] subblocks refined, [4] calls skipped at a proven fixed
+ * point, [5] failed allocations (pool exhausted; the reference device-printf's,
+ * dcgrid_utils.cuh:120-124), [6] kernel launches issued so far, [7] reserved.     */
+DCG_API int dcg_get_counters(dcg_sim *sim, uint64_t out[8]);
+
+/* Device time (ms, CUDA events on the instance's stream) of the last dcg_step
+ * batch; valid after dcg_synchronize().                                            */
+DCG_API int dcg_last_step_ms(dcg_sim *sim, float *out);
+
+/* Algorithmic field bytes of one full step at the current topology
+ * (SURVEY.md §8d / DESIGN.md formulas) and active-block count per level.           */
+DCG_API int dcg_algorithmic_bytes(dcg_sim *sim, double *bytes_per_step,
+                                  uint64_t *active_blocks_total);
+
+/* Last error text of this instance (or of creation when sim == NULL). */
+DCG_API const char *dcg_last_error(const dcg_sim *sim);
+DCG_API const char *dcg_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DCGRID_B200_H */
