@@ -1,0 +1,14 @@
+"""dcgrid_b200 — B200-native drop-in for the per-timestep fluid solve of wouterraateland/dcgrid.
+
+Only what the hot path needs: ``csrc/`` (hand-written sm_100a CUDA + the C ABI of
+include/dcgrid_b200.h) and this thin host-side mirror of the reference's FluidSimulation
+interface.  Importing the package does not load CUDA; constructing a simulation does and
+fails loudly when the extension or a GPU is missing.
+"""
+from .params import SimParams, default_params, scene_params  # noqa: F401
+from .simulation import (  # noqa: F401
+    DcgError,
+    FluidSimulation,
+    FluidSimulationDCGrid,
+    FluidSimulationUniform,
+)

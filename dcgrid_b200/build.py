@@ -1,0 +1,65 @@
+"""In-tree build of libdcgrid_b200.so (hand-written sm_100a CUDA behind the C ABI).
+
+nvcc cross-compiles without a GPU.  ``-fmad=false`` is part of the numerics contract: the
+kernels keep the reference's expression order and must not be contracted into FMAs, so that
+fields are bit-identical to the reference CUDA built the same way and to the CPU oracle.
+"""
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libdcgrid_b200.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+SOURCES = ["api.cu", "uniform.cu", "dcgrid.cu"]
+FLAGS = [
+    "-O3", "-std=c++17", "-fmad=false", "-lineinfo",
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
+    "-Xptxas", "-v",
+]
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
+    headers.append(os.path.join(HERE, "..", "include", "dcgrid_b200.h"))
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    objs, jobs = [], []
+    for src in SOURCES:
+        s = os.path.join(CSRC, src)
+        o = os.path.join(objdir, src + ".o")
+        objs.append(o)
+        if force or _stale(o, [s] + headers):
+            jobs.append([NVCC] + FLAGS + ["-c", s, "-o", o])
+
+    def run(cmd):
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose or r.returncode != 0:
+            sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed: " + " ".join(cmd))
+        return r.stderr
+
+    logs = []
+    if jobs:
+        with ThreadPoolExecutor(max_workers=len(jobs)) as ex:
+            logs = list(ex.map(run, jobs))
+        with open(os.path.join(objdir, "ptxas.log"), "w") as f:
+            f.write("\n".join(logs))
+    if jobs or force or _stale(LIB, objs):
+        run([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,122 @@
+// Host-side base of one solver instance behind the C ABI (include/dcgrid_b200.h).
+// Mirrors the reference's abstract class FluidSimulation (src/fluid_simulation.h:4-27):
+// the same nine operations, but returning status codes instead of exit()ing.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+
+#include "common.cuh"
+
+#define DCG_CUDA_TRY(expr)                                                                   \
+  do {                                                                                       \
+    cudaError_t e__ = (expr);                                                                \
+    if (e__ != cudaSuccess) return this->fail_cuda(e__, #expr, __FILE__, __LINE__);          \
+  } while (0)
+
+#define DCG_TRY(expr)                 \
+  do {                                \
+    int rc__ = (expr);                \
+    if (rc__ != DCG_OK) return rc__;  \
+  } while (0)
+
+struct dcg_sim {
+  dcg_sim_params params{};
+  dcg::KParams kp{};
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  bool dcgrid = false;
+
+  // Jacobi schedule in pairs (jacobi + jacobi_inv); defaults = the reference's constants
+  int project_coarsest_pairs = 0, project_level_pairs = 0, local_pairs = 0;
+
+  uint64_t launches = 0;  // kernels launched by this instance (graph replays count their nodes)
+  cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+  float last_step_ms = 0.f;
+  bool step_timing_pending = false;
+
+  virtual ~dcg_sim() {}
+
+  // allocation + reset(), like the reference constructors
+  virtual int construct(const dcg_sim_params *p, int device) = 0;
+  virtual void invalidate_graphs() {}
+
+  // the FluidSimulation virtuals
+  virtual int init() = 0;
+  virtual int reset() = 0;
+  virtual int adapt_topology() = 0;
+  virtual int advect_velocity() = 0;
+  virtual int project() = 0;
+  virtual int project_local() = 0;
+  virtual int advect_density() = 0;
+  virtual int debug_stats(float *out) = 0;
+
+  // additions
+  virtual int step(int n);
+  virtual int on_params_changed() = 0;
+  virtual int total_density(double *out) = 0;
+  virtual uint64_t num_cells() const = 0;
+  virtual uint64_t max_num_blocks() const { return 0; }
+  virtual int num_levels() const = 0;
+  virtual int sparse_levels() const { return 0; }
+  virtual int get_field(int field, int layout, float *dst, uint64_t count) = 0;
+  virtual int get_level_table(uint64_t *, uint64_t *, uint64_t *, uint64_t *) { return fail(DCG_ERR_UNSUPPORTED, "uniform grid has no level table"); }
+  virtual int get_topology(int32_t *, uint8_t *, uint64_t *, uint64_t *, uint64_t *) { return fail(DCG_ERR_UNSUPPORTED, "uniform grid has no block pool"); }
+  virtual int lookup_blocks(const int32_t *, uint64_t, uint64_t *, uint8_t *) { return fail(DCG_ERR_UNSUPPORTED, "uniform grid has no block pool"); }
+  virtual int get_counters(uint64_t out[8]) {
+    for (int i = 0; i < 8; i++) out[i] = 0;
+    out[6] = launches;
+    return DCG_OK;
+  }
+  virtual int algorithmic_bytes(double *bytes, uint64_t *active_blocks) = 0;
+
+  int set_params(const dcg_sim_params *p) {
+    params = *p;
+    kp = dcg::make_kparams(params);
+    return on_params_changed();
+  }
+  int synchronize() {
+    DCG_CUDA_TRY(cudaStreamSynchronize(stream));
+    if (step_timing_pending) {
+      DCG_CUDA_TRY(cudaEventElapsedTime(&last_step_ms, ev_begin, ev_end));
+      step_timing_pending = false;
+    }
+    return DCG_OK;
+  }
+
+  int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    err = buf;
+    return code;
+  }
+  int fail_cuda(cudaError_t e, const char *expr, const char *file, int line) {
+    return fail(DCG_ERR_CUDA, "%s failed: %s (%s:%d)", expr, cudaGetErrorString(e), file, line);
+  }
+  int base_setup(const dcg_sim_params *p, int dev) {
+    params = *p;
+    kp = dcg::make_kparams(params);
+    device = dev;
+    DCG_CUDA_TRY(cudaSetDevice(device));
+    DCG_CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    DCG_CUDA_TRY(cudaEventCreate(&ev_begin));
+    DCG_CUDA_TRY(cudaEventCreate(&ev_end));
+    return DCG_OK;
+  }
+  void base_teardown() {
+    if (ev_begin) cudaEventDestroy(ev_begin);
+    if (ev_end) cudaEventDestroy(ev_end);
+    if (stream) cudaStreamDestroy(stream);
+    ev_begin = ev_end = nullptr;
+    stream = nullptr;
+  }
+};
+
+dcg_sim *dcg_make_uniform();
+dcg_sim *dcg_make_dcgrid(uint64_t max_num_blocks);

@@ -1,0 +1,541 @@
+// B200-native dense-grid solver: drop-in for FluidSimulationUniform
+// (reference src/uniformgrid/fluid_simulation_uniform.{h,cu}, kernels in
+// src/uniformgrid/uniformgrid_{structure,fluid}.cu).
+//
+// HBM layout (all fp32, x fastest: idx = (z*gy+y)*gx+x, src/utils/grid_math.cuh:10):
+//   vw[2]      float4[N]   (vx,vy,vz,fluidity) ping-pong — one 16-byte load per gather corner;
+//                          replaces velocity float3[N] + the level-0 fluidity read + the
+//                          whole-field D2D memcpy of fluid_simulation_uniform.cu:92-93
+//   q[2]       float[N]    density ping-pong (no D2D memcpy, :139-140)
+//   fluidity   float[pyr]  full mip pyramid (mipmapCells/mipmapIdx, grid_math.cuh:24-52);
+//                          static: recomputed only when SimParams change (the reference
+//                          recomputes every step, :143-147)
+//   p, tp, div float[pyr]  pressure / t_pressure / divergence pyramids (explicit buffers
+//                          instead of the aliased `temporary`, uniformgrid_structure.cu:7-13)
+// Arithmetic keeps the reference's expression order; compiled with -fmad=false.
+#include <algorithm>
+#include <vector>
+
+#include "sim.h"
+
+namespace dcg {
+namespace {
+
+constexpr int BX = 32, BY = 4, BZ = 2;  // 256 threads, x-contiguous 128-byte rows
+
+struct UGrid {
+  int gx, gy, gz;
+  uint64_t N;
+};
+
+__device__ __forceinline__ uint64_t lidx(const KParams &P, int x, int y, int z) {
+  return ((uint64_t)z * P.gy + y) * P.gx + x;
+}
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return max(lo, min(v, hi)); }
+
+// k_uniform_set_solidity_ratio, uniformgrid_structure.cu:23-31
+__global__ void __launch_bounds__(256) k_u_fluidity(KParams P, float *__restrict__ fluidity, uint64_t off, int level,
+                                                    float4 *__restrict__ vw0, float4 *__restrict__ vw1) {
+  const int x = blockIdx.x * BX + threadIdx.x, y = blockIdx.y * BY + threadIdx.y, z = blockIdx.z * BZ + threadIdx.z;
+  const int w = P.gx >> level, h = P.gy >> level, d = P.gz >> level;
+  if (x >= w || y >= h || z >= d) return;
+  const int scale = 1 << level;
+  const float f = cell_fluidity(P, x, y, z, scale);
+  const uint64_t i = ((uint64_t)z * (P.gy / scale) + y) * (P.gx / scale) + x;
+  fluidity[off + i] = f;
+  if (level == 0) {  // keep the packed copies in sync
+    vw0[i].w = f;
+    vw1[i].w = f;
+  }
+}
+
+// Common gather set-up: INIT_SAMPLE, uniformgrid_fluid.cu:7-27
+struct USample {
+  uint64_t id[8];
+  int x0, y0, z0;
+  float fx, fy, fz;
+};
+__device__ __forceinline__ USample u_sample(const KParams &P, float px, float py, float pz) {
+  USample s;
+  const float x = px - .5f, y = py - .5f, z = pz - .5f;
+  const float xf = floorf(x), yf = floorf(y), zf = floorf(z);
+  s.x0 = (int)xf; s.y0 = (int)yf; s.z0 = (int)zf;
+  s.fx = x - xf; s.fy = y - yf; s.fz = z - zf;
+  const int xa = clampi(s.x0, 0, P.gx - 1), xb = clampi(s.x0 + 1, 0, P.gx - 1);
+  const int ya = clampi(s.y0, 0, P.gy - 1), yb = clampi(s.y0 + 1, 0, P.gy - 1);
+  const int za = clampi(s.z0, 0, P.gz - 1), zb = clampi(s.z0 + 1, 0, P.gz - 1);
+  s.id[0] = lidx(P, xa, ya, za); s.id[1] = lidx(P, xa, ya, zb);
+  s.id[2] = lidx(P, xa, yb, za); s.id[3] = lidx(P, xa, yb, zb);
+  s.id[4] = lidx(P, xb, ya, za); s.id[5] = lidx(P, xb, ya, zb);
+  s.id[6] = lidx(P, xb, yb, za); s.id[7] = lidx(P, xb, yb, zb);
+  return s;
+}
+
+// k_uniform_advect_velocity, uniformgrid_fluid.cu:50-67,88-95
+__global__ void __launch_bounds__(256) k_u_advect_velocity(KParams P, const float4 *__restrict__ vin, float4 *__restrict__ vout) {
+  const int x = blockIdx.x * BX + threadIdx.x, y = blockIdx.y * BY + threadIdx.y, z = blockIdx.z * BZ + threadIdx.z;
+  if (x >= P.gx || y >= P.gy || z >= P.gz) return;
+  const uint64_t i = lidx(P, x, y, z);
+  const float4 me = vin[i];
+  const float bx = ((float)x + .5f) - me.x * P.dt * P.rdx;
+  const float by = ((float)y + .5f) - me.y * P.dt * P.rdx;
+  const float bz = ((float)z + .5f) - me.z * P.dt * P.rdx;
+  const USample s = u_sample(P, bx, by, bz);
+  float4 c[8];
+  float f[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    c[k] = vin[s.id[k]];
+    f[k] = c[k].w;
+  }
+  const Weights8 W = corner_weights(f, s.fx, s.fy, s.fz);
+  float3 out = make_float3(0.f, 0.f, 0.f);
+  if (!(W.acc < 1e-6f)) {
+    float vx[8], vy[8], vz[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const float3 v = velocity_bc(P, make_float3(c[k].x, c[k].y, c[k].z), s.x0 + ((k >> 2) & 1), s.y0 + ((k >> 1) & 1),
+                                   s.z0 + (k & 1), 1);
+      vx[k] = v.x; vy[k] = v.y; vz[k] = v.z;
+    }
+    out = make_float3(blend8(vx, W.w), blend8(vy, W.w), blend8(vz, W.w));
+  }
+  vout[i] = make_float4(out.x, out.y, out.z, me.w);
+}
+
+// k_uniform_advect_density, uniformgrid_fluid.cu:69-86,97-105
+__global__ void __launch_bounds__(256) k_u_advect_density(KParams P, const float4 *__restrict__ vw, const float *__restrict__ qin,
+                                                          float *__restrict__ qout) {
+  const int x = blockIdx.x * BX + threadIdx.x, y = blockIdx.y * BY + threadIdx.y, z = blockIdx.z * BZ + threadIdx.z;
+  if (x >= P.gx || y >= P.gy || z >= P.gz) return;
+  const uint64_t i = lidx(P, x, y, z);
+  const float4 me = vw[i];
+  const float bx = ((float)x + .5f) - me.x * P.dt * P.rdx;
+  const float by = ((float)y + .5f) - me.y * P.dt * P.rdx;
+  const float bz = ((float)z + .5f) - me.z * P.dt * P.rdx;
+  const USample s = u_sample(P, bx, by, bz);
+  float q[8], f[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    f[k] = vw[s.id[k]].w;
+    q[k] = qin[s.id[k]];
+  }
+  const Weights8 W = corner_weights(f, s.fx, s.fy, s.fz);
+  float out = 0.f;
+  if (!(W.acc < 1e-6f)) {
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      q[k] = density_bc(P, q[k], s.x0 + ((k >> 2) & 1), s.y0 + ((k >> 1) & 1), s.z0 + (k & 1), 1);
+    out = blend8(q, W.w);
+  }
+  qout[i] = out;
+}
+
+// k_uniform_calc_divergence, uniformgrid_fluid.cu:107-132
+__global__ void __launch_bounds__(256) k_u_divergence(KParams P, const float4 *__restrict__ vw, float *__restrict__ div,
+                                                      float *__restrict__ p, float *__restrict__ tp) {
+  const int x = blockIdx.x * BX + threadIdx.x, y = blockIdx.y * BY + threadIdx.y, z = blockIdx.z * BZ + threadIdx.z;
+  if (x >= P.gx || y >= P.gy || z >= P.gz) return;
+  const uint64_t i = lidx(P, x, y, z);
+  const uint64_t sx = 1, sy = P.gx, sz = (uint64_t)P.gx * P.gy;
+  const float4 l = vw[x > 0 ? i - sx : i], r = vw[x < P.gx - 1 ? i + sx : i];
+  const float4 dn = vw[y > 0 ? i - sy : i], up = vw[y < P.gy - 1 ? i + sy : i];
+  const float4 b = vw[z > 0 ? i - sz : i], f = vw[z < P.gz - 1 ? i + sz : i];
+  const float3 vl = velocity_bc(P, make_float3(l.x, l.y, l.z), x - 1, y, z, 1);
+  const float3 vr = velocity_bc(P, make_float3(r.x, r.y, r.z), x + 1, y, z, 1);
+  const float3 vd = velocity_bc(P, make_float3(dn.x, dn.y, dn.z), x, y - 1, z, 1);
+  const float3 vu = velocity_bc(P, make_float3(up.x, up.y, up.z), x, y + 1, z, 1);
+  const float3 vb = velocity_bc(P, make_float3(b.x, b.y, b.z), x, y, z - 1, 1);
+  const float3 vf = velocity_bc(P, make_float3(f.x, f.y, f.z), x, y, z + 1, 1);
+  p[i] = 0.f;
+  tp[i] = 0.f;
+  div[i] = .5f * P.rdx * (r.w * vr.x - l.w * vl.x + up.w * vu.y - dn.w * vd.y + f.w * vf.z - b.w * vb.z);
+}
+
+// k_uniform_restrict, uniformgrid_fluid.cu:134-160.  `off`/`coff` = pyramid offsets of this/child level.
+__global__ void __launch_bounds__(256) k_u_restrict(KParams P, int level, uint64_t off, uint64_t coff, float *__restrict__ div,
+                                                    float *__restrict__ p, float *__restrict__ tp) {
+  const int x = blockIdx.x * BX + threadIdx.x, y = blockIdx.y * BY + threadIdx.y, z = blockIdx.z * BZ + threadIdx.z;
+  const int W = P.gx >> level, H = P.gy >> level, D = P.gz >> level;
+  if (x >= W || y >= H || z >= D) return;
+  const uint64_t cw = (uint64_t)(P.gx >> (level - 1)), ch = (uint64_t)(P.gy >> (level - 1));
+  const uint64_t i = off + ((uint64_t)z * H + y) * W + x;
+  const float *c = div + coff + ((uint64_t)(2 * z) * ch + 2 * y) * cw + 2 * x;
+  p[i] = 0.f;
+  tp[i] = 0.f;
+  div[i] = .125f * (c[0] + c[1] + c[cw] + c[cw + 1] + c[cw * ch] + c[cw * ch + 1] + c[cw * ch + cw] + c[cw * ch + cw + 1]);
+}
+
+// calcPressure<in,out>, uniformgrid_fluid.cu:162-192 (k_uniform_jacobi / k_uniform_jacobi_inv :194-204)
+__global__ void __launch_bounds__(256) k_u_jacobi(KParams P, int level, uint64_t off, const float *__restrict__ in,
+                                                  float *__restrict__ out, const float *__restrict__ div) {
+  const int x = blockIdx.x * BX + threadIdx.x, y = blockIdx.y * BY + threadIdx.y, z = blockIdx.z * BZ + threadIdx.z;
+  const int w = P.gx >> level, h = P.gy >> level, d = P.gz >> level;
+  if (x >= w || y >= h || z >= d) return;
+  const int scale = 1 << level;
+  const float alpha = P.dx * P.dx * scale * scale;
+  const uint64_t i = off + ((uint64_t)z * h + y) * w + x;
+  const uint64_t sy = w, sz = (uint64_t)w * h;
+  const float pl = in[x > 0 ? i - 1 : i], pr = in[x < w - 1 ? i + 1 : i];
+  const float pd = in[y > 0 ? i - sy : i], pu = in[y < h - 1 ? i + sy : i];
+  const float pb = in[z > 0 ? i - sz : i], pf = in[z < d - 1 ? i + sz : i];
+  out[i] = (pl + pr + pd + pu + pb + pf - alpha * div[i]) / 6.f;
+}
+
+// k_uniform_prolongate, uniformgrid_fluid.cu:206-237
+__global__ void __launch_bounds__(256) k_u_prolongate(KParams P, int level, uint64_t off, uint64_t poff, float *__restrict__ p) {
+  const int x = blockIdx.x * BX + threadIdx.x, y = blockIdx.y * BY + threadIdx.y, z = blockIdx.z * BZ + threadIdx.z;
+  const int w = P.gx >> level, h = P.gy >> level, d = P.gz >> level;
+  if (x >= w || y >= h || z >= d) return;
+  const uint64_t i = off + ((uint64_t)z * h + y) * w + x;
+  const int64_t pw = w / 2, ph = h / 2;
+  const int64_t i000 = (int64_t)poff + ((int64_t)(z / 2) * ph + y / 2) * pw + x / 2;
+  const int sx = (x == 0 || x == w - 1) ? 0 : 2 * (x % 2) - 1;
+  const int sy = (y == 0 || y == h - 1) ? 0 : 2 * (y % 2) - 1;
+  const int sz = (z == 0 || z == d - 1) ? 0 : 2 * (z % 2) - 1;
+  const int64_t ox = sx, oy = sy * pw, oz = sz * pw * ph;
+  const float p000 = p[i000], p001 = p[i000 + ox], p010 = p[i000 + oy], p011 = p[i000 + oy + ox];
+  const float p100 = p[i000 + oz], p101 = p[i000 + oz + ox], p110 = p[i000 + oz + oy], p111 = p[i000 + oz + oy + ox];
+  p[i] = (27.f * p000 + 9.f * (p001 + p010 + p100) + 3.f * (p011 + p101 + p110) + p111) / 64.f;
+}
+
+// k_uniform_apply_pressure, uniformgrid_fluid.cu:239-260
+__global__ void __launch_bounds__(256) k_u_apply_pressure(KParams P, const float *__restrict__ p, const float *__restrict__ fl,
+                                                          float4 *__restrict__ vw) {
+  const int x = blockIdx.x * BX + threadIdx.x, y = blockIdx.y * BY + threadIdx.y, z = blockIdx.z * BZ + threadIdx.z;
+  if (x >= P.gx || y >= P.gy || z >= P.gz) return;
+  const uint64_t i = lidx(P, x, y, z);
+  const uint64_t sy = P.gx, sz = (uint64_t)P.gx * P.gy;
+  const uint64_t il = x > 0 ? i - 1 : i, ir = x < P.gx - 1 ? i + 1 : i;
+  const uint64_t id = y > 0 ? i - sy : i, iu = y < P.gy - 1 ? i + sy : i;
+  const uint64_t ib = z > 0 ? i - sz : i, iff = z < P.gz - 1 ? i + sz : i;
+  const float alpha = .5f * P.rdx;
+  const float pc = p[i];
+  float4 v = vw[i];
+  // neighbours' fluidity comes from the level-0 part of the pyramid so that the in-place float4
+  // update of vw never races with a neighbour's read
+  const float wl = fl[il], wr = fl[ir], wd = fl[id], wu = fl[iu], wb = fl[ib], wf = fl[iff];
+  v.x -= alpha * (wr * (p[ir] - pc) + wl * (pc - p[il]));
+  v.y -= alpha * (wu * (p[iu] - pc) + wd * (pc - p[id]));
+  v.z -= alpha * (wf * (p[iff] - pc) + wb * (pc - p[ib]));
+  vw[i] = v;
+}
+
+// k_uniform_debug_stats, uniformgrid_structure.cu:33-43: per-256-cell bins, sequential sums
+__global__ void k_u_debug_stats(const float *__restrict__ q, const float4 *__restrict__ vw, float *__restrict__ stats, uint64_t bins) {
+  const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= bins) return;
+  float s = 0.f;
+  for (uint64_t i = b * 256; i < b * 256 + 256; i++) s += q[i] * vw[i].w;
+  stats[b] = s;
+}
+
+// deterministic total (double accumulation, fixed tree): dcg_total_density
+__global__ void __launch_bounds__(256) k_u_total_density(const float *__restrict__ q, const float4 *__restrict__ vw, uint64_t n,
+                                                         double *__restrict__ partial) {
+  __shared__ double sh[256];
+  double s = 0.0;
+  for (uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (uint64_t)gridDim.x * 256)
+    s += (double)(q[i] * vw[i].w);
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+
+__global__ void k_unpack_velocity(const float4 *__restrict__ vw, float *__restrict__ out, uint64_t n) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 v = vw[i];
+  out[3 * i] = v.x; out[3 * i + 1] = v.y; out[3 * i + 2] = v.z;
+}
+
+uint64_t pyramid_cells(uint64_t w, uint64_t h, uint64_t d) {  // grid_math.cuh:24-30
+  uint64_t n = 0;
+  for (uint64_t s = 1; w % s == 0 && h % s == 0 && d % s == 0; s *= 2) n += (w * h * d) / (s * s * s);
+  return n;
+}
+uint64_t pyramid_offset(uint64_t w, uint64_t h, uint64_t d, uint64_t scale) {  // grid_math.cuh:46-48
+  uint64_t off = 0;
+  for (uint64_t s = 1; s < scale; s *= 2) off += (w * h * d) / (s * s * s);
+  return off;
+}
+
+struct UniformSim : dcg_sim {
+  int gx = 0, gy = 0, gz = 0, mip_levels = 1;
+  uint64_t N = 0, pyr = 0;
+  float4 *vw[2] = {nullptr, nullptr};
+  float *q[2] = {nullptr, nullptr};
+  float *fluidity = nullptr, *p = nullptr, *tp = nullptr, *div = nullptr;
+  float *scratch = nullptr;       // 3N floats: accessor staging / stats bins
+  double *d_partial = nullptr;    // total-density partials
+  double *h_partial = nullptr;    // pinned
+  int cur_v = 0, cur_q = 0;
+  bool fluidity_dirty = true;
+  std::vector<uint64_t> level_off;
+
+  // CUDA graph of one full step (advectVelocity, adaptTopology, project, advectDensity)
+  cudaGraphExec_t step_graph[4] = {nullptr, nullptr, nullptr, nullptr};  // one per (cur_v, cur_q) start state
+  uint64_t step_graph_launches = 0;
+
+  ~UniformSim() override {
+    cudaSetDevice(device);
+    drop_graphs();
+    for (int i = 0; i < 2; i++) { cudaFree(vw[i]); cudaFree(q[i]); }
+    cudaFree(fluidity); cudaFree(p); cudaFree(tp); cudaFree(div); cudaFree(scratch); cudaFree(d_partial);
+    if (h_partial) cudaFreeHost(h_partial);
+    base_teardown();
+  }
+  void drop_graphs() {
+    for (auto &g : step_graph) {
+      if (g) cudaGraphExecDestroy(g);
+      g = nullptr;
+    }
+  }
+
+  void invalidate_graphs() override { drop_graphs(); }
+
+  int construct(const dcg_sim_params *prm, int dev) override {
+    DCG_TRY(base_setup(prm, dev));
+    project_coarsest_pairs = 2; project_level_pairs = 1; local_pairs = 5;  // fluid_simulation_uniform.cu:103,116,129
+    gx = prm->gx; gy = prm->gy; gz = prm->gz;
+    if (gx <= 0 || gy <= 0 || gz <= 0) return fail(DCG_ERR_INVALID, "grid size must be positive");
+    N = (uint64_t)gx * gy * gz;
+    // mipmapLevels rule, fluid_simulation_uniform.cu:8-17
+    uint64_t min_dim = (gx < gy && gx < gz) ? gx : (gy < gz ? gy : gz);
+    uint64_t cell = 2;
+    mip_levels = 1;
+    while (gx % cell == 0 && gy % cell == 0 && gz % cell == 0 && cell * 4 <= min_dim) {
+      mip_levels++;
+      cell *= 2;
+    }
+    pyr = pyramid_cells(gx, gy, gz);
+    level_off.resize(mip_levels);
+    for (int l = 0; l < mip_levels; l++) level_off[l] = pyramid_offset(gx, gy, gz, 1ull << l);
+    for (int i = 0; i < 2; i++) {
+      DCG_CUDA_TRY(cudaMalloc(&vw[i], N * sizeof(float4)));
+      DCG_CUDA_TRY(cudaMalloc(&q[i], N * sizeof(float)));
+    }
+    DCG_CUDA_TRY(cudaMalloc(&fluidity, pyr * sizeof(float)));
+    DCG_CUDA_TRY(cudaMalloc(&p, pyr * sizeof(float)));
+    DCG_CUDA_TRY(cudaMalloc(&tp, pyr * sizeof(float)));
+    DCG_CUDA_TRY(cudaMalloc(&div, pyr * sizeof(float)));
+    DCG_CUDA_TRY(cudaMalloc(&scratch, 3 * N * sizeof(float)));
+    DCG_CUDA_TRY(cudaMalloc(&d_partial, 1024 * sizeof(double)));
+    DCG_CUDA_TRY(cudaMallocHost(&h_partial, 1024 * sizeof(double)));
+    return reset();
+  }
+
+  dim3 grid_for(int level) const {
+    return dim3(idiv_up(gx >> level, BX), idiv_up(gy >> level, BY), idiv_up(gz >> level, BZ));
+  }
+  static dim3 block() { return dim3(BX, BY, BZ); }
+
+  int on_params_changed() override {
+    if (params.gx != gx || params.gy != gy || params.gz != gz)
+      return fail(DCG_ERR_INVALID, "grid size is fixed at construction (the reference sizes its buffers in the ctor)");
+    fluidity_dirty = true;
+    drop_graphs();
+    return DCG_OK;
+  }
+
+  int reset() override {  // fluid_simulation_uniform.cu:81-88
+    DCG_CUDA_TRY(cudaSetDevice(device));
+    DCG_CUDA_TRY(cudaMemsetAsync(p, 0, pyr * sizeof(float), stream));
+    DCG_CUDA_TRY(cudaMemsetAsync(tp, 0, pyr * sizeof(float), stream));
+    DCG_CUDA_TRY(cudaMemsetAsync(div, 0, pyr * sizeof(float), stream));
+    DCG_CUDA_TRY(cudaMemsetAsync(fluidity, 0, pyr * sizeof(float), stream));
+    cur_v = cur_q = 0;
+    return init();
+  }
+  int init() override {  // fluid_simulation_uniform.cu:76-79: adaptTopology + k_uniform_init (zero density, velocity)
+    DCG_CUDA_TRY(cudaSetDevice(device));
+    for (int i = 0; i < 2; i++) {
+      DCG_CUDA_TRY(cudaMemsetAsync(vw[i], 0, N * sizeof(float4), stream));
+      DCG_CUDA_TRY(cudaMemsetAsync(q[i], 0, N * sizeof(float), stream));
+    }
+    fluidity_dirty = true;  // the memset cleared the packed .w lanes
+    return adapt_topology();
+  }
+
+  int adapt_topology() override {  // fluid_simulation_uniform.cu:143-147
+    if (!fluidity_dirty) return DCG_OK;  // static field: identical values every step in the reference
+    for (int l = 0; l < mip_levels; l++) {
+      k_u_fluidity<<<grid_for(l), block(), 0, stream>>>(kp, fluidity, level_off[l], l, vw[0], vw[1]);
+      launches++;
+    }
+    DCG_CUDA_TRY(cudaGetLastError());
+    fluidity_dirty = false;
+    return DCG_OK;
+  }
+
+  int advect_velocity() override {  // fluid_simulation_uniform.cu:90-94
+    k_u_advect_velocity<<<grid_for(0), block(), 0, stream>>>(kp, vw[cur_v], vw[cur_v ^ 1]);
+    launches++;
+    cur_v ^= 1;
+    DCG_CUDA_TRY(cudaGetLastError());
+    return DCG_OK;
+  }
+  int advect_density() override {  // fluid_simulation_uniform.cu:137-141
+    k_u_advect_density<<<grid_for(0), block(), 0, stream>>>(kp, vw[cur_v], q[cur_q], q[cur_q ^ 1]);
+    launches++;
+    cur_q ^= 1;
+    DCG_CUDA_TRY(cudaGetLastError());
+    return DCG_OK;
+  }
+  void jacobi_pair(int l) {
+    k_u_jacobi<<<grid_for(l), block(), 0, stream>>>(kp, l, level_off[l], p, tp, div);
+    k_u_jacobi<<<grid_for(l), block(), 0, stream>>>(kp, l, level_off[l], tp, p, div);
+    launches += 2;
+  }
+  int project() override {  // fluid_simulation_uniform.cu:96-124
+    k_u_divergence<<<grid_for(0), block(), 0, stream>>>(kp, vw[cur_v], div, p, tp);
+    launches++;
+    for (int l = 1; l < mip_levels; l++) {
+      k_u_restrict<<<grid_for(l), block(), 0, stream>>>(kp, l, level_off[l], level_off[l - 1], div, p, tp);
+      launches++;
+    }
+    for (int i = 0; i < project_coarsest_pairs; i++) jacobi_pair(mip_levels - 1);
+    for (int l = mip_levels - 2; l >= 0; l--) {
+      k_u_prolongate<<<grid_for(l), block(), 0, stream>>>(kp, l, level_off[l], level_off[l + 1], p);
+      launches++;
+      for (int i = 0; i < project_level_pairs; i++) jacobi_pair(l);
+    }
+    k_u_apply_pressure<<<grid_for(0), block(), 0, stream>>>(kp, p, fluidity, vw[cur_v]);
+    launches++;
+    DCG_CUDA_TRY(cudaGetLastError());
+    return DCG_OK;
+  }
+  int project_local() override {  // fluid_simulation_uniform.cu:126-135
+    k_u_divergence<<<grid_for(0), block(), 0, stream>>>(kp, vw[cur_v], div, p, tp);
+    launches++;
+    for (int i = 0; i < local_pairs; i++) jacobi_pair(0);
+    k_u_apply_pressure<<<grid_for(0), block(), 0, stream>>>(kp, p, fluidity, vw[cur_v]);
+    launches++;
+    DCG_CUDA_TRY(cudaGetLastError());
+    return DCG_OK;
+  }
+
+  // One full step = src/simulation.cpp:104-111.  Two steps return the ping-pong buffers to their
+  // starting parity, so a 2-step sequence is captured once as a CUDA graph and replayed.
+  int step(int n) override {
+    DCG_CUDA_TRY(cudaSetDevice(device));
+    DCG_TRY(adapt_topology());  // flush a pending fluidity rebuild outside the graph
+    DCG_CUDA_TRY(cudaEventRecord(ev_begin, stream));
+    int done = 0;
+    if (n >= 2) {
+      cudaGraphExec_t &ge = step_graph[cur_v * 2 + cur_q];
+      if (!ge) {
+        const uint64_t before = launches;
+        cudaGraph_t g = nullptr;
+        DCG_CUDA_TRY(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+        int rc = DCG_OK;
+        for (int s = 0; s < 2 && rc == DCG_OK; s++) rc = dcg_sim::step(1);
+        cudaError_t ce = cudaStreamEndCapture(stream, &g);
+        if (rc != DCG_OK) return rc;
+        DCG_CUDA_TRY(ce);
+        step_graph_launches = launches - before;
+        launches = before;  // capture does not execute
+        DCG_CUDA_TRY(cudaGraphInstantiate(&ge, g, 0));
+        cudaGraphDestroy(g);
+      }
+      while (n - done >= 2) {
+        DCG_CUDA_TRY(cudaGraphLaunch(ge, stream));
+        launches += step_graph_launches;
+        done += 2;
+      }
+    }
+    if (done < n) DCG_TRY(dcg_sim::step(n - done));
+    DCG_CUDA_TRY(cudaEventRecord(ev_end, stream));
+    step_timing_pending = true;
+    return DCG_OK;
+  }
+
+  int debug_stats(float *out) override {  // fluid_simulation_uniform.cu:160-176 (host sums the bins in order)
+    DCG_CUDA_TRY(cudaSetDevice(device));
+    const uint64_t bins = N / 256;
+    if (bins == 0) { *out = 0.f; return DCG_OK; }
+    k_u_debug_stats<<<(unsigned)((bins + 255) / 256), 256, 0, stream>>>(q[cur_q], vw[cur_v], scratch, bins);
+    launches++;
+    std::vector<float> h(bins);
+    DCG_CUDA_TRY(cudaMemcpyAsync(h.data(), scratch, bins * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    DCG_CUDA_TRY(cudaStreamSynchronize(stream));
+    float sum = 0.f;
+    for (uint64_t i = 0; i < bins; i++) sum += h[i];
+    *out = sum;
+    return DCG_OK;
+  }
+
+  int total_density(double *out) override {
+    DCG_CUDA_TRY(cudaSetDevice(device));
+    const int blocks = (int)std::min<uint64_t>(1024, (N + 255) / 256);
+    k_u_total_density<<<blocks, 256, 0, stream>>>(q[cur_q], vw[cur_v], N, d_partial);
+    launches++;
+    DCG_CUDA_TRY(cudaMemcpyAsync(h_partial, d_partial, blocks * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    DCG_TRY(synchronize());
+    double s = 0.0;
+    for (int i = 0; i < blocks; i++) s += h_partial[i];
+    *out = s;
+    return DCG_OK;
+  }
+
+  uint64_t num_cells() const override { return N; }
+  int num_levels() const override { return mip_levels; }
+
+  int get_field(int field, int layout, float *dst, uint64_t count) override {
+    DCG_CUDA_TRY(cudaSetDevice(device));
+    (void)layout;  // NATIVE == DENSE_L0 on the uniform grid
+    const uint64_t need = field == DCG_FIELD_VELOCITY ? 3 * N : N;
+    if (!dst || count < need) return fail(DCG_ERR_INVALID, "get_field: destination too small (%llu < %llu)", (unsigned long long)count, (unsigned long long)need);
+    const float *src = nullptr;
+    switch (field) {
+      case DCG_FIELD_DENSITY: src = q[cur_q]; break;
+      case DCG_FIELD_VELOCITY:
+        k_unpack_velocity<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(vw[cur_v], scratch, N);
+        launches++;
+        src = scratch;
+        break;
+      case DCG_FIELD_FLUIDITY: src = fluidity; break;
+      case DCG_FIELD_PRESSURE: src = p; break;
+      case DCG_FIELD_DIVERGENCE: src = div; break;
+      case DCG_FIELD_T_PRESSURE: src = tp; break;
+      default: return fail(DCG_ERR_INVALID, "get_field: unknown field %d", field);
+    }
+    DCG_CUDA_TRY(cudaMemcpyAsync(dst, src, need * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    return synchronize();
+  }
+
+  // fields only, fp32, each field read once + written once per stage.
+  int algorithmic_bytes(double *bytes, uint64_t *active_blocks) override {
+    double per_level0 = 28.0 /*advectV*/ + 28.0 /*divergence*/ + 32.0 /*apply*/ + 24.0 /*advectQ*/;
+    double b = per_level0 * (double)N;
+    for (int l = 0; l < mip_levels; l++) {
+      const double n = (double)((uint64_t)(gx >> l) * (gy >> l) * (gz >> l));
+      const int pairs = (l == mip_levels - 1) ? project_coarsest_pairs : project_level_pairs;
+      b += n * 12.0 * 2 * pairs;               // Jacobi sweeps
+      if (l >= 1) b += n * (8 * 4.0 + 12.0);   // restrict: read 8 children, write div,p,tp
+      if (l < mip_levels - 1) b += n * 4.5;    // prolongate: write p, read 1/8 coarse
+    }
+    if (bytes) *bytes = b;
+    if (active_blocks) *active_blocks = 0;
+    return DCG_OK;
+  }
+};
+
+}  // namespace
+}  // namespace dcg
+
+int dcg_sim::step(int n) {
+  for (int i = 0; i < n; i++) {
+    DCG_TRY(advect_velocity());
+    DCG_TRY(adapt_topology());
+    DCG_TRY(project());
+    DCG_TRY(advect_density());
+  }
+  return DCG_OK;
+}
+
+dcg_sim *dcg_make_uniform() { return new dcg::UniformSim(); }

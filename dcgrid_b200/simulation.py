@@ -1,0 +1,192 @@
+"""Host-side mirror of the reference's solver interface over the C ABI.
+
+``FluidSimulation`` keeps the names of the reference's abstract class
+(src/fluid_simulation.h:4-27): ``init, reset, adaptTopology, advectVelocity, project,
+projectLocal, advectDensity, render, debugStats`` — plus ``step`` (the 4-call sequence of
+src/simulation.cpp:104-111) and field accessors, which the reference lacks.
+``FluidSimulationUniform(size)`` / ``FluidSimulationDCGrid(size, maxNumBlocks)`` take the
+same constructor arguments as the reference classes (src/simulation.cpp:28-35); the
+SimParams that the reference uploads to a global ``__constant__`` before construction
+(src/simulation.cpp:19) are passed explicitly.
+
+All compute happens in libdcgrid_b200.so on the GPU; this module holds no numerics and
+has no CPU fallback.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from .params import SimParams
+
+FIELDS = {"density": 0, "velocity": 1, "fluidity": 2, "pressure": 3, "divergence": 4, "t_pressure": 5}
+LAYOUT_NATIVE, LAYOUT_DENSE_L0 = 0, 1
+
+
+class DcgError(RuntimeError):
+    pass
+
+
+def _ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+
+
+class FluidSimulation:
+    """Base: one opaque ``dcg_sim*``."""
+
+    def __init__(self):
+        self._L = _lib.load()
+        self._h = ctypes.c_void_p()
+
+    # -- plumbing -----------------------------------------------------------------
+    def _check(self, rc):
+        if rc != 0:
+            msg = self._L.dcg_last_error(self._h if self._h else None)
+            raise DcgError(f"dcgrid_b200 error {rc}: {msg.decode() if msg else ''}")
+
+    def close(self):
+        if self._h:
+            self._L.dcg_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- the reference's nine virtuals ------------------------------------------------
+    def init(self):
+        self._check(self._L.dcg_init(self._h))
+
+    def reset(self):
+        self._check(self._L.dcg_reset(self._h))
+
+    def adaptTopology(self):
+        self._check(self._L.dcg_adapt_topology(self._h))
+
+    def advectVelocity(self):
+        self._check(self._L.dcg_advect_velocity(self._h))
+
+    def project(self):
+        self._check(self._L.dcg_project(self._h))
+
+    def projectLocal(self):
+        self._check(self._L.dcg_project_local(self._h))
+
+    def advectDensity(self):
+        self._check(self._L.dcg_advect_density(self._h))
+
+    def render(self, *a, **k):
+        self._check(self._L.dcg_render(self._h))  # out of scope -> raises DcgError(UNSUPPORTED)
+
+    def debugStats(self):
+        out = ctypes.c_float()
+        self._check(self._L.dcg_debug_stats(self._h, ctypes.byref(out)))
+        return float(out.value)
+
+    # -- additions ------------------------------------------------------------------
+    def setParams(self, params: SimParams):
+        self._check(self._L.dcg_set_params(self._h, ctypes.byref(params)))
+
+    def step(self, n=1, sync=True):
+        self._check(self._L.dcg_step(self._h, n))
+        if sync:
+            self.synchronize()
+
+    def synchronize(self):
+        self._check(self._L.dcg_synchronize(self._h))
+
+    def setJacobiSchedule(self, project_coarsest_pairs, project_level_pairs, local_pairs):
+        self._check(self._L.dcg_set_jacobi_schedule(self._h, project_coarsest_pairs, project_level_pairs, local_pairs))
+
+    def totalDensity(self):
+        out = ctypes.c_double()
+        self._check(self._L.dcg_total_density(self._h, ctypes.byref(out)))
+        return float(out.value)
+
+    def lastStepMs(self):
+        out = ctypes.c_float()
+        self._check(self._L.dcg_last_step_ms(self._h, ctypes.byref(out)))
+        return float(out.value)
+
+    def algorithmicBytes(self):
+        b = ctypes.c_double()
+        n = ctypes.c_uint64()
+        self._check(self._L.dcg_algorithmic_bytes(self._h, ctypes.byref(b), ctypes.byref(n)))
+        return float(b.value), int(n.value)
+
+    def counters(self):
+        out = np.zeros(8, dtype=np.uint64)
+        self._check(self._L.dcg_get_counters(self._h, _ptr(out)))
+        return out
+
+    @property
+    def numCells(self):
+        return int(self._L.dcg_num_cells(self._h))
+
+    @property
+    def levels(self):
+        return int(self._L.dcg_num_levels(self._h))
+
+    def field(self, name, layout=LAYOUT_NATIVE, count=None):
+        comps = 3 if name == "velocity" else 1
+        n = self.numCells if count is None else count
+        out = np.empty(n * comps, dtype=np.float32)
+        self._check(self._L.dcg_get_field(self._h, FIELDS[name], layout, _ptr(out), out.size))
+        return out.reshape(-1, 3) if comps == 3 else out
+
+
+class FluidSimulationUniform(FluidSimulation):
+    """FluidSimulationUniform(size) — src/uniformgrid/fluid_simulation_uniform.h:5-39."""
+
+    def __init__(self, size, params: SimParams, device=0):
+        super().__init__()
+        p = SimParams.from_buffer_copy(params)
+        p.gx, p.gy, p.gz = size
+        self.params = p
+        self._check(self._L.dcg_create_uniform(ctypes.byref(p), device, ctypes.byref(self._h)))
+
+
+class FluidSimulationDCGrid(FluidSimulation):
+    """FluidSimulationDCGrid(size, maxNumBlocks) — src/dcgrid/fluid_simulation_dcgrid.h:5-61."""
+
+    def __init__(self, size, maxNumBlocks, params: SimParams, device=0):
+        super().__init__()
+        p = SimParams.from_buffer_copy(params)
+        p.gx, p.gy, p.gz = size
+        self.params = p
+        self.maxNumBlocks = int(maxNumBlocks)
+        self._check(self._L.dcg_create_dcgrid(ctypes.byref(p), self.maxNumBlocks, device, ctypes.byref(self._h)))
+
+    @property
+    def sparseLevels(self):
+        return int(self._L.dcg_sparse_levels(self._h))
+
+    def levelTable(self):
+        L = self.levels
+        arrs = [np.zeros(L, dtype=np.uint64) for _ in range(4)]
+        self._check(self._L.dcg_get_level_table(self._h, *[_ptr(a) for a in arrs]))
+        return dict(zip(("max_blocks", "full_blocks", "loads", "offsets"), arrs))
+
+    def topology(self, with_apron=True):
+        M = self.maxNumBlocks
+        pos = np.zeros((M, 3), dtype=np.int32)
+        lvl = np.zeros(M, dtype=np.uint8)
+        parent = np.zeros(M, dtype=np.uint64)
+        child = np.zeros((M, 8), dtype=np.uint64)
+        apron = np.zeros((M, 216), dtype=np.uint64) if with_apron else None
+        self._check(self._L.dcg_get_topology(self._h, _ptr(pos), _ptr(lvl), _ptr(parent), _ptr(child), _ptr(apron)))
+        return dict(pos=pos, level=lvl, parent=parent, child=child, apron=apron)
+
+    def lookupBlocks(self, positions):
+        positions = np.ascontiguousarray(positions, dtype=np.int32)
+        n = positions.shape[0]
+        slot = np.zeros(n, dtype=np.uint64)
+        lvl = np.zeros(n, dtype=np.uint8)
+        self._check(self._L.dcg_lookup_blocks(self._h, _ptr(positions), n, _ptr(slot), _ptr(lvl)))
+        return slot, lvl
+
+    def denseField(self, name):
+        p = self.params
+        return self.field(name, LAYOUT_DENSE_L0, count=p.gx * p.gy * p.gz)

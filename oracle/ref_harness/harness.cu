@@ -17,9 +17,17 @@
 //   out=<file>           binary dump (see tests/_refio.py for the container format)
 //   dump_reset=1         also dump the state right after construction/reset
 //   trace=1              per-step FNV-1a digest of density+velocity in the JSON line
-//   reps=1               repeat the whole run (determinism check, prints one line each)
+//   reps=1               repeat the whole run (determinism check, prints one line each; rep r>0
+//                        dumps to <out>.rep<r>)
+//   serialize=1          DCGrid only: run the reference's one racy kernel
+//                        (k_dcgrid_refine_subblocks: atomicAdd slot allocation,
+//                        dcgrid_utils.cuh:118-127) one rank per launch, in rank order.  All
+//                        kernels are still the reference's own; only the launch shape of that
+//                        kernel changes, which makes the run reproducible.
+#include <algorithm>
 #include <chrono>
 #include <cstdint>
+#include <functional>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -37,6 +45,64 @@
 #undef protected
 #include "data/sim_params.h"
 #include "utils/sim_utils.h"
+
+#include "dcgrid/dcgrid.h"
+
+static void die(const char *msg);
+
+// The reference's DCGrid solver with adaptTopology() re-issued so that slot allocation happens in
+// rank order.  Host logic follows fluid_simulation_dcgrid.cu:320-346 (adaptTopology) and :439-483
+// (refineSubblocks); every kernel launched is the reference's.  moveBlocks() is called unchanged.
+struct SerializedDCGrid : public FluidSimulationDCGrid {
+  SerializedDCGrid(const int3 &size, const size_t &maxNumBlocks) : FluidSimulationDCGrid(size, maxNumBlocks) {}
+
+  void refineInRankOrder(size_t &touchedCount) {
+    const size_t M = h_grid->maxNumBlocks;
+    k_dcgrid_calc_subblock_scores<<<(unsigned)((M * 8 + 63) / 64), 64>>>(d_grid, d_subblockScores);
+    cudaMemcpy(h_subblockScores, d_subblockScores, M * 8 * sizeof(float), cudaMemcpyDeviceToHost);
+    cudaMemcpy(h_blockLoads, h_grid->blockLoads, h_grid->levels * sizeof(size_t), cudaMemcpyDeviceToHost);
+    size_t total = 0;
+    for (int level = 1; level < h_grid->levels; level++) {
+      const size_t room = h_maxNumBlocksLevel[level - 1] - h_blockLoads[level - 1];
+      const size_t cap = 8 * h_blockLoads[level] - h_blockLoads[level - 1];
+      const size_t limit = std::min(room, cap);
+      if (limit == 0) continue;
+      size_t *list = h_destSubblockIndices + total;
+      size_t n = 0;
+      const size_t first = 8 * h_levelOffsets[level];
+      for (size_t i = first; i < first + 8 * h_maxNumBlocksLevel[level]; i++)
+        if (h_subblockScores[i] > 1e-4f) list[n++] = i;
+      if (n > limit) std::nth_element(list, list + limit, list + n, std::greater{});
+      total += std::min(n, limit);
+    }
+    if (total == 0) return;
+    cudaMemcpy(d_destSubblockIndices, h_destSubblockIndices, total * sizeof(size_t), cudaMemcpyHostToDevice);
+    for (size_t r = 0; r < total; r++)  // one rank per launch => atomics execute in rank order
+      k_dcgrid_refine_subblocks<<<1, 1>>>(d_grid, d_destSubblockIndices + r, 1, touchedCount + r, d_touchedBlockIndices);
+    if (cudaDeviceSynchronize() != cudaSuccess) die("serialized refine failed");
+    touchedCount += total;
+  }
+
+  void adaptTopology() override {
+    k_dcgrid_calc_vorticity<<<(unsigned)h_grid->maxNumBlocks, DCGrid::blockV>>>(d_grid);
+    size_t touchedCount = 0;
+    moveBlocks(touchedCount);
+    if (touchedCount > 0) {
+      cudaMemset(h_grid->hashKey, 0xff, hashTableSize * sizeof(uint32_t));
+      cudaMemset(h_grid->hashVal, 0xff, hashTableSize * sizeof(size_t));
+      k_dcgrid_refill_hash_table<<<(unsigned)gridSize, (unsigned)blockSize>>>(d_grid);
+      cudaDeviceSynchronize();
+    }
+    refineInRankOrder(touchedCount);
+    if (touchedCount > 0) {
+      k_dcgrid_refresh_apron_indices<<<(unsigned)h_grid->maxNumBlocks, DCGrid::apronV>>>(d_grid);
+      cudaDeviceSynchronize();
+      for (int level = h_grid->levels - 2; level >= 0; level--)
+        k_dcgrid_propagate_values<<<(unsigned)touchedCount, DCGrid::blockV>>>(d_grid, d_touchedBlockIndices, level);
+      cudaDeviceSynchronize();
+    }
+  }
+};
 
 static void die(const char *msg) {
   fprintf(stderr, "ref_harness: %s\n", msg);
@@ -93,7 +159,7 @@ static uint64_t fnv1a(const void *p, size_t n, uint64_t h = 1469598103934665603u
 
 struct Args {
   std::string grid = "uniform", schedule = "project", out;
-  int gx = 64, gy = 64, gz = 64, solids = 0, steps = 10, dump_reset = 0, trace = 0, reps = 1;
+  int gx = 64, gy = 64, gz = 64, solids = 0, steps = 10, dump_reset = 0, trace = 0, reps = 1, serialize = 0;
   size_t M = 4096;
 };
 
@@ -117,6 +183,7 @@ static Args parse(int argc, char **argv) {
     else if (k == "dump_reset") a.dump_reset = atoi(v.c_str());
     else if (k == "trace") a.trace = atoi(v.c_str());
     else if (k == "reps") a.reps = atoi(v.c_str());
+    else if (k == "serialize") a.serialize = atoi(v.c_str());
     else die("unknown key");
   }
   return a;
@@ -191,13 +258,18 @@ int main(int argc, char **argv) {
 
   for (int rep = 0; rep < a.reps; rep++) {
     Dump d;
-    if (rep == 0) d.open(a.out);
+    if (!a.out.empty()) d.open(rep == 0 ? a.out : a.out + ".rep" + std::to_string(rep));
     const int3 size = make_int3(a.gx, a.gy, a.gz);
     FluidSimulationUniform *u = nullptr;
     FluidSimulationDCGrid *g = nullptr;
     double t0 = now_ms();
     if (a.grid == "uniform") u = new FluidSimulationUniform(size);
-    else if (a.grid == "dcgrid") g = new FluidSimulationDCGrid(size, a.M);
+    else if (a.grid == "dcgrid" && a.serialize) {
+      // the constructor's own reset() still runs the base-class adaptTopology (no virtual dispatch
+      // during construction); a second reset() re-initialises everything through the override
+      g = new SerializedDCGrid(size, a.M);
+      g->reset();
+    } else if (a.grid == "dcgrid") g = new FluidSimulationDCGrid(size, a.M);
     else die("grid must be uniform or dcgrid");
     FluidSimulation *sim = u ? (FluidSimulation *)u : (FluidSimulation *)g;
     CK(cudaDeviceSynchronize());
@@ -267,10 +339,10 @@ int main(int argc, char **argv) {
     }
     const double t_step = a.steps > 0 ? (t_av + t_ad + t_pr + t_aq) / a.steps : 0.0;
     printf("{\"impl\": \"reference_cuda\", \"grid\": \"%s\", \"gx\": %d, \"gy\": %d, \"gz\": %d, \"M\": %zu, \"solids\": %d, "
-           "\"schedule\": \"%s\", \"steps\": %d, \"rep\": %d, \"create_ms\": %.3f, \"ms_per_step\": %.4f, "
+           "\"schedule\": \"%s\", \"serialize\": %d, \"steps\": %d, \"rep\": %d, \"create_ms\": %.3f, \"ms_per_step\": %.4f, "
            "\"advect_velocity_ms\": %.4f, \"adapt_topology_ms\": %.4f, \"project_ms\": %.4f, \"advect_density_ms\": %.4f, "
            "\"final_digest\": \"%016llx\"",
-           a.grid.c_str(), a.gx, a.gy, a.gz, a.M, a.solids, a.schedule.c_str(), a.steps, rep, t_create, t_step,
+           a.grid.c_str(), a.gx, a.gy, a.gz, a.M, a.solids, a.schedule.c_str(), a.serialize, a.steps, rep, t_create, t_step,
            a.steps ? t_av / a.steps : 0, a.steps ? t_ad / a.steps : 0, a.steps ? t_pr / a.steps : 0,
            a.steps ? t_aq / a.steps : 0, (unsigned long long)dig);
     if (a.trace) {

@@ -1,0 +1,139 @@
+"""Parity of the CUDA DCGrid solver (through the C ABI) against the CPU oracle.
+
+The oracle is pinned bit-for-bit against the reference's own CUDA kernels (tests/golden/summary.json),
+so equality with the oracle is equality with the reference under rank-order slot allocation.
+Integer structures (block pool, parent/child links, the 6^3 apron map, level loads) are compared
+raw, slot by slot; floating-point fields are compared bit for bit."""
+import numpy as np
+import pytest
+
+from dcgrid_b200 import DcgError, FluidSimulationDCGrid, scene_params
+from tests._oracle import Oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def assert_same_topology(sim, orc, where=""):
+    st, ot = sim.topology(), orc.topology()
+    np.testing.assert_array_equal(st["level"], ot["level"], err_msg=f"levels {where}")
+    act = ot["level"] != 0xFF
+    np.testing.assert_array_equal(st["pos"][act], ot["pos"][act], err_msg=f"positions {where}")
+    np.testing.assert_array_equal(st["parent"][act], ot["parent"][act], err_msg=f"parent {where}")
+    np.testing.assert_array_equal(st["child"][act], ot["child"][act], err_msg=f"children {where}")
+    np.testing.assert_array_equal(st["apron"][act], ot["apron"][act], err_msg=f"apron {where}")
+    np.testing.assert_array_equal(sim.levelTable()["loads"], orc.level_table()["loads"], err_msg=f"loads {where}")
+    return act
+
+
+def assert_same_fields(sim, orc, names, act, where=""):
+    cells = np.repeat(act, 64)
+    for f in names:
+        a, b = sim.field(f), orc.field(f)
+        if f == "velocity":
+            a, b = a[cells], b[cells]
+        else:
+            a, b = a[cells], b[cells]
+        np.testing.assert_array_equal(_bits(a), _bits(b), err_msg=f"{f} {where}")
+
+
+def run_pair(d, M, solids, steps, schedule="project", check_every=1):
+    p = scene_params(d, solids=solids)
+    sim = FluidSimulationDCGrid((d, d, d), M, p)
+    orc = Oracle(p, M)
+    assert sim.levels == orc.levels and sim.sparseLevels == orc.sparse_levels
+    act = assert_same_topology(sim, orc, "after reset")
+    assert_same_fields(sim, orc, ("density", "velocity", "fluidity"), act, "after reset")
+    for s in range(steps):
+        sim.advectVelocity(); orc.advect_velocity()
+        sim.adaptTopology(); orc.adapt_topology()
+        if schedule == "project":
+            sim.project(); orc.project()
+        else:
+            sim.projectLocal(); orc.project_local()
+        if s % check_every == 0 or s == steps - 1:
+            act = assert_same_topology(sim, orc, f"step {s}")
+            assert_same_fields(sim, orc, ("pressure", "t_pressure", "divergence", "velocity"), act, f"after project, step {s}")
+        sim.advectDensity(); orc.advect_density()
+        if s % check_every == 0 or s == steps - 1:
+            assert_same_fields(sim, orc, ("density", "velocity", "fluidity"), act, f"end of step {s}")
+    return sim, orc
+
+
+@pytest.mark.parametrize("d,M,solids,steps,schedule", [
+    (32, 300, False, 12, "project"),
+    (32, 300, True, 8, "local"),
+    (64, 4096, False, 14, "project"),   # perpetual 2-block move cycle: adaptation runs every step
+    (64, 2000, True, 12, "project"),
+    (128, 16384, True, 6, "project"),
+])
+def test_dcgrid_bit_exact_vs_oracle(gpu, d, M, solids, steps, schedule):
+    sim, orc = run_pair(d, M, solids, steps, schedule)
+    assert sim.debugStats() == orc.debug_stats()
+    c, oc = sim.counters(), orc.counters()
+    assert c[2] == oc[2] and c[3] == oc[3], "moved / refined counts"
+    assert c[5] == 0, "failed allocations"
+    assert orc.field("density").max() > 0
+
+
+def test_dcgrid_steady_state_skip_and_graph(gpu):
+    """Once the (topology, moveLimit) fixed point is proven adaptTopology is skipped and dcg_step replays a
+    CUDA graph; results must equal the call-by-call path and the oracle."""
+    d, M = 64, 2000
+    p = scene_params(d, solids=True)
+    a = FluidSimulationDCGrid((d, d, d), M, p)
+    orc = Oracle(p, M)
+    a.step(9)
+    orc.step(9)
+    c = a.counters()
+    assert c[7] == 1 and c[4] > 0, "steady state reached and adaptTopology skipped"
+    act = assert_same_topology(a, orc, "after 9 steps")
+    assert_same_fields(a, orc, ("density", "velocity"), act, "graph path")
+    assert a.lastStepMs() > 0
+
+
+def test_dcgrid_lookup_and_dense_resample(gpu):
+    d, M = 64, 2000
+    p = scene_params(d, solids=True)
+    sim = FluidSimulationDCGrid((d, d, d), M, p)
+    orc = Oracle(p, M)
+    sim.step(3); orc.step(3)
+    rng = np.random.default_rng(0)
+    pos = rng.integers(0, d, size=(4096, 3)).astype(np.int32)
+    s1, l1 = sim.lookupBlocks(pos)
+    s2, l2 = orc.lookup_blocks(pos)
+    np.testing.assert_array_equal(s1, s2)
+    np.testing.assert_array_equal(l1, l2)
+    dense = sim.denseField("density").reshape(d, d, d)  # [z][y][x]
+    q = orc.field("density")
+    topo = orc.topology(with_apron=False)
+    for (x, y, z), slot, lvl in list(zip(pos, s2, l2))[:512]:
+        bp = topo["pos"][slot]
+        cx, cy, cz = (x >> lvl) - bp[0], (y >> lvl) - bp[1], (z >> lvl) - bp[2]
+        bits = ((cx >> 1) << 5) | ((cy >> 1) << 4) | ((cz >> 1) << 3) | ((cx & 1) << 2) | ((cy & 1) << 1) | (cz & 1)
+        assert dense[z, y, x] == q[int(slot) * 64 + bits]
+
+
+def test_dcgrid_pool_too_small_is_an_error_not_an_exit(gpu):
+    p = scene_params(256)
+    with pytest.raises(DcgError):
+        FluidSimulationDCGrid((256, 256, 256), 0, p)
+    # 64^3 has 5 levels; 4 blocks leave nothing for level 0 ("Too few blocks to reach highest resolution")
+    with pytest.raises(DcgError):
+        FluidSimulationDCGrid((64, 64, 64), 4, scene_params(64))
+
+
+def test_dcgrid_reset_is_reproducible(gpu):
+    d, M = 64, 4096
+    p = scene_params(d)
+    a = FluidSimulationDCGrid((d, d, d), M, p)
+    t0 = a.topology()
+    a.step(5)
+    a.reset()
+    t1 = a.topology()
+    for k in ("pos", "level", "parent", "child", "apron"):
+        np.testing.assert_array_equal(t0[k], t1[k], err_msg=k)
+    assert np.abs(a.field("velocity")).max() == 0
