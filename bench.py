@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""bench.py — effective cell-updates/s per full step of the DCGrid solve, and % of HBM roofline.
+
+Contract (see the task statement):  python bench.py --gpus N --steps K --warmup W  prints ONE JSON
+line from rank 0.  A "step" is one pass of the hot path (advectVelocity -> adaptTopology -> project
+-> advectDensity, reference src/simulation.cpp:104-111) over one synthetic scene.
+
+Workload at N=1: BASELINE.json configs[2], the configuration the north_star metric is quoted on —
+DCGrid cloud scene, 512^3 effective, 4^3 blocks, pool M = 524,288, sphere-SDF solids on (the
+reference has no terrain SDF).  N>1: the slab-decomposed solver is not implemented in
+this round; each rank runs an independent replica of the same scene (weak scaling, no data-path
+collective) and the JSON says so.
+
+--impl reference  times the CPU restatement of the reference's step (oracle/liboracle.so, OpenMP over
+all host cores) on the same scene: the reference itself has no CPU path, its own implementation is
+CUDA.  That CUDA implementation (oracle/_ref/ref_harness) is timed too and reported as
+"reference_cuda" for context.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (grid, d, M, solids)
+    "dcgrid512": ("dcgrid", 512, 524288, True),   # BASELINE.json configs[2] (C3)
+    "dcgrid256": ("dcgrid", 256, 65536, False),   # configs[1] (C2)
+    "uniform64": ("uniform", 64, 0, False),       # configs[0] (C1)
+    "dcgrid64": ("dcgrid", 64, 4096, False),      # tiny, adaptation never settles (tests)
+}
+METRIC = "effective cell-updates/s per full step"
+UNIT = "cell-updates/s"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            with open(path) as f:
+                return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        sm, mx, reasons = [], 0.0, set()
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx = max(mx, float(s[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_sim(workload, device):
+    from dcgrid_b200 import FluidSimulationDCGrid, FluidSimulationUniform, scene_params
+
+    grid, d, M, solids = WORKLOADS[workload]
+    p = scene_params(d, solids=solids)
+    sim = FluidSimulationDCGrid((d, d, d), M, p, device=device) if grid == "dcgrid" else FluidSimulationUniform((d, d, d), p, device=device)
+    return sim, p
+
+
+def cpu_port_step_time(workload, steps, warmup, threads=None):
+    """Times the CPU restatement (oracle) on the host cores.  Returns (seconds per step, cores, create seconds)."""
+    if threads:
+        os.environ["OMP_NUM_THREADS"] = str(threads)
+    from dcgrid_b200.params import scene_params
+    from tests._oracle import Oracle
+
+    grid, d, M, solids = WORKLOADS[workload]
+    p = scene_params(d, solids=solids)
+    t0 = time.perf_counter()
+    o = Oracle(p, M if grid == "dcgrid" else 0)
+    create = time.perf_counter() - t0
+    for _ in range(warmup):
+        o.step(1)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        o.step(1)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    o.close()
+    return dt, (threads or os.cpu_count()), create
+
+
+def reference_cuda_time(workload, steps):
+    """The reference's own CUDA step (unmodified sources, default flags) on the same GPU, when its harness was built."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
+    if not os.path.exists(exe):
+        return None
+    grid, d, M, solids = WORKLOADS[workload]
+    try:
+        r = subprocess.run([exe, f"grid={grid}", f"d={d}", f"M={max(M, 1)}", f"solids={int(solids)}", f"steps={steps}"],
+                           capture_output=True, text=True, timeout=600)
+        line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
+        j = json.loads(line)
+        return {"ms_per_step": j["ms_per_step"], "value": d ** 3 / (j["ms_per_step"] * 1e-3), "unit": UNIT, "steps": steps,
+                "adapt_topology_ms": j["adapt_topology_ms"], "project_ms": j["project_ms"],
+                "advect_velocity_ms": j["advect_velocity_ms"], "advect_density_ms": j["advect_density_ms"],
+                "how": "oracle/_ref/ref_harness: unmodified reference sources, nvcc default flags, same GPU, host-timed with syncs"}
+    except Exception as e:  # noqa: BLE001
+        return {"error": str(e)[:200]}
+
+
+def run_reference_arm(args, rank, world):
+    """--impl reference: the CPU port of the reference's step, all host threads, rank 0 only."""
+    if rank != 0:
+        return
+    grid, d, M, solids = WORKLOADS[args.workload]
+    # each oracle step of the 512^3 scene costs seconds; bound the run to a few minutes
+    budget_s = 150.0
+    probe, cores, create = cpu_port_step_time(args.workload, 1, 0)
+    steps = max(1, min(args.steps, int(budget_s / max(probe, 1e-6))))
+    warm = min(args.warmup, 1)
+    dt, cores, _ = cpu_port_step_time(args.workload, steps, warm) if steps > 1 else (probe, cores, create)
+    value = d ** 3 / dt
+    sample = f"{steps} full step(s) of the same scene after reset ({create:.1f} s construction untimed), OpenMP over {cores} threads"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "grid": grid, "effective_cells": d ** 3, "max_num_blocks": M, "solids": bool(solids),
+                   "note": "reference has no CPU path; this is the strict-IEEE CPU restatement (oracle/), pinned bit-exactly to the reference CUDA"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="dcgrid512", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-reference-cuda", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3  # timing rule: W >= 3
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch  # plumbing only: device selection, barrier, max-over-ranks
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    grid, d, M, solids = WORKLOADS[args.workload]
+    sim, p = make_sim(args.workload, local_rank)
+    ctr0 = sim.counters()
+
+    # ---- warm-up: also walks the topology to its fixed point and captures the step graphs ----
+    sim.step(args.warmup)
+    barrier()
+
+    # ---- timed region: EXACTLY K steps, device-timed on the launching stream ----
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = int(sim.counters()[6])
+    barrier()
+    sim.step(args.steps, sync=True)
+    barrier()
+    ms_total = sim.lastStepMs()
+    launches = int(sim.counters()[6]) - l0
+    clocks = sampler.summary()
+    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    cells = d ** 3
+    value = world * cells / (ms_per_step * 1e-3)
+
+    # ---- end-to-end through the C ABI with host buffers: params in (100 B), step, metric out ----
+    from dcgrid_b200.params import SimParams
+
+    host_params = SimParams.from_buffer_copy(p)
+    d2h = 8 * min(1024, (sim.numCells + 255) // 256)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        sim.setParams(host_params)      # copySimParamsToDevice every frame (src/simulation.cpp:94)
+        sim.step(1, sync=False)
+        total = sim.totalDensity()      # D2H of the per-CTA partial sums + host sync
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * cells / float(t.item())
+
+    alg_bytes, active_blocks = sim.algorithmicBytes()
+    ctr = sim.counters()
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        # dominant kernel: the Jacobi sweep on the most populated level, timed alone (L2-cold working set:
+        # p, t_p, div of one level = 3 x 62 MB at 512^3, rotating through 5 pairs)
+        roof = None
+        per_stage = {}
+        try:
+            if grid == "dcgrid":
+                tab = sim.levelTable()
+                lvl = int(max(range(len(tab["loads"])), key=lambda l: int(tab["loads"][l])))
+            else:
+                lvl = 0
+            sim.benchStage("jacobi", lvl, 10)
+            ms, b = sim.benchStage("jacobi", lvl, 40)
+            ach = b / (ms * 1e-3) / 1e9
+            roof = {"bound": "hbm", "kernel": "k_dc_jacobi" if grid == "dcgrid" else "k_u_jacobi", "level": lvl, "achieved": ach,
+                    "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                    "ms_per_launch": ms, "alg_bytes_per_launch": b}
+            for st in ("advect_velocity", "divergence", "apply_pressure", "advect_density"):
+                sim.benchStage(st, 0, 2)
+                ms_s, b_s = sim.benchStage(st, 0, 6)
+                per_stage[st] = {"ms": ms_s, "alg_GBps": b_s / (ms_s * 1e-3) / 1e9, "frac": b_s / (ms_s * 1e-3) / 1e9 / peak}
+        except Exception as e:  # noqa: BLE001
+            roof = {"error": str(e)[:200]}
+        step_ach = alg_bytes / (ms_per_step * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": args.workload, "grid": grid, "effective_cells": cells, "max_num_blocks": M, "solids": bool(solids),
+                       "active_blocks": active_blocks, "allocated_cell_updates_per_s": world * 64 * active_blocks / (ms_per_step * 1e-3),
+                       "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (slab decomposition not implemented yet)",
+                       "l2": "working set (2.5 GB at 512^3) >> 126 MB L2, no flush needed" if cells >= 256 ** 3 else "L2-resident working set (correctness config)",
+                       "schedule": "reference project(): 5 Jacobi pairs per level, cascadic"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": ctypes.sizeof(SimParams), "d2h_bytes_per_step": d2h,
+                    "what": "dcg_set_params(host struct) + dcg_step(1) + dcg_total_density (device reduction, partials copied to pinned host memory) per step, host wall clock",
+                    "last_total_density": total},
+            "gpu_launches": launches,
+            "roofline": roof,
+            "step_roofline": {"bound": "hbm", "achieved": step_ach, "peak": peak, "unit": "GB/s", "frac": step_ach / peak,
+                              "alg_bytes_per_step": alg_bytes, "frac_of_8TBps_nominal": step_ach / 8000.0, "peak_source": peak_src},
+            "stages": per_stage,
+            "topology": {"adapt_calls": int(ctr[0] - ctr0[0]), "calls_that_changed_topology": int(ctr[1]), "blocks_moved": int(ctr[2]),
+                         "subblocks_refined": int(ctr[3]), "calls_skipped_at_fixed_point": int(ctr[4]), "steady": bool(ctr[7])},
+        }
+        if not args.no_reference_cuda and world == 1:
+            line["reference_cuda"] = reference_cuda_time(args.workload, 10)
+        if not args.no_cpu_baseline and world == 1:
+            try:
+                dt, cores, create = cpu_port_step_time(args.workload, 2 if cells >= 256 ** 3 else 20, 0)
+                line["cpu_baseline"] = {"value": cells / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                                        "sample": f"{2 if cells >= 256 ** 3 else 20} full steps of the same scene after reset ({create:.1f} s construction untimed), oracle/liboracle.so with OpenMP"}
+            except Exception as e:  # noqa: BLE001
+                line["cpu_baseline"] = {"error": str(e)[:200]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -48,6 +48,7 @@ SYMBOLS = {
     "dcg_get_counters": (_int, [_vp, _vp]),
     "dcg_last_step_ms": (_int, [_vp, ctypes.POINTER(ctypes.c_float)]),
     "dcg_algorithmic_bytes": (_int, [_vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_u64)]),
+    "dcg_bench_stage": (_int, [_vp, ctypes.c_char_p, _int, _int, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double)]),
     "dcg_last_error": (ctypes.c_char_p, [_vp]),
     "dcg_version": (ctypes.c_char_p, []),
 }

@@ -187,6 +187,12 @@ int dcg_algorithmic_bytes(dcg_sim *sim, double *bytes, uint64_t *active) {
   return sim->algorithmic_bytes(bytes, active);
 }
 
+int dcg_bench_stage(dcg_sim *sim, const char *stage, int level, int reps, float *ms_per_launch, double *alg_bytes) {
+  NEED(sim);
+  if (!stage || reps <= 0) return sim->fail(DCG_ERR_INVALID, "bench_stage: bad arguments");
+  return sim->bench_stage(stage, level, reps, ms_per_launch, alg_bytes);
+}
+
 const char *dcg_last_error(const dcg_sim *sim) {
   if (sim) return sim->err.c_str();
   std::lock_guard<std::mutex> lk(g_err_mutex);

@@ -19,6 +19,7 @@
 #include <cfloat>
 #include <functional>
 #include <numeric>
+#include <string>
 #include <vector>
 
 #include "dcgrid_kernels.cuh"
@@ -428,36 +429,82 @@ struct DCGridSim : dcg_sim {
   int step(int n) override {
     DCG_CUDA_TRY(cudaSetDevice(device));
     DCG_CUDA_TRY(cudaEventRecord(ev_begin, stream));
-    int done = 0;
-    while (done < n) {
-      if (steady && n - done >= 2) {
-        cudaGraphExec_t &ge = step_graph[cur_v * 2 + cur_q];
-        if (!ge) {
-          const uint64_t before = launches, adapt_before = n_adapt, skipped_before = n_skipped;
-          cudaGraph_t g = nullptr;
-          DCG_CUDA_TRY(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
-          int rc = dcg_sim::step(2);  // adapt_topology() is a no-op in the steady state
-          cudaError_t ce = cudaStreamEndCapture(stream, &g);
-          if (rc != DCG_OK) return rc;
-          DCG_CUDA_TRY(ce);
-          step_graph_launches = launches - before;
-          launches = before; n_adapt = adapt_before; n_skipped = skipped_before;
-          DCG_CUDA_TRY(cudaGraphInstantiate(&ge, g, 0));
-          cudaGraphDestroy(g);
-        }
-        while (n - done >= 2) {
-          DCG_CUDA_TRY(cudaGraphLaunch(ge, stream));
-          launches += step_graph_launches;
-          n_adapt += 2; n_skipped += 2;
-          done += 2;
-        }
-      } else {
+    for (int done = 0; done < n; done++) {
+      if (!steady) {  // transient: adaptation needs host round trips, run call by call
         DCG_TRY(dcg_sim::step(1));
-        done++;
+        continue;
       }
+      cudaGraphExec_t &ge = step_graph[cur_v * 2 + cur_q];
+      if (!ge) {
+        const uint64_t before = launches, adapt_before = n_adapt, skipped_before = n_skipped;
+        const int sv = cur_v, sq = cur_q;
+        cudaGraph_t g = nullptr;
+        DCG_CUDA_TRY(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+        const int rc = dcg_sim::step(1);  // adapt_topology() is a no-op in the steady state
+        const cudaError_t ce = cudaStreamEndCapture(stream, &g);
+        cur_v = sv; cur_q = sq;  // capture records, it does not execute
+        step_graph_launches = launches - before;
+        launches = before; n_adapt = adapt_before; n_skipped = skipped_before;
+        if (rc != DCG_OK) return rc;
+        DCG_CUDA_TRY(ce);
+        DCG_CUDA_TRY(cudaGraphInstantiate(&ge, g, 0));
+        cudaGraphDestroy(g);
+      }
+      DCG_CUDA_TRY(cudaGraphLaunch(ge, stream));
+      launches += step_graph_launches;
+      n_adapt++; n_skipped++;
+      cur_v ^= 1;
+      cur_q ^= 1;
     }
     DCG_CUDA_TRY(cudaEventRecord(ev_end, stream));
     step_timing_pending = true;
+    return DCG_OK;
+  }
+
+  // one launch of a single stage, `reps` times, CUDA-event timed on the instance's stream
+  int bench_stage(const char *stage, int level, int reps, float *ms_per_launch, double *alg_bytes) override {
+    DCG_CUDA_TRY(cudaSetDevice(device));
+    const std::string st(stage);
+    if (level < 0 || level >= levels) return fail(DCG_ERR_INVALID, "bench_stage: bad level");
+    double call = 0;
+    for (int l = 0; l < levels; l++) call += 64.0 * (double)loads[l];
+    const double cl = 64.0 * (double)loads[level];
+    double bytes = 0;
+    DCG_CUDA_TRY(cudaEventRecord(ev_begin, stream));
+    for (int r = 0; r < reps; r++) {
+      if (st == "jacobi") {
+        k_dc_jacobi<<<blocks_for(max_blocks[level], kBPC), kCTA, 0, stream>>>(T, kp, level, (r & 1) ? tp : p, (r & 1) ? p : tp, div);
+        bytes = 12.0 * cl;
+      } else if (st == "advect_velocity") {
+        k_dc_advect_velocity<<<blocks_for(M, kBPC), kCTA, 0, stream>>>(T, kp, vw[cur_v], vw[cur_v ^ 1]);
+        cur_v ^= 1;
+        bytes = 28.0 * call;
+      } else if (st == "advect_density") {
+        k_dc_advect_density<<<blocks_for(M, kBPC), kCTA, 0, stream>>>(T, kp, vw[cur_v], fl, q[cur_q], q[cur_q ^ 1]);
+        cur_q ^= 1;
+        bytes = 24.0 * call;
+      } else if (st == "divergence") {
+        k_dc_divergence<<<blocks_for(M, kBPC), kCTA, 0, stream>>>(T, kp, vw[cur_v], div, p, tp);
+        bytes = 28.0 * call;
+      } else if (st == "apply_pressure") {
+        k_dc_apply_pressure<<<blocks_for(M, kBPC), kCTA, 0, stream>>>(T, kp, p, fl, vw[cur_v]);
+        bytes = 32.0 * call;
+      } else if (st == "accumulate_velocity") {
+        k_dc_accumulate_velocity<<<blocks_for(8 * max_blocks[level], 256), 256, 0, stream>>>(T, level, vw[cur_v]);
+        bytes = 13.5 * cl;
+      } else if (st == "prolongate") {
+        k_dc_prolongate<<<blocks_for(max_blocks[level], kBPC), kCTA, 0, stream>>>(T, level, p);
+        bytes = 4.5 * cl;
+      } else return fail(DCG_ERR_INVALID, "bench_stage: unknown stage %s", stage);
+      launches++;
+    }
+    DCG_CUDA_TRY(cudaEventRecord(ev_end, stream));
+    DCG_CUDA_TRY(cudaStreamSynchronize(stream));
+    float ms = 0.f;
+    DCG_CUDA_TRY(cudaEventElapsedTime(&ms, ev_begin, ev_end));
+    step_timing_pending = false;
+    if (ms_per_launch) *ms_per_launch = ms / reps;
+    if (alg_bytes) *alg_bytes = bytes;
     return DCG_OK;
   }
 

@@ -6,6 +6,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstring>
 #include <string>
 
 #include "common.cuh"
@@ -72,8 +73,12 @@ struct dcg_sim {
     return DCG_OK;
   }
   virtual int algorithmic_bytes(double *bytes, uint64_t *active_blocks) = 0;
+  virtual int bench_stage(const char *stage, int level, int reps, float *ms_per_launch, double *alg_bytes) = 0;
 
   int set_params(const dcg_sim_params *p) {
+    // the reference re-uploads SimParams every frame (src/simulation.cpp:94); identical bytes change
+    // nothing here: kernels take the parameters by value and captured graphs stay valid
+    if (std::memcmp(&params, p, sizeof params) == 0) return DCG_OK;
     params = *p;
     kp = dcg::make_kparams(params);
     return on_params_changed();

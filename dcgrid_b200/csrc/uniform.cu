@@ -14,6 +14,7 @@
 //                          instead of the aliased `temporary`, uniformgrid_structure.cu:7-13)
 // Arithmetic keeps the reference's expression order; compiled with -fmad=false.
 #include <algorithm>
+#include <string>
 #include <vector>
 
 #include "sim.h"
@@ -419,36 +420,34 @@ struct UniformSim : dcg_sim {
     return DCG_OK;
   }
 
-  // One full step = src/simulation.cpp:104-111.  Two steps return the ping-pong buffers to their
-  // starting parity, so a 2-step sequence is captured once as a CUDA graph and replayed.
+  // One full step = src/simulation.cpp:104-111, captured once per ping-pong parity as a CUDA graph
+  // (29 launches at 64^3 become one graph launch) and replayed.
   int step(int n) override {
     DCG_CUDA_TRY(cudaSetDevice(device));
     DCG_TRY(adapt_topology());  // flush a pending fluidity rebuild outside the graph
     DCG_CUDA_TRY(cudaEventRecord(ev_begin, stream));
-    int done = 0;
-    if (n >= 2) {
+    for (int done = 0; done < n; done++) {
       cudaGraphExec_t &ge = step_graph[cur_v * 2 + cur_q];
       if (!ge) {
         const uint64_t before = launches;
+        const int sv = cur_v, sq = cur_q;
         cudaGraph_t g = nullptr;
         DCG_CUDA_TRY(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
-        int rc = DCG_OK;
-        for (int s = 0; s < 2 && rc == DCG_OK; s++) rc = dcg_sim::step(1);
-        cudaError_t ce = cudaStreamEndCapture(stream, &g);
+        const int rc = dcg_sim::step(1);
+        const cudaError_t ce = cudaStreamEndCapture(stream, &g);
+        cur_v = sv; cur_q = sq;  // capture records, it does not execute
+        step_graph_launches = launches - before;
+        launches = before;
         if (rc != DCG_OK) return rc;
         DCG_CUDA_TRY(ce);
-        step_graph_launches = launches - before;
-        launches = before;  // capture does not execute
         DCG_CUDA_TRY(cudaGraphInstantiate(&ge, g, 0));
         cudaGraphDestroy(g);
       }
-      while (n - done >= 2) {
-        DCG_CUDA_TRY(cudaGraphLaunch(ge, stream));
-        launches += step_graph_launches;
-        done += 2;
-      }
+      DCG_CUDA_TRY(cudaGraphLaunch(ge, stream));
+      launches += step_graph_launches;
+      cur_v ^= 1;
+      cur_q ^= 1;
     }
-    if (done < n) DCG_TRY(dcg_sim::step(n - done));
     DCG_CUDA_TRY(cudaEventRecord(ev_end, stream));
     step_timing_pending = true;
     return DCG_OK;
@@ -484,6 +483,41 @@ struct UniformSim : dcg_sim {
 
   uint64_t num_cells() const override { return N; }
   int num_levels() const override { return mip_levels; }
+
+  // one launch of a single stage, `reps` times, CUDA-event timed on the instance's stream
+  int bench_stage(const char *stage, int level, int reps, float *ms_per_launch, double *alg_bytes) override {
+    DCG_CUDA_TRY(cudaSetDevice(device));
+    const std::string st(stage);
+    if (level < 0 || level >= mip_levels) return fail(DCG_ERR_INVALID, "bench_stage: bad level");
+    const double n0 = (double)N, nl = (double)((uint64_t)(gx >> level) * (gy >> level) * (gz >> level));
+    double bytes = 0;
+    DCG_CUDA_TRY(cudaEventRecord(ev_begin, stream));
+    for (int r = 0; r < reps; r++) {
+      if (st == "jacobi") {
+        k_u_jacobi<<<grid_for(level), block(), 0, stream>>>(kp, level, level_off[level], (r & 1) ? tp : p, (r & 1) ? p : tp, div);
+        launches++;
+        bytes = 12.0 * nl;
+      } else if (st == "advect_velocity") { DCG_TRY(advect_velocity()); bytes = 28.0 * n0; }
+      else if (st == "advect_density") { DCG_TRY(advect_density()); bytes = 24.0 * n0; }
+      else if (st == "divergence") {
+        k_u_divergence<<<grid_for(0), block(), 0, stream>>>(kp, vw[cur_v], div, p, tp);
+        launches++;
+        bytes = 28.0 * n0;
+      } else if (st == "apply_pressure") {
+        k_u_apply_pressure<<<grid_for(0), block(), 0, stream>>>(kp, p, fluidity, vw[cur_v]);
+        launches++;
+        bytes = 32.0 * n0;
+      } else return fail(DCG_ERR_INVALID, "bench_stage: unknown stage %s", stage);
+    }
+    DCG_CUDA_TRY(cudaEventRecord(ev_end, stream));
+    DCG_CUDA_TRY(cudaStreamSynchronize(stream));
+    float ms = 0.f;
+    DCG_CUDA_TRY(cudaEventElapsedTime(&ms, ev_begin, ev_end));
+    step_timing_pending = false;
+    if (ms_per_launch) *ms_per_launch = ms / reps;
+    if (alg_bytes) *alg_bytes = bytes;
+    return DCG_OK;
+  }
 
   int get_field(int field, int layout, float *dst, uint64_t count) override {
     DCG_CUDA_TRY(cudaSetDevice(device));

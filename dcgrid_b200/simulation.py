@@ -116,6 +116,13 @@ class FluidSimulation:
         self._check(self._L.dcg_algorithmic_bytes(self._h, ctypes.byref(b), ctypes.byref(n)))
         return float(b.value), int(n.value)
 
+    def benchStage(self, stage, level=0, reps=10):
+        """(mean ms per launch, algorithmic bytes per launch) of one stage kernel; see dcg_bench_stage."""
+        ms = ctypes.c_float()
+        b = ctypes.c_double()
+        self._check(self._L.dcg_bench_stage(self._h, stage.encode(), level, reps, ctypes.byref(ms), ctypes.byref(b)))
+        return float(ms.value), float(b.value)
+
     def counters(self):
         out = np.zeros(8, dtype=np.uint64)
         self._check(self._L.dcg_get_counters(self._h, _ptr(out)))

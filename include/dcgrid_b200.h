@@ -183,6 +183,15 @@ DCG_API int dcg_last_step_ms(dcg_sim *sim, float *out);
 DCG_API int dcg_algorithmic_bytes(dcg_sim *sim, double *bytes_per_step,
                                   uint64_t *active_blocks_total);
 
+/* Measurement hook (bench.py's roofline leg): launches ONE stage kernel `reps` times back to back,
+ * CUDA-event timed on the instance's stream.  stage = "jacobi" | "advect_velocity" |
+ * "advect_density" | "divergence" | "apply_pressure" | "accumulate_velocity" | "prolongate";
+ * `level` selects the level for per-level stages.  Returns the mean device time per launch and the
+ * stage's algorithmic bytes per launch (SURVEY.md §8d per-cell figure x cells it processes).
+ * Scribbles over the pressure / ping-pong buffers: call it after the timed steps.          */
+DCG_API int dcg_bench_stage(dcg_sim *sim, const char *stage, int level, int reps,
+                            float *ms_per_launch, double *alg_bytes_per_launch);
+
 /* Last error text of this instance (or of creation when sim == NULL). */
 DCG_API const char *dcg_last_error(const dcg_sim *sim);
 DCG_API const char *dcg_version(void);

@@ -57,6 +57,10 @@ def run_pair(d, M, solids, steps, schedule="project", check_every=1):
         if s % check_every == 0 or s == steps - 1:
             act = assert_same_topology(sim, orc, f"step {s}")
             assert_same_fields(sim, orc, ("pressure", "t_pressure", "divergence", "velocity"), act, f"after project, step {s}")
+        if s == steps - 1:
+            # the residual is only defined between project() and advectDensity(): in the reference
+            # `divergence` aliases `t_density` (dcgrid_structure.cu:94-102)
+            assert sim.debugStats() == orc.debug_stats()
         sim.advectDensity(); orc.advect_density()
         if s % check_every == 0 or s == steps - 1:
             assert_same_fields(sim, orc, ("density", "velocity", "fluidity"), act, f"end of step {s}")
@@ -72,7 +76,6 @@ def run_pair(d, M, solids, steps, schedule="project", check_every=1):
 ])
 def test_dcgrid_bit_exact_vs_oracle(gpu, d, M, solids, steps, schedule):
     sim, orc = run_pair(d, M, solids, steps, schedule)
-    assert sim.debugStats() == orc.debug_stats()
     c, oc = sim.counters(), orc.counters()
     assert c[2] == oc[2] and c[3] == oc[3], "moved / refined counts"
     assert c[5] == 0, "failed allocations"
