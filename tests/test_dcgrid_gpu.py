@@ -124,9 +124,10 @@ def test_dcgrid_pool_too_small_is_an_error_not_an_exit(gpu):
     p = scene_params(256)
     with pytest.raises(DcgError):
         FluidSimulationDCGrid((256, 256, 256), 0, p)
-    # 64^3 has 5 levels; 4 blocks leave nothing for level 0 ("Too few blocks to reach highest resolution")
+    # 64^3 has 5 levels; the coarsest takes the only block, nothing is left for level 0
+    # ("Too few blocks to reach highest resolution", fluid_simulation_dcgrid.cu:50-53)
     with pytest.raises(DcgError):
-        FluidSimulationDCGrid((64, 64, 64), 4, scene_params(64))
+        FluidSimulationDCGrid((64, 64, 64), 1, scene_params(64))
 
 
 def test_dcgrid_reset_is_reproducible(gpu):
