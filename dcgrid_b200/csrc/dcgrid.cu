@@ -39,9 +39,13 @@ struct DCGridSim : dcg_sim {
   std::vector<size_t> map_size;
 
   Pool T{};
-  uint32_t *d_flags = nullptr, *d_free = nullptr, *d_touched = nullptr, *d_to_move = nullptr, *d_dest = nullptr, *d_errors = nullptr;
+  uint32_t *d_flags = nullptr, *d_free = nullptr, *d_touched = nullptr, *d_to_move = nullptr, *d_dest = nullptr;
   int4 *d_new_posl = nullptr;
   float *d_sub_scores = nullptr, *d_block_scores = nullptr;
+  ScoreSummary *d_summary = nullptr, *h_summary = nullptr;  // per-level score extrema (device-reduced, 192 B D2H)
+  uint32_t *d_flag_bits = nullptr;  // one bit per slot: flags != 0 (k_dc_flag_bits)
+  uint32_t *d_counters = nullptr;  // [0] failed allocations, [1] irregular-face blocks (last build)
+  uint64_t n_irregular = 0, n_host_selections = 0, n_levels_shortcut = 0;
   float4 *vw[2] = {nullptr, nullptr};
   float *q[2] = {nullptr, nullptr};
   float *fl = nullptr, *p = nullptr, *tp = nullptr, *div = nullptr;
@@ -65,9 +69,10 @@ struct DCGridSim : dcg_sim {
   ~DCGridSim() override {
     cudaSetDevice(device);
     drop_graphs();
-    cudaFree(T.posl); cudaFree(T.parent); cudaFree(T.child); cudaFree(T.apron); cudaFree(T.face);
+    cudaFree(T.posl); cudaFree(T.parent); cudaFree(T.child); cudaFree(T.apron); cudaFree(T.face); cudaFree(T.fd);
     for (int l = 0; l < kMaxLevels; l++) cudaFree(T.map[l]);
-    cudaFree(d_flags); cudaFree(d_free); cudaFree(d_touched); cudaFree(d_to_move); cudaFree(d_dest); cudaFree(d_errors);
+    cudaFree(d_flags); cudaFree(d_free); cudaFree(d_touched); cudaFree(d_to_move); cudaFree(d_dest); cudaFree(d_counters); cudaFree(d_flag_bits); cudaFree(d_summary);
+    if (h_summary) cudaFreeHost(h_summary);
     cudaFree(d_new_posl); cudaFree(d_sub_scores); cudaFree(d_block_scores);
     for (int i = 0; i < 2; i++) { cudaFree(vw[i]); cudaFree(q[i]); }
     cudaFree(fl); cudaFree(p); cudaFree(tp); cudaFree(div); cudaFree(scratch); cudaFree(d_partial);
@@ -129,6 +134,7 @@ struct DCGridSim : dcg_sim {
     DCG_CUDA_TRY(cudaMalloc(&T.child, (size_t)M * 8 * 4));
     DCG_CUDA_TRY(cudaMalloc(&T.apron, (size_t)M * kAV * 4));
     DCG_CUDA_TRY(cudaMalloc(&T.face, (size_t)M * 96 * 4));
+    DCG_CUDA_TRY(cudaMalloc(&T.fd, (size_t)M * 12 * 4));
     map_size.assign(levels, 0);
     for (int l = 0; l < sparse; l++) {
       map_size[l] = full_blocks[l];
@@ -139,7 +145,10 @@ struct DCGridSim : dcg_sim {
     DCG_CUDA_TRY(cudaMalloc(&d_touched, (size_t)M * 4 * 2));
     DCG_CUDA_TRY(cudaMalloc(&d_to_move, (size_t)M * 4));
     DCG_CUDA_TRY(cudaMalloc(&d_dest, (size_t)M * 8 * 4));
-    DCG_CUDA_TRY(cudaMalloc(&d_errors, 4));
+    DCG_CUDA_TRY(cudaMalloc(&d_flag_bits, ((size_t)M / 32 + 2) * 4));
+    DCG_CUDA_TRY(cudaMalloc(&d_counters, 2 * 4));
+    DCG_CUDA_TRY(cudaMalloc(&d_summary, sizeof(ScoreSummary)));
+    DCG_CUDA_TRY(cudaMallocHost(&h_summary, sizeof(ScoreSummary)));
     DCG_CUDA_TRY(cudaMalloc(&d_new_posl, (size_t)M * sizeof(int4)));
     DCG_CUDA_TRY(cudaMalloc(&d_sub_scores, ((size_t)M * 8 + 1) * 4));
     DCG_CUDA_TRY(cudaMalloc(&d_block_scores, (size_t)M * 4));
@@ -180,6 +189,7 @@ struct DCGridSim : dcg_sim {
     DCG_CUDA_TRY(cudaMemsetAsync(T.parent, 0xff, (size_t)M * 4, stream));
     DCG_CUDA_TRY(cudaMemsetAsync(T.child, 0xff, (size_t)M * 8 * 4, stream));
     DCG_CUDA_TRY(cudaMemsetAsync(T.face, 0, (size_t)M * 96 * 4, stream));
+    DCG_CUDA_TRY(cudaMemsetAsync(T.fd, 0, (size_t)M * 12 * 4, stream));
     for (int l = 0; l < sparse; l++) DCG_CUDA_TRY(cudaMemsetAsync(T.map[l], 0xff, map_size[l] * 4, stream));
     for (int i = 0; i < 2; i++) {
       DCG_CUDA_TRY(cudaMemsetAsync(vw[i], 0, cells * sizeof(float4), stream));
@@ -189,7 +199,7 @@ struct DCGridSim : dcg_sim {
     DCG_CUDA_TRY(cudaMemsetAsync(p, 0, cells * 4, stream));
     DCG_CUDA_TRY(cudaMemsetAsync(tp, 0, cells * 4, stream));
     DCG_CUDA_TRY(cudaMemsetAsync(div, 0, cells * 4, stream));
-    DCG_CUDA_TRY(cudaMemsetAsync(d_errors, 0, 4, stream));
+    DCG_CUDA_TRY(cudaMemsetAsync(d_counters, 0, 2 * 4, stream));
     k_fill_u32<<<blocks_for((size_t)M * 8 + 1, 256), 256, 0, stream>>>(reinterpret_cast<uint32_t *>(d_sub_scores), 0xFF7FFFFFu /* -FLT_MAX */,
                                                                        (size_t)M * 8 + 1);
     k_iota_u32<<<blocks_for(M, 256), 256, 0, stream>>>(d_free, M);  // freeBlockIndices[i] = i, :243-249
@@ -199,6 +209,7 @@ struct DCGridSim : dcg_sim {
       loads[l] = (max_blocks[l] == full_blocks[l]) ? max_blocks[l] : 0;
       move_limit[l] = 0;
     }
+    sync_loads();
     return init();
   }
 
@@ -210,14 +221,21 @@ struct DCGridSim : dcg_sim {
       k_dc_activate_level<<<(unsigned)full_blocks[l], 64, 0, stream>>>(T, kp, l, vw[0], vw[1], q[0], q[1], fl);
       launches++;
     }
-    k_dc_build_faces<<<blocks_for((size_t)M * 96, 256), 256, 0, stream>>>(T);
-    launches++;
+    build_face_descriptors();
     DCG_CUDA_TRY(cudaGetLastError());
     for (int i = 0; i < 5; i++) DCG_TRY(adapt_topology());
     return DCG_OK;
   }
 
   // ---- adaptation: fluid_simulation_dcgrid.cu:320-483 --------------------------------------------
+  void sync_loads() {
+    for (int l = 0; l < levels; l++) T.loads[l] = (uint32_t)loads[l];
+  }
+  void build_face_descriptors() {
+    cudaMemsetAsync(d_counters + 1, 0, 4, stream);
+    k_dc_build_fdesc<<<blocks_for((size_t)M * 8, 256), 256, 0, stream>>>(T, d_counters + 1);
+    launches++;
+  }
   uint32_t finer_full_mask() const {
     uint32_t m = 0;
     for (int l = 0; l < levels; l++)
@@ -225,26 +243,83 @@ struct DCGridSim : dcg_sim {
     return m;
   }
 
+  // Scores stay on the device; only the 192-byte per-level summary comes back.
   int compute_scores(bool with_block_scores) {
     const uint32_t mask = finer_full_mask();
-    k_dc_subblock_scores<<<blocks_for((size_t)M * 8, 256), 256, 0, stream>>>(T, kp, mask, d_sub_scores);
+    ScoreSummary init;
+    for (int l = 0; l < kMaxLevels; l++) { init.max_ss[l] = -1; init.min_bs[l] = 0xFFFFFFFFu; init.n_refine[l] = 0; }
+    *h_summary = init;
+    DCG_CUDA_TRY(cudaMemcpyAsync(d_summary, h_summary, sizeof(ScoreSummary), cudaMemcpyHostToDevice, stream));
+    k_dc_subblock_scores<<<blocks_for((size_t)M * 8, 256), 256, 0, stream>>>(T, kp, mask, d_sub_scores, d_summary);
     launches++;
     if (with_block_scores) {
-      k_dc_block_scores<<<blocks_for(M, 256), 256, 0, stream>>>(T, mask, d_sub_scores, d_block_scores);
+      k_dc_block_scores<<<blocks_for(M, 256), 256, 0, stream>>>(T, mask, d_sub_scores, d_block_scores, d_summary);
       launches++;
     }
-    DCG_CUDA_TRY(cudaMemcpyAsync(h_sub_scores, d_sub_scores, ((size_t)M * 8 + 1) * 4, cudaMemcpyDeviceToHost, stream));
-    if (with_block_scores)
-      DCG_CUDA_TRY(cudaMemcpyAsync(h_block_scores, d_block_scores, (size_t)M * 4, cudaMemcpyDeviceToHost, stream));
+    DCG_CUDA_TRY(cudaMemcpyAsync(h_summary, d_summary, sizeof(ScoreSummary), cudaMemcpyDeviceToHost, stream));
     DCG_CUDA_TRY(cudaStreamSynchronize(stream));
     return DCG_OK;
   }
 
-  // moveBlocks, :348-437.  The selection below is the reference's, statement for statement in meaning:
-  // same comparators, same std algorithms on the same value sequences => same permutations.
+  uint64_t move_candidates(int level) const {
+    const uint64_t d0 = max_blocks[level], d1 = 8 * max_blocks[level + 1];
+    uint64_t l = std::min({d0, d1, loads[level], full_blocks[level] - loads[level]});
+    if (move_limit[level] > 0) l = std::min(l, move_limit[level]);
+    return l;
+  }
+
+  // moveBlocks, :348-437.
+  //
+  // The reference copies all 9*M scores to the host every step and runs std::nth_element / std::sort
+  // over every level (:365-422).  The outcome of a level's greedy match (:410-418) is "no match" —
+  // and then nothing of that level's selection is observable — whenever
+  //     no subblock of level+1 has a score >= 0,  or  no block of the level has a score >= 0,  or
+  //     min{non-negative block scores} >= max{subblock scores}
+  // because the loop tests bs[mc[0]] >= 0 && ss[dc[0]] >= 0 && bs[mc[0]] < ss[dc[0]], where ss[dc[0]] is
+  // the maximum and bs[mc[0]] is either negative or >= the minimum, whatever permutation the
+  // (non-strict-weak, App. B-2) comparator produces.  Those three quantities are reduced on the
+  // device (ScoreSummary).  Only levels that can match take the reference's host selection, verbatim
+  // (same comparators, same std algorithms, same value sequences => same permutations), on that
+  // level's slice of the scores.
   int move_blocks(uint32_t &num_touched) {
     DCG_TRY(compute_scores(true));
     DCG_CUDA_TRY(cudaMemsetAsync(d_flags, 0, (size_t)M * 4, stream));  // :369
+    std::vector<char> need(levels, 0);
+    bool any = false;
+    for (int level = 0; level < levels - 1; level++) {
+      if (move_candidates(level) == 0) continue;
+      const int mx = h_summary->max_ss[level + 1];
+      const uint32_t mn = h_summary->min_bs[level];
+      if (mx < 0 || mn == 0xFFFFFFFFu || mn >= (uint32_t)mx) {  // non-negative floats order like their bit patterns
+        n_levels_shortcut++;
+        continue;
+      }
+      need[level] = 1;
+      any = true;
+    }
+    if (!any) {
+      for (int level = 0; level < levels - 1; level++)
+        if (move_candidates(level) > 0) move_limit[level] = 0;  // matches == 0 => moveLimit = 0 (:420)
+      return DCG_OK;
+    }
+    // slices the host selection reads: block scores of level l and l+1 (the protect-next-parent write,
+    // :417, lands in level l+1), subblock scores of level l+1
+    std::vector<char> got_bs(levels, 0), got_ss(levels, 0);
+    for (int level = 0; level < levels - 1; level++) {
+      if (!need[level]) continue;
+      for (int l2 = level; l2 <= level + 1; l2++)
+        if (!got_bs[l2]) {
+          got_bs[l2] = 1;
+          DCG_CUDA_TRY(cudaMemcpyAsync(h_block_scores + offsets[l2], d_block_scores + offsets[l2], max_blocks[l2] * 4, cudaMemcpyDeviceToHost, stream));
+        }
+      if (!got_ss[level + 1]) {
+        got_ss[level + 1] = 1;
+        // +1 float: dc[matches] may index one past the level's last subblock (App. B-3)
+        DCG_CUDA_TRY(cudaMemcpyAsync(h_sub_scores + 8 * offsets[level + 1], d_sub_scores + 8 * offsets[level + 1],
+                                     (8 * max_blocks[level + 1] + 1) * 4, cudaMemcpyDeviceToHost, stream));
+      }
+    }
+    DCG_CUDA_TRY(cudaStreamSynchronize(stream));
     const float *bs = h_block_scores, *ss = h_sub_scores;
     float *bsw = h_block_scores;
     auto block_order = [bs](uint32_t a, uint32_t b) { return bs[a] < 0.f ? false : bs[a] < bs[b]; };  // :350-353
@@ -252,9 +327,13 @@ struct DCGridSim : dcg_sim {
     uint64_t n_move = 0;
     for (int level = 0; level < levels - 1; level++) {
       const uint64_t d0 = max_blocks[level], d1 = 8 * max_blocks[level + 1];
-      uint64_t l = std::min({d0, d1, loads[level], full_blocks[level] - loads[level]});
-      if (move_limit[level] > 0) l = std::min(l, move_limit[level]);
+      const uint64_t l = move_candidates(level);
       if (l == 0) continue;
+      if (!need[level]) {
+        move_limit[level] = 0;
+        continue;
+      }
+      n_host_selections++;
       uint32_t *mc = h_to_move + n_move;
       std::iota(mc, mc + d0, (uint32_t)offsets[level]);
       if (d0 <= l)
@@ -274,7 +353,9 @@ struct DCGridSim : dcg_sim {
       uint64_t matches = 0;
       while (matches < l && bs[mc[matches]] >= 0.f && ss[dc[matches]] >= 0.f && bs[mc[matches]] < ss[dc[matches]]) {
         matches++;
-        bsw[dc[matches] / 8] = -FLT_MAX;  // :417 — protects the NEXT candidate's parent (App. B-3)
+        // :417 — protects the NEXT candidate's parent (App. B-3); that parent is a level+1 block, whose
+        // scores were fetched above.  (matches == d1 would read past the list in the reference too.)
+        if (matches < d1) bsw[dc[matches] / 8] = -FLT_MAX;
       }
       move_limit[level] = (uint64_t)(matches * 1.2f);  // :420
       n_move += matches;
@@ -295,18 +376,35 @@ struct DCGridSim : dcg_sim {
     return DCG_OK;
   }
 
-  // refineSubblocks, :439-483
+  // refineSubblocks, :439-483.  Levels with no room (limit == 0, the normal case once the pool is
+  // full) or no candidate (device-counted) are skipped without copying scores.
   int refine_subblocks(uint32_t &num_touched) {
+    std::vector<uint64_t> limits(levels, 0);
+    bool any = false;
+    for (int level = 1; level < levels; level++) {
+      limits[level] = std::min(max_blocks[level - 1] - loads[level - 1], 8 * loads[level] - loads[level - 1]);
+      any = any || limits[level] > 0;
+    }
+    if (!any) return DCG_OK;
     DCG_TRY(compute_scores(false));
+    any = false;
+    for (int level = 1; level < levels; level++) {
+      if (limits[level] == 0 || h_summary->n_refine[level] == 0) continue;
+      any = true;
+      DCG_CUDA_TRY(cudaMemcpyAsync(h_sub_scores + 8 * offsets[level], d_sub_scores + 8 * offsets[level], 8 * max_blocks[level] * 4,
+                                   cudaMemcpyDeviceToHost, stream));
+    }
+    if (!any) return DCG_OK;
+    DCG_CUDA_TRY(cudaStreamSynchronize(stream));
     const float *ss = h_sub_scores;
     uint64_t n_ref = 0;
     RefineGroups G{};
     std::vector<uint64_t> added(levels, 0);
     for (int level = 1; level < levels; level++) {
-      const uint64_t limit = std::min(max_blocks[level - 1] - loads[level - 1], 8 * loads[level] - loads[level - 1]);
+      const uint64_t limit = limits[level];
       G.start[level - 1] = (uint32_t)n_ref;
       G.base[level - 1] = (uint32_t)(offsets[level - 1] + loads[level - 1]);
-      if (limit == 0) continue;
+      if (limit == 0 || h_summary->n_refine[level] == 0) continue;
       const uint64_t start = 8 * offsets[level], end = start + 8 * max_blocks[level];
       uint32_t *di = h_dest + n_ref;
       uint64_t n = 0;
@@ -320,9 +418,10 @@ struct DCGridSim : dcg_sim {
       const uint32_t n = (uint32_t)n_ref;
       if ((size_t)num_touched + n > (size_t)2 * M) return fail(DCG_ERR_POOL, "touched list overflow");
       DCG_CUDA_TRY(cudaMemcpyAsync(d_dest, h_dest, (size_t)n * 4, cudaMemcpyHostToDevice, stream));
-      k_dc_refine<<<blocks_for(n, 256), 256, 0, stream>>>(T, kp, d_dest, n, G, d_free, d_flags, d_touched, num_touched, d_errors);
+      k_dc_refine<<<blocks_for(n, 256), 256, 0, stream>>>(T, kp, d_dest, n, G, d_free, d_flags, d_touched, num_touched, d_counters);
       launches++;
       for (int l = 0; l < levels; l++) loads[l] += added[l];
+      sync_loads();
       num_touched += n;
       n_refined += n;
     }
@@ -343,17 +442,19 @@ struct DCGridSim : dcg_sim {
     if (num_touched > 0) {
       n_changed++;
       drop_graphs();
-      k_dc_refresh_apron<<<M, kAV, 0, stream>>>(T, kp, d_flags);
-      k_dc_build_faces<<<blocks_for((size_t)M * 96, 256), 256, 0, stream>>>(T);
+      k_dc_flag_bits<<<blocks_for(M, 256), 256, 0, stream>>>(d_flags, M, d_flag_bits);
+      k_dc_refresh_apron<<<blocks_for(M, 8), 256, 0, stream>>>(T, kp, d_flags, d_flag_bits);
       launches += 2;
+      build_face_descriptors();
       for (int l = levels - 2; l >= 0; l--) {
         k_dc_propagate<<<num_touched, 64, 0, stream>>>(T, kp, d_touched, l, vw[cur_v], q[cur_q], fl);
         launches++;
       }
-      uint32_t h_err = 0;
-      DCG_CUDA_TRY(cudaMemcpyAsync(&h_err, d_errors, 4, cudaMemcpyDeviceToHost, stream));
+      uint32_t h_cnt[2] = {0, 0};
+      DCG_CUDA_TRY(cudaMemcpyAsync(h_cnt, d_counters, 8, cudaMemcpyDeviceToHost, stream));
       DCG_CUDA_TRY(cudaStreamSynchronize(stream));
-      n_failed = h_err;
+      n_failed = h_cnt[0];
+      n_irregular = h_cnt[1];
     } else if (move_limit == limit_before) {
       steady = true;  // nothing changed and the selection state is unchanged: fixed point
     }
@@ -362,18 +463,27 @@ struct DCGridSim : dcg_sim {
   }
 
   // ---- fluid stages ----------------------------------------------------------------------------------
-  void accumulate_velocity() {  // :496-501
-    for (int l = 0; l < levels - 1; l++) {
-      k_dc_accumulate_velocity<<<blocks_for(8 * max_blocks[l], 256), 256, 0, stream>>>(T, l, vw[cur_v]);
+  // first level of the "small" tail: every level >= the returned one has at most `cap` active blocks
+  int small_levels_from(uint64_t cap) const {
+    int l = levels - 1;
+    while (l > 0 && loads[l - 1] <= cap) l--;
+    return l;
+  }
+  void accumulate(float4 *v, float *ch) {  // :496-515, fine -> coarse
+    const int tail = small_levels_from(512);
+    for (int l = 0; l < levels - 1 && l < tail; l++) {
+      if (loads[l] == 0) continue;
+      if (v) k_dc_accumulate_velocity<<<blocks_for(8 * loads[l], 256), 256, 0, stream>>>(T, l, v);
+      else k_dc_accumulate_scalar<<<blocks_for(8 * loads[l], 256), 256, 0, stream>>>(T, l, ch);
+      launches++;
+    }
+    if (tail < levels - 1) {
+      k_dc_accumulate_coarse<<<1, 1024, 0, stream>>>(T, tail, v, ch);
       launches++;
     }
   }
-  void accumulate_scalar(float *ch) {  // :503-515
-    for (int l = 0; l < levels - 1; l++) {
-      k_dc_accumulate_scalar<<<blocks_for(8 * max_blocks[l], 256), 256, 0, stream>>>(T, l, ch);
-      launches++;
-    }
-  }
+  void accumulate_velocity() { accumulate(vw[cur_v], nullptr); }
+  void accumulate_scalar(float *ch) { accumulate(nullptr, ch); }
   int advect_velocity() override {  // :263-268
     k_dc_advect_velocity<<<blocks_for(M, kBPC), kCTA, 0, stream>>>(T, kp, vw[cur_v], vw[cur_v ^ 1]);
     launches++;
@@ -391,25 +501,30 @@ struct DCGridSim : dcg_sim {
     return DCG_OK;
   }
   void jacobi_pair(int l) {
-    k_dc_jacobi<<<blocks_for(max_blocks[l], kBPC), kCTA, 0, stream>>>(T, kp, l, p, tp, div);
-    k_dc_jacobi<<<blocks_for(max_blocks[l], kBPC), kCTA, 0, stream>>>(T, kp, l, tp, p, div);
+    if (loads[l] == 0) return;
+    k_dc_jacobi4<<<blocks_for(loads[l], kB4), kCTA4, 0, stream>>>(T, kp, l, p, tp, div);
+    k_dc_jacobi4<<<blocks_for(loads[l], kB4), kCTA4, 0, stream>>>(T, kp, l, tp, p, div);
     launches += 2;
   }
   void divergence_stage() {
-    k_dc_divergence<<<blocks_for(M, kBPC), kCTA, 0, stream>>>(T, kp, vw[cur_v], div, p, tp);
+    k_dc_divergence4<<<blocks_for(M, kB4), kCTA4, 0, stream>>>(T, kp, vw[cur_v], div, p, tp);
     launches++;
     accumulate_scalar(div);
   }
   void apply_stage() {
-    k_dc_apply_pressure<<<blocks_for(M, kBPC), kCTA, 0, stream>>>(T, kp, p, fl, vw[cur_v]);
+    k_dc_apply_pressure4<<<blocks_for(M, kB4), kCTA4, 0, stream>>>(T, kp, p, fl, vw[cur_v]);
     launches++;
     accumulate_velocity();
   }
   int project() override {  // :270-294
     divergence_stage();
-    for (int i = 0; i < project_coarsest_pairs; i++) jacobi_pair(levels - 1);
-    for (int l = levels - 2; l >= 0; l--) {
-      k_dc_prolongate<<<blocks_for(max_blocks[l], kBPC), kCTA, 0, stream>>>(T, l, p);
+    // levels with <= kCoarseBlocks blocks: the whole coarse part of the cascade in one single-CTA launch
+    const int cf = small_levels_from(kCoarseBlocks);
+    k_dc_coarse_cascade<<<1, 1024, 0, stream>>>(T, kp, cf, 0, project_coarsest_pairs, project_level_pairs, 1, p, tp, div);
+    launches++;
+    for (int l = cf - 1; l >= 0; l--) {
+      if (loads[l] == 0) continue;
+      k_dc_prolongate4<<<blocks_for(loads[l], kB4), kCTA4, 0, stream>>>(T, l, p);
       launches++;
       for (int i = 0; i < project_level_pairs; i++) jacobi_pair(l);
     }
@@ -419,7 +534,10 @@ struct DCGridSim : dcg_sim {
   }
   int project_local() override {  // :296-311
     divergence_stage();
-    for (int l = levels - 1; l >= 0; l--)
+    const int cf = small_levels_from(kCoarseBlocks);
+    k_dc_coarse_cascade<<<1, 1024, 0, stream>>>(T, kp, cf, 0, local_pairs, local_pairs, 0, p, tp, div);
+    launches++;
+    for (int l = cf - 1; l >= 0; l--)
       for (int i = 0; i < local_pairs; i++) jacobi_pair(l);
     apply_stage();
     DCG_CUDA_TRY(cudaGetLastError());
@@ -473,7 +591,8 @@ struct DCGridSim : dcg_sim {
     DCG_CUDA_TRY(cudaEventRecord(ev_begin, stream));
     for (int r = 0; r < reps; r++) {
       if (st == "jacobi") {
-        k_dc_jacobi<<<blocks_for(max_blocks[level], kBPC), kCTA, 0, stream>>>(T, kp, level, (r & 1) ? tp : p, (r & 1) ? p : tp, div);
+        if (loads[level] == 0) return fail(DCG_ERR_INVALID, "bench_stage: level %d has no active blocks", level);
+        k_dc_jacobi4<<<blocks_for(loads[level], kB4), kCTA4, 0, stream>>>(T, kp, level, (r & 1) ? tp : p, (r & 1) ? p : tp, div);
         bytes = 12.0 * cl;
       } else if (st == "advect_velocity") {
         k_dc_advect_velocity<<<blocks_for(M, kBPC), kCTA, 0, stream>>>(T, kp, vw[cur_v], vw[cur_v ^ 1]);
@@ -484,16 +603,16 @@ struct DCGridSim : dcg_sim {
         cur_q ^= 1;
         bytes = 24.0 * call;
       } else if (st == "divergence") {
-        k_dc_divergence<<<blocks_for(M, kBPC), kCTA, 0, stream>>>(T, kp, vw[cur_v], div, p, tp);
+        k_dc_divergence4<<<blocks_for(M, kB4), kCTA4, 0, stream>>>(T, kp, vw[cur_v], div, p, tp);
         bytes = 28.0 * call;
       } else if (st == "apply_pressure") {
-        k_dc_apply_pressure<<<blocks_for(M, kBPC), kCTA, 0, stream>>>(T, kp, p, fl, vw[cur_v]);
+        k_dc_apply_pressure4<<<blocks_for(M, kB4), kCTA4, 0, stream>>>(T, kp, p, fl, vw[cur_v]);
         bytes = 32.0 * call;
       } else if (st == "accumulate_velocity") {
-        k_dc_accumulate_velocity<<<blocks_for(8 * max_blocks[level], 256), 256, 0, stream>>>(T, level, vw[cur_v]);
+        k_dc_accumulate_velocity<<<blocks_for(8 * loads[level], 256), 256, 0, stream>>>(T, level, vw[cur_v]);
         bytes = 13.5 * cl;
       } else if (st == "prolongate") {
-        k_dc_prolongate<<<blocks_for(max_blocks[level], kBPC), kCTA, 0, stream>>>(T, level, p);
+        k_dc_prolongate4<<<blocks_for(loads[level], kB4), kCTA4, 0, stream>>>(T, level, p);
         bytes = 4.5 * cl;
       } else return fail(DCG_ERR_INVALID, "bench_stage: unknown stage %s", stage);
       launches++;

@@ -5,6 +5,7 @@
 #include <cfloat>
 
 #include "dcgrid_layout.cuh"
+#include "dcgrid_stencil.cuh"
 
 namespace dcg {
 
@@ -76,71 +77,67 @@ __global__ void __launch_bounds__(64) k_dc_activate_level(Pool T, KParams P, int
   }
 }
 
-// k_dcgrid_refresh_apron_indices, dcgrid_structure.cu:30-92.  <<<M, 216>>>; rim entries only.
-__global__ void __launch_bounds__(216) k_dc_refresh_apron(Pool T, KParams P, const uint32_t *__restrict__ flags) {
-  const uint32_t b = blockIdx.x;
-  const int ai = threadIdx.x;
-  const int4 pl = T.posl[b];
-  if (pl.w == kFree) return;
-  const int i = ai / kAA, j = (ai / kAW) % kAW, k = ai % kAW;
-  if (i % (kAW - 1) != 0 && j % (kAW - 1) != 0 && k % (kAW - 1) != 0) return;
-  const int level = pl.w;
-  uint32_t *entry = &T.apron[(size_t)b * kAV + ai];
-  uint32_t nb = kNone;
-  const int nx = pl.x + i - 1, ny = pl.y + j - 1, nz = pl.z + k - 1;
-  if (flags[b] & kFlagMoved) {
-    const int scale = 1 << level;
-    if (nx < 0 || ny < 0 || nz < 0 || nx * scale >= P.gx || ny * scale >= P.gy || nz * scale >= P.gz) {
-      // :54-60 feeds APRON coordinates (1..4) to SPREAD where cell coordinates (0..3) are meant
-      // (SURVEY App. B-5).  Reproduced on purpose: parity with the reference's Neumann ghosts.
-      *entry = b * kBV + spread(min(max(i, 1), kBW), 2) + spread(min(max(j, 1), kBW), 1) + spread(min(max(k, 1), kBW), 0);
-      return;
-    }
-    int nl = level;
-    nb = block_index_deep(T, P, nx, ny, nz, nl);
-  } else {
-    const uint32_t old = *entry;
-    const uint32_t prev = old / kBV;
-    const uint32_t cf = flags[prev];
-    if (cf & kFlagMoved) {
-      int nl = level;
-      nb = block_index_deep(T, P, nx, ny, nz, nl);
-    } else if ((cf & kFlagRefined) && T.posl[prev].w > level) {
-      nb = T.child[old / kSV];
-    }
-  }
-  if (nb == kNone) return;
-  const int4 np = T.posl[nb];
-  const int s = 1 << (np.w - level);
-  *entry = nb * kBV + cell_bits(nx / s - np.x, ny / s - np.y, nz / s - np.z);
+// one bit per pool slot: "this block moved or was refined in this adaptTopology()" — 64 KiB at M = 524,288,
+// cache-resident, so that the refresh below does not gather a 4-byte flag per rim entry
+__global__ void __launch_bounds__(256) k_dc_flag_bits(const uint32_t *__restrict__ flags, uint32_t M, uint32_t *__restrict__ bits) {
+  const uint32_t b = blockIdx.x * 256 + threadIdx.x;
+  const unsigned w = __ballot_sync(0xFFFFFFFFu, b < M && flags[b] != 0);
+  if ((threadIdx.x & 31) == 0 && b < M) bits[b >> 5] = w;
 }
 
-// face table = the 6 x 16 rim entries that 7-point stencils read
-__device__ __forceinline__ int face_apron_index(int g) {
-  const int f = g >> 4, a = (g >> 2) & 3, b = g & 3;
-  const int fixed = (f & 1) ? (kAW - 1) : 0;
-  switch (f >> 1) {
-    case 0: return kAA * fixed + kAW * (1 + a) + (1 + b);
-    case 1: return kAA * (1 + a) + kAW * fixed + (1 + b);
-    default: return kAA * (1 + a) + kAW * (1 + b) + fixed;
+// k_dcgrid_refresh_apron_indices, dcgrid_structure.cu:30-92 (reference: <<<M, 216>>>).  One warp per
+// block walks its 6^3 map in 7 strides of 32 and touches rim entries only; a block whose flag bit and
+// whose neighbours' flag bits are all clear leaves after the bitmap tests.
+__device__ __forceinline__ bool flag_bit(const uint32_t *__restrict__ bits, uint32_t b) { return (bits[b >> 5] >> (b & 31)) & 1u; }
+__global__ void __launch_bounds__(256) k_dc_refresh_apron(Pool T, KParams P, const uint32_t *__restrict__ flags,
+                                                          const uint32_t *__restrict__ flag_bits) {
+  const uint32_t b = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (b >= T.M) return;
+  const int4 pl = T.posl[b];
+  if (pl.w == kFree) return;
+  const int level = pl.w;
+  const bool self_moved = flag_bit(flag_bits, b) && (flags[b] & kFlagMoved) != 0;
+  for (int ai = threadIdx.x & 31; ai < kAV; ai += 32) {
+    const int i = ai / kAA, j = (ai / kAW) % kAW, k = ai % kAW;
+    if (i % (kAW - 1) != 0 && j % (kAW - 1) != 0 && k % (kAW - 1) != 0) continue;
+    uint32_t *entry = &T.apron[(size_t)b * kAV + ai];
+    uint32_t nb = kNone;
+    const int nx = pl.x + i - 1, ny = pl.y + j - 1, nz = pl.z + k - 1;
+    if (self_moved) {
+      const int scale = 1 << level;
+      if (nx < 0 || ny < 0 || nz < 0 || nx * scale >= P.gx || ny * scale >= P.gy || nz * scale >= P.gz) {
+        // :54-60 feeds APRON coordinates (1..4) to SPREAD where cell coordinates (0..3) are meant
+        // (SURVEY App. B-5).  Reproduced on purpose: parity with the reference's Neumann ghosts.
+        *entry = b * kBV + spread(min(max(i, 1), kBW), 2) + spread(min(max(j, 1), kBW), 1) + spread(min(max(k, 1), kBW), 0);
+        continue;
+      }
+      int nl = level;
+      nb = block_index_deep(T, P, nx, ny, nz, nl);
+    } else {
+      const uint32_t old = *entry;
+      const uint32_t prev = old / kBV;
+      if (!flag_bit(flag_bits, prev)) continue;  // neighbour untouched: entry stays
+      const uint32_t cf = flags[prev];
+      if (cf & kFlagMoved) {
+        int nl = level;
+        nb = block_index_deep(T, P, nx, ny, nz, nl);
+      } else if ((cf & kFlagRefined) && T.posl[prev].w > level) {
+        nb = T.child[old / kSV];
+      }
+    }
+    if (nb == kNone) continue;
+    const int4 np = T.posl[nb];
+    const int s = 1 << (np.w - level);
+    *entry = nb * kBV + cell_bits(nx / s - np.x, ny / s - np.y, nz / s - np.z);
   }
-}
-__global__ void __launch_bounds__(256) k_dc_build_faces(Pool T) {
-  const size_t t = (size_t)blockIdx.x * 256 + threadIdx.x;
-  if (t >= (size_t)T.M * 96) return;
-  const uint32_t b = (uint32_t)(t / 96);
-  const int g = (int)(t % 96);
-  if (T.posl[b].w == kFree) return;
-  T.face[t] = T.apron[(size_t)b * kAV + face_apron_index(g)];
 }
 
 // accumulate<T>, dcgrid_structure.cu:188-222: parent cell = .125 * sequential sum of the 8 cells of a
 // child subblock.  One thread per subblock of `level`.
 __global__ void __launch_bounds__(256) k_dc_accumulate_velocity(Pool T, int level, float4 *__restrict__ vw) {
   const uint32_t t = blockIdx.x * 256 + threadIdx.x;
-  if (t >= 8 * T.max_blocks[level]) return;
+  if (t >= 8 * T.loads[level]) return;
   const uint32_t sb = 8 * T.offsets[level] + t, b = sb / 8;
-  if (T.posl[b].w != level) return;
   const uint32_t ps = T.parent[b];
   if (ps == kNone) return;
   const float4 *c = vw + (size_t)kSV * sb;
@@ -155,9 +152,8 @@ __global__ void __launch_bounds__(256) k_dc_accumulate_velocity(Pool T, int leve
 }
 __global__ void __launch_bounds__(256) k_dc_accumulate_scalar(Pool T, int level, float *__restrict__ ch) {
   const uint32_t t = blockIdx.x * 256 + threadIdx.x;
-  if (t >= 8 * T.max_blocks[level]) return;
+  if (t >= 8 * T.loads[level]) return;
   const uint32_t sb = 8 * T.offsets[level] + t, b = sb / 8;
-  if (T.posl[b].w != level) return;
   const uint32_t ps = T.parent[b];
   if (ps == kNone) return;
   const float4 lo = *reinterpret_cast<const float4 *>(ch + (size_t)kSV * sb);
@@ -171,39 +167,82 @@ __global__ void __launch_bounds__(256) k_dc_accumulate_scalar(Pool T, int level,
 // adaptation (dcgrid_adaptation.cu)
 // ======================================================================================
 
+// Per-level summary of one score pass, reduced on the device so that the host can decide without
+// copying the score arrays which levels can possibly move or refine anything (dcgrid.cu, move_blocks).
+struct ScoreSummary {
+  int max_ss[kMaxLevels];        // float bits of the largest non-negative subblock score of the level, -1 = none
+  uint32_t min_bs[kMaxLevels];   // float bits of the smallest non-negative block score of the level, ~0 = none
+  uint32_t n_refine[kMaxLevels]; // subblocks of the level with score > 1e-4 (refineSubblocks candidates)
+};
+__device__ __forceinline__ bool warp_uniform(int v) {
+  const int v0 = __shfl_sync(0xFFFFFFFFu, v, 0);
+  return __all_sync(0xFFFFFFFFu, v == v0);
+}
+
 // k_dcgrid_calc_subblock_scores, :10-40.  finer_full bit l = "level l cannot be refined further"
 // ((l==0 && loads[0]==full[0]) || (l>0 && loads[l-1]==full[l-1]), :19-21).
-__global__ void __launch_bounds__(256) k_dc_subblock_scores(Pool T, KParams P, uint32_t finer_full, float *__restrict__ sub_scores) {
+__global__ void __launch_bounds__(256) k_dc_subblock_scores(Pool T, KParams P, uint32_t finer_full, float *__restrict__ sub_scores,
+                                                            ScoreSummary *__restrict__ sum) {
   const uint32_t sb = blockIdx.x * 256 + threadIdx.x;
-  if (sb >= 8 * T.M) return;
-  const int4 pl = T.posl[sb / 8];
-  if (T.child[sb] != kNone || pl.w == kFree || ((finer_full >> pl.w) & 1)) {
-    sub_scores[sb] = -FLT_MAX;
-    return;
+  int level = kFree;
+  float score = -FLT_MAX;
+  if (sb < 8 * T.M) {
+    const int4 pl = T.posl[sb / 8];
+    level = pl.w;
+    if (!(T.child[sb] != kNone || pl.w == kFree || ((finer_full >> pl.w) & 1))) {
+      const float s = (float)(1 << pl.w);
+      const float px = s * ((float)pl.x + 2.f * (float)((sb >> 2) & 1) + 1.f);
+      const float py = s * ((float)pl.y + 2.f * (float)((sb >> 1) & 1) + 1.f);
+      const float pz = s * ((float)pl.z + 2.f * (float)(sb & 1) + 1.f);
+      const float ex = px - .5f * (float)P.gx, ey = py - .45f * (float)P.gy, ez = pz - .5f * (float)P.gz;
+      const float d = sqrtf(ex * ex + ey * ey + ez * ez);
+      score = d < .2f * (float)P.gx ? 0.f : (float)P.gx / d;
+    }
+    sub_scores[sb] = score;
   }
-  const float s = (float)(1 << pl.w);
-  const float px = s * ((float)pl.x + 2.f * (float)((sb >> 2) & 1) + 1.f);
-  const float py = s * ((float)pl.y + 2.f * (float)((sb >> 1) & 1) + 1.f);
-  const float pz = s * ((float)pl.z + 2.f * (float)(sb & 1) + 1.f);
-  const float ex = px - .5f * (float)P.gx, ey = py - .45f * (float)P.gy, ez = pz - .5f * (float)P.gz;
-  const float d = sqrtf(ex * ex + ey * ey + ez * ez);
-  sub_scores[sb] = d < .2f * (float)P.gx ? 0.f : (float)P.gx / d;
+  // summary: warp-shuffle reduction, one atomic per warp when the warp sits inside one level
+  int mx = score >= 0.f ? __float_as_int(score) : -1;
+  uint32_t cnt = score > 1e-4f ? 1u : 0u;
+  if (warp_uniform(level)) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mx = max(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
+      cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
+    }
+    if ((threadIdx.x & 31) == 0 && level != kFree) {
+      if (mx >= 0) atomicMax(&sum->max_ss[level], mx);
+      if (cnt) atomicAdd(&sum->n_refine[level], cnt);
+    }
+  } else if (level != kFree) {
+    if (mx >= 0) atomicMax(&sum->max_ss[level], mx);
+    if (cnt) atomicAdd(&sum->n_refine[level], cnt);
+  }
 }
 
 // k_dcgrid_accumulate_subblock_scores, :42-63.  Sums NINE floats s[0..8]: the 9th
 // is subblock 0 of the next pool slot.  sub_scores has 8*M+1 entries, the last one = -FLT_MAX.
 __global__ void __launch_bounds__(256) k_dc_block_scores(Pool T, uint32_t finer_full, const float *__restrict__ sub_scores,
-                                                         float *__restrict__ block_scores) {
+                                                         float *__restrict__ block_scores, ScoreSummary *__restrict__ sum) {
   const uint32_t b = blockIdx.x * 256 + threadIdx.x;
-  if (b >= T.M) return;
   float out = -FLT_MAX;
-  const int level = T.posl[b].w;
-  if (level != kFree && !((finer_full >> level) & 1)) {
-    const float *s = sub_scores + 8 * (size_t)b;
-    if (s[0] > 0.f && s[1] > 0.f && s[2] > 0.f && s[3] > 0.f && s[4] > 0.f && s[5] > 0.f && s[6] > 0.f && s[7] > 0.f)
-      out = .125f * (s[0] + s[1] + s[2] + s[3] + s[4] + s[5] + s[6] + s[7] + s[8]);
+  int level = kFree;
+  if (b < T.M) {
+    level = T.posl[b].w;
+    if (level != kFree && !((finer_full >> level) & 1)) {
+      const float *s = sub_scores + 8 * (size_t)b;
+      if (s[0] > 0.f && s[1] > 0.f && s[2] > 0.f && s[3] > 0.f && s[4] > 0.f && s[5] > 0.f && s[6] > 0.f && s[7] > 0.f)
+        out = .125f * (s[0] + s[1] + s[2] + s[3] + s[4] + s[5] + s[6] + s[7] + s[8]);
+    }
+    block_scores[b] = out;
   }
-  block_scores[b] = out;
+  uint32_t mn = out >= 0.f ? __float_as_uint(out) : 0xFFFFFFFFu;
+  if (warp_uniform(level)) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mn = min(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, o));
+    if ((threadIdx.x & 31) == 0 && level != kFree && mn != 0xFFFFFFFFu) atomicMin(&sum->min_bs[level], mn);
+  } else if (level != kFree && mn != 0xFFFFFFFFu) {
+    atomicMin(&sum->min_bs[level], mn);
+  }
 }
 
 // k_dcgrid_move_blocks, :65-90, split in two so that the rank-order (sequential) semantics hold in
@@ -314,42 +353,87 @@ struct DSample {
   int x0, y0, z0, scale;
   float fx, fy, fz;
 };
-__device__ __forceinline__ DSample d_sample(const Pool &T, const KParams &P, float px, float py, float pz) {
+// Second half of INIT_SAMPLE: sample set-up inside the resolved block `bp` (level, position) whose 6^3
+// apron map starts at `apron` (global memory, or the CTA's staged copy in shared memory).
+__device__ __forceinline__ DSample d_sample_in(const uint32_t *apron, const int4 bp, float px, float py, float pz) {
   DSample s;
-  int ix = min(max((int)floorf(px), 0), P.gx - 1), iy = min(max((int)floorf(py), 0), P.gy - 1), iz = min(max((int)floorf(pz), 0), P.gz - 1);
-  int level = 0;
-  const uint32_t b = block_index_deep(T, P, ix, iy, iz, level);
-  s.scale = 1 << level;
+  s.scale = 1 << bp.w;
   const float inv = 1.f / (float)s.scale;
   const float x = px * inv - .5f, y = py * inv - .5f, z = pz * inv - .5f;
   const float xf = floorf(x), yf = floorf(y), zf = floorf(z);
   s.fx = x - xf; s.fy = y - yf; s.fz = z - zf;
   s.x0 = (int)xf; s.y0 = (int)yf; s.z0 = (int)zf;
-  const int4 bp = T.posl[b];
   const int i = min(max(s.x0 + 1 - bp.x, 0), kAW - 2), j = min(max(s.y0 + 1 - bp.y, 0), kAW - 2), k = min(max(s.z0 + 1 - bp.z, 0), kAW - 2);
-  const uint32_t *a = T.apron + (size_t)b * kAV + kAA * i + kAW * j + k;
+  const uint32_t *a = apron + kAA * i + kAW * j + k;
   s.id[0] = a[0]; s.id[1] = a[1]; s.id[2] = a[kAW]; s.id[3] = a[kAW + 1];
   s.id[4] = a[kAA]; s.id[5] = a[kAA + 1]; s.id[6] = a[kAA + kAW]; s.id[7] = a[kAA + kAW + 1];
   return s;
 }
 
+// Gather set-up for one cell.  The reference resolves every sample with getBlockIndexDeep + two more
+// dependent loads (block position, 8 apron ids).  Most backtraced samples stay inside the block they
+// started from, so each CTA stages its blocks' apron maps and child links in shared memory (loads
+// that do not depend on the velocity) and only samples that leave the block — or land in one of its
+// refined subblocks — walk the level maps.  Both paths produce the ids of the reference's lookup:
+// a sample inside an unrefined subblock of its own leaf block resolves to that block
+// (dcgrid_utils.cuh:201-233 finds the finest covering block; a finer one would be a descendant of
+// that subblock).
+__device__ __forceinline__ DSample d_sample(const Pool &T, const KParams &P, const uint32_t *own_apron, const uint32_t *own_child,
+                                            const int4 pl, float px, float py, float pz) {
+  const int ix = min(max((int)floorf(px), 0), P.gx - 1), iy = min(max((int)floorf(py), 0), P.gy - 1), iz = min(max((int)floorf(pz), 0), P.gz - 1);
+  const int lx = (ix >> pl.w) - pl.x, ly = (iy >> pl.w) - pl.y, lz = (iz >> pl.w) - pl.z;
+  if ((unsigned)lx < (unsigned)kBW && (unsigned)ly < (unsigned)kBW && (unsigned)lz < (unsigned)kBW &&
+      own_child[((lx >> 1) << 2) | ((ly >> 1) << 1) | (lz >> 1)] == kNone)
+    return d_sample_in(own_apron, pl, px, py, pz);
+  int level = 0;
+  const uint32_t b = block_index_deep(T, P, ix, iy, iz, level);
+  return d_sample_in(T.apron + (size_t)b * kAV, T.posl[b], px, py, pz);
+}
+
+__device__ __forceinline__ bool slot_active(const Pool &T, uint32_t b) {
+  if (b >= T.M) return false;
+  int level = 0;
+  while (level + 1 < T.levels && b >= T.offsets[level + 1]) level++;
+  return b - T.offsets[level] < T.loads[level];
+}
+
+// stage the apron maps + child links of the CTA's kBPC blocks
+__device__ __forceinline__ void stage_apron(const Pool &T, uint32_t b, bool active, uint32_t g, uint32_t t, uint32_t (*sa)[kAV], uint32_t (*sc)[kSV]) {
+  if (active) {
+    const uint32_t *ap = T.apron + (size_t)b * kAV;
+    for (int i = t; i < kAV; i += kBV) sa[g][i] = ap[i];
+    if (t < kSV) sc[g][t] = T.child[(size_t)b * kSV + t];
+  }
+  __syncthreads();
+}
+
 // k_dcgrid_advect_velocity, dcgrid_fluid.cu:74-91,112-127.  Writes the other ping-pong buffer (no
 // whole-pool D2D memcpy, fluid_simulation_dcgrid.cu:265-266).
-__global__ void __launch_bounds__(kCTA) k_dc_advect_velocity(Pool T, KParams P, const float4 *__restrict__ vin, float4 *__restrict__ vout) {
-  const uint32_t b = blockIdx.x * kBPC + (threadIdx.x >> 6);
-  if (b >= T.M) return;
-  const int4 pl = T.posl[b];
-  if (pl.w == kFree) return;
-  const uint32_t t = threadIdx.x & 63, c = b * kBV + t;
-  const float4 me = vin[c];
+__global__ void __launch_bounds__(kCTA, 5) k_dc_advect_velocity(Pool T, KParams P, const float4 *__restrict__ vin, float4 *__restrict__ vout) {
+  __shared__ uint32_t sa[kBPC][kAV];
+  __shared__ uint32_t sc[kBPC][kSV];
+  const uint32_t g = threadIdx.x >> 6, t = threadIdx.x & 63;
+  const uint32_t b = blockIdx.x * kBPC + g;
+  // active-ness from the slot number alone (level pools are slot ranges with a compact active prefix), so
+  // that position, velocity and apron map are fetched by independent loads
+  const bool active = slot_active(T, b);
+  const uint32_t c = b * kBV + t;
+  int4 pl = make_int4(0, 0, 0, 0);
+  float4 me = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (active) {
+    pl = T.posl[b];
+    me = vin[c];
+  }
+  stage_apron(T, b, active, g, t, sa, sc);
+  if (!active) return;
   float3 out = make_float3(0.f, 0.f, 0.f);
-  if (T.child[c >> 3] == kNone) {
+  if (sc[g][t >> 3] == kNone) {
     const float scale = (float)(1 << pl.w);
     const float alpha = P.dt * P.rdx;
     const float bx = ((float)(pl.x | cell_x(t)) + .5f) * scale - me.x * alpha;
     const float by = ((float)(pl.y | cell_y(t)) + .5f) * scale - me.y * alpha;
     const float bz = ((float)(pl.z | cell_z(t)) + .5f) * scale - me.z * alpha;
-    const DSample s = d_sample(T, P, bx, by, bz);
+    const DSample s = d_sample(T, P, sa[g], sc[g], pl, bx, by, bz);
     float4 cv[8];
     float f[8];
 #pragma unroll
@@ -375,20 +459,30 @@ __global__ void __launch_bounds__(kCTA) k_dc_advect_velocity(Pool T, KParams P, 
 // k_dcgrid_advect_density, dcgrid_fluid.cu:93-110,129-144
 __global__ void __launch_bounds__(kCTA) k_dc_advect_density(Pool T, KParams P, const float4 *__restrict__ vw, const float *__restrict__ fl,
                                                             const float *__restrict__ qin, float *__restrict__ qout) {
-  const uint32_t b = blockIdx.x * kBPC + (threadIdx.x >> 6);
-  if (b >= T.M) return;
-  const int4 pl = T.posl[b];
-  if (pl.w == kFree) return;
-  const uint32_t t = threadIdx.x & 63, c = b * kBV + t;
+  __shared__ uint32_t sa[kBPC][kAV];
+  __shared__ uint32_t sc[kBPC][kSV];
+  const uint32_t g = threadIdx.x >> 6, t = threadIdx.x & 63;
+  const uint32_t b = blockIdx.x * kBPC + g;
+  // active-ness from the slot number alone (level pools are slot ranges with a compact active prefix), so
+  // that position, velocity and apron map are fetched by independent loads
+  const bool active = slot_active(T, b);
+  const uint32_t c = b * kBV + t;
+  int4 pl = make_int4(0, 0, 0, 0);
+  float4 me = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (active) {
+    pl = T.posl[b];
+    me = vw[c];
+  }
+  stage_apron(T, b, active, g, t, sa, sc);
+  if (!active) return;
   float out = 0.f;
-  if (T.child[c >> 3] == kNone) {
-    const float4 me = vw[c];
+  if (sc[g][t >> 3] == kNone) {
     const float scale = (float)(1 << pl.w);
     const float alpha = P.dt * P.rdx;
     const float bx = ((float)(pl.x | cell_x(t)) + .5f) * scale - me.x * alpha;
     const float by = ((float)(pl.y | cell_y(t)) + .5f) * scale - me.y * alpha;
     const float bz = ((float)(pl.z | cell_z(t)) + .5f) * scale - me.z * alpha;
-    const DSample s = d_sample(T, P, bx, by, bz);
+    const DSample s = d_sample(T, P, sa[g], sc[g], pl, bx, by, bz);
     float qv[8], f[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) {
@@ -406,126 +500,42 @@ __global__ void __launch_bounds__(kCTA) k_dc_advect_density(Pool T, KParams P, c
   qout[c] = out;
 }
 
-// Stage one block's 6^3 apron of a scalar field in shared memory: own 64 cells + 6 x 16 face ghosts
-// through the face table.  `sp` = this block's 216-float tile.
-__device__ __forceinline__ void stage_scalar(float *sp, const float *__restrict__ src, const uint32_t *__restrict__ face, uint32_t b, uint32_t t) {
-  sp[apron_of(t)] = src[b * kBV + t];
-  const uint32_t *f = face + (size_t)b * 96;
-  sp[face_apron_index(t)] = src[f[t]];
-  if (t < 32) sp[face_apron_index(64 + t)] = src[f[64 + t]];
+// k_dcgrid_prolongate, dcgrid_multigrid_solver.cu:43-76.  One thread per quad (1x2x2 cells): the four cells
+// share their parent cell, so the 4 x 8 coarse reads of the reference collapse to 2x3x3 = 18.
+__device__ __forceinline__ float prolong_one(const float (*c)[3][3], int j, int k) {
+  // c[di][dj+1][dk+1], di = 0 (parent cell) / 1 (its x neighbour); j,k = -1/+1 toward the nearer neighbour
+  const float p000 = c[0][1][1], p001 = c[0][1][1 + k], p010 = c[0][1 + j][1], p100 = c[1][1][1];
+  const float p011 = c[0][1 + j][1 + k], p101 = c[1][1][1 + k], p110 = c[1][1 + j][1], p111 = c[1][1 + j][1 + k];
+  return (27.f * p000 + 9.f * (p001 + p010 + p100) + 3.f * (p011 + p101 + p110) + p111) / 64.f;
 }
-
-// k_dcgrid_calc_divergence, dcgrid_fluid.cu:174-230
-__global__ void __launch_bounds__(kCTA) k_dc_divergence(Pool T, KParams P, const float4 *__restrict__ vw, float *__restrict__ div,
-                                                        float *__restrict__ p, float *__restrict__ tp) {
-  __shared__ float4 sv[kBPC][kAV];
-  const uint32_t g = threadIdx.x >> 6, t = threadIdx.x & 63;
-  const uint32_t b = blockIdx.x * kBPC + g;
-  int4 pl = make_int4(0, 0, 0, kFree);
-  if (b < T.M) pl = T.posl[b];
-  const bool active = pl.w != kFree;
-  const uint32_t c = b * kBV + t;
-  const int scale = active ? (1 << pl.w) : 1;
-  const int x = pl.x | cell_x(t), y = pl.y | cell_y(t), z = pl.z | cell_z(t);
-  if (active) {
-    float4 *s = sv[g];
-    s[apron_of(t)] = vw[c];
-    const uint32_t *f = T.face + (size_t)b * 96;
-    // ghost cells: boundary conditions are evaluated at the ghost's own position (:193-210)
-    for (int gi = t; gi < 96; gi += 64) {
-      const int fc = gi >> 4, a = (gi >> 2) & 3, bb = gi & 3;
-      int gx, gy, gz;
-      const int fixed = (fc & 1) ? kBW : -1;
-      if ((fc >> 1) == 0) { gx = fixed; gy = a; gz = bb; }
-      else if ((fc >> 1) == 1) { gx = a; gy = fixed; gz = bb; }
-      else { gx = a; gy = bb; gz = fixed; }
-      const float4 v = vw[f[gi]];
-      const float3 vb = velocity_bc(P, make_float3(v.x, v.y, v.z), pl.x + gx, pl.y + gy, pl.z + gz, scale);
-      s[face_apron_index(gi)] = make_float4(vb.x, vb.y, vb.z, v.w);
-    }
-  }
-  __syncthreads();
-  if (!active) return;
-  p[c] = 0.f;
-  tp[c] = 0.f;
-  float d = 0.f;
-  if (T.child[c >> 3] == kNone) {
-    const float4 *s = sv[g];
-    const int ai = apron_of(t);
-    const float alpha = .5f * P.rdx / (float)scale;
-    const float4 l = s[ai - kAA], r = s[ai + kAA], dn = s[ai - kAW], up = s[ai + kAW], bk = s[ai - 1], fr = s[ai + 1];
-    d = alpha * (r.w * r.x - l.w * l.x + up.w * up.y - dn.w * dn.y + fr.w * fr.z - bk.w * bk.z);
-  }
-  div[c] = d;
-  (void)x; (void)y; (void)z;
-}
-
-// k_dcgrid_jacobi / k_dcgrid_jacobi_inv, dcgrid_multigrid_solver.cu:5-41.  `in`/`out` = (pressure,
-// t_pressure) or (t_pressure, pressure).  Ghosts of coarser neighbours are read from `in` of the
-// coarse cell — for jacobi_inv that is the coarse level's t_pressure, as in the reference (:32-37).
-__global__ void __launch_bounds__(kCTA) k_dc_jacobi(Pool T, KParams P, int level, const float *__restrict__ in, float *__restrict__ out,
-                                                    const float *__restrict__ div) {
-  __shared__ float sp[kBPC][kAV];
-  const uint32_t g = threadIdx.x >> 6, t = threadIdx.x & 63;
-  const uint32_t li = blockIdx.x * kBPC + g;
+__global__ void __launch_bounds__(kCTA4) k_dc_prolongate4(Pool T, int level, float *__restrict__ p) {
+  const uint32_t g = threadIdx.x >> 4;
+  const int t = threadIdx.x & 15;
+  const uint32_t li = blockIdx.x * kB4 + g;
+  if (li >= T.loads[level]) return;
   const uint32_t b = T.offsets[level] + li;
-  const bool active = li < T.max_blocks[level] && T.posl[b].w == level;
-  if (active) stage_scalar(sp[g], in, T.face, b, t);
-  __syncthreads();
-  if (!active) return;
-  const float alpha = (float)((1 << level) * (1 << level)) * P.dx * P.dx;
-  const float *s = sp[g];
-  const int ai = apron_of(t);
-  const uint32_t c = b * kBV + t;
-  out[c] = (s[ai - kAA] + s[ai + kAA] + s[ai - kAW] + s[ai + kAW] + s[ai - 1] + s[ai + 1] - alpha * div[c]) / 6.f;
-}
-
-// k_dcgrid_prolongate, dcgrid_multigrid_solver.cu:43-76
-__global__ void __launch_bounds__(kCTA) k_dc_prolongate(Pool T, int level, float *__restrict__ p) {
-  const uint32_t g = threadIdx.x >> 6, t = threadIdx.x & 63;
-  const uint32_t li = blockIdx.x * kBPC + g;
-  if (li >= T.max_blocks[level]) return;
-  const uint32_t b = T.offsets[level] + li;
-  const int4 pl = T.posl[b];
-  if (pl.w != level) return;
   const uint32_t ps = T.parent[b];
   if (ps == kNone) return;
   const uint32_t *pa = T.apron + (size_t)(ps / 8) * kAV;
-  const int x = pl.x | cell_x(t), y = pl.y | cell_y(t), z = pl.z | cell_z(t);
-  const int idx = kAA * (1 + (x / 2) % kBW) + kAW * (1 + (y / 2) % kBW) + (1 + (z / 2) % kBW);
-  const int i = x % 2 ? kAA : -kAA, j = y % 2 ? kAW : -kAW, k = z % 2 ? 1 : -1;
-  const float p000 = p[pa[idx]], p001 = p[pa[idx + k]], p010 = p[pa[idx + j]], p100 = p[pa[idx + i]];
-  const float p011 = p[pa[idx + j + k]], p101 = p[pa[idx + i + k]], p110 = p[pa[idx + i + j]], p111 = p[pa[idx + i + j + k]];
-  p[b * kBV + t] = (27.f * p000 + 9.f * (p001 + p010 + p100) + 3.f * (p011 + p101 + p110) + p111) / 64.f;
-}
-
-// k_dcgrid_apply_pressure, dcgrid_fluid.cu:232-259
-__global__ void __launch_bounds__(kCTA) k_dc_apply_pressure(Pool T, KParams P, const float *__restrict__ p, const float *__restrict__ fl,
-                                                            float4 *__restrict__ vw) {
-  __shared__ float sp[kBPC][kAV];
-  __shared__ float sw[kBPC][kAV];
-  const uint32_t g = threadIdx.x >> 6, t = threadIdx.x & 63;
-  const uint32_t b = blockIdx.x * kBPC + g;
-  int level = kFree;
-  if (b < T.M) level = T.posl[b].w;
-  const bool active = level != kFree;
-  if (active) {
-    stage_scalar(sp[g], p, T.face, b, t);
-    stage_scalar(sw[g], fl, T.face, b, t);
-  }
-  __syncthreads();
-  if (!active) return;
-  const uint32_t c = b * kBV + t;
-  if (T.child[c >> 3] != kNone) return;
-  const float alpha = .5f * P.rdx / (float)(1 << level);
-  const float *s = sp[g], *w = sw[g];
-  const int ai = apron_of(t);
-  const float pc = s[ai];
-  float4 v = vw[c];
-  v.x -= alpha * (w[ai + kAA] * (s[ai + kAA] - pc) + w[ai - kAA] * (pc - s[ai - kAA]));
-  v.y -= alpha * (w[ai + kAW] * (s[ai + kAW] - pc) + w[ai - kAW] * (pc - s[ai - kAW]));
-  v.z -= alpha * (w[ai + 1] * (s[ai + 1] - pc) + w[ai - 1] * (pc - s[ai - 1]));
-  vw[c] = v;
+  int X, Y0, Z0;
+  quad_coords(t, X, Y0, Z0);
+  // a child block covers subblock (ps & 7) of its parent: parent cell = 2*subblock bit + (child cell >> 1)
+  const int PX = (int)((ps >> 2) & 1u) * 2 + (X >> 1), PY = (int)((ps >> 1) & 1u) * 2 + (Y0 >> 1), PZ = (int)(ps & 1u) * 2 + (Z0 >> 1);
+  const int idx = kAA * (1 + PX) + kAW * (1 + PY) + (1 + PZ);
+  const int i = (X & 1) ? kAA : -kAA;
+  float c[2][3][3];
+#pragma unroll
+  for (int di = 0; di < 2; di++)
+#pragma unroll
+    for (int dj = -1; dj <= 1; dj++)
+#pragma unroll
+      for (int dk = -1; dk <= 1; dk++) c[di][dj + 1][dk + 1] = p[pa[idx + di * i + dj * kAW + dk]];
+  float4 o;
+  o.x = prolong_one(c, -1, -1);
+  o.y = prolong_one(c, -1, 1);
+  o.z = prolong_one(c, 1, -1);
+  o.w = prolong_one(c, 1, 1);
+  *reinterpret_cast<float4 *>(p + (size_t)b * kBV + 4 * t) = o;
 }
 
 // k_dcgrid_debug_stats, dcgrid_structure.cu:224-251: one thread per block, sequential i,j,k order

@@ -12,8 +12,9 @@
 //    move/refine instead of memset + refill of the whole table
 //    (fluid_simulation_dcgrid.cu:326-331).  4 B per potential block of a sparse level: 8 MiB
 //    + 1 MiB at 512^3, sized for 180 GB of HBM.
-//  * A compact face table (6 faces x 16 ids per block) derived from the 6^3 apron map, so
-//    stencil kernels read 384 B of indices per block instead of the scattered 6^3 x 8 B map.
+//  * Face descriptors (6 neighbour slots + 6 closed-form codes = 48 B per block) derived from, and
+//    verified entry by entry against, the 6^3 apron map, so stencil kernels read 48 B of indices
+//    per block instead of the scattered 6^3 x 8 B map (dcgrid_stencil.cuh).
 #pragma once
 #include "common.cuh"
 
@@ -31,12 +32,14 @@ struct Pool {
   int levels, sparse_levels;
   uint32_t offsets[kMaxLevels];     // levelOffsets
   uint32_t max_blocks[kMaxLevels];  // maxNumBlocksLevel
+  uint32_t loads[kMaxLevels];       // blockLoads: active blocks of level l = slots [offsets[l], offsets[l]+loads[l])
   int4 *posl;                       // (x, y, z, level) per slot; level 0xFF = free slot
   uint8_t *flags;                   // blockFlags
   uint32_t *parent;                 // parentIndices: 8*parentSlot + subblock
   uint32_t *child;                  // childIndices[8*slot + subblock]
   uint32_t *apron;                  // cellIndices[216*slot + 36*X + 6*Y + Z]
-  uint32_t *face;                   // [96*slot + 16*f + 4*a + b], f = -x,+x,-y,+y,-z,+z
+  uint32_t *fd;                     // [12*slot]: 6 face-neighbour slots + 6 face codes (dcgrid_stencil.cuh)
+  uint32_t *face;                   // [96*slot + 16*f + 4*a + b], f = -x,+x,-y,+y,-z,+z; irregular blocks only
   uint32_t *map[kMaxLevels];        // dense block-coordinate -> slot map of each sparse level
 };
 

@@ -1,0 +1,441 @@
+// 7-point stencil kernels of the DCGrid solve (divergence, Jacobi sweeps, pressure gradient), second
+// generation: 4 cells per thread (one float4 = the 1x2x2 quad that is contiguous in the reference's
+// in-block bit layout), 16 threads per logical 4^3 block, 16 blocks per 256-thread CTA, neighbours
+// exchanged through half-warp shuffles (no shared memory, no barrier), and NO per-cell index table on
+// the hot path.
+//
+// Index traffic.  The reference resolves every neighbour through cellIndices[216] (8-byte ids,
+// 1,728 B per block and sweep).  Every face of that 6^3 apron map is one of three
+// closed forms (checked entry by entry when the map changes, k_dc_build_fdesc):
+//   * all 16 ghosts lie in ONE block `nb` that is dl >= 0 levels coarser (dl = 0: the same-level
+//     neighbour; nb = the block itself: the ordered-level wall clamp, dcgrid_structure.cu:157-167),
+//     at cell  o + (a >> dl, b >> dl)  of that block;
+//   * the moved-block wall entry of k_dcgrid_refresh_apron_indices (dcgrid_structure.cu:54-60, SURVEY
+//     App. B-5): own cell ((a+1)&3, (b+1)&3) on the tangential axes;
+//   * anything else marks the block irregular and its 96 face ids are read from an explicit table.
+// A block therefore carries 12 words (6 neighbour slots + 6 codes) = 48 B instead of 1,728 B, and the
+// ids the kernels use are, by construction, exactly the entries of the reference's apron map.
+//
+// Numerics: same expressions in the same order as dcgrid_kernels.cuh / the reference; -fmad=false.
+#pragma once
+#include "dcgrid_layout.cuh"
+
+namespace dcg {
+
+constexpr int kQT = 16;    // threads per logical block (4 cells each)
+constexpr int kB4 = 16;    // logical blocks per CTA
+constexpr int kCTA4 = kQT * kB4;
+constexpr uint32_t kFdIrregular = 0x80000000u;
+constexpr uint32_t kFdQuirk = 1u << 10;
+
+// ghost (face axis, tangential a, b) -> cell id, from one face descriptor
+__device__ __forceinline__ uint32_t fd_ghost(uint32_t nb, uint32_t code, int axis, int a, int b) {
+  const int dl = (int)(code & 15u);
+  int ta, tb;
+  if (code & kFdQuirk) {
+    ta = (a + 1) & 3;
+    tb = (b + 1) & 3;
+  } else {
+    ta = a >> dl;
+    tb = b >> dl;
+  }
+  int ox = (int)((code >> 4) & 3u), oy = (int)((code >> 6) & 3u), oz = (int)((code >> 8) & 3u);
+  if (axis == 0) { oy += ta; oz += tb; }
+  else if (axis == 1) { ox += ta; oz += tb; }
+  else { ox += ta; oy += tb; }
+  return nb * kBV + cell_bits(ox, oy, oz);
+}
+
+// apron index of ghost g = 16*f + 4*a + b (f = -x,+x,-y,+y,-z,+z)
+__device__ __forceinline__ int face_apron_index(int g) {
+  const int f = g >> 4, a = (g >> 2) & 3, b = g & 3;
+  const int fixed = (f & 1) ? (kAW - 1) : 0;
+  switch (f >> 1) {
+    case 0: return kAA * fixed + kAW * (1 + a) + (1 + b);
+    case 1: return kAA * (1 + a) + kAW * fixed + (1 + b);
+    default: return kAA * (1 + a) + kAW * (1 + b) + fixed;
+  }
+}
+
+// Derives the 6 face descriptors of every active block from its apron map, verifying all 16 entries
+// of each face against the closed form.  8 lanes per block (6 used).  Irregular blocks get their 96
+// face ids copied to T.face and are counted in *irregular.
+__global__ void __launch_bounds__(256) k_dc_build_fdesc(Pool T, uint32_t *__restrict__ irregular) {
+  const uint32_t gid = blockIdx.x * 256 + threadIdx.x;
+  const uint32_t b = gid >> 3;
+  const int f = (int)(gid & 7u);
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned grp_mask = 0xFFu << (lane & 24u);
+  bool bad = false;
+  uint32_t nb = kNone, code = 0;
+  uint32_t e[16];
+  const bool live = b < T.M && f < 6 && T.posl[b].w != kFree;
+  if (live) {
+    const uint32_t *ap = T.apron + (size_t)b * kAV;
+#pragma unroll
+    for (int k = 0; k < 16; k++) e[k] = ap[face_apron_index(16 * f + k)];
+    const int axis = f >> 1;
+    const int level = T.posl[b].w;
+    if (e[0] == kNone) bad = true;
+    if (!bad) {
+      nb = e[0] >> 6;
+      const uint32_t c00 = e[0] & 63u;
+      const int ox = cell_x(c00), oy = cell_y(c00), oz = cell_z(c00);
+      const int nl = nb < T.M ? T.posl[nb].w : kFree;
+      const int dl = nl - level;
+      bool regular = nl != kFree && dl >= 0 && dl <= 15;
+      if (regular) {
+        code = (uint32_t)dl | ((uint32_t)ox << 4) | ((uint32_t)oy << 6) | ((uint32_t)oz << 8);
+#pragma unroll
+        for (int k = 0; k < 16; k++) regular = regular && e[k] == fd_ghost(nb, code, axis, k >> 2, k & 3);
+      }
+      if (!regular) {
+        // moved-block wall entry: own block, normal coordinate from e[0], tangential (a+1)&3
+        const int n = axis == 0 ? ox : (axis == 1 ? oy : oz);
+        code = kFdQuirk | ((uint32_t)(axis == 0 ? n : 0) << 4) | ((uint32_t)(axis == 1 ? n : 0) << 6) | ((uint32_t)(axis == 2 ? n : 0) << 8);
+        bool quirk = nb == b;
+#pragma unroll
+        for (int k = 0; k < 16; k++) quirk = quirk && e[k] == fd_ghost(nb, code, axis, k >> 2, k & 3);
+        bad = !quirk;
+      }
+    }
+  }
+  const unsigned any_bad = __ballot_sync(0xFFFFFFFFu, bad) & grp_mask;
+  if (!live) return;
+  uint32_t *fd = T.fd + 12 * (size_t)b;
+  fd[f] = nb;
+  fd[6 + f] = (code & ~kFdIrregular) | (any_bad ? kFdIrregular : 0u);
+  if (any_bad) {
+#pragma unroll
+    for (int k = 0; k < 16; k++) T.face[(size_t)b * 96 + 16 * f + k] = e[k];
+    if (f == 0) atomicAdd(irregular, 1u);
+  }
+}
+
+// thread t of a block owns the quad (X, Y0..Y0+1, Z0..Z0+1): t = sx<<3 | sy<<2 | sz<<1 | cx
+__device__ __forceinline__ void quad_coords(int t, int &X, int &Y0, int &Z0) {
+  X = ((t >> 3) << 1) | (t & 1);
+  Y0 = ((t >> 2) & 1) << 1;
+  Z0 = ((t >> 1) & 1) << 1;
+}
+__device__ __forceinline__ unsigned half_mask() { return 0xFFFFu << (threadIdx.x & 16u); }
+
+// Ghost ids a quad needs itself: 4 on an x face (only quads with X = 0 or 3), 2 on its y face, 2 on its
+// z face (every quad touches exactly one y and one z face of the block).
+struct QuadGhosts {
+  uint32_t x[4];  // cells k = 2*cy+cz, valid iff has_x
+  uint32_t y[2];  // [cz], the quad's boundary row (cy = sy)
+  uint32_t z[2];  // [cy], the quad's boundary column (cz = sz)
+  bool has_x;
+};
+__device__ __forceinline__ QuadGhosts quad_ghosts(const Pool &T, uint32_t b, int t) {
+  const uint4 *p = reinterpret_cast<const uint4 *>(T.fd + 12 * (size_t)b);
+  const uint4 w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);
+  int X, Y0, Z0;
+  quad_coords(t, X, Y0, Z0);
+  const int sy = (t >> 2) & 1, sz = (t >> 1) & 1;
+  const int fx = X == 3 ? 1 : 0, fy = 2 + sy, fz = 4 + sz;
+  QuadGhosts q;
+  q.has_x = X == 0 || X == 3;
+  if (w1.z & kFdIrregular) {
+    const uint32_t *ft = T.face + (size_t)b * 96;
+#pragma unroll
+    for (int k = 0; k < 4; k++) q.x[k] = q.has_x ? ft[16 * fx + 4 * (Y0 + (k >> 1)) + (Z0 + (k & 1))] : 0u;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+      q.y[k] = ft[16 * fy + 4 * X + (Z0 + k)];
+      q.z[k] = ft[16 * fz + 4 * X + (Y0 + k)];
+    }
+    return q;
+  }
+  const uint32_t nbx = fx ? w0.y : w0.x, cdx = fx ? w1.w : w1.z;
+  const uint32_t nby = sy ? w0.w : w0.z, cdy = sy ? w2.y : w2.x;
+  const uint32_t nbz = sz ? w1.y : w1.x, cdz = sz ? w2.w : w2.z;
+#pragma unroll
+  for (int k = 0; k < 4; k++) q.x[k] = fd_ghost(nbx, cdx, 0, Y0 + (k >> 1), Z0 + (k & 1));
+#pragma unroll
+  for (int k = 0; k < 2; k++) {
+    q.y[k] = fd_ghost(nby, cdy, 1, X, Z0 + k);
+    q.z[k] = fd_ghost(nbz, cdz, 2, X, Y0 + k);
+  }
+  return q;
+}
+
+// The 6-neighbourhood of a quad of one scalar field, exchanged through half-warp shuffles (no shared
+// memory): in-block neighbours come from the registers of the lane that owns them, block-boundary
+// neighbours from the ghost values this lane loaded.
+struct QuadNbr {
+  float4 xm, xp;             // x-1 / x+1 neighbours of cells k = 0..3
+  float ym0, ym1, yp0, yp1;  // y-1 of (cy=0; cz=0,1), y+1 of (cy=1; cz=0,1)
+  float zm0, zm1, zp0, zp1;  // z-1 of (cz=0; cy=0,1), z+1 of (cz=1; cy=0,1)
+};
+__device__ __forceinline__ void quad_exchange_x(QuadNbr &n, float4 own, int t, float4 gx) {
+  const unsigned hm = half_mask();
+  const int lb = threadIdx.x & 16;
+  const int cx = t & 1, sx = t >> 3;
+  const int lxm = lb + ((cx ? t - 1 : t - 7) & 15), lxp = lb + ((cx ? t + 7 : t + 1) & 15);
+  n.xm.x = __shfl_sync(hm, own.x, lxm); n.xm.y = __shfl_sync(hm, own.y, lxm);
+  n.xm.z = __shfl_sync(hm, own.z, lxm); n.xm.w = __shfl_sync(hm, own.w, lxm);
+  n.xp.x = __shfl_sync(hm, own.x, lxp); n.xp.y = __shfl_sync(hm, own.y, lxp);
+  n.xp.z = __shfl_sync(hm, own.z, lxp); n.xp.w = __shfl_sync(hm, own.w, lxp);
+  if (!cx && !sx) n.xm = gx;
+  if (cx && sx) n.xp = gx;
+}
+__device__ __forceinline__ void quad_exchange_y(QuadNbr &n, float4 own, int t, float gy0, float gy1) {
+  const unsigned hm = half_mask();
+  const int lb = threadIdx.x & 16;
+  const int sy = (t >> 2) & 1;
+  const int lym = lb + ((t - 4) & 15), lyp = lb + ((t + 4) & 15);
+  n.ym0 = __shfl_sync(hm, own.z, lym); n.ym1 = __shfl_sync(hm, own.w, lym);
+  n.yp0 = __shfl_sync(hm, own.x, lyp); n.yp1 = __shfl_sync(hm, own.y, lyp);
+  if (!sy) { n.ym0 = gy0; n.ym1 = gy1; } else { n.yp0 = gy0; n.yp1 = gy1; }
+}
+__device__ __forceinline__ void quad_exchange_z(QuadNbr &n, float4 own, int t, float gz0, float gz1) {
+  const unsigned hm = half_mask();
+  const int lb = threadIdx.x & 16;
+  const int sz = (t >> 1) & 1;
+  const int lzm = lb + ((t - 2) & 15), lzp = lb + ((t + 2) & 15);
+  n.zm0 = __shfl_sync(hm, own.y, lzm); n.zm1 = __shfl_sync(hm, own.w, lzm);
+  n.zp0 = __shfl_sync(hm, own.x, lzp); n.zp1 = __shfl_sync(hm, own.z, lzp);
+  if (!sz) { n.zm0 = gz0; n.zm1 = gz1; } else { n.zp0 = gz0; n.zp1 = gz1; }
+}
+__device__ __forceinline__ QuadNbr quad_exchange(float4 own, int t, float4 gx, float gy0, float gy1, float gz0, float gz1) {
+  QuadNbr n;
+  quad_exchange_x(n, own, t, gx);
+  quad_exchange_y(n, own, t, gy0, gy1);
+  quad_exchange_z(n, own, t, gz0, gz1);
+  return n;
+}
+__device__ __forceinline__ QuadNbr quad_neighbours(const float *__restrict__ src, float4 own, int t, const QuadGhosts &q) {
+  float4 gx = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (q.has_x) gx = make_float4(src[q.x[0]], src[q.x[1]], src[q.x[2]], src[q.x[3]]);
+  const float gy0 = src[q.y[0]], gy1 = src[q.y[1]], gz0 = src[q.z[0]], gz1 = src[q.z[1]];
+  return quad_exchange(own, t, gx, gy0, gy1, gz0, gz1);
+}
+
+// ---- k_dcgrid_jacobi / k_dcgrid_jacobi_inv, dcgrid_multigrid_solver.cu:5-41 -------------------------
+// Active blocks of a level are the compact slot prefix [offset, offset + blockLoads): slots come
+// from freeBlockIndices[offset + load] with the identity free list (fluid_simulation_dcgrid.cu:243-249,
+// dcgrid_utils.cuh:118-127) and deleteBlock is never called.
+// Sum order of the reference: left + right + down + up + back + front.
+__global__ void __launch_bounds__(kCTA4) k_dc_jacobi4(Pool T, KParams P, int level, const float *__restrict__ in, float *__restrict__ out,
+                                                      const float *__restrict__ div) {
+  const uint32_t g = threadIdx.x >> 4;
+  const int t = threadIdx.x & 15;
+  const uint32_t li = blockIdx.x * kB4 + g;
+  if (li >= T.loads[level]) return;
+  const uint32_t b = T.offsets[level] + li;
+  const size_t c0 = (size_t)b * kBV + 4 * t;
+  const float4 own = *reinterpret_cast<const float4 *>(in + c0);
+  const float4 dv = __ldcs(reinterpret_cast<const float4 *>(div + c0));  // streamed: keep L2 for the ghosts
+  const QuadGhosts q = quad_ghosts(T, b, t);
+  const QuadNbr n = quad_neighbours(in, own, t, q);
+  const float alpha = (float)((1 << level) * (1 << level)) * P.dx * P.dx;
+  float4 o;
+  o.x = (n.xm.x + n.xp.x + n.ym0 + own.z + n.zm0 + own.y - alpha * dv.x) / 6.f;
+  o.y = (n.xm.y + n.xp.y + n.ym1 + own.w + own.x + n.zp0 - alpha * dv.y) / 6.f;
+  o.z = (n.xm.z + n.xp.z + own.x + n.yp0 + n.zm1 + own.w - alpha * dv.z) / 6.f;
+  o.w = (n.xm.w + n.xp.w + own.y + n.yp1 + own.z + n.zp1 - alpha * dv.w) / 6.f;
+  *reinterpret_cast<float4 *>(out + c0) = o;
+}
+
+// ---- k_dcgrid_calc_divergence, dcgrid_fluid.cu:174-230 -----------------------------------------------
+// Each lane forms fluidity*velocity-component products of its quad; x products travel to the x
+// neighbours, y to y, z to z.  Ghosts pass through velocityBndCond at the ghost's own-level position
+// first (:193-210).
+__device__ __forceinline__ float ghost_product(const KParams &P, const float4 *__restrict__ vw, uint32_t id, int axis, int gx, int gy, int gz,
+                                               int scale) {
+  const float4 v = vw[id];
+  const float3 vb = velocity_bc(P, make_float3(v.x, v.y, v.z), gx, gy, gz, scale);
+  return v.w * (axis == 0 ? vb.x : (axis == 1 ? vb.y : vb.z));
+}
+__global__ void __launch_bounds__(kCTA4) k_dc_divergence4(Pool T, KParams P, const float4 *__restrict__ vw, float *__restrict__ div,
+                                                          float *__restrict__ p, float *__restrict__ tp) {
+  const uint32_t g = threadIdx.x >> 4;
+  const int t = threadIdx.x & 15;
+  const uint32_t b = blockIdx.x * kB4 + g;
+  if (b >= T.M) return;
+  const int4 pl = T.posl[b];
+  if (pl.w == kFree) return;
+  const size_t c0 = (size_t)b * kBV + 4 * t;
+  float4 v[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) v[k] = vw[c0 + k];
+  const uint32_t child = T.child[(size_t)b * 8 + (t >> 1)];
+  const QuadGhosts q = quad_ghosts(T, b, t);
+  int X, Y0, Z0;
+  quad_coords(t, X, Y0, Z0);
+  const int scale = 1 << pl.w;
+  const int sy = (t >> 2) & 1, sz = (t >> 1) & 1;
+  float4 gx = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (q.has_x) {
+    const int nx = pl.x + (X == 3 ? kBW : -1);
+    gx.x = ghost_product(P, vw, q.x[0], 0, nx, pl.y + Y0, pl.z + Z0, scale);
+    gx.y = ghost_product(P, vw, q.x[1], 0, nx, pl.y + Y0, pl.z + Z0 + 1, scale);
+    gx.z = ghost_product(P, vw, q.x[2], 0, nx, pl.y + Y0 + 1, pl.z + Z0, scale);
+    gx.w = ghost_product(P, vw, q.x[3], 0, nx, pl.y + Y0 + 1, pl.z + Z0 + 1, scale);
+  }
+  const int ny = pl.y + (sy ? kBW : -1), nz = pl.z + (sz ? kBW : -1);
+  const float gy0 = ghost_product(P, vw, q.y[0], 1, pl.x + X, ny, pl.z + Z0, scale);
+  const float gy1 = ghost_product(P, vw, q.y[1], 1, pl.x + X, ny, pl.z + Z0 + 1, scale);
+  const float gz0 = ghost_product(P, vw, q.z[0], 2, pl.x + X, pl.y + Y0, nz, scale);
+  const float gz1 = ghost_product(P, vw, q.z[1], 2, pl.x + X, pl.y + Y0 + 1, nz, scale);
+  const float4 px = make_float4(v[0].w * v[0].x, v[1].w * v[1].x, v[2].w * v[2].x, v[3].w * v[3].x);
+  const float4 py = make_float4(v[0].w * v[0].y, v[1].w * v[1].y, v[2].w * v[2].y, v[3].w * v[3].y);
+  const float4 pz = make_float4(v[0].w * v[0].z, v[1].w * v[1].z, v[2].w * v[2].z, v[3].w * v[3].z);
+  // x products to x neighbours, y to y, z to z: three exchanges, each using only its own axis
+  QuadNbr nx_, ny_, nz_;
+  quad_exchange_x(nx_, px, t, gx);
+  quad_exchange_y(ny_, py, t, gy0, gy1);
+  quad_exchange_z(nz_, pz, t, gz0, gz1);
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  __stcs(reinterpret_cast<float4 *>(p + c0), zero);
+  __stcs(reinterpret_cast<float4 *>(tp + c0), zero);
+  float4 d = zero;
+  if (child == kNone) {
+    const float alpha = .5f * P.rdx / (float)scale;
+    // alpha * (r - l + u - d + f - b), k = 2*cy + cz
+    d.x = alpha * (nx_.xp.x - nx_.xm.x + py.z - ny_.ym0 + pz.y - nz_.zm0);
+    d.y = alpha * (nx_.xp.y - nx_.xm.y + py.w - ny_.ym1 + nz_.zp0 - pz.x);
+    d.z = alpha * (nx_.xp.z - nx_.xm.z + ny_.yp0 - py.x + pz.w - nz_.zm1);
+    d.w = alpha * (nx_.xp.w - nx_.xm.w + ny_.yp1 - py.y + nz_.zp1 - pz.z);
+  }
+  __stcs(reinterpret_cast<float4 *>(div + c0), d);
+}
+
+// ---- k_dcgrid_apply_pressure, dcgrid_fluid.cu:232-259 --------------------------------------------------
+__global__ void __launch_bounds__(kCTA4) k_dc_apply_pressure4(Pool T, KParams P, const float *__restrict__ p, const float *__restrict__ fl,
+                                                              float4 *__restrict__ vw) {
+  const uint32_t g = threadIdx.x >> 4;
+  const int t = threadIdx.x & 15;
+  const uint32_t b = blockIdx.x * kB4 + g;
+  if (b >= T.M) return;
+  // slot -> level without touching posl: level pools are consecutive slot ranges
+  int level = 0;
+  while (level + 1 < T.levels && b >= T.offsets[level + 1]) level++;
+  if (b - T.offsets[level] >= T.loads[level]) return;
+  const size_t c0 = (size_t)b * kBV + 4 * t;
+  const float4 op = *reinterpret_cast<const float4 *>(p + c0);
+  const float4 ow = *reinterpret_cast<const float4 *>(fl + c0);
+  const uint32_t child = T.child[(size_t)b * 8 + (t >> 1)];
+  float4 v[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) v[k] = vw[c0 + k];
+  const QuadGhosts q = quad_ghosts(T, b, t);
+  const QuadNbr s = quad_neighbours(p, op, t, q);
+  const QuadNbr w = quad_neighbours(fl, ow, t, q);
+  if (child != kNone) return;
+  const float alpha = .5f * P.rdx / (float)(1 << level);
+  // v.x -= alpha * (w_r * (p_r - pc) + w_l * (pc - p_l)), likewise y (up/down), z (front/back)
+  v[0].x -= alpha * (w.xp.x * (s.xp.x - op.x) + w.xm.x * (op.x - s.xm.x));
+  v[0].y -= alpha * (ow.z * (op.z - op.x) + w.ym0 * (op.x - s.ym0));
+  v[0].z -= alpha * (ow.y * (op.y - op.x) + w.zm0 * (op.x - s.zm0));
+  v[1].x -= alpha * (w.xp.y * (s.xp.y - op.y) + w.xm.y * (op.y - s.xm.y));
+  v[1].y -= alpha * (ow.w * (op.w - op.y) + w.ym1 * (op.y - s.ym1));
+  v[1].z -= alpha * (w.zp0 * (s.zp0 - op.y) + ow.x * (op.y - op.x));
+  v[2].x -= alpha * (w.xp.z * (s.xp.z - op.z) + w.xm.z * (op.z - s.xm.z));
+  v[2].y -= alpha * (w.yp0 * (s.yp0 - op.z) + ow.x * (op.z - op.x));
+  v[2].z -= alpha * (ow.w * (op.w - op.z) + w.zm1 * (op.z - s.zm1));
+  v[3].x -= alpha * (w.xp.w * (s.xp.w - op.w) + w.xm.w * (op.w - s.xm.w));
+  v[3].y -= alpha * (w.yp1 * (s.yp1 - op.w) + ow.y * (op.w - op.y));
+  v[3].z -= alpha * (w.zp1 * (s.zp1 - op.w) + ow.z * (op.w - op.z));
+#pragma unroll
+  for (int k = 0; k < 4; k++) vw[c0 + k] = v[k];
+}
+
+// ---- coarse levels: the whole cascade of the small levels in ONE single-CTA launch ---------------------
+// Levels with at most kCoarseBlocks blocks (<= 4 cells per thread and sweep) are launch-latency bound:
+// at 512^3 levels 5..7 hold 64/8/1 blocks and take 33 launches of ~4 us each.  One CTA walks them
+// coarse -> fine exactly like FluidSimulationDCGrid::project (fluid_simulation_dcgrid.cu:270-294):
+// [prolongate] then `pairs` x (jacobi, jacobi_inv), with block-wide barriers between the phases.
+// Plain (coherent) loads only: the data changes inside the kernel.
+constexpr uint32_t kCoarseBlocks = 64;
+
+__device__ __forceinline__ uint32_t face_neighbour_cell(const Pool &T, uint32_t b, int f, int a, int bb) {
+  const uint32_t *fd = T.fd + 12 * (size_t)b;
+  if (fd[6] & kFdIrregular) return T.face[(size_t)b * 96 + 16 * f + 4 * a + bb];
+  return fd_ghost(fd[f], fd[6 + f], f >> 1, a, bb);
+}
+// value of the neighbour of cell (X,Y,Z) of block b across direction f (-x,+x,-y,+y,-z,+z)
+__device__ __forceinline__ float neighbour_value(const Pool &T, const float *src, uint32_t b, int X, int Y, int Z, int f) {
+  int c[3] = {X, Y, Z};
+  const int axis = f >> 1;
+  c[axis] += (f & 1) ? 1 : -1;
+  if ((unsigned)c[axis] < (unsigned)kBW) return src[b * kBV + cell_bits(c[0], c[1], c[2])];
+  const int a = axis == 0 ? Y : X, bb = axis == 2 ? Y : Z;
+  return src[face_neighbour_cell(T, b, f, a, bb)];
+}
+__device__ __forceinline__ void coarse_sweep(const Pool &T, const KParams &P, int level, const float *in, float *out, const float *div) {
+  const float alpha = (float)((1 << level) * (1 << level)) * P.dx * P.dx;
+  const uint32_t n = T.loads[level] * kBV;
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const uint32_t b = T.offsets[level] + (i >> 6), c = i & 63u;
+    const int X = cell_x(c), Y = cell_y(c), Z = cell_z(c);
+    const float l = neighbour_value(T, in, b, X, Y, Z, 0), r = neighbour_value(T, in, b, X, Y, Z, 1);
+    const float dn = neighbour_value(T, in, b, X, Y, Z, 2), up = neighbour_value(T, in, b, X, Y, Z, 3);
+    const float bk = neighbour_value(T, in, b, X, Y, Z, 4), fr = neighbour_value(T, in, b, X, Y, Z, 5);
+    out[b * kBV + c] = (l + r + dn + up + bk + fr - alpha * div[b * kBV + c]) / 6.f;
+  }
+}
+__global__ void __launch_bounds__(1024) k_dc_coarse_cascade(Pool T, KParams P, int finest, int prolong_coarsest, int pairs_coarsest,
+                                                            int pairs_level, int prolong_levels, float *p, float *tp, const float *div) {
+  for (int level = T.levels - 1; level >= finest; level--) {
+    const bool top = level == T.levels - 1;
+    if (top ? prolong_coarsest : prolong_levels) {  // k_dcgrid_prolongate, dcgrid_multigrid_solver.cu:43-76
+      const uint32_t n = T.loads[level] * kBV;
+      for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint32_t b = T.offsets[level] + (i >> 6), c = i & 63u;
+        const uint32_t ps = T.parent[b];
+        if (ps == kNone) continue;
+        const uint32_t *pa = T.apron + (size_t)(ps / 8) * kAV;
+        const int X = cell_x(c), Y = cell_y(c), Z = cell_z(c);
+        const int idx = kAA * (1 + (int)((ps >> 2) & 1u) * 2 + (X >> 1)) + kAW * (1 + (int)((ps >> 1) & 1u) * 2 + (Y >> 1)) +
+                        (1 + (int)(ps & 1u) * 2 + (Z >> 1));
+        const int ii = (X & 1) ? kAA : -kAA, jj = (Y & 1) ? kAW : -kAW, kk = (Z & 1) ? 1 : -1;
+        const float p000 = p[pa[idx]], p001 = p[pa[idx + kk]], p010 = p[pa[idx + jj]], p100 = p[pa[idx + ii]];
+        const float p011 = p[pa[idx + jj + kk]], p101 = p[pa[idx + ii + kk]], p110 = p[pa[idx + ii + jj]], p111 = p[pa[idx + ii + jj + kk]];
+        p[b * kBV + c] = (27.f * p000 + 9.f * (p001 + p010 + p100) + 3.f * (p011 + p101 + p110) + p111) / 64.f;
+      }
+      __syncthreads();
+    }
+    const int pairs = top ? pairs_coarsest : pairs_level;
+    for (int s = 0; s < pairs; s++) {
+      coarse_sweep(T, P, level, p, tp, div);
+      __syncthreads();
+      coarse_sweep(T, P, level, tp, p, div);
+      __syncthreads();
+    }
+  }
+}
+
+// accumulate<T> (dcgrid_structure.cu:188-222) for the small levels first..levels-2, fine -> coarse, one CTA
+__global__ void __launch_bounds__(1024) k_dc_accumulate_coarse(Pool T, int first, float4 *vw, float *ch) {
+  for (int level = first; level < T.levels - 1; level++) {
+    const uint32_t n = 8 * T.loads[level];
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+      const uint32_t sb = 8 * T.offsets[level] + i, b = sb / 8;
+      const uint32_t ps = T.parent[b];
+      if (ps == kNone) continue;
+      if (vw) {
+        const float4 *c = vw + (size_t)kSV * sb;
+        float ax = 0.f, ay = 0.f, az = 0.f;
+#pragma unroll
+        for (int k = 0; k < kSV; k++) {
+          const float4 v = c[k];
+          ax += v.x; ay += v.y; az += v.z;
+        }
+        float *dst = reinterpret_cast<float *>(vw + ((size_t)kSV * ps + (sb % 8)));
+        dst[0] = ax * .125f; dst[1] = ay * .125f; dst[2] = az * .125f;
+      } else {
+        const float *c = ch + (size_t)kSV * sb;
+        float a = 0.f;
+#pragma unroll
+        for (int k = 0; k < kSV; k++) a += c[k];
+        ch[(size_t)kSV * ps + (sb % 8)] = a * .125f;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace dcg

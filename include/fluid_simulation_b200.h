@@ -133,7 +133,8 @@ public:
   explicit FluidSimulationB200Uniform(const int3 &size, int device = 0) : FluidSimulationB200(size) {
     const dcg_sim_params p = startParams(size);
     dcg_sim *s = nullptr;
-    adopt(dcg_create_uniform(&p, device, &s), s);
+    const int rc = dcg_create_uniform(&p, device, &s);  // sequenced before `s` is read
+    adopt(rc, s);
   }
 };
 
@@ -143,7 +144,8 @@ public:
   FluidSimulationB200DCGrid(const int3 &size, const size_t &maxNumBlocks, int device = 0) : FluidSimulationB200(size) {
     const dcg_sim_params p = startParams(size);
     dcg_sim *s = nullptr;
-    adopt(dcg_create_dcgrid(&p, (uint64_t)maxNumBlocks, device, &s), s);
+    const int rc = dcg_create_dcgrid(&p, (uint64_t)maxNumBlocks, device, &s);
+    adopt(rc, s);
   }
 };
 
