@@ -12,3 +12,4 @@ from .simulation import (  # noqa: F401
     FluidSimulationDCGrid,
     FluidSimulationUniform,
 )
+from .sharding import FluidSimulationUniformSharded  # noqa: F401,E402

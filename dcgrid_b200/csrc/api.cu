@@ -44,6 +44,8 @@ int finish_create(dcg_sim *s, const dcg_sim_params *params, int device, dcg_sim 
 }
 }  // namespace
 
+void dcg_set_create_error(const char *msg) { set_create_error(msg ? msg : ""); }
+
 #define NEED(sim)                 \
   do {                            \
     if (!(sim)) return DCG_ERR_INVALID; \

@@ -353,6 +353,10 @@ struct DSample {
   int x0, y0, z0, scale;
   float fx, fy, fz;
 };
+// true iff all 8 corners of the sample lie inside the domain, i.e. bc_kind() == 0 for each of them
+__device__ __forceinline__ bool sample_inside(const KParams &P, const DSample &s) {
+  return s.x0 >= 0 && s.y0 >= 0 && s.z0 >= 0 && (s.x0 + 1) * s.scale < P.gx && (s.y0 + 1) * s.scale < P.gy && (s.z0 + 1) * s.scale < P.gz;
+}
 // Second half of INIT_SAMPLE: sample set-up inside the resolved block `bp` (level, position) whose 6^3
 // apron map starts at `apron` (global memory, or the CTA's staged copy in shared memory).
 __device__ __forceinline__ DSample d_sample_in(const uint32_t *apron, const int4 bp, float px, float py, float pz) {
@@ -390,13 +394,6 @@ __device__ __forceinline__ DSample d_sample(const Pool &T, const KParams &P, con
   return d_sample_in(T.apron + (size_t)b * kAV, T.posl[b], px, py, pz);
 }
 
-__device__ __forceinline__ bool slot_active(const Pool &T, uint32_t b) {
-  if (b >= T.M) return false;
-  int level = 0;
-  while (level + 1 < T.levels && b >= T.offsets[level + 1]) level++;
-  return b - T.offsets[level] < T.loads[level];
-}
-
 // stage the apron maps + child links of the CTA's kBPC blocks
 __device__ __forceinline__ void stage_apron(const Pool &T, uint32_t b, bool active, uint32_t g, uint32_t t, uint32_t (*sa)[kAV], uint32_t (*sc)[kSV]) {
   if (active) {
@@ -416,7 +413,7 @@ __global__ void __launch_bounds__(kCTA, 5) k_dc_advect_velocity(Pool T, KParams 
   const uint32_t b = blockIdx.x * kBPC + g;
   // active-ness from the slot number alone (level pools are slot ranges with a compact active prefix), so
   // that position, velocity and apron map are fetched by independent loads
-  const bool active = slot_active(T, b);
+  const bool active = slot_is_active(T, b);
   const uint32_t c = b * kBV + t;
   int4 pl = make_int4(0, 0, 0, 0);
   float4 me = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -444,10 +441,13 @@ __global__ void __launch_bounds__(kCTA, 5) k_dc_advect_velocity(Pool T, KParams 
     const Weights8 W = corner_weights(f, s.fx, s.fy, s.fz);
     if (!(W.acc < 1e-6f)) {
       float vx[8], vy[8], vz[8];
+      // boundary conditions only substitute values of corners OUTSIDE the domain (sim_utils.cu:24-39):
+      // one test for the whole 2x2x2 footprint skips them for interior samples
+      const bool inside = sample_inside(P, s);
 #pragma unroll
       for (int k = 0; k < 8; k++) {
-        const float3 v = velocity_bc(P, make_float3(cv[k].x, cv[k].y, cv[k].z), s.x0 + ((k >> 2) & 1), s.y0 + ((k >> 1) & 1),
-                                     s.z0 + (k & 1), s.scale);
+        float3 v = make_float3(cv[k].x, cv[k].y, cv[k].z);
+        if (!inside) v = velocity_bc(P, v, s.x0 + ((k >> 2) & 1), s.y0 + ((k >> 1) & 1), s.z0 + (k & 1), s.scale);
         vx[k] = v.x; vy[k] = v.y; vz[k] = v.z;
       }
       out = make_float3(blend8(vx, W.w), blend8(vy, W.w), blend8(vz, W.w));
@@ -465,7 +465,7 @@ __global__ void __launch_bounds__(kCTA) k_dc_advect_density(Pool T, KParams P, c
   const uint32_t b = blockIdx.x * kBPC + g;
   // active-ness from the slot number alone (level pools are slot ranges with a compact active prefix), so
   // that position, velocity and apron map are fetched by independent loads
-  const bool active = slot_active(T, b);
+  const bool active = slot_is_active(T, b);
   const uint32_t c = b * kBV + t;
   int4 pl = make_int4(0, 0, 0, 0);
   float4 me = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -491,9 +491,11 @@ __global__ void __launch_bounds__(kCTA) k_dc_advect_density(Pool T, KParams P, c
     }
     const Weights8 W = corner_weights(f, s.fx, s.fy, s.fz);
     if (!(W.acc < 1e-6f)) {
+      if (!sample_inside(P, s)) {
 #pragma unroll
-      for (int k = 0; k < 8; k++)
-        qv[k] = density_bc(P, qv[k], s.x0 + ((k >> 2) & 1), s.y0 + ((k >> 1) & 1), s.z0 + (k & 1), s.scale);
+        for (int k = 0; k < 8; k++)
+          qv[k] = density_bc(P, qv[k], s.x0 + ((k >> 2) & 1), s.y0 + ((k >> 1) & 1), s.z0 + (k & 1), s.scale);
+      }
       out = blend8(qv, W.w);
     }
   }

@@ -26,10 +26,18 @@ constexpr int kQT = 16;    // threads per logical block (4 cells each)
 constexpr int kB4 = 16;    // logical blocks per CTA
 constexpr int kCTA4 = kQT * kB4;
 constexpr uint32_t kFdIrregular = 0x80000000u;
-constexpr uint32_t kFdQuirk = 1u << 10;
+constexpr uint32_t kFdQuirk = 1u << 4;
+// in-block cell bits of the two tangential axes of a face (the normal axis' bits cleared):
+// x faces keep (y,z) = 0b011011, y faces (x,z) = 0b101101, z faces (x,y) = 0b110110
+__host__ __device__ __forceinline__ uint32_t tang_mask(int axis) { return axis == 0 ? 27u : (axis == 1 ? 45u : 54u); }
 
-// ghost (face axis, tangential a, b) -> cell id, from one face descriptor
-__device__ __forceinline__ uint32_t fd_ghost(uint32_t nb, uint32_t code, int axis, int a, int b) {
+// Face descriptor = (base, code).  base = id of the ghost cell at tangential (0,0) [for the quirk form:
+// with its tangential bits cleared]; code = dl | quirk << 4 (| kFdIrregular on face 0).  The ghost at
+// tangential (a,b) is base + bits(ta) + bits(tb) with ta = a >> dl (quirk: (a+1)&3): the sum never
+// carries because the tangential origin is 0 for dl = 0, even for dl = 1, and ta = 0 for dl >= 2.
+// code == 0 (same-level neighbour, the common case): ghost = base + the tangential bits of the cell
+// the ghost is for, which each lane already knows.
+__device__ __forceinline__ uint32_t fd_ghost(uint32_t base, uint32_t code, int axis, int a, int b) {
   const int dl = (int)(code & 15u);
   int ta, tb;
   if (code & kFdQuirk) {
@@ -39,11 +47,13 @@ __device__ __forceinline__ uint32_t fd_ghost(uint32_t nb, uint32_t code, int axi
     ta = a >> dl;
     tb = b >> dl;
   }
-  int ox = (int)((code >> 4) & 3u), oy = (int)((code >> 6) & 3u), oz = (int)((code >> 8) & 3u);
-  if (axis == 0) { oy += ta; oz += tb; }
-  else if (axis == 1) { ox += ta; oz += tb; }
-  else { ox += ta; oy += tb; }
-  return nb * kBV + cell_bits(ox, oy, oz);
+  const int s1 = axis == 0 ? 1 : 2, s2 = axis == 2 ? 1 : 0;
+  return base + spread(ta, s1) + spread(tb, s2);
+}
+// `own_tang` = tangential bits of the cell the ghost belongs to (its in-block index & tang_mask(axis))
+__device__ __forceinline__ uint32_t fd_ghost_fast(uint32_t base, uint32_t code, int axis, int a, int b, uint32_t own_tang) {
+  if (code == 0) return base + own_tang;
+  return fd_ghost(base, code, axis, a, b);
 }
 
 // apron index of ghost g = 16*f + 4*a + b (f = -x,+x,-y,+y,-z,+z)
@@ -67,7 +77,7 @@ __global__ void __launch_bounds__(256) k_dc_build_fdesc(Pool T, uint32_t *__rest
   const unsigned lane = threadIdx.x & 31u;
   const unsigned grp_mask = 0xFFu << (lane & 24u);
   bool bad = false;
-  uint32_t nb = kNone, code = 0;
+  uint32_t base = kNone, code = 0;
   uint32_t e[16];
   const bool live = b < T.M && f < 6 && T.posl[b].w != kFree;
   if (live) {
@@ -78,24 +88,23 @@ __global__ void __launch_bounds__(256) k_dc_build_fdesc(Pool T, uint32_t *__rest
     const int level = T.posl[b].w;
     if (e[0] == kNone) bad = true;
     if (!bad) {
-      nb = e[0] >> 6;
-      const uint32_t c00 = e[0] & 63u;
-      const int ox = cell_x(c00), oy = cell_y(c00), oz = cell_z(c00);
+      const uint32_t nb = e[0] >> 6;
       const int nl = nb < T.M ? T.posl[nb].w : kFree;
       const int dl = nl - level;
       bool regular = nl != kFree && dl >= 0 && dl <= 15;
       if (regular) {
-        code = (uint32_t)dl | ((uint32_t)ox << 4) | ((uint32_t)oy << 6) | ((uint32_t)oz << 8);
+        base = e[0];
+        code = (uint32_t)dl;
 #pragma unroll
-        for (int k = 0; k < 16; k++) regular = regular && e[k] == fd_ghost(nb, code, axis, k >> 2, k & 3);
+        for (int k = 0; k < 16; k++) regular = regular && e[k] == fd_ghost(base, code, axis, k >> 2, k & 3);
       }
       if (!regular) {
         // moved-block wall entry: own block, normal coordinate from e[0], tangential (a+1)&3
-        const int n = axis == 0 ? ox : (axis == 1 ? oy : oz);
-        code = kFdQuirk | ((uint32_t)(axis == 0 ? n : 0) << 4) | ((uint32_t)(axis == 1 ? n : 0) << 6) | ((uint32_t)(axis == 2 ? n : 0) << 8);
+        base = e[0] & ~tang_mask(axis);
+        code = kFdQuirk;
         bool quirk = nb == b;
 #pragma unroll
-        for (int k = 0; k < 16; k++) quirk = quirk && e[k] == fd_ghost(nb, code, axis, k >> 2, k & 3);
+        for (int k = 0; k < 16; k++) quirk = quirk && e[k] == fd_ghost(base, code, axis, k >> 2, k & 3);
         bad = !quirk;
       }
     }
@@ -103,13 +112,21 @@ __global__ void __launch_bounds__(256) k_dc_build_fdesc(Pool T, uint32_t *__rest
   const unsigned any_bad = __ballot_sync(0xFFFFFFFFu, bad) & grp_mask;
   if (!live) return;
   uint32_t *fd = T.fd + 12 * (size_t)b;
-  fd[f] = nb;
-  fd[6 + f] = (code & ~kFdIrregular) | (any_bad ? kFdIrregular : 0u);
+  fd[f] = base;
+  fd[6 + f] = code | ((any_bad && f == 0) ? kFdIrregular : 0u);
   if (any_bad) {
 #pragma unroll
     for (int k = 0; k < 16; k++) T.face[(size_t)b * 96 + 16 * f + k] = e[k];
     if (f == 0) atomicAdd(irregular, 1u);
   }
+}
+
+// level pools are consecutive slot ranges whose active blocks form a compact prefix
+__device__ __forceinline__ bool slot_is_active(const Pool &T, uint32_t b) {
+  if (b >= T.M) return false;
+  int level = 0;
+  while (level + 1 < T.levels && b >= T.offsets[level + 1]) level++;
+  return b - T.offsets[level] < T.loads[level];
 }
 
 // thread t of a block owns the quad (X, Y0..Y0+1, Z0..Z0+1): t = sx<<3 | sy<<2 | sz<<1 | cx
@@ -118,7 +135,6 @@ __device__ __forceinline__ void quad_coords(int t, int &X, int &Y0, int &Z0) {
   Y0 = ((t >> 2) & 1) << 1;
   Z0 = ((t >> 1) & 1) << 1;
 }
-__device__ __forceinline__ unsigned half_mask() { return 0xFFFFu << (threadIdx.x & 16u); }
 
 // Ghost ids a quad needs itself: 4 on an x face (only quads with X = 0 or 3), 2 on its y face, 2 on its
 // z face (every quad touches exactly one y and one z face of the block).
@@ -148,15 +164,16 @@ __device__ __forceinline__ QuadGhosts quad_ghosts(const Pool &T, uint32_t b, int
     }
     return q;
   }
-  const uint32_t nbx = fx ? w0.y : w0.x, cdx = fx ? w1.w : w1.z;
+  const uint32_t nbx = fx ? w0.y : w0.x, cdx = (fx ? w1.w : w1.z) & ~kFdIrregular;
   const uint32_t nby = sy ? w0.w : w0.z, cdy = sy ? w2.y : w2.x;
   const uint32_t nbz = sz ? w1.y : w1.x, cdz = sz ? w2.w : w2.z;
+  const uint32_t c = 4u * (uint32_t)t;  // in-block index of the quad's first cell
 #pragma unroll
-  for (int k = 0; k < 4; k++) q.x[k] = fd_ghost(nbx, cdx, 0, Y0 + (k >> 1), Z0 + (k & 1));
+  for (int k = 0; k < 4; k++) q.x[k] = q.has_x ? fd_ghost_fast(nbx, cdx, 0, Y0 + (k >> 1), Z0 + (k & 1), (c + k) & 27u) : 0u;
 #pragma unroll
   for (int k = 0; k < 2; k++) {
-    q.y[k] = fd_ghost(nby, cdy, 1, X, Z0 + k);
-    q.z[k] = fd_ghost(nbz, cdz, 2, X, Y0 + k);
+    q.y[k] = fd_ghost_fast(nby, cdy, 1, X, Z0 + k, (c + 2 * sy + k) & 45u);
+    q.z[k] = fd_ghost_fast(nbz, cdz, 2, X, Y0 + k, (c + 2 * k + sz) & 54u);
   }
   return q;
 }
@@ -170,7 +187,7 @@ struct QuadNbr {
   float zm0, zm1, zp0, zp1;  // z-1 of (cz=0; cy=0,1), z+1 of (cz=1; cy=0,1)
 };
 __device__ __forceinline__ void quad_exchange_x(QuadNbr &n, float4 own, int t, float4 gx) {
-  const unsigned hm = half_mask();
+  const unsigned hm = 0xFFFFFFFFu;  // callers keep whole warps converged (inactive halves run along)
   const int lb = threadIdx.x & 16;
   const int cx = t & 1, sx = t >> 3;
   const int lxm = lb + ((cx ? t - 1 : t - 7) & 15), lxp = lb + ((cx ? t + 7 : t + 1) & 15);
@@ -182,7 +199,7 @@ __device__ __forceinline__ void quad_exchange_x(QuadNbr &n, float4 own, int t, f
   if (cx && sx) n.xp = gx;
 }
 __device__ __forceinline__ void quad_exchange_y(QuadNbr &n, float4 own, int t, float gy0, float gy1) {
-  const unsigned hm = half_mask();
+  const unsigned hm = 0xFFFFFFFFu;  // callers keep whole warps converged (inactive halves run along)
   const int lb = threadIdx.x & 16;
   const int sy = (t >> 2) & 1;
   const int lym = lb + ((t - 4) & 15), lyp = lb + ((t + 4) & 15);
@@ -191,7 +208,7 @@ __device__ __forceinline__ void quad_exchange_y(QuadNbr &n, float4 own, int t, f
   if (!sy) { n.ym0 = gy0; n.ym1 = gy1; } else { n.yp0 = gy0; n.yp1 = gy1; }
 }
 __device__ __forceinline__ void quad_exchange_z(QuadNbr &n, float4 own, int t, float gz0, float gz1) {
-  const unsigned hm = half_mask();
+  const unsigned hm = 0xFFFFFFFFu;  // callers keep whole warps converged (inactive halves run along)
   const int lb = threadIdx.x & 16;
   const int sz = (t >> 1) & 1;
   const int lzm = lb + ((t - 2) & 15), lzp = lb + ((t + 2) & 15);
@@ -223,8 +240,11 @@ __global__ void __launch_bounds__(kCTA4) k_dc_jacobi4(Pool T, KParams P, int lev
   const uint32_t g = threadIdx.x >> 4;
   const int t = threadIdx.x & 15;
   const uint32_t li = blockIdx.x * kB4 + g;
-  if (li >= T.loads[level]) return;
-  const uint32_t b = T.offsets[level] + li;
+  // the two half-warps of a warp hold two blocks; a trailing inactive half runs along (on the level's
+  // first block, results discarded) so that the shuffles below stay full-warp collectives
+  const bool active = li < T.loads[level];
+  if (!__any_sync(0xFFFFFFFFu, active)) return;
+  const uint32_t b = T.offsets[level] + (active ? li : 0u);
   const size_t c0 = (size_t)b * kBV + 4 * t;
   const float4 own = *reinterpret_cast<const float4 *>(in + c0);
   const float4 dv = __ldcs(reinterpret_cast<const float4 *>(div + c0));  // streamed: keep L2 for the ghosts
@@ -236,7 +256,7 @@ __global__ void __launch_bounds__(kCTA4) k_dc_jacobi4(Pool T, KParams P, int lev
   o.y = (n.xm.y + n.xp.y + n.ym1 + own.w + own.x + n.zp0 - alpha * dv.y) / 6.f;
   o.z = (n.xm.z + n.xp.z + own.x + n.yp0 + n.zm1 + own.w - alpha * dv.z) / 6.f;
   o.w = (n.xm.w + n.xp.w + own.y + n.yp1 + own.z + n.zp1 - alpha * dv.w) / 6.f;
-  *reinterpret_cast<float4 *>(out + c0) = o;
+  if (active) *reinterpret_cast<float4 *>(out + c0) = o;
 }
 
 // ---- k_dcgrid_calc_divergence, dcgrid_fluid.cu:174-230 -----------------------------------------------
@@ -253,10 +273,11 @@ __global__ void __launch_bounds__(kCTA4) k_dc_divergence4(Pool T, KParams P, con
                                                           float *__restrict__ p, float *__restrict__ tp) {
   const uint32_t g = threadIdx.x >> 4;
   const int t = threadIdx.x & 15;
-  const uint32_t b = blockIdx.x * kB4 + g;
-  if (b >= T.M) return;
+  const uint32_t b0 = blockIdx.x * kB4 + g;
+  const bool active = slot_is_active(T, b0);
+  if (!__any_sync(0xFFFFFFFFu, active)) return;
+  const uint32_t b = active ? b0 : T.offsets[T.levels - 1];  // inactive half: runs along on the root block
   const int4 pl = T.posl[b];
-  if (pl.w == kFree) return;
   const size_t c0 = (size_t)b * kBV + 4 * t;
   float4 v[4];
 #pragma unroll
@@ -288,6 +309,7 @@ __global__ void __launch_bounds__(kCTA4) k_dc_divergence4(Pool T, KParams P, con
   quad_exchange_x(nx_, px, t, gx);
   quad_exchange_y(ny_, py, t, gy0, gy1);
   quad_exchange_z(nz_, pz, t, gz0, gz1);
+  if (!active) return;
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
   __stcs(reinterpret_cast<float4 *>(p + c0), zero);
   __stcs(reinterpret_cast<float4 *>(tp + c0), zero);
@@ -308,12 +330,13 @@ __global__ void __launch_bounds__(kCTA4) k_dc_apply_pressure4(Pool T, KParams P,
                                                               float4 *__restrict__ vw) {
   const uint32_t g = threadIdx.x >> 4;
   const int t = threadIdx.x & 15;
-  const uint32_t b = blockIdx.x * kB4 + g;
-  if (b >= T.M) return;
+  const uint32_t b0 = blockIdx.x * kB4 + g;
+  const bool active = slot_is_active(T, b0);
+  if (!__any_sync(0xFFFFFFFFu, active)) return;
+  const uint32_t b = active ? b0 : T.offsets[T.levels - 1];
   // slot -> level without touching posl: level pools are consecutive slot ranges
   int level = 0;
   while (level + 1 < T.levels && b >= T.offsets[level + 1]) level++;
-  if (b - T.offsets[level] >= T.loads[level]) return;
   const size_t c0 = (size_t)b * kBV + 4 * t;
   const float4 op = *reinterpret_cast<const float4 *>(p + c0);
   const float4 ow = *reinterpret_cast<const float4 *>(fl + c0);
@@ -324,7 +347,7 @@ __global__ void __launch_bounds__(kCTA4) k_dc_apply_pressure4(Pool T, KParams P,
   const QuadGhosts q = quad_ghosts(T, b, t);
   const QuadNbr s = quad_neighbours(p, op, t, q);
   const QuadNbr w = quad_neighbours(fl, ow, t, q);
-  if (child != kNone) return;
+  if (!active || child != kNone) return;
   const float alpha = .5f * P.rdx / (float)(1 << level);
   // v.x -= alpha * (w_r * (p_r - pc) + w_l * (pc - p_l)), likewise y (up/down), z (front/back)
   v[0].x -= alpha * (w.xp.x * (s.xp.x - op.x) + w.xm.x * (op.x - s.xm.x));

@@ -123,5 +123,6 @@ struct dcg_sim {
   }
 };
 
+void dcg_set_create_error(const char *msg);  // text returned by dcg_last_error(NULL)
 dcg_sim *dcg_make_uniform();
 dcg_sim *dcg_make_dcgrid(uint64_t max_num_blocks);

@@ -192,6 +192,24 @@ DCG_API int dcg_algorithmic_bytes(dcg_sim *sim, double *bytes_per_step,
 DCG_API int dcg_bench_stage(dcg_sim *sim, const char *stage, int level, int reps,
                             float *ms_per_launch, double *alg_bytes_per_launch);
 
+/* ---- multi-GPU: z-slab sharding of the uniform grid -------------------------------------------
+ * The reference is single-GPU (src/main.cpp:46-48); these entry points have no counterpart there.
+ * One instance holds `nlocal` consecutive ranks [rank, rank+nlocal) of a `world`-rank decomposition of
+ * the gx*gy*gz grid into equal z-slabs (gz % world == 0).  nlocal == 1: one rank per process/GPU
+ * (torchrun); the ranks exchange dcg_shard_export_handle() blobs (dcg_shard_handle_bytes() each,
+ * rank order) through any host channel and pass the concatenation to dcg_shard_import_handles(),
+ * which maps every peer's slab over NVLink (CUDA IPC) and resets.  nlocal == world: all ranks live in
+ * this instance on one device (used to test the decomposition on a single GPU); ready after create.
+ * All ranks must then issue the same sequence of solver calls (lock-step flag barriers over peer
+ * memory).  Accessors return the LOCAL slab(s); dcg_total_density / dcg_debug_stats return local
+ * partial sums to be combined by the host (sum over ranks, e.g. an allreduce).
+ * dcg_get_counters()[7] = number of barriers executed.                                          */
+DCG_API int dcg_create_uniform_sharded(const dcg_sim_params *params, int device, int rank, int world,
+                                       int nlocal, dcg_sim **out);
+DCG_API uint64_t dcg_shard_handle_bytes(void);
+DCG_API int dcg_shard_export_handle(dcg_sim *sim, void *out, uint64_t capacity);
+DCG_API int dcg_shard_import_handles(dcg_sim *sim, const void *handles, int count);
+
 /* Last error text of this instance (or of creation when sim == NULL). */
 DCG_API const char *dcg_last_error(const dcg_sim *sim);
 DCG_API const char *dcg_version(void);

@@ -1,0 +1,76 @@
+"""CPU tests of the multi-GPU host logic: slab / mip-plane ownership arithmetic and the bootstrap
+collectives (handle all-gather, partial-sum all-reduce) over gloo with world_size 2."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from dcgrid_b200 import sharding
+
+
+def test_slabs_partition_every_level():
+    for gz, world in ((64, 2), (64, 8), (48, 3), (1024, 8), (32, 8)):
+        levels = 1
+        while gz % (1 << levels) == 0 and (1 << levels) * 4 <= gz:
+            levels += 1
+        assert sharding.slab_range(gz, world, 0)[0] == 0 and sharding.slab_range(gz, world, world - 1)[1] == gz
+        for l in range(levels):
+            planes = gz >> l
+            owned = np.full(planes, -1)
+            for r in range(world):
+                z0, z1 = sharding.level_planes(gz, world, r, l)
+                assert (owned[z0:z1] == -1).all()
+                owned[z0:z1] = r
+                for z in range(z0, z1):
+                    assert sharding.plane_owner(gz, world, l, z) == r
+            assert (owned >= 0).all(), (gz, world, l)   # every plane has exactly one owner
+            # a coarse plane lives where its first fine plane lives
+            if l > 0:
+                for z in range(planes):
+                    assert owned[z] == sharding.plane_owner(gz, world, l - 1, 2 * z) or (gz // world) % (1 << l) != 0
+
+
+def test_slab_range_rejects_ragged():
+    with pytest.raises(ValueError):
+        sharding.slab_range(30, 4, 0)
+
+
+def test_halo_traffic_is_two_planes_for_interior_ranks():
+    assert sharding.halo_bytes_per_sweep(1024, 1024, 1024, 8, 3) == 2 * 1024 * 1024 * 4
+    assert sharding.halo_bytes_per_sweep(1024, 1024, 1024, 8, 0) == 1024 * 1024 * 4
+    assert sharding.halo_bytes_per_sweep(64, 64, 64, 1, 0) == 0
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        blob = bytes([rank + 1]) * 64                      # stands in for a cudaIpcMemHandle_t
+        got = sharding.all_gather_bytes(blob, dist)
+        total = sharding.all_reduce_sum(1.5 * (rank + 1), dist)
+        q.put((rank, [g[0] for g in got], [len(g) for g in got], total, sharding.slab_range(64, world, rank)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_bootstrap_collectives_gloo_world2():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, firsts, lens, total, zr in res:
+        assert firsts == [1, 2] and lens == [64, 64]       # rank order, fixed size
+        assert total == 4.5
+        assert zr == (32 * rank, 32 * rank + 32)
