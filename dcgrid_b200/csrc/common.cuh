@@ -99,6 +99,17 @@ __device__ __forceinline__ float blend8(const float q[8], const float w[8]) {
          q[7] * w[7];
 }
 
+// x / 6.f, correctly rounded, without the generic division routine: q = RN(x*r), rem = x - 6q (exact, one
+// FMA), q' = RN(q + rem*r) with r = RN(1/6).  Checked exhaustively over all 2^32 inputs against x / 6.f
+// (tests/tools/div6_exhaustive.c): identical for every |x| >= 2^-125; smaller magnitudes (denormal
+// quotients) take the IEEE division.  The explicit fmaf is a single-rounding FMA regardless of -fmad.
+__device__ __forceinline__ float div6(float x) {
+  const float r = 0x1.555556p-3f;
+  if (fabsf(x) < 0x1p-120f) return x / 6.f;
+  const float q = x * r;
+  return fmaf(fmaf(-6.f, q, x), r, q);
+}
+
 // ---- misc ------------------------------------------------------------------------
 __host__ __device__ __forceinline__ int idiv_up(int a, int b) { return (a + b - 1) / b; }
 

@@ -411,18 +411,16 @@ __global__ void __launch_bounds__(kCTA, 5) k_dc_advect_velocity(Pool T, KParams 
   __shared__ uint32_t sc[kBPC][kSV];
   const uint32_t g = threadIdx.x >> 6, t = threadIdx.x & 63;
   const uint32_t b = blockIdx.x * kBPC + g;
-  // active-ness from the slot number alone (level pools are slot ranges with a compact active prefix), so
-  // that position, velocity and apron map are fetched by independent loads
-  const bool active = slot_is_active(T, b);
+  const bool in_pool = b < T.M;
   const uint32_t c = b * kBV + t;
-  int4 pl = make_int4(0, 0, 0, 0);
+  int4 pl = make_int4(0, 0, 0, kFree);
   float4 me = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (active) {
+  if (in_pool) {  // position, velocity and apron map are fetched by independent loads (free slots: zeroed data, unused)
     pl = T.posl[b];
     me = vin[c];
   }
-  stage_apron(T, b, active, g, t, sa, sc);
-  if (!active) return;
+  stage_apron(T, b, in_pool, g, t, sa, sc);
+  if (pl.w == kFree) return;
   float3 out = make_float3(0.f, 0.f, 0.f);
   if (sc[g][t >> 3] == kNone) {
     const float scale = (float)(1 << pl.w);
@@ -463,18 +461,16 @@ __global__ void __launch_bounds__(kCTA) k_dc_advect_density(Pool T, KParams P, c
   __shared__ uint32_t sc[kBPC][kSV];
   const uint32_t g = threadIdx.x >> 6, t = threadIdx.x & 63;
   const uint32_t b = blockIdx.x * kBPC + g;
-  // active-ness from the slot number alone (level pools are slot ranges with a compact active prefix), so
-  // that position, velocity and apron map are fetched by independent loads
-  const bool active = slot_is_active(T, b);
+  const bool in_pool = b < T.M;
   const uint32_t c = b * kBV + t;
-  int4 pl = make_int4(0, 0, 0, 0);
+  int4 pl = make_int4(0, 0, 0, kFree);
   float4 me = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (active) {
+  if (in_pool) {  // position, velocity and apron map are fetched by independent loads (free slots: zeroed data, unused)
     pl = T.posl[b];
     me = vw[c];
   }
-  stage_apron(T, b, active, g, t, sa, sc);
-  if (!active) return;
+  stage_apron(T, b, in_pool, g, t, sa, sc);
+  if (pl.w == kFree) return;
   float out = 0.f;
   if (sc[g][t >> 3] == kNone) {
     const float scale = (float)(1 << pl.w);

@@ -168,12 +168,24 @@ __device__ __forceinline__ QuadGhosts quad_ghosts(const Pool &T, uint32_t b, int
   const uint32_t nby = sy ? w0.w : w0.z, cdy = sy ? w2.y : w2.x;
   const uint32_t nbz = sz ? w1.y : w1.x, cdz = sz ? w2.w : w2.z;
   const uint32_t c = 4u * (uint32_t)t;  // in-block index of the quad's first cell
+  if ((cdx | cdy | cdz) == 0) {
+    // all three faces border same-level blocks (or the ordered-level wall clamp): ghost = face base + the
+    // tangential bits of the cell it belongs to
 #pragma unroll
-  for (int k = 0; k < 4; k++) q.x[k] = q.has_x ? fd_ghost_fast(nbx, cdx, 0, Y0 + (k >> 1), Z0 + (k & 1), (c + k) & 27u) : 0u;
+    for (int k = 0; k < 4; k++) q.x[k] = nbx + ((c + k) & 27u);
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+      q.y[k] = nby + ((c + 2 * sy + k) & 45u);
+      q.z[k] = nbz + ((c + 2 * k + sz) & 54u);
+    }
+    return q;
+  }
+#pragma unroll
+  for (int k = 0; k < 4; k++) q.x[k] = q.has_x ? fd_ghost(nbx, cdx, 0, Y0 + (k >> 1), Z0 + (k & 1)) : 0u;
 #pragma unroll
   for (int k = 0; k < 2; k++) {
-    q.y[k] = fd_ghost_fast(nby, cdy, 1, X, Z0 + k, (c + 2 * sy + k) & 45u);
-    q.z[k] = fd_ghost_fast(nbz, cdz, 2, X, Y0 + k, (c + 2 * k + sz) & 54u);
+    q.y[k] = fd_ghost(nby, cdy, 1, X, Z0 + k);
+    q.z[k] = fd_ghost(nbz, cdz, 2, X, Y0 + k);
   }
   return q;
 }
@@ -252,10 +264,10 @@ __global__ void __launch_bounds__(kCTA4) k_dc_jacobi4(Pool T, KParams P, int lev
   const QuadNbr n = quad_neighbours(in, own, t, q);
   const float alpha = (float)((1 << level) * (1 << level)) * P.dx * P.dx;
   float4 o;
-  o.x = (n.xm.x + n.xp.x + n.ym0 + own.z + n.zm0 + own.y - alpha * dv.x) / 6.f;
-  o.y = (n.xm.y + n.xp.y + n.ym1 + own.w + own.x + n.zp0 - alpha * dv.y) / 6.f;
-  o.z = (n.xm.z + n.xp.z + own.x + n.yp0 + n.zm1 + own.w - alpha * dv.z) / 6.f;
-  o.w = (n.xm.w + n.xp.w + own.y + n.yp1 + own.z + n.zp1 - alpha * dv.w) / 6.f;
+  o.x = div6(n.xm.x + n.xp.x + n.ym0 + own.z + n.zm0 + own.y - alpha * dv.x);
+  o.y = div6(n.xm.y + n.xp.y + n.ym1 + own.w + own.x + n.zp0 - alpha * dv.y);
+  o.z = div6(n.xm.z + n.xp.z + own.x + n.yp0 + n.zm1 + own.w - alpha * dv.z);
+  o.w = div6(n.xm.w + n.xp.w + own.y + n.yp1 + own.z + n.zp1 - alpha * dv.w);
   if (active) *reinterpret_cast<float4 *>(out + c0) = o;
 }
 
@@ -274,19 +286,19 @@ __global__ void __launch_bounds__(kCTA4) k_dc_divergence4(Pool T, KParams P, con
   const uint32_t g = threadIdx.x >> 4;
   const int t = threadIdx.x & 15;
   const uint32_t b0 = blockIdx.x * kB4 + g;
-  const bool active = slot_is_active(T, b0);
-  if (!__any_sync(0xFFFFFFFFu, active)) return;
-  const uint32_t b = active ? b0 : T.offsets[T.levels - 1];  // inactive half: runs along on the root block
-  const int4 pl = T.posl[b];
+  const uint32_t b = b0 < T.M ? b0 : T.M - 1;  // out-of-range half: runs along on the last slot, results discarded
+  const int4 pl = T.posl[b];                   // free slots carry level 0xFF; their (zeroed) fields are loaded but unused
+  const bool active = b0 < T.M && pl.w != kFree;
   const size_t c0 = (size_t)b * kBV + 4 * t;
   float4 v[4];
 #pragma unroll
   for (int k = 0; k < 4; k++) v[k] = vw[c0 + k];
   const uint32_t child = T.child[(size_t)b * 8 + (t >> 1)];
+  if (!__any_sync(0xFFFFFFFFu, active)) return;
   const QuadGhosts q = quad_ghosts(T, b, t);
   int X, Y0, Z0;
   quad_coords(t, X, Y0, Z0);
-  const int scale = 1 << pl.w;
+  const int scale = 1 << (pl.w & 15);
   const int sy = (t >> 2) & 1, sz = (t >> 1) & 1;
   float4 gx = make_float4(0.f, 0.f, 0.f, 0.f);
   if (q.has_x) {
@@ -331,12 +343,10 @@ __global__ void __launch_bounds__(kCTA4) k_dc_apply_pressure4(Pool T, KParams P,
   const uint32_t g = threadIdx.x >> 4;
   const int t = threadIdx.x & 15;
   const uint32_t b0 = blockIdx.x * kB4 + g;
-  const bool active = slot_is_active(T, b0);
+  const uint32_t b = b0 < T.M ? b0 : T.M - 1;  // out-of-range half: runs along, results discarded
+  const int level = T.posl[b].w;               // 0xFF = free slot (its zeroed fields are loaded but unused)
+  const bool active = b0 < T.M && level != kFree;
   if (!__any_sync(0xFFFFFFFFu, active)) return;
-  const uint32_t b = active ? b0 : T.offsets[T.levels - 1];
-  // slot -> level without touching posl: level pools are consecutive slot ranges
-  int level = 0;
-  while (level + 1 < T.levels && b >= T.offsets[level + 1]) level++;
   const size_t c0 = (size_t)b * kBV + 4 * t;
   const float4 op = *reinterpret_cast<const float4 *>(p + c0);
   const float4 ow = *reinterpret_cast<const float4 *>(fl + c0);
@@ -348,7 +358,7 @@ __global__ void __launch_bounds__(kCTA4) k_dc_apply_pressure4(Pool T, KParams P,
   const QuadNbr s = quad_neighbours(p, op, t, q);
   const QuadNbr w = quad_neighbours(fl, ow, t, q);
   if (!active || child != kNone) return;
-  const float alpha = .5f * P.rdx / (float)(1 << level);
+  const float alpha = .5f * P.rdx / (float)(1 << (level & 15));
   // v.x -= alpha * (w_r * (p_r - pc) + w_l * (pc - p_l)), likewise y (up/down), z (front/back)
   v[0].x -= alpha * (w.xp.x * (s.xp.x - op.x) + w.xm.x * (op.x - s.xm.x));
   v[0].y -= alpha * (ow.z * (op.z - op.x) + w.ym0 * (op.x - s.ym0));
