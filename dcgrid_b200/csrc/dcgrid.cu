@@ -23,6 +23,7 @@
 #include <vector>
 
 #include "dcgrid_kernels.cuh"
+#include "dcgrid_pipe.cuh"
 #include "sim.h"
 
 namespace dcg {
@@ -60,6 +61,13 @@ struct DCGridSim : dcg_sim {
 
   bool steady = false;
   uint64_t n_adapt = 0, n_changed = 0, n_moved = 0, n_refined = 0, n_skipped = 0, n_failed = 0;
+
+  // persistent TMA-ring kernels (dcgrid_pipe.cuh): resident CTAs per device, sweep direction toggle
+  int sm_count = 0, jacobi_pipe_ctas = 0, advect_pipe_ctas = 0;
+  bool use_advect_pipe = true;
+  bool use_pipe = true, snake = true;
+  unsigned pipe_min_tiles = 0;  // levels with fewer tiles take the one-CTA-per-tile kernel
+  int sweep_parity = 0;
 
   cudaGraphExec_t step_graph[4] = {nullptr, nullptr, nullptr, nullptr};
   uint64_t step_graph_launches = 0;
@@ -168,6 +176,30 @@ struct DCGridSim : dcg_sim {
     DCG_CUDA_TRY(cudaMallocHost(&h_block_scores, (size_t)M * 4));
     DCG_CUDA_TRY(cudaMallocHost(&h_to_move, (size_t)M * 4));
     DCG_CUDA_TRY(cudaMallocHost(&h_dest, (size_t)M * 8 * 4));
+    {
+      DCG_CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
+      DCG_CUDA_TRY(cudaFuncSetAttribute(k_dc_jacobi_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kJacobiPipeSmem));
+      int per_sm = 0;
+      DCG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_dc_jacobi_pipe, kCTA4, kJacobiPipeSmem));
+      if (per_sm < 1) return fail(DCG_ERR_CUDA, "k_dc_jacobi_pipe does not fit on an SM");
+      jacobi_pipe_ctas = per_sm * sm_count;
+      DCG_CUDA_TRY(cudaFuncSetAttribute(k_dc_advect_pipe<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAdvectPipeSmem));
+      DCG_CUDA_TRY(cudaFuncSetAttribute(k_dc_advect_pipe<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAdvectPipeSmem));
+      int av = 0, ad = 0;
+      DCG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&av, k_dc_advect_pipe<false>, kCTA, kAdvectPipeSmem));
+      DCG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ad, k_dc_advect_pipe<true>, kCTA, kAdvectPipeSmem));
+      if (av < 1 || ad < 1) return fail(DCG_ERR_CUDA, "k_dc_advect_pipe does not fit on an SM");
+      advect_pipe_ctas = std::min(av, ad) * sm_count;
+      if (const char *e = getenv("DCG_ADVECT")) use_advect_pipe = std::string(e) != "legacy";
+      if (const char *e = getenv("DCG_ADVECT_CTAS")) advect_pipe_ctas = std::max(1, atoi(e)) * sm_count;
+      pipe_min_tiles = 2u * (unsigned)sm_count;
+      if (const char *e = getenv("DCG_JACOBI")) {
+        use_pipe = std::string(e) != "legacy";
+        if (std::string(e) == "pipe_all") pipe_min_tiles = 1;  // tests: exercise the ring on small levels too
+      }
+      if (const char *e = getenv("DCG_SNAKE")) snake = std::string(e) != "0";
+      if (const char *e = getenv("DCG_JACOBI_CTAS")) jacobi_pipe_ctas = std::max(1, atoi(e)) * sm_count;
+    }
     return reset();
   }
 
@@ -484,27 +516,53 @@ struct DCGridSim : dcg_sim {
   }
   void accumulate_velocity() { accumulate(vw[cur_v], nullptr); }
   void accumulate_scalar(float *ch) { accumulate(nullptr, ch); }
-  int advect_velocity() override {  // :263-268
-    k_dc_advect_velocity<<<blocks_for(M, kBPC), kCTA, 0, stream>>>(T, kp, vw[cur_v], vw[cur_v ^ 1]);
+  void launch_advect_velocity(const float4 *in, float4 *out) {
+    if (use_advect_pipe) {
+      const unsigned grid = std::min<unsigned>(blocks_for(M, kBPC), (unsigned)advect_pipe_ctas);
+      k_dc_advect_pipe<false><<<grid, kCTA, kAdvectPipeSmem, stream>>>(T, kp, in, out, nullptr, nullptr, nullptr);
+    } else {
+      k_dc_advect_velocity<<<blocks_for(M, kBPC), kCTA, 0, stream>>>(T, kp, in, out);
+    }
     launches++;
+  }
+  void launch_advect_density(const float4 *v, const float *qi, float *qo) {
+    if (use_advect_pipe) {
+      const unsigned grid = std::min<unsigned>(blocks_for(M, kBPC), (unsigned)advect_pipe_ctas);
+      k_dc_advect_pipe<true><<<grid, kCTA, kAdvectPipeSmem, stream>>>(T, kp, v, nullptr, fl, qi, qo);
+    } else {
+      k_dc_advect_density<<<blocks_for(M, kBPC), kCTA, 0, stream>>>(T, kp, v, fl, qi, qo);
+    }
+    launches++;
+  }
+  int advect_velocity() override {  // :263-268
+    launch_advect_velocity(vw[cur_v], vw[cur_v ^ 1]);
     cur_v ^= 1;
     accumulate_velocity();
     DCG_CUDA_TRY(cudaGetLastError());
     return DCG_OK;
   }
   int advect_density() override {  // :313-318
-    k_dc_advect_density<<<blocks_for(M, kBPC), kCTA, 0, stream>>>(T, kp, vw[cur_v], fl, q[cur_q], q[cur_q ^ 1]);
-    launches++;
+    launch_advect_density(vw[cur_v], q[cur_q], q[cur_q ^ 1]);
     cur_q ^= 1;
     accumulate_scalar(q[cur_q]);
     DCG_CUDA_TRY(cudaGetLastError());
     return DCG_OK;
   }
+  // one sweep of a level; persistent TMA-ring kernel for levels with enough tiles to fill the machine
+  void jacobi_sweep(int l, const float *in, float *out) {
+    const unsigned tiles = blocks_for(loads[l], kB4);
+    if (use_pipe && tiles >= pipe_min_tiles) {
+      const unsigned grid = std::min<unsigned>(tiles, (unsigned)jacobi_pipe_ctas);
+      k_dc_jacobi_pipe<<<grid, kCTA4, kJacobiPipeSmem, stream>>>(T, kp, l, in, out, div, snake ? (sweep_parity ^= 1) : 0);
+    } else {
+      k_dc_jacobi4<<<tiles, kCTA4, 0, stream>>>(T, kp, l, in, out, div);
+    }
+    launches++;
+  }
   void jacobi_pair(int l) {
     if (loads[l] == 0) return;
-    k_dc_jacobi4<<<blocks_for(loads[l], kB4), kCTA4, 0, stream>>>(T, kp, l, p, tp, div);
-    k_dc_jacobi4<<<blocks_for(loads[l], kB4), kCTA4, 0, stream>>>(T, kp, l, tp, p, div);
-    launches += 2;
+    jacobi_sweep(l, p, tp);
+    jacobi_sweep(l, tp, p);
   }
   void divergence_stage() {
     k_dc_divergence4<<<blocks_for(M, kB4), kCTA4, 0, stream>>>(T, kp, vw[cur_v], div, p, tp);
@@ -590,16 +648,28 @@ struct DCGridSim : dcg_sim {
     double bytes = 0;
     DCG_CUDA_TRY(cudaEventRecord(ev_begin, stream));
     for (int r = 0; r < reps; r++) {
-      if (st == "jacobi") {
+      if (st == "jacobi" || st == "jacobi_legacy" || st == "jacobi_pipe") {
         if (loads[level] == 0) return fail(DCG_ERR_INVALID, "bench_stage: level %d has no active blocks", level);
-        k_dc_jacobi4<<<blocks_for(loads[level], kB4), kCTA4, 0, stream>>>(T, kp, level, (r & 1) ? tp : p, (r & 1) ? p : tp, div);
+        const bool saved = use_pipe;
+        if (st != "jacobi") use_pipe = st == "jacobi_pipe";
+        jacobi_sweep(level, (r & 1) ? tp : p, (r & 1) ? p : tp);
+        launches--;
+        use_pipe = saved;
         bytes = 12.0 * cl;
-      } else if (st == "advect_velocity") {
-        k_dc_advect_velocity<<<blocks_for(M, kBPC), kCTA, 0, stream>>>(T, kp, vw[cur_v], vw[cur_v ^ 1]);
+      } else if (st == "advect_velocity" || st == "advect_velocity_legacy") {
+        const bool saved = use_advect_pipe;
+        if (st != "advect_velocity") use_advect_pipe = false;
+        launch_advect_velocity(vw[cur_v], vw[cur_v ^ 1]);
+        use_advect_pipe = saved;
+        launches--;
         cur_v ^= 1;
         bytes = 28.0 * call;
-      } else if (st == "advect_density") {
-        k_dc_advect_density<<<blocks_for(M, kBPC), kCTA, 0, stream>>>(T, kp, vw[cur_v], fl, q[cur_q], q[cur_q ^ 1]);
+      } else if (st == "advect_density" || st == "advect_density_legacy") {
+        const bool saved = use_advect_pipe;
+        if (st != "advect_density") use_advect_pipe = false;
+        launch_advect_density(vw[cur_v], q[cur_q], q[cur_q ^ 1]);
+        use_advect_pipe = saved;
+        launches--;
         cur_q ^= 1;
         bytes = 24.0 * call;
       } else if (st == "divergence") {

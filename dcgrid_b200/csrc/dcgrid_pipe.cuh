@@ -1,0 +1,329 @@
+// Persistent, TMA-fed variants of the DCGrid stencil kernels (sm_100a).
+//
+// Why: the one-CTA-per-16-blocks kernels of dcgrid_stencil.cuh are latency-bound (profiles/README.md r1a:
+// 48 % of DRAM peak with two dependent load rounds per CTA and a CTA lifetime of ~3 us).  The active blocks
+// of a level are a compact slot prefix and a slot's 64 cells are contiguous, so the fields of 16
+// consecutive blocks are ONE contiguous 4 KiB range per field and their face descriptors one 768-byte range.
+// Here each CTA stays resident, walks tiles of 16 blocks, and an elected thread streams the next tiles'
+// ranges into a multi-stage shared-memory ring with cp.async.bulk (UBLKCP) completing on mbarriers, so the
+// bytes in flight per SM are set by the ring depth instead of by occupancy x one load round.  Ghost values
+// (other blocks' cells, mostly L2 hits) are still gathered with ordinary loads through the face
+// descriptors.  Arithmetic, operand order and the shuffle exchange are those of dcgrid_stencil.cuh.
+#pragma once
+#include "dcgrid_stencil.cuh"
+
+namespace dcg {
+namespace pipe {
+
+__device__ __forceinline__ uint32_t saddr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(saddr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(saddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(saddr(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+// global -> shared bulk copy (bytes % 16 == 0, both addresses 16-byte aligned), completes on `bar`
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(saddr(dst)), "l"(src),
+               "r"(bytes), "r"(saddr(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_hint(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(saddr(dst)),
+               "l"(src), "r"(bytes), "r"(saddr(bar)), "l"(pol)
+               : "memory");
+}
+
+}  // namespace pipe
+
+// ---- Jacobi sweep (k_dcgrid_jacobi / _inv, dcgrid_multigrid_solver.cu:5-41), persistent + TMA ring --------
+// CTA = 256 threads = one tile of 16 consecutive blocks per iteration (16 threads per block, one 1x2x2 quad
+// each, half-warp shuffle exchange exactly as in k_dc_jacobi4).  in[], div[] and the face descriptors of a
+// tile are three contiguous ranges streamed through a kJStages-deep ring by cp.async.bulk; the ghost
+// values of tile i+1 are gathered into registers (vector loads, quad_ghost_values) while tile i is
+// computed, so no thread ever waits for DRAM or L2 inside an iteration.
+// (Two variants that kept the neighbour exchange and the ghosts in shared memory — LDS at loop-invariant
+// offsets, ghosts gathered by 4-byte cp.async — were slower: they saturate the shared-memory data pipe,
+// l1tex__data_pipe_lsu_wavefronts 71 %, profiles/README.md.)
+constexpr int kJStages = 4;
+struct alignas(128) JacobiStage {
+  float p[kB4 * kBV];     // 4 KiB: in[] of the tile's 16 blocks
+  float dv[kB4 * kBV];    // 4 KiB: div[]
+  uint32_t fd[kB4 * 12];  // 768 B: face descriptors
+};
+constexpr size_t kJacobiPipeSmem = kJStages * sizeof(JacobiStage) + kJStages * sizeof(uint64_t);
+
+// tile order: `reverse` walks the level's tiles from the last to the first, so that a sweep starts on the
+// tiles the previous sweep wrote last (still L2-resident: a level-0 field is 62 MB at 512^3, L2 is 126 MB)
+__global__ void __launch_bounds__(kCTA4, 4) k_dc_jacobi_pipe(Pool T, KParams P, int level, const float *__restrict__ in, float *__restrict__ out,
+                                                            const float *__restrict__ div, int reverse) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  JacobiStage *st = reinterpret_cast<JacobiStage *>(smem_raw);
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + kJStages * sizeof(JacobiStage));
+  const uint32_t loads = T.loads[level], off = T.offsets[level];
+  const uint32_t ntiles = (loads + kB4 - 1) / kB4;
+  const uint32_t g = threadIdx.x >> 4;
+  const int t = threadIdx.x & 15;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < kJStages; s++) pipe::mbar_init(&full[s], 1);
+    pipe::fence_barrier_init();
+  }
+  __syncthreads();
+  const uint64_t pol_stream = pipe::policy_evict_first();
+  auto tile_of = [&](uint32_t it) -> uint32_t {  // this CTA's it-th tile, ntiles = none
+    const uint32_t tl = blockIdx.x + it * gridDim.x;
+    if (tl >= ntiles) return ntiles;
+    return reverse ? ntiles - 1 - tl : tl;
+  };
+  auto issue_tile = [&](uint32_t it) {  // producer (thread 0): tile `it` of this CTA -> ring slot it % kJStages
+    const uint32_t tl = tile_of(it);
+    if (tl >= ntiles) return;
+    const uint32_t li0 = tl * kB4;
+    const uint32_t nvalid = min((uint32_t)kB4, loads - li0);
+    const size_t b0 = (size_t)off + li0;
+    JacobiStage &S = st[it % kJStages];
+    uint64_t *bar = &full[it % kJStages];
+    pipe::mbar_expect_tx(bar, nvalid * (2u * kBV * 4u + 48u));
+    pipe::bulk_g2s(S.p, in + b0 * kBV, nvalid * kBV * 4u, bar);
+    pipe::bulk_g2s_hint(S.dv, div + b0 * kBV, nvalid * kBV * 4u, bar, pol_stream);
+    pipe::bulk_g2s(S.fd, T.fd + b0 * 12, nvalid * 48u, bar);
+  };
+  // ghost values of tile `it` (waits for its ring slot; an inactive trailing block holds stale descriptors)
+  auto load_ghosts = [&](uint32_t it) -> GhostVals {
+    GhostVals gv;
+    gv.gx = make_float4(0.f, 0.f, 0.f, 0.f);
+    gv.gy0 = gv.gy1 = gv.gz0 = gv.gz1 = 0.f;
+    const uint32_t tl = tile_of(it);
+    if (tl < ntiles) {
+      pipe::mbar_wait(&full[it % kJStages], (it / kJStages) & 1u);
+      const uint32_t li = tl * kB4 + g;
+      if (li < loads) {
+        const uint4 *fdp = reinterpret_cast<const uint4 *>(&st[it % kJStages].fd[g * 12]);
+        gv = quad_ghost_values(T, in, off + li, t, fdp[0], fdp[1], fdp[2]);
+      }
+    }
+    return gv;
+  };
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (uint32_t it = 0; it < (uint32_t)kJStages; it++) issue_tile(it);
+  }
+  const float alpha = (float)((1 << level) * (1 << level)) * P.dx * P.dx;
+  GhostVals gv = load_ghosts(0);
+  for (uint32_t it = 0;; it++) {
+    const uint32_t tl = tile_of(it);
+    if (tl >= ntiles) break;
+    const uint32_t s = it % kJStages;
+    const GhostVals gn = load_ghosts(it + 1);  // in flight while this tile is computed
+    const uint32_t li = tl * kB4 + g;
+    const bool active = li < loads;
+    const JacobiStage &S = st[s];  // its barrier was waited for by load_ghosts(it)
+    const float4 own = *reinterpret_cast<const float4 *>(&S.p[g * kBV + 4 * t]);
+    const float4 dv = *reinterpret_cast<const float4 *>(&S.dv[g * kBV + 4 * t]);
+    __syncthreads();  // every thread holds its part of ring slot s in registers: the slot can be refilled
+    if (threadIdx.x == 0) issue_tile(it + kJStages);
+    const QuadNbr n = quad_exchange(own, t, gv.gx, gv.gy0, gv.gy1, gv.gz0, gv.gz1);
+    float4 o;
+    o.x = div6(n.xm.x + n.xp.x + n.ym0 + own.z + n.zm0 + own.y - alpha * dv.x);
+    o.y = div6(n.xm.y + n.xp.y + n.ym1 + own.w + own.x + n.zp0 - alpha * dv.y);
+    o.z = div6(n.xm.z + n.xp.z + own.x + n.yp0 + n.zm1 + own.w - alpha * dv.z);
+    o.w = div6(n.xm.w + n.xp.w + own.y + n.yp1 + own.z + n.zp1 - alpha * dv.w);
+    if (active) *reinterpret_cast<float4 *>(out + ((size_t)off + li) * kBV + 4 * t) = o;
+    gv = gn;
+  }
+}
+
+// ---- semi-Lagrangian advection (k_dcgrid_advect_velocity / _density, dcgrid_fluid.cu:7-144), persistent ----
+// The one-CTA-per-4-blocks kernels of dcgrid_kernels.cuh spend ~45 % of their stall samples staging the
+// blocks' 6^3 apron maps (LDG -> STS -> barrier) before the first gather can be issued
+// (profiles/README.md).  A tile's apron maps (4 x 864 B), own velocities (4 KiB), child links and
+// positions are four contiguous ranges, so a resident CTA streams them through a ring of cp.async.bulk
+// stages and the only latency a thread waits for is that of its own gathers.
+//
+// Samples that leave their block (69 % of the warps hold at least one in the developed flow) resolve the
+// covering block with all sparse-level map probes issued at once (the reference walks them one dependent
+// load at a time, dcgrid_utils.cuh:201-233) and derive the block origin from the sample position (block
+// origins are multiples of 4 cells of their level) instead of loading it.
+constexpr int kAStages = 4;
+struct alignas(128) AdvectStage {
+  uint32_t apron[kBPC * kAV];  // 3456 B
+  float4 me[kBPC * kBV];       // 4096 B: the cells' own velocity (+ fluidity)
+  uint32_t child[kBPC * kSV];  // 128 B
+  int4 posl[kBPC];             // 64 B
+};
+constexpr size_t kAdvectPipeSmem = kAStages * sizeof(AdvectStage) + kAStages * sizeof(uint64_t);
+
+// getBlockIndexDeep(position, 0) with independent probes; returns the slot and sets (level, origin)
+__device__ __forceinline__ uint32_t block_index_deep_par(const Pool &T, const KParams &P, int ix, int iy, int iz, int4 &bp) {
+  uint32_t cand[4];
+  const int ns = T.sparse_levels < 4 ? T.sparse_levels : 4;
+#pragma unroll
+  for (int l = 0; l < 4; l++) cand[l] = l < ns ? map_lookup(T, P, ix >> l, iy >> l, iz >> l, l) : kNone;
+  int level = 0;
+  uint32_t b = kNone;
+#pragma unroll
+  for (int l = 3; l >= 0; l--)
+    if (cand[l] != kNone) { b = cand[l]; level = l; }
+  if (b == kNone) {
+    level = ns;
+    int x = ix >> ns, y = iy >> ns, z = iz >> ns;
+    b = block_index_deep(T, P, x, y, z, level);  // remaining sparse levels (if > 4), then the ordered one
+  }
+  bp = make_int4((ix >> level) & ~(kBW - 1), (iy >> level) & ~(kBW - 1), (iz >> level) & ~(kBW - 1), level);
+  return b;
+}
+
+__device__ __forceinline__ DSample d_sample_pipe(const Pool &T, const KParams &P, const uint32_t *own_apron, const uint32_t *own_child,
+                                                 const int4 pl, float px, float py, float pz) {
+  const int ix = min(max((int)floorf(px), 0), P.gx - 1), iy = min(max((int)floorf(py), 0), P.gy - 1), iz = min(max((int)floorf(pz), 0), P.gz - 1);
+  const int lx = (ix >> pl.w) - pl.x, ly = (iy >> pl.w) - pl.y, lz = (iz >> pl.w) - pl.z;
+  if ((unsigned)lx < (unsigned)kBW && (unsigned)ly < (unsigned)kBW && (unsigned)lz < (unsigned)kBW &&
+      own_child[((lx >> 1) << 2) | ((ly >> 1) << 1) | (lz >> 1)] == kNone)
+    return d_sample_in(own_apron, pl, px, py, pz);
+  int4 bp;
+  const uint32_t b = block_index_deep_par(T, P, ix, iy, iz, bp);
+  return d_sample_in(T.apron + (size_t)b * kAV, bp, px, py, pz);
+}
+
+template <bool kDensity>
+__global__ void __launch_bounds__(kCTA, 4) k_dc_advect_pipe(Pool T, KParams P, const float4 *__restrict__ vin, float4 *__restrict__ vout,
+                                                            const float *__restrict__ fl, const float *__restrict__ qin, float *__restrict__ qout) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  AdvectStage *st = reinterpret_cast<AdvectStage *>(smem_raw);
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + kAStages * sizeof(AdvectStage));
+  const uint32_t ntiles = (T.M + kBPC - 1) / kBPC;
+  const uint32_t g = threadIdx.x >> 6, t = threadIdx.x & 63;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < kAStages; s++) pipe::mbar_init(&full[s], 1);
+    pipe::fence_barrier_init();
+  }
+  __syncthreads();
+  const uint64_t pol_stream = pipe::policy_evict_first();
+  auto issue_tile = [&](uint32_t it) {
+    const uint32_t tl = blockIdx.x + it * gridDim.x;
+    if (tl >= ntiles) return;
+    const size_t b0 = (size_t)tl * kBPC;
+    const uint32_t nvalid = min((uint32_t)kBPC, T.M - (uint32_t)b0);
+    AdvectStage &S = st[it % kAStages];
+    uint64_t *bar = &full[it % kAStages];
+    pipe::mbar_expect_tx(bar, nvalid * (kAV * 4u + kBV * 16u + kSV * 4u + 16u));
+    pipe::bulk_g2s_hint(S.apron, T.apron + b0 * kAV, nvalid * kAV * 4u, bar, pol_stream);
+    pipe::bulk_g2s(S.me, vin + b0 * kBV, nvalid * kBV * 16u, bar);
+    pipe::bulk_g2s(S.child, T.child + b0 * kSV, nvalid * kSV * 4u, bar);
+    pipe::bulk_g2s(S.posl, T.posl + b0, nvalid * 16u, bar);
+  };
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (uint32_t it = 0; it < (uint32_t)kAStages; it++) issue_tile(it);
+  }
+  const float alpha = P.dt * P.rdx;
+  for (uint32_t it = 0;; it++) {
+    const uint32_t tl = blockIdx.x + it * gridDim.x;
+    if (tl >= ntiles) break;
+    const uint32_t s = it % kAStages;
+    pipe::mbar_wait(&full[s], (it / kAStages) & 1u);
+    const AdvectStage &S = st[s];
+    const uint32_t b = tl * kBPC + g;
+    const uint32_t c = b * kBV + t;
+    const bool in_pool = b < T.M;
+    int4 pl = make_int4(0, 0, 0, kFree);
+    float4 me = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (in_pool) {
+      pl = S.posl[g];
+      me = S.me[g * kBV + t];
+    }
+    const bool live = pl.w != kFree;
+    const bool leaf = live && S.child[g * kSV + (t >> 3)] == kNone;
+    DSample smp;
+    if (leaf) {
+      const float scale = (float)(1 << pl.w);
+      const float bx = ((float)(pl.x | cell_x(t)) + .5f) * scale - me.x * alpha;
+      const float by = ((float)(pl.y | cell_y(t)) + .5f) * scale - me.y * alpha;
+      const float bz = ((float)(pl.z | cell_z(t)) + .5f) * scale - me.z * alpha;
+      smp = d_sample_pipe(T, P, S.apron + g * kAV, S.child + g * kSV, pl, bx, by, bz);
+    }
+    __syncthreads();  // every thread is done with ring slot s (positions, velocities, apron ids): refill it
+    if (threadIdx.x == 0) issue_tile(it + kAStages);
+    if (!live) continue;
+    if (!kDensity) {
+      float3 out = make_float3(0.f, 0.f, 0.f);
+      if (leaf) {
+        float4 cv[8];
+        float f[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          cv[k] = vin[smp.id[k]];
+          f[k] = cv[k].w;
+        }
+        const Weights8 W = corner_weights(f, smp.fx, smp.fy, smp.fz);
+        if (!(W.acc < 1e-6f)) {
+          float vx[8], vy[8], vz[8];
+          const bool inside = sample_inside(P, smp);
+#pragma unroll
+          for (int k = 0; k < 8; k++) {
+            float3 v = make_float3(cv[k].x, cv[k].y, cv[k].z);
+            if (!inside) v = velocity_bc(P, v, smp.x0 + ((k >> 2) & 1), smp.y0 + ((k >> 1) & 1), smp.z0 + (k & 1), smp.scale);
+            vx[k] = v.x; vy[k] = v.y; vz[k] = v.z;
+          }
+          out = make_float3(blend8(vx, W.w), blend8(vy, W.w), blend8(vz, W.w));
+        }
+      }
+      vout[c] = make_float4(out.x, out.y, out.z, me.w);
+    } else {
+      float out = 0.f;
+      if (leaf) {
+        float qv[8], f[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          f[k] = fl[smp.id[k]];
+          qv[k] = qin[smp.id[k]];
+        }
+        const Weights8 W = corner_weights(f, smp.fx, smp.fy, smp.fz);
+        if (!(W.acc < 1e-6f)) {
+          if (!sample_inside(P, smp)) {
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+              qv[k] = density_bc(P, qv[k], smp.x0 + ((k >> 2) & 1), smp.y0 + ((k >> 1) & 1), smp.z0 + (k & 1), smp.scale);
+          }
+          out = blend8(qv, W.w);
+        }
+      }
+      qout[c] = out;
+    }
+  }
+}
+
+}  // namespace dcg

@@ -144,9 +144,8 @@ struct QuadGhosts {
   uint32_t z[2];  // [cy], the quad's boundary column (cz = sz)
   bool has_x;
 };
-__device__ __forceinline__ QuadGhosts quad_ghosts(const Pool &T, uint32_t b, int t) {
-  const uint4 *p = reinterpret_cast<const uint4 *>(T.fd + 12 * (size_t)b);
-  const uint4 w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);
+// w0..w2 = the block's 12 descriptor words (6 bases, 6 codes)
+__device__ __forceinline__ QuadGhosts quad_ghosts_from(const Pool &T, uint32_t b, int t, const uint4 w0, const uint4 w1, const uint4 w2) {
   int X, Y0, Z0;
   quad_coords(t, X, Y0, Z0);
   const int sy = (t >> 2) & 1, sz = (t >> 1) & 1;
@@ -188,6 +187,11 @@ __device__ __forceinline__ QuadGhosts quad_ghosts(const Pool &T, uint32_t b, int
     q.z[k] = fd_ghost(nbz, cdz, 2, X, Y0 + k);
   }
   return q;
+}
+
+__device__ __forceinline__ QuadGhosts quad_ghosts(const Pool &T, uint32_t b, int t) {
+  const uint4 *p = reinterpret_cast<const uint4 *>(T.fd + 12 * (size_t)b);
+  return quad_ghosts_from(T, b, t, __ldg(p), __ldg(p + 1), __ldg(p + 2));
 }
 
 // The 6-neighbourhood of a quad of one scalar field, exchanged through half-warp shuffles (no shared
@@ -242,6 +246,61 @@ __device__ __forceinline__ QuadNbr quad_neighbours(const float *__restrict__ src
   return quad_exchange(own, t, gx, gy0, gy1, gz0, gz1);
 }
 
+// Ghost values of one scalar field for a quad, with vector loads where the face is a same-level neighbour
+// (code 0, the common case): the 4 x-face ghosts of a quad are 16 contiguous bytes of the neighbour block,
+// the 2 y-face ghosts 8 contiguous bytes, the 2 z-face ghosts elements 0 and 2 of one aligned float4 —
+// 3 load instructions touching 3 cache lines instead of 8 touching up to 8 (the L1 tag stage, not DRAM,
+// was the busiest unit of the scalar version: profiles/README.md).  Other faces use the scalar ids.
+struct GhostVals {
+  float4 gx;
+  float gy0, gy1, gz0, gz1;
+};
+__device__ __forceinline__ GhostVals quad_ghost_values(const Pool &T, const float *__restrict__ src, uint32_t b, int t, const uint4 w0,
+                                                      const uint4 w1, const uint4 w2) {
+  GhostVals g;
+  g.gx = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int sy = (t >> 2) & 1, sz = (t >> 1) & 1;
+  const int X = ((t >> 3) << 1) | (t & 1);
+  const bool has_x = X == 0 || X == 3;
+  const int fx = X == 3 ? 1 : 0;
+  const uint32_t c = 4u * (uint32_t)t;
+  if (!(w1.z & kFdIrregular)) {
+    const uint32_t nbx = fx ? w0.y : w0.x, cdx = fx ? w1.w : w1.z;
+    const uint32_t nby = sy ? w0.w : w0.z, cdy = sy ? w2.y : w2.x;
+    const uint32_t nbz = sz ? w1.y : w1.x, cdz = sz ? w2.w : w2.z;
+    if (has_x) {
+      if (cdx == 0) {
+        g.gx = *reinterpret_cast<const float4 *>(src + nbx + (c & 27u));
+      } else {
+        const int Y0 = sy << 1, Z0 = sz << 1;
+        g.gx.x = src[fd_ghost(nbx, cdx, 0, Y0, Z0)];
+        g.gx.y = src[fd_ghost(nbx, cdx, 0, Y0, Z0 + 1)];
+        g.gx.z = src[fd_ghost(nbx, cdx, 0, Y0 + 1, Z0)];
+        g.gx.w = src[fd_ghost(nbx, cdx, 0, Y0 + 1, Z0 + 1)];
+      }
+    }
+    if (cdy == 0) {
+      const float2 v = *reinterpret_cast<const float2 *>(src + nby + (c & 45u));
+      g.gy0 = v.x; g.gy1 = v.y;
+    } else {
+      g.gy0 = src[fd_ghost(nby, cdy, 1, X, sz << 1)];
+      g.gy1 = src[fd_ghost(nby, cdy, 1, X, (sz << 1) + 1)];
+    }
+    if (cdz == 0) {
+      const float4 v = *reinterpret_cast<const float4 *>(src + nbz + (c & 54u));
+      g.gz0 = v.x; g.gz1 = v.z;
+    } else {
+      g.gz0 = src[fd_ghost(nbz, cdz, 2, X, sy << 1)];
+      g.gz1 = src[fd_ghost(nbz, cdz, 2, X, (sy << 1) + 1)];
+    }
+    return g;
+  }
+  const QuadGhosts q = quad_ghosts_from(T, b, t, w0, w1, w2);
+  if (q.has_x) g.gx = make_float4(src[q.x[0]], src[q.x[1]], src[q.x[2]], src[q.x[3]]);
+  g.gy0 = src[q.y[0]]; g.gy1 = src[q.y[1]]; g.gz0 = src[q.z[0]]; g.gz1 = src[q.z[1]];
+  return g;
+}
+
 // ---- k_dcgrid_jacobi / k_dcgrid_jacobi_inv, dcgrid_multigrid_solver.cu:5-41 -------------------------
 // Active blocks of a level are the compact slot prefix [offset, offset + blockLoads): slots come
 // from freeBlockIndices[offset + load] with the identity free list (fluid_simulation_dcgrid.cu:243-249,
@@ -260,8 +319,9 @@ __global__ void __launch_bounds__(kCTA4) k_dc_jacobi4(Pool T, KParams P, int lev
   const size_t c0 = (size_t)b * kBV + 4 * t;
   const float4 own = *reinterpret_cast<const float4 *>(in + c0);
   const float4 dv = __ldcs(reinterpret_cast<const float4 *>(div + c0));  // streamed: keep L2 for the ghosts
-  const QuadGhosts q = quad_ghosts(T, b, t);
-  const QuadNbr n = quad_neighbours(in, own, t, q);
+  const uint4 *fdp = reinterpret_cast<const uint4 *>(T.fd + 12 * (size_t)b);
+  const GhostVals gv = quad_ghost_values(T, in, b, t, __ldg(fdp), __ldg(fdp + 1), __ldg(fdp + 2));
+  const QuadNbr n = quad_exchange(own, t, gv.gx, gv.gy0, gv.gy1, gv.gz0, gv.gz1);
   const float alpha = (float)((1 << level) * (1 << level)) * P.dx * P.dx;
   float4 o;
   o.x = div6(n.xm.x + n.xp.x + n.ym0 + own.z + n.zm0 + own.y - alpha * dv.x);

@@ -82,6 +82,21 @@ def test_dcgrid_bit_exact_vs_oracle(gpu, d, M, solids, steps, schedule):
     assert orc.field("density").max() > 0
 
 
+@pytest.mark.parametrize("env", [
+    {"DCG_JACOBI": "pipe_all"},                            # TMA-ring Jacobi on every level, incl. ragged last tiles
+    {"DCG_JACOBI": "pipe_all", "DCG_SNAKE": "0"},
+    {"DCG_JACOBI": "legacy", "DCG_ADVECT": "legacy"},      # one-CTA-per-tile kernels
+    {"DCG_JACOBI_CTAS": "1", "DCG_ADVECT_CTAS": "1"},      # one resident CTA per SM: every CTA walks several tiles
+])
+@pytest.mark.parametrize("d,M,solids,steps", [(64, 2000, True, 8), (32, 301, False, 6), (128, 16384, True, 4)])
+def test_dcgrid_kernel_variants_bit_exact(gpu, monkeypatch, env, d, M, solids, steps):
+    """The persistent cp.async.bulk (TMA ring) kernels and the one-CTA-per-tile kernels are interchangeable:
+    each combination must reproduce the oracle bit for bit (variants are chosen when the instance is created)."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    run_pair(d, M, solids, steps, "project", check_every=steps)
+
+
 def test_dcgrid_steady_state_skip_and_graph(gpu):
     """Once the (topology, moveLimit) fixed point is proven adaptTopology is skipped and dcg_step replays a
     CUDA graph; results must equal the call-by-call path and the oracle."""
