@@ -501,12 +501,14 @@ struct DCGridSim : dcg_sim {
     while (l > 0 && loads[l - 1] <= cap) l--;
     return l;
   }
-  void accumulate(float4 *v, float *ch) {  // :496-515, fine -> coarse
+  // `fused`: the kernel that produced the field restricted every block without children itself, so level 0
+  // (never refined) needs no pass at all and the other levels only push up blocks that have children.
+  void accumulate(float4 *v, float *ch, bool fused) {  // :496-515, fine -> coarse
     const int tail = small_levels_from(512);
-    for (int l = 0; l < levels - 1 && l < tail; l++) {
+    for (int l = fused ? 1 : 0; l < levels - 1 && l < tail; l++) {
       if (loads[l] == 0) continue;
-      if (v) k_dc_accumulate_velocity<<<blocks_for(8 * loads[l], 256), 256, 0, stream>>>(T, l, v);
-      else k_dc_accumulate_scalar<<<blocks_for(8 * loads[l], 256), 256, 0, stream>>>(T, l, ch);
+      if (v) k_dc_accumulate_velocity<<<blocks_for(8 * loads[l], 256), 256, 0, stream>>>(T, l, v, fused ? 1 : 0);
+      else k_dc_accumulate_scalar<<<blocks_for(8 * loads[l], 256), 256, 0, stream>>>(T, l, ch, fused ? 1 : 0);
       launches++;
     }
     if (tail < levels - 1) {
@@ -514,8 +516,8 @@ struct DCGridSim : dcg_sim {
       launches++;
     }
   }
-  void accumulate_velocity() { accumulate(vw[cur_v], nullptr); }
-  void accumulate_scalar(float *ch) { accumulate(nullptr, ch); }
+  void accumulate_velocity(bool fused) { accumulate(vw[cur_v], nullptr, fused); }
+  void accumulate_scalar(float *ch, bool fused) { accumulate(nullptr, ch, fused); }
   void launch_advect_velocity(const float4 *in, float4 *out) {
     if (use_advect_pipe) {
       const unsigned grid = std::min<unsigned>(blocks_for(M, kBPC), (unsigned)advect_pipe_ctas);
@@ -537,14 +539,14 @@ struct DCGridSim : dcg_sim {
   int advect_velocity() override {  // :263-268
     launch_advect_velocity(vw[cur_v], vw[cur_v ^ 1]);
     cur_v ^= 1;
-    accumulate_velocity();
+    accumulate_velocity(false);
     DCG_CUDA_TRY(cudaGetLastError());
     return DCG_OK;
   }
   int advect_density() override {  // :313-318
     launch_advect_density(vw[cur_v], q[cur_q], q[cur_q ^ 1]);
     cur_q ^= 1;
-    accumulate_scalar(q[cur_q]);
+    accumulate_scalar(q[cur_q], false);
     DCG_CUDA_TRY(cudaGetLastError());
     return DCG_OK;
   }
@@ -567,12 +569,12 @@ struct DCGridSim : dcg_sim {
   void divergence_stage() {
     k_dc_divergence4<<<blocks_for(M, kB4), kCTA4, 0, stream>>>(T, kp, vw[cur_v], div, p, tp);
     launches++;
-    accumulate_scalar(div);
+    accumulate_scalar(div, true);
   }
   void apply_stage() {
     k_dc_apply_pressure4<<<blocks_for(M, kB4), kCTA4, 0, stream>>>(T, kp, p, fl, vw[cur_v]);
     launches++;
-    accumulate_velocity();
+    accumulate_velocity(true);
   }
   int project() override {  // :270-294
     divergence_stage();
@@ -679,7 +681,7 @@ struct DCGridSim : dcg_sim {
         k_dc_apply_pressure4<<<blocks_for(M, kB4), kCTA4, 0, stream>>>(T, kp, p, fl, vw[cur_v]);
         bytes = 32.0 * call;
       } else if (st == "accumulate_velocity") {
-        k_dc_accumulate_velocity<<<blocks_for(8 * loads[level], 256), 256, 0, stream>>>(T, level, vw[cur_v]);
+        k_dc_accumulate_velocity<<<blocks_for(8 * loads[level], 256), 256, 0, stream>>>(T, level, vw[cur_v], 0);
         bytes = 13.5 * cl;
       } else if (st == "prolongate") {
         k_dc_prolongate4<<<blocks_for(loads[level], kB4), kCTA4, 0, stream>>>(T, level, p);

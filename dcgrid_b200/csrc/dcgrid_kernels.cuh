@@ -134,12 +134,21 @@ __global__ void __launch_bounds__(256) k_dc_refresh_apron(Pool T, KParams P, con
 
 // accumulate<T>, dcgrid_structure.cu:188-222: parent cell = .125 * sequential sum of the 8 cells of a
 // child subblock.  One thread per subblock of `level`.
-__global__ void __launch_bounds__(256) k_dc_accumulate_velocity(Pool T, int level, float4 *__restrict__ vw) {
+// skip_childless: the producing kernel already restricted the blocks that have no children (fused
+// restriction in k_dc_advect_pipe / k_dc_apply_pressure4 / k_dc_divergence4); only blocks holding restricted
+// cells of their own (= with children) still have to be pushed up.
+__device__ __forceinline__ bool block_has_children(const Pool &T, uint32_t b) {
+  const uint4 *c = reinterpret_cast<const uint4 *>(T.child + (size_t)b * kSV);
+  const uint4 c0 = c[0], c1 = c[1];
+  return (c0.x & c0.y & c0.z & c0.w & c1.x & c1.y & c1.z & c1.w) != kNone;
+}
+__global__ void __launch_bounds__(256) k_dc_accumulate_velocity(Pool T, int level, float4 *__restrict__ vw, int skip_childless) {
   const uint32_t t = blockIdx.x * 256 + threadIdx.x;
   if (t >= 8 * T.loads[level]) return;
   const uint32_t sb = 8 * T.offsets[level] + t, b = sb / 8;
   const uint32_t ps = T.parent[b];
   if (ps == kNone) return;
+  if (skip_childless && !block_has_children(T, b)) return;
   const float4 *c = vw + (size_t)kSV * sb;
   float ax = 0.f, ay = 0.f, az = 0.f;
 #pragma unroll
@@ -150,12 +159,13 @@ __global__ void __launch_bounds__(256) k_dc_accumulate_velocity(Pool T, int leve
   float *dst = reinterpret_cast<float *>(vw + ((size_t)kSV * ps + (sb % 8)));
   dst[0] = ax * .125f; dst[1] = ay * .125f; dst[2] = az * .125f;  // .w (fluidity) untouched
 }
-__global__ void __launch_bounds__(256) k_dc_accumulate_scalar(Pool T, int level, float *__restrict__ ch) {
+__global__ void __launch_bounds__(256) k_dc_accumulate_scalar(Pool T, int level, float *__restrict__ ch, int skip_childless) {
   const uint32_t t = blockIdx.x * 256 + threadIdx.x;
   if (t >= 8 * T.loads[level]) return;
   const uint32_t sb = 8 * T.offsets[level] + t, b = sb / 8;
   const uint32_t ps = T.parent[b];
   if (ps == kNone) return;
+  if (skip_childless && !block_has_children(T, b)) return;
   const float4 lo = *reinterpret_cast<const float4 *>(ch + (size_t)kSV * sb);
   const float4 hi = *reinterpret_cast<const float4 *>(ch + (size_t)kSV * sb + 4);
   float a = 0.f;

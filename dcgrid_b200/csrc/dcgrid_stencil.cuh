@@ -381,12 +381,10 @@ __global__ void __launch_bounds__(kCTA4) k_dc_divergence4(Pool T, KParams P, con
   quad_exchange_x(nx_, px, t, gx);
   quad_exchange_y(ny_, py, t, gy0, gy1);
   quad_exchange_z(nz_, pz, t, gz0, gz1);
-  if (!active) return;
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-  __stcs(reinterpret_cast<float4 *>(p + c0), zero);
-  __stcs(reinterpret_cast<float4 *>(tp + c0), zero);
   float4 d = zero;
-  if (child == kNone) {
+  const bool leaf = active && child == kNone;
+  if (leaf) {
     const float alpha = .5f * P.rdx / (float)scale;
     // alpha * (r - l + u - d + f - b), k = 2*cy + cz
     d.x = alpha * (nx_.xp.x - nx_.xm.x + py.z - ny_.ym0 + pz.y - nz_.zm0);
@@ -394,7 +392,26 @@ __global__ void __launch_bounds__(kCTA4) k_dc_divergence4(Pool T, KParams P, con
     d.z = alpha * (nx_.xp.z - nx_.xm.z + ny_.yp0 - py.x + pz.w - nz_.zm1);
     d.w = alpha * (nx_.xp.w - nx_.xm.w + ny_.yp1 - py.y + nz_.zp1 - pz.z);
   }
-  __stcs(reinterpret_cast<float4 *>(div + c0), d);
+  // Fused restriction (accumulate<float>, dcgrid_structure.cu:188-222) of blocks without children: a subblock =
+  // the quads of lanes t (cx = 0: cells 0..3) and t+1 (cx = 1: cells 4..7); sequential sum, then * .125.
+  const unsigned half = 0xFFFFu << (threadIdx.x & 16u);
+  const bool childless = (__ballot_sync(0xFFFFFFFFu, child != kNone) & half) == 0;
+  float s = 0.f;
+  s += d.x; s += d.y; s += d.z; s += d.w;
+  const float lo = __shfl_sync(0xFFFFFFFFu, s, (threadIdx.x & 31u) ^ 1u);
+  if (!active) return;
+  __stcs(reinterpret_cast<float4 *>(p + c0), zero);
+  __stcs(reinterpret_cast<float4 *>(tp + c0), zero);
+  // quads of refined subblocks are always overwritten by their children's restriction: nothing to store
+  if (leaf) __stcs(reinterpret_cast<float4 *>(div + c0), d);
+  if (childless && (t & 1)) {
+    const uint32_t ps = T.parent[b];
+    if (ps != kNone) {
+      float a = lo;
+      a += d.x; a += d.y; a += d.z; a += d.w;
+      div[(size_t)kSV * ps + (t >> 1)] = a * .125f;
+    }
+  }
 }
 
 // ---- k_dcgrid_apply_pressure, dcgrid_fluid.cu:232-259 --------------------------------------------------
@@ -417,7 +434,11 @@ __global__ void __launch_bounds__(kCTA4) k_dc_apply_pressure4(Pool T, KParams P,
   const QuadGhosts q = quad_ghosts(T, b, t);
   const QuadNbr s = quad_neighbours(p, op, t, q);
   const QuadNbr w = quad_neighbours(fl, ow, t, q);
-  if (!active || child != kNone) return;
+  const unsigned half = 0xFFFFu << (threadIdx.x & 16u);
+  const unsigned with_child = __ballot_sync(0xFFFFFFFFu, child != kNone);  // every lane votes (no short-circuit)
+  const bool childless = active && (with_child & half) == 0;
+  if (!__any_sync(0xFFFFFFFFu, active && child == kNone)) return;
+  const bool leaf = active && child == kNone;
   const float alpha = .5f * P.rdx / (float)(1 << (level & 15));
   // v.x -= alpha * (w_r * (p_r - pc) + w_l * (pc - p_l)), likewise y (up/down), z (front/back)
   v[0].x -= alpha * (w.xp.x * (s.xp.x - op.x) + w.xm.x * (op.x - s.xm.x));
@@ -432,8 +453,27 @@ __global__ void __launch_bounds__(kCTA4) k_dc_apply_pressure4(Pool T, KParams P,
   v[3].x -= alpha * (w.xp.w * (s.xp.w - op.w) + w.xm.w * (op.w - s.xm.w));
   v[3].y -= alpha * (w.yp1 * (s.yp1 - op.w) + ow.y * (op.w - op.y));
   v[3].z -= alpha * (w.zp1 * (s.zp1 - op.w) + ow.z * (op.w - op.z));
+  if (leaf) {
 #pragma unroll
-  for (int k = 0; k < 4; k++) vw[c0 + k] = v[k];
+    for (int k = 0; k < 4; k++) vw[c0 + k] = v[k];
+  }
+  // Fused restriction (accumulate<float3>, dcgrid_structure.cu:188-222) of blocks without children: lane t
+  // (cx = 0) sums cells 0..3 of the subblock, lane t+1 (cx = 1) continues with cells 4..7 and stores.
+  float ax = 0.f, ay = 0.f, az = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; k++) { ax += v[k].x; ay += v[k].y; az += v[k].z; }
+  const unsigned src = (threadIdx.x & 31u) ^ 1u;
+  const float lx = __shfl_sync(0xFFFFFFFFu, ax, src), ly = __shfl_sync(0xFFFFFFFFu, ay, src), lz = __shfl_sync(0xFFFFFFFFu, az, src);
+  if (childless && (t & 1)) {
+    const uint32_t ps = T.parent[b];
+    if (ps != kNone) {
+      ax = lx; ay = ly; az = lz;
+#pragma unroll
+      for (int k = 0; k < 4; k++) { ax += v[k].x; ay += v[k].y; az += v[k].z; }
+      float *dst = reinterpret_cast<float *>(vw + ((size_t)kSV * ps + (t >> 1)));
+      dst[0] = ax * .125f; dst[1] = ay * .125f; dst[2] = az * .125f;
+    }
+  }
 }
 
 // ---- coarse levels: the whole cascade of the small levels in ONE single-CTA launch ---------------------

@@ -1,4 +1,3 @@
 set -x
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"k_dc" -c 40000 --csv --log-file gpurun_out/launches_steady.csv python tools/exp_stage.py --warm 130 --steps 4 > gpurun_out/ncu_ls.log 2>&1
-tail -2 gpurun_out/ncu_ls.log
-wc -l gpurun_out/launches_steady.csv
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_dc_advect_pipe" --launch-skip 300 -c 2 -o gpurun_out/advp_steady -f python tools/exp_stage.py --reps 4 advect_velocity advect_density > gpurun_out/ncu_adv.log 2>&1
+tail -3 gpurun_out/ncu_adv.log
