@@ -22,6 +22,8 @@
 #include <string>
 #include <vector>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include "dcgrid_kernels.cuh"
 #include "dcgrid_pipe.cuh"
 #include "sim.h"
@@ -63,8 +65,19 @@ struct DCGridSim : dcg_sim {
   uint64_t n_adapt = 0, n_changed = 0, n_moved = 0, n_refined = 0, n_skipped = 0, n_failed = 0;
 
   // persistent TMA-ring kernels (dcgrid_pipe.cuh): resident CTAs per device, sweep direction toggle
-  int sm_count = 0, jacobi_pipe_ctas = 0, advect_pipe_ctas = 0;
+  int sm_count = 0, jacobi_pipe_ctas = 0, advect_per_sm[3] = {0, 0, 0};
   bool use_advect_pipe = true;
+  // k_dc_advect_pipe<2>: advect_density() also produces the NEXT step's advected velocity in vw[cur_v ^ 1];
+  // spec_velocity = that buffer is valid, i.e. nothing has touched velocity, topology or parameters since
+  bool fuse_advect = true, spec_velocity = false;
+  // processing order of the advection kernels: active slots sorted along a Morton curve (k_dc_order_keys)
+  uint32_t *d_order = nullptr, *d_order_keys[2] = {nullptr, nullptr}, *d_order_vals = nullptr;
+  void *d_sort_tmp = nullptr;
+  size_t sort_tmp_bytes = 0;
+  uint32_t n_order = 0;  // padded to a multiple of kBPC
+  int order_mode = 1;    // 0 = pool-slot order, 1 = Morton
+  bool skip_dead_zeroing = true;  // k_dc_divergence4: no pressure clears that project() never reads
+  int advect_min_blocks = 4;  // __launch_bounds__ variant of the advection kernels (3 or 4 CTAs per SM)
   bool use_pipe = true, snake = true;
   unsigned pipe_min_tiles = 0;  // levels with fewer tiles take the one-CTA-per-tile kernel
   int sweep_parity = 0;
@@ -82,6 +95,7 @@ struct DCGridSim : dcg_sim {
     cudaFree(d_flags); cudaFree(d_free); cudaFree(d_touched); cudaFree(d_to_move); cudaFree(d_dest); cudaFree(d_counters); cudaFree(d_flag_bits); cudaFree(d_summary);
     if (h_summary) cudaFreeHost(h_summary);
     cudaFree(d_new_posl); cudaFree(d_sub_scores); cudaFree(d_block_scores);
+    cudaFree(d_order); cudaFree(d_order_keys[0]); cudaFree(d_order_keys[1]); cudaFree(d_order_vals); cudaFree(d_sort_tmp);
     for (int i = 0; i < 2; i++) { cudaFree(vw[i]); cudaFree(q[i]); }
     cudaFree(fl); cudaFree(p); cudaFree(tp); cudaFree(div); cudaFree(scratch); cudaFree(d_partial);
     if (h_partial) cudaFreeHost(h_partial);
@@ -139,6 +153,13 @@ struct DCGridSim : dcg_sim {
     for (int l = 0; l < levels; l++) { T.offsets[l] = (uint32_t)offsets[l]; T.max_blocks[l] = (uint32_t)max_blocks[l]; }
     DCG_CUDA_TRY(cudaMalloc(&T.posl, (size_t)M * sizeof(int4)));
     DCG_CUDA_TRY(cudaMalloc(&T.parent, (size_t)M * 4));
+    DCG_CUDA_TRY(cudaMalloc(&d_order, ((size_t)M + kBPC) * 4));
+    DCG_CUDA_TRY(cudaMalloc(&d_order_keys[0], (size_t)M * 4));
+    DCG_CUDA_TRY(cudaMalloc(&d_order_keys[1], (size_t)M * 4));
+    DCG_CUDA_TRY(cudaMalloc(&d_order_vals, (size_t)M * 4));
+    DCG_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp_bytes, d_order_keys[0], d_order_keys[1], d_order_vals, d_order, (int)M, 0, 32,
+                                                 stream));
+    DCG_CUDA_TRY(cudaMalloc(&d_sort_tmp, sort_tmp_bytes + 16));
     DCG_CUDA_TRY(cudaMalloc(&T.child, (size_t)M * 8 * 4));
     DCG_CUDA_TRY(cudaMalloc(&T.apron, (size_t)M * kAV * 4));
     DCG_CUDA_TRY(cudaMalloc(&T.face, (size_t)M * 96 * 4));
@@ -183,15 +204,18 @@ struct DCGridSim : dcg_sim {
       DCG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_dc_jacobi_pipe, kCTA4, kJacobiPipeSmem));
       if (per_sm < 1) return fail(DCG_ERR_CUDA, "k_dc_jacobi_pipe does not fit on an SM");
       jacobi_pipe_ctas = per_sm * sm_count;
-      DCG_CUDA_TRY(cudaFuncSetAttribute(k_dc_advect_pipe<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAdvectPipeSmem));
-      DCG_CUDA_TRY(cudaFuncSetAttribute(k_dc_advect_pipe<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAdvectPipeSmem));
-      int av = 0, ad = 0;
-      DCG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&av, k_dc_advect_pipe<false>, kCTA, kAdvectPipeSmem));
-      DCG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ad, k_dc_advect_pipe<true>, kCTA, kAdvectPipeSmem));
-      if (av < 1 || ad < 1) return fail(DCG_ERR_CUDA, "k_dc_advect_pipe does not fit on an SM");
-      advect_pipe_ctas = std::min(av, ad) * sm_count;
       if (const char *e = getenv("DCG_ADVECT")) use_advect_pipe = std::string(e) != "legacy";
-      if (const char *e = getenv("DCG_ADVECT_CTAS")) advect_pipe_ctas = std::max(1, atoi(e)) * sm_count;
+      if (const char *e = getenv("DCG_ADVECT_ORDER")) order_mode = std::string(e) == "slot" ? 0 : 1;
+      if (const char *e = getenv("DCG_ZERO_ALL")) skip_dead_zeroing = std::string(e) == "0";
+      if (const char *e = getenv("DCG_ADVECT_FUSE")) fuse_advect = std::string(e) != "0";
+      if (const char *e = getenv("DCG_ADVECT_MINB")) advect_min_blocks = atoi(e) == 3 ? 3 : 4;
+      for (int mode = 0; mode < 3; mode++) {
+        const void *fn = advect_fn(mode);
+        DCG_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAdvectPipeSmem));
+        DCG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&advect_per_sm[mode], fn, kAdvectThreads, kAdvectPipeSmem));
+        if (advect_per_sm[mode] < 1) return fail(DCG_ERR_CUDA, "k_dc_advect_pipe does not fit on an SM");
+        if (const char *e = getenv("DCG_ADVECT_CTAS")) advect_per_sm[mode] = std::max(1, atoi(e));
+      }
       pipe_min_tiles = 2u * (unsigned)sm_count;
       if (const char *e = getenv("DCG_JACOBI")) {
         use_pipe = std::string(e) != "legacy";
@@ -207,6 +231,7 @@ struct DCGridSim : dcg_sim {
     if (params.gx != gx || params.gy != gy || params.gz != gz)
       return fail(DCG_ERR_INVALID, "grid size is fixed at construction (the reference sizes its pool in the ctor)");
     steady = false;  // scores depend on SimParams: the fixed-point proof no longer holds
+    spec_velocity = false;
     drop_graphs();
     return DCG_OK;
   }
@@ -216,6 +241,7 @@ struct DCGridSim : dcg_sim {
     DCG_CUDA_TRY(cudaSetDevice(device));
     drop_graphs();
     steady = false;
+    spec_velocity = false;
     k_fill_posl<<<blocks_for(M, 256), 256, 0, stream>>>(T.posl, M);
     DCG_CUDA_TRY(cudaMemsetAsync(d_flags, 0, (size_t)M * 4, stream));
     DCG_CUDA_TRY(cudaMemsetAsync(T.parent, 0xff, (size_t)M * 4, stream));
@@ -267,6 +293,18 @@ struct DCGridSim : dcg_sim {
     cudaMemsetAsync(d_counters + 1, 0, 4, stream);
     k_dc_build_fdesc<<<blocks_for((size_t)M * 8, 256), 256, 0, stream>>>(T, d_counters + 1);
     launches++;
+    rebuild_order();
+  }
+  // called whenever block positions or the set of active blocks changed
+  void rebuild_order() {
+    uint64_t n = 0;
+    for (int l = 0; l < levels; l++) n += loads[l];
+    k_dc_order_keys<<<blocks_for(M, 256), 256, 0, stream>>>(T, order_mode, d_order_keys[0], d_order_vals);
+    size_t bytes = sort_tmp_bytes;
+    cub::DeviceRadixSort::SortPairs(d_sort_tmp, bytes, d_order_keys[0], d_order_keys[1], d_order_vals, d_order, (int)M, 0, 32, stream);
+    n_order = (uint32_t)((n + kBPC - 1) / kBPC * kBPC);
+    if (n_order > n) k_dc_order_pad<<<1, 256, 0, stream>>>(d_order, (uint32_t)n, n_order);
+    launches += 2;
   }
   uint32_t finer_full_mask() const {
     uint32_t m = 0;
@@ -463,6 +501,7 @@ struct DCGridSim : dcg_sim {
   int adapt_topology() override {  // :320-346
     DCG_CUDA_TRY(cudaSetDevice(device));
     n_adapt++;
+    spec_velocity = false;
     if (steady) {
       n_skipped++;
       return DCG_OK;
@@ -518,35 +557,59 @@ struct DCGridSim : dcg_sim {
   }
   void accumulate_velocity(bool fused) { accumulate(vw[cur_v], nullptr, fused); }
   void accumulate_scalar(float *ch, bool fused) { accumulate(nullptr, ch, fused); }
-  void launch_advect_velocity(const float4 *in, float4 *out) {
-    if (use_advect_pipe) {
-      const unsigned grid = std::min<unsigned>(blocks_for(M, kBPC), (unsigned)advect_pipe_ctas);
-      k_dc_advect_pipe<false><<<grid, kCTA, kAdvectPipeSmem, stream>>>(T, kp, in, out, nullptr, nullptr, nullptr);
-    } else {
-      k_dc_advect_velocity<<<blocks_for(M, kBPC), kCTA, 0, stream>>>(T, kp, in, out);
+  const void *advect_fn(int mode) const {
+    if (advect_min_blocks == 3) {
+      if (mode == 0) return (const void *)k_dc_advect_pipe<0, 3>;
+      if (mode == 1) return (const void *)k_dc_advect_pipe<1, 3>;
+      return (const void *)k_dc_advect_pipe<2, 3>;
     }
-    launches++;
+    if (mode == 0) return (const void *)k_dc_advect_pipe<0, 4>;
+    if (mode == 1) return (const void *)k_dc_advect_pipe<1, 4>;
+    return (const void *)k_dc_advect_pipe<2, 4>;
   }
-  void launch_advect_density(const float4 *v, const float *qi, float *qo) {
-    if (use_advect_pipe) {
-      const unsigned grid = std::min<unsigned>(blocks_for(M, kBPC), (unsigned)advect_pipe_ctas);
-      k_dc_advect_pipe<true><<<grid, kCTA, kAdvectPipeSmem, stream>>>(T, kp, v, nullptr, fl, qi, qo);
-    } else {
-      k_dc_advect_density<<<blocks_for(M, kBPC), kCTA, 0, stream>>>(T, kp, v, fl, qi, qo);
-    }
+  // mode 0: vout <- advected velocity; 1: qout <- advected density; 2: both (k_dc_advect_pipe)
+  void launch_advect_pipe(int mode, const float4 *vin, float4 *vout, const float *qi, float *qo) {
+    if (n_order == 0) return;
+    const unsigned grid = std::min<unsigned>(n_order / kBPC, (unsigned)(advect_per_sm[mode] * sm_count));
+    const float *flp = fl;
+    const uint32_t *ord = d_order;
+    void *args[] = {&T, &kp, &ord, &n_order, &vin, &vout, &flp, &qi, &qo};
+    cudaLaunchKernel(advect_fn(mode), dim3(grid), dim3(kAdvectThreads), args, kAdvectPipeSmem, stream);
     launches++;
   }
   int advect_velocity() override {  // :263-268
-    launch_advect_velocity(vw[cur_v], vw[cur_v ^ 1]);
-    cur_v ^= 1;
-    accumulate_velocity(false);
+    DCG_CUDA_TRY(cudaSetDevice(device));
+    if (spec_velocity) {
+      // vw[cur_v ^ 1] already holds this step's advected velocity (written by the previous advect_density())
+      spec_velocity = false;
+      cur_v ^= 1;
+      accumulate_velocity(true);
+    } else if (use_advect_pipe) {
+      launch_advect_pipe(0, vw[cur_v], vw[cur_v ^ 1], nullptr, nullptr);
+      cur_v ^= 1;
+      accumulate_velocity(true);
+    } else {
+      k_dc_advect_velocity<<<blocks_for(M, kBPC), kCTA, 0, stream>>>(T, kp, vw[cur_v], vw[cur_v ^ 1]);
+      launches++;
+      cur_v ^= 1;
+      accumulate_velocity(false);
+    }
     DCG_CUDA_TRY(cudaGetLastError());
     return DCG_OK;
   }
   int advect_density() override {  // :313-318
-    launch_advect_density(vw[cur_v], q[cur_q], q[cur_q ^ 1]);
-    cur_q ^= 1;
-    accumulate_scalar(q[cur_q], false);
+    DCG_CUDA_TRY(cudaSetDevice(device));
+    if (use_advect_pipe) {
+      launch_advect_pipe(fuse_advect ? 2 : 1, vw[cur_v], vw[cur_v ^ 1], q[cur_q], q[cur_q ^ 1]);
+      spec_velocity = fuse_advect;
+      cur_q ^= 1;
+      accumulate_scalar(q[cur_q], true);
+    } else {
+      k_dc_advect_density<<<blocks_for(M, kBPC), kCTA, 0, stream>>>(T, kp, vw[cur_v], fl, q[cur_q], q[cur_q ^ 1]);
+      launches++;
+      cur_q ^= 1;
+      accumulate_scalar(q[cur_q], false);
+    }
     DCG_CUDA_TRY(cudaGetLastError());
     return DCG_OK;
   }
@@ -566,8 +629,8 @@ struct DCGridSim : dcg_sim {
     jacobi_sweep(l, p, tp);
     jacobi_sweep(l, tp, p);
   }
-  void divergence_stage() {
-    k_dc_divergence4<<<blocks_for(M, kB4), kCTA4, 0, stream>>>(T, kp, vw[cur_v], div, p, tp);
+  void divergence_stage(int zero_from) {
+    k_dc_divergence4<<<blocks_for(M, kB4), kCTA4, 0, stream>>>(T, kp, vw[cur_v], div, p, tp, zero_from);
     launches++;
     accumulate_scalar(div, true);
   }
@@ -577,7 +640,8 @@ struct DCGridSim : dcg_sim {
     accumulate_velocity(true);
   }
   int project() override {  // :270-294
-    divergence_stage();
+    spec_velocity = false;
+    divergence_stage(skip_dead_zeroing && project_level_pairs >= 1 ? levels - 1 : 0);
     // levels with <= kCoarseBlocks blocks: the whole coarse part of the cascade in one single-CTA launch
     const int cf = small_levels_from(kCoarseBlocks);
     k_dc_coarse_cascade<<<1, 1024, 0, stream>>>(T, kp, cf, 0, project_coarsest_pairs, project_level_pairs, 1, p, tp, div);
@@ -593,7 +657,8 @@ struct DCGridSim : dcg_sim {
     return DCG_OK;
   }
   int project_local() override {  // :296-311
-    divergence_stage();
+    spec_velocity = false;
+    divergence_stage(0);
     const int cf = small_levels_from(kCoarseBlocks);
     k_dc_coarse_cascade<<<1, 1024, 0, stream>>>(T, kp, cf, 0, local_pairs, local_pairs, 0, p, tp, div);
     launches++;
@@ -608,7 +673,7 @@ struct DCGridSim : dcg_sim {
     DCG_CUDA_TRY(cudaSetDevice(device));
     DCG_CUDA_TRY(cudaEventRecord(ev_begin, stream));
     for (int done = 0; done < n; done++) {
-      if (!steady) {  // transient: adaptation needs host round trips, run call by call
+      if (!steady || spec_velocity != (fuse_advect && use_advect_pipe)) {  // transient: adaptation needs host round trips, run call by call
         DCG_TRY(dcg_sim::step(1));
         continue;
       }
@@ -616,11 +681,12 @@ struct DCGridSim : dcg_sim {
       if (!ge) {
         const uint64_t before = launches, adapt_before = n_adapt, skipped_before = n_skipped;
         const int sv = cur_v, sq = cur_q;
+        const bool sspec = spec_velocity;
         cudaGraph_t g = nullptr;
         DCG_CUDA_TRY(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
         const int rc = dcg_sim::step(1);  // adapt_topology() is a no-op in the steady state
         const cudaError_t ce = cudaStreamEndCapture(stream, &g);
-        cur_v = sv; cur_q = sq;  // capture records, it does not execute
+        cur_v = sv; cur_q = sq; spec_velocity = sspec;  // capture records, it does not execute
         step_graph_launches = launches - before;
         launches = before; n_adapt = adapt_before; n_skipped = skipped_before;
         if (rc != DCG_OK) return rc;
@@ -643,6 +709,7 @@ struct DCGridSim : dcg_sim {
   int bench_stage(const char *stage, int level, int reps, float *ms_per_launch, double *alg_bytes) override {
     DCG_CUDA_TRY(cudaSetDevice(device));
     const std::string st(stage);
+    spec_velocity = false;
     if (level < 0 || level >= levels) return fail(DCG_ERR_INVALID, "bench_stage: bad level");
     double call = 0;
     for (int l = 0; l < levels; l++) call += 64.0 * (double)loads[l];
@@ -659,23 +726,24 @@ struct DCGridSim : dcg_sim {
         use_pipe = saved;
         bytes = 12.0 * cl;
       } else if (st == "advect_velocity" || st == "advect_velocity_legacy") {
-        const bool saved = use_advect_pipe;
-        if (st != "advect_velocity") use_advect_pipe = false;
-        launch_advect_velocity(vw[cur_v], vw[cur_v ^ 1]);
-        use_advect_pipe = saved;
+        if (st == "advect_velocity") launch_advect_pipe(0, vw[cur_v], vw[cur_v ^ 1], nullptr, nullptr);
+        else k_dc_advect_velocity<<<blocks_for(M, kBPC), kCTA, 0, stream>>>(T, kp, vw[cur_v], vw[cur_v ^ 1]), launches++;
         launches--;
         cur_v ^= 1;
         bytes = 28.0 * call;
       } else if (st == "advect_density" || st == "advect_density_legacy") {
-        const bool saved = use_advect_pipe;
-        if (st != "advect_density") use_advect_pipe = false;
-        launch_advect_density(vw[cur_v], q[cur_q], q[cur_q ^ 1]);
-        use_advect_pipe = saved;
+        if (st == "advect_density") launch_advect_pipe(1, vw[cur_v], nullptr, q[cur_q], q[cur_q ^ 1]);
+        else k_dc_advect_density<<<blocks_for(M, kBPC), kCTA, 0, stream>>>(T, kp, vw[cur_v], fl, q[cur_q], q[cur_q ^ 1]), launches++;
         launches--;
         cur_q ^= 1;
         bytes = 24.0 * call;
+      } else if (st == "advect_both") {  // density of this step + velocity of the next one (k_dc_advect_pipe<2>)
+        launch_advect_pipe(2, vw[cur_v], vw[cur_v ^ 1], q[cur_q], q[cur_q ^ 1]);
+        launches--;
+        cur_q ^= 1;
+        bytes = 52.0 * call;
       } else if (st == "divergence") {
-        k_dc_divergence4<<<blocks_for(M, kB4), kCTA4, 0, stream>>>(T, kp, vw[cur_v], div, p, tp);
+        k_dc_divergence4<<<blocks_for(M, kB4), kCTA4, 0, stream>>>(T, kp, vw[cur_v], div, p, tp, skip_dead_zeroing && project_level_pairs >= 1 ? levels - 1 : 0);
         bytes = 28.0 * call;
       } else if (st == "apply_pressure") {
         k_dc_apply_pressure4<<<blocks_for(M, kB4), kCTA4, 0, stream>>>(T, kp, p, fl, vw[cur_v]);

@@ -26,6 +26,9 @@ __device__ __forceinline__ void fence_barrier_init() {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(saddr(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(saddr(bar)) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -177,13 +180,15 @@ __global__ void __launch_bounds__(kCTA4, 4) k_dc_jacobi_pipe(Pool T, KParams P, 
 // load at a time, dcgrid_utils.cuh:201-233) and derive the block origin from the sample position (block
 // origins are multiples of 4 cells of their level) instead of loading it.
 constexpr int kAStages = 4;
+constexpr int kAdvectThreads = kCTA + 32;  // 8 consumer warps (4 blocks) + 1 producer warp
 struct alignas(128) AdvectStage {
   uint32_t apron[kBPC * kAV];  // 3456 B
   float4 me[kBPC * kBV];       // 4096 B: the cells' own velocity (+ fluidity)
   uint32_t child[kBPC * kSV];  // 128 B
   int4 posl[kBPC];             // 64 B
+  uint32_t slot[kBPC];         // 16 B: the tile's pool slots (kNone = padding), written by the producer
 };
-constexpr size_t kAdvectPipeSmem = kAStages * sizeof(AdvectStage) + kAStages * sizeof(uint64_t);
+constexpr size_t kAdvectPipeSmem = kAStages * sizeof(AdvectStage) + 2 * kAStages * sizeof(uint64_t);
 
 // getBlockIndexDeep(position, 0) with independent probes; returns the slot and sets (level, origin)
 __device__ __forceinline__ uint32_t block_index_deep_par(const Pool &T, const KParams &P, int ix, int iy, int iz, int4 &bp) {
@@ -217,113 +222,202 @@ __device__ __forceinline__ DSample d_sample_pipe(const Pool &T, const KParams &P
   return d_sample_in(T.apron + (size_t)b * kAV, bp, px, py, pz);
 }
 
-template <bool kDensity>
-__global__ void __launch_bounds__(kCTA, 4) k_dc_advect_pipe(Pool T, KParams P, const float4 *__restrict__ vin, float4 *__restrict__ vout,
-                                                            const float *__restrict__ fl, const float *__restrict__ qin, float *__restrict__ qout) {
+// kMode 0: velocity (k_dcgrid_advect_velocity), 1: density (k_dcgrid_advect_density), 2: both at once.
+//
+// Mode 2.  advectDensity() of step n and advectVelocity() of step n+1 backtrace every cell through the SAME
+// velocity field (nothing runs between them, simulation.cpp:104-111), so both resolve the same sample: the same
+// covering block, the same 8 cell ids and the same fluidity-weighted weights.  The reference does that work
+// twice; here the density pass also gathers the velocities at the 8 ids it already holds and writes the next
+// step's advected velocity into the idle ping-pong buffer.  The host consumes it in the next advect_velocity()
+// if nothing touched the state in between (dcgrid.cu, `spec_velocity`).
+//
+// Fused restriction (accumulate<T>, dcgrid_structure.cu:188-222) of blocks without children, as in
+// k_dc_divergence4: the 8 cells of a subblock are 8 consecutive lanes; every lane sums them in cell order
+// (sequentially, starting from 0.f like the reference) and lane 7 of the group stores into the parent cell.
+// Cells of refined subblocks are not stored: their children's restriction owns those words (the fluidity in
+// .w is stored separately, it is the one component restriction leaves alone).
+__device__ __forceinline__ float subblock_sum(float v) {
+  const unsigned base = threadIdx.x & 24u;
+  float a = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; k++) a += __shfl_sync(0xFFFFFFFFu, v, base + k);
+  return a;
+}
+
+// Processing order.  Tiles are kBPC consecutive entries of `order` (active slots, padded with kNone), not
+// consecutive slots: the host sorts the active blocks along a Morton curve of their positions (dcgrid.cu,
+// rebuild_order) so that the blocks in flight at any time — and the upstream cells their samples gather — form
+// a compact region that stays in L2; in slot order 2/3 of the gathered sectors came from DRAM
+// (profiles/README.md r1d).  Every block's inputs are four contiguous ranges, fetched by one cp.async.bulk each.
+//
+// Warp specialisation.  Warp 8 is the producer (one lane: waits for a ring slot to drain, issues the copies);
+// the 8 consumer warps never meet at a CTA barrier: each waits for the `full` mbarrier of its tile, resolves
+// its samples, releases the slot (`empty` mbarrier, one arrival per warp) and goes on to its gathers, so the
+// warps of a CTA drift apart by up to kAStages tiles and their load rounds overlap.
+template <int kMode, int kMinBlocks>
+__global__ void __launch_bounds__(kAdvectThreads, kMinBlocks) k_dc_advect_pipe(Pool T, KParams P, const uint32_t *__restrict__ order, uint32_t norder,
+                                                                               const float4 *__restrict__ vin, float4 *__restrict__ vout,
+                                                                               const float *__restrict__ fl, const float *__restrict__ qin,
+                                                                               float *__restrict__ qout) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   AdvectStage *st = reinterpret_cast<AdvectStage *>(smem_raw);
   uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + kAStages * sizeof(AdvectStage));
-  const uint32_t ntiles = (T.M + kBPC - 1) / kBPC;
-  const uint32_t g = threadIdx.x >> 6, t = threadIdx.x & 63;
+  uint64_t *empty = full + kAStages;
+  const uint32_t ntiles = norder / kBPC;  // norder is a multiple of kBPC
   if (threadIdx.x == 0) {
 #pragma unroll
-    for (int s = 0; s < kAStages; s++) pipe::mbar_init(&full[s], 1);
+    for (int s = 0; s < kAStages; s++) {
+      pipe::mbar_init(&full[s], 1);
+      pipe::mbar_init(&empty[s], kCTA / 32);
+    }
     pipe::fence_barrier_init();
   }
   __syncthreads();
-  const uint64_t pol_stream = pipe::policy_evict_first();
-  auto issue_tile = [&](uint32_t it) {
-    const uint32_t tl = blockIdx.x + it * gridDim.x;
-    if (tl >= ntiles) return;
-    const size_t b0 = (size_t)tl * kBPC;
-    const uint32_t nvalid = min((uint32_t)kBPC, T.M - (uint32_t)b0);
-    AdvectStage &S = st[it % kAStages];
-    uint64_t *bar = &full[it % kAStages];
-    pipe::mbar_expect_tx(bar, nvalid * (kAV * 4u + kBV * 16u + kSV * 4u + 16u));
-    pipe::bulk_g2s_hint(S.apron, T.apron + b0 * kAV, nvalid * kAV * 4u, bar, pol_stream);
-    pipe::bulk_g2s(S.me, vin + b0 * kBV, nvalid * kBV * 16u, bar);
-    pipe::bulk_g2s(S.child, T.child + b0 * kSV, nvalid * kSV * 4u, bar);
-    pipe::bulk_g2s(S.posl, T.posl + b0, nvalid * 16u, bar);
-  };
-  if (threadIdx.x == 0) {
+  if (threadIdx.x >= kCTA) {  // ---- producer warp ----
+    if (threadIdx.x != kCTA) return;
+    const uint64_t pol_stream = pipe::policy_evict_first();
+    const uint4 *order4 = reinterpret_cast<const uint4 *>(order);
+    uint32_t tl = blockIdx.x;
+    uint4 nxt = tl < ntiles ? __ldg(order4 + tl) : make_uint4(kNone, kNone, kNone, kNone);
+    for (uint32_t it = 0; tl < ntiles; it++, tl += gridDim.x) {
+      const uint4 cur = nxt;
+      if (tl + gridDim.x < ntiles) nxt = __ldg(order4 + tl + gridDim.x);  // in flight while this tile is issued
+      const uint32_t s = it % kAStages;
+      if (it >= (uint32_t)kAStages) pipe::mbar_wait(&empty[s], ((it / kAStages) - 1u) & 1u);
+      AdvectStage &S = st[s];
+      *reinterpret_cast<uint4 *>(S.slot) = cur;
+      const uint32_t b4[kBPC] = {cur.x, cur.y, cur.z, cur.w};
+      uint32_t nvalid = 0;
 #pragma unroll
-    for (uint32_t it = 0; it < (uint32_t)kAStages; it++) issue_tile(it);
+      for (int g = 0; g < kBPC; g++) nvalid += b4[g] != kNone ? 1u : 0u;
+      pipe::mbar_expect_tx(&full[s], nvalid * (kAV * 4u + kBV * 16u + kSV * 4u + 16u));
+#pragma unroll
+      for (int g = 0; g < kBPC; g++) {
+        const size_t b = b4[g];
+        if (b4[g] == kNone) continue;
+        pipe::bulk_g2s_hint(S.apron + g * kAV, T.apron + b * kAV, kAV * 4u, &full[s], pol_stream);
+        pipe::bulk_g2s(S.me + g * kBV, vin + b * kBV, kBV * 16u, &full[s]);
+        pipe::bulk_g2s(S.child + g * kSV, T.child + b * kSV, kSV * 4u, &full[s]);
+        pipe::bulk_g2s(S.posl + g, T.posl + b, 16u, &full[s]);
+      }
+    }
+    return;
   }
+  // ---- consumer warps ----
+  const uint32_t g = threadIdx.x >> 6, t = threadIdx.x & 63;
   const float alpha = P.dt * P.rdx;
-  for (uint32_t it = 0;; it++) {
-    const uint32_t tl = blockIdx.x + it * gridDim.x;
-    if (tl >= ntiles) break;
+  uint32_t tl = blockIdx.x;
+  for (uint32_t it = 0; tl < ntiles; it++, tl += gridDim.x) {
     const uint32_t s = it % kAStages;
     pipe::mbar_wait(&full[s], (it / kAStages) & 1u);
     const AdvectStage &S = st[s];
-    const uint32_t b = tl * kBPC + g;
-    const uint32_t c = b * kBV + t;
-    const bool in_pool = b < T.M;
-    int4 pl = make_int4(0, 0, 0, kFree);
+    const uint32_t b = S.slot[g];
+    const bool live = b != kNone;  // uniform over the block's two warps
+    int4 pl = make_int4(0, 0, 0, 0);
     float4 me = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (in_pool) {
+    uint32_t ps = kNone;
+    bool childless = false, leaf = false;
+    DSample smp;
+    if (live) {
+      ps = __ldg(T.parent + b);
       pl = S.posl[g];
       me = S.me[g * kBV + t];
-    }
-    const bool live = pl.w != kFree;
-    const bool leaf = live && S.child[g * kSV + (t >> 3)] == kNone;
-    DSample smp;
-    if (leaf) {
-      const float scale = (float)(1 << pl.w);
-      const float bx = ((float)(pl.x | cell_x(t)) + .5f) * scale - me.x * alpha;
-      const float by = ((float)(pl.y | cell_y(t)) + .5f) * scale - me.y * alpha;
-      const float bz = ((float)(pl.z | cell_z(t)) + .5f) * scale - me.z * alpha;
-      smp = d_sample_pipe(T, P, S.apron + g * kAV, S.child + g * kSV, pl, bx, by, bz);
-    }
-    __syncthreads();  // every thread is done with ring slot s (positions, velocities, apron ids): refill it
-    if (threadIdx.x == 0) issue_tile(it + kAStages);
-    if (!live) continue;
-    if (!kDensity) {
-      float3 out = make_float3(0.f, 0.f, 0.f);
+      const uint4 c0 = *reinterpret_cast<const uint4 *>(&S.child[g * kSV]), c1 = *reinterpret_cast<const uint4 *>(&S.child[g * kSV + 4]);
+      childless = (c0.x & c0.y & c0.z & c0.w & c1.x & c1.y & c1.z & c1.w) == kNone;
+      leaf = S.child[g * kSV + (t >> 3)] == kNone;
       if (leaf) {
-        float4 cv[8];
-        float f[8];
+        const float scale = (float)(1 << pl.w);
+        const float bx = ((float)(pl.x | cell_x(t)) + .5f) * scale - me.x * alpha;
+        const float by = ((float)(pl.y | cell_y(t)) + .5f) * scale - me.y * alpha;
+        const float bz = ((float)(pl.z | cell_z(t)) + .5f) * scale - me.z * alpha;
+        smp = d_sample_pipe(T, P, S.apron + g * kAV, S.child + g * kSV, pl, bx, by, bz);
+      }
+    }
+    __syncwarp();  // every lane is done with ring slot s (positions, velocities, apron ids)
+    if ((threadIdx.x & 31u) == 0) pipe::mbar_arrive(&empty[s]);
+    if (!live) continue;
+    const uint32_t c = b * kBV + t;
+    float3 vo = make_float3(0.f, 0.f, 0.f);
+    float qo = 0.f;
+    if (leaf) {
+      float4 cv[8];
+      float qv[8], f[8];
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-          cv[k] = vin[smp.id[k]];
-          f[k] = cv[k].w;
-        }
-        const Weights8 W = corner_weights(f, smp.fx, smp.fy, smp.fz);
-        if (!(W.acc < 1e-6f)) {
+      for (int k = 0; k < 8; k++) {
+        if (kMode != 1) cv[k] = vin[smp.id[k]];
+        if (kMode != 0) qv[k] = qin[smp.id[k]];
+        f[k] = kMode == 1 ? fl[smp.id[k]] : cv[k].w;
+      }
+      const Weights8 W = corner_weights(f, smp.fx, smp.fy, smp.fz);
+      if (!(W.acc < 1e-6f)) {
+        const bool inside = sample_inside(P, smp);
+        if (kMode != 1) {
           float vx[8], vy[8], vz[8];
-          const bool inside = sample_inside(P, smp);
 #pragma unroll
           for (int k = 0; k < 8; k++) {
             float3 v = make_float3(cv[k].x, cv[k].y, cv[k].z);
             if (!inside) v = velocity_bc(P, v, smp.x0 + ((k >> 2) & 1), smp.y0 + ((k >> 1) & 1), smp.z0 + (k & 1), smp.scale);
             vx[k] = v.x; vy[k] = v.y; vz[k] = v.z;
           }
-          out = make_float3(blend8(vx, W.w), blend8(vy, W.w), blend8(vz, W.w));
+          vo = make_float3(blend8(vx, W.w), blend8(vy, W.w), blend8(vz, W.w));
         }
-      }
-      vout[c] = make_float4(out.x, out.y, out.z, me.w);
-    } else {
-      float out = 0.f;
-      if (leaf) {
-        float qv[8], f[8];
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-          f[k] = fl[smp.id[k]];
-          qv[k] = qin[smp.id[k]];
-        }
-        const Weights8 W = corner_weights(f, smp.fx, smp.fy, smp.fz);
-        if (!(W.acc < 1e-6f)) {
-          if (!sample_inside(P, smp)) {
+        if (kMode != 0) {
+          if (!inside) {
 #pragma unroll
             for (int k = 0; k < 8; k++)
               qv[k] = density_bc(P, qv[k], smp.x0 + ((k >> 2) & 1), smp.y0 + ((k >> 1) & 1), smp.z0 + (k & 1), smp.scale);
           }
-          out = blend8(qv, W.w);
+          qo = blend8(qv, W.w);
         }
       }
-      qout[c] = out;
+    }
+    const bool push = childless && ps != kNone;  // uniform over the block
+    if (kMode != 1) {
+      if (leaf) vout[c] = make_float4(vo.x, vo.y, vo.z, me.w);
+      else reinterpret_cast<float *>(vout + c)[3] = me.w;
+      if (push) {
+        const float ax = subblock_sum(vo.x), ay = subblock_sum(vo.y), az = subblock_sum(vo.z);
+        if ((t & 7u) == 7u) {
+          float *dst = reinterpret_cast<float *>(vout + ((size_t)kSV * ps + (t >> 3)));
+          dst[0] = ax * .125f; dst[1] = ay * .125f; dst[2] = az * .125f;
+        }
+      }
+    }
+    if (kMode != 0) {
+      if (leaf) qout[c] = qo;
+      if (push) {
+        const float a = subblock_sum(qo);
+        if ((t & 7u) == 7u) qout[(size_t)kSV * ps + (t >> 3)] = a * .125f;
+      }
     }
   }
+}
+
+// Morton key of a block for the processing order: its origin in level-0 block units (4 cells), bits interleaved
+__device__ __forceinline__ uint32_t spread3(uint32_t v) {  // 10 bits -> every third bit
+  v &= 0x3FFu;
+  v = (v | (v << 16)) & 0x030000FFu;
+  v = (v | (v << 8)) & 0x0300F00Fu;
+  v = (v | (v << 4)) & 0x030C30C3u;
+  v = (v | (v << 2)) & 0x09249249u;
+  return v;
+}
+// mode 0: key = slot (pool order); 1: Morton.  Free slots get key 0xFFFFFFFF and sort to the end.
+__global__ void __launch_bounds__(256) k_dc_order_keys(Pool T, int mode, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+  const uint32_t b = blockIdx.x * 256 + threadIdx.x;
+  if (b >= T.M) return;
+  const int4 pl = T.posl[b];
+  uint32_t key = 0xFFFFFFFFu;
+  if (pl.w != kFree) {
+    if (mode == 0) key = b;
+    else key = (spread3((uint32_t)(pl.x << pl.w) >> 2) << 2) | (spread3((uint32_t)(pl.y << pl.w) >> 2) << 1) | spread3((uint32_t)(pl.z << pl.w) >> 2);
+  }
+  keys[b] = key;
+  vals[b] = b;
+}
+__global__ void __launch_bounds__(256) k_dc_order_pad(uint32_t *__restrict__ order, uint32_t n, uint32_t padded) {
+  const uint32_t i = n + blockIdx.x * 256 + threadIdx.x;
+  if (i < padded) order[i] = kNone;
 }
 
 }  // namespace dcg

@@ -341,8 +341,13 @@ __device__ __forceinline__ float ghost_product(const KParams &P, const float4 *_
   const float3 vb = velocity_bc(P, make_float3(v.x, v.y, v.z), gx, gy, gz, scale);
   return v.w * (axis == 0 ? vb.x : (axis == 1 ? vb.y : vb.z));
 }
+// zero_from: the reference clears pressure and t_pressure of the whole pool here (:186-187).  In project() every
+// level below the coarsest gets its pressure from the prolongation and its t_pressure from the level's first
+// sweep before either is read (ghosts included: they lie in coarser levels, which are finished by then), so
+// only blocks of level >= zero_from (= the coarsest level) need the stores; project_local() starts every
+// level from zero and passes 0.
 __global__ void __launch_bounds__(kCTA4) k_dc_divergence4(Pool T, KParams P, const float4 *__restrict__ vw, float *__restrict__ div,
-                                                          float *__restrict__ p, float *__restrict__ tp) {
+                                                          float *__restrict__ p, float *__restrict__ tp, int zero_from) {
   const uint32_t g = threadIdx.x >> 4;
   const int t = threadIdx.x & 15;
   const uint32_t b0 = blockIdx.x * kB4 + g;
@@ -400,8 +405,10 @@ __global__ void __launch_bounds__(kCTA4) k_dc_divergence4(Pool T, KParams P, con
   s += d.x; s += d.y; s += d.z; s += d.w;
   const float lo = __shfl_sync(0xFFFFFFFFu, s, (threadIdx.x & 31u) ^ 1u);
   if (!active) return;
-  __stcs(reinterpret_cast<float4 *>(p + c0), zero);
-  __stcs(reinterpret_cast<float4 *>(tp + c0), zero);
+  if (pl.w >= zero_from) {
+    __stcs(reinterpret_cast<float4 *>(p + c0), zero);
+    __stcs(reinterpret_cast<float4 *>(tp + c0), zero);
+  }
   // quads of refined subblocks are always overwritten by their children's restriction: nothing to store
   if (leaf) __stcs(reinterpret_cast<float4 *>(div + c0), d);
   if (childless && (t & 1)) {

@@ -88,6 +88,10 @@ class Oracle:
     def set_jacobi_schedule(self, coarse, level, local):
         self.L.orc_set_jacobi_schedule(self.h, coarse, level, local)
 
+    def set_params(self, params: SimParams):
+        self.params = params
+        self.L.orc_set_params(self.h, ctypes.byref(params))
+
     def reset(self):
         self.L.orc_reset(self.h)
 

@@ -87,6 +87,8 @@ def test_dcgrid_bit_exact_vs_oracle(gpu, d, M, solids, steps, schedule):
     {"DCG_JACOBI": "pipe_all", "DCG_SNAKE": "0"},
     {"DCG_JACOBI": "legacy", "DCG_ADVECT": "legacy"},      # one-CTA-per-tile kernels
     {"DCG_JACOBI_CTAS": "1", "DCG_ADVECT_CTAS": "1"},      # one resident CTA per SM: every CTA walks several tiles
+    {"DCG_ADVECT_FUSE": "0", "DCG_ADVECT_ORDER": "slot"},  # density and velocity advection as separate passes, pool order
+    {"DCG_ADVECT_MINB": "3", "DCG_STENCIL": "legacy"},     # 3-CTA/SM advection build; one-CTA-per-tile divergence / gradient
 ])
 @pytest.mark.parametrize("d,M,solids,steps", [(64, 2000, True, 8), (32, 301, False, 6), (128, 16384, True, 4)])
 def test_dcgrid_kernel_variants_bit_exact(gpu, monkeypatch, env, d, M, solids, steps):
@@ -111,6 +113,35 @@ def test_dcgrid_steady_state_skip_and_graph(gpu):
     act = assert_same_topology(a, orc, "after 9 steps")
     assert_same_fields(a, orc, ("density", "velocity"), act, "graph path")
     assert a.lastStepMs() > 0
+
+
+def test_dcgrid_speculative_velocity_is_dropped_when_state_changes(gpu):
+    """advectDensity() also writes the next step's advected velocity into the idle ping-pong buffer
+    (k_dc_advect_pipe<2>); advectVelocity() may only use it if nothing touched the state in between.  Drive the
+    nine virtuals in orders the reference's UI never uses and compare with the oracle after every call."""
+    d, M = 64, 2000
+    p = scene_params(d, solids=True)
+    sim = FluidSimulationDCGrid((d, d, d), M, p)
+    orc = Oracle(p, M)
+    sim.step(3); orc.step(3)
+    seq = ["advect_density", "project", "advect_velocity",          # project between producer and consumer
+           "advect_density", "advect_velocity", "advect_velocity",  # consumed once, second call runs the kernel
+           "advect_density", "adapt_topology", "advect_velocity",
+           "advect_density", "project_local", "advect_density", "advect_velocity",
+           "advect_density", "set_params", "advect_velocity", "project", "advect_density"]
+    names = {"advect_density": "advectDensity", "advect_velocity": "advectVelocity", "project": "project",
+             "project_local": "projectLocal", "adapt_topology": "adaptTopology"}
+    for i, op in enumerate(seq):
+        if op == "set_params":
+            p.dt = 2.5
+            sim.setParams(p); orc.set_params(p)
+        else:
+            getattr(sim, names[op])(); getattr(orc, op)()
+        act = assert_same_topology(sim, orc, f"call {i} ({op})")
+        assert_same_fields(sim, orc, ("density", "velocity"), act, f"call {i} ({op})")
+    sim.step(4); orc.step(4)  # back on the graph / fused path
+    act = assert_same_topology(sim, orc, "after the sequence")
+    assert_same_fields(sim, orc, ("density", "velocity"), act, "after the sequence")
 
 
 def test_dcgrid_lookup_and_dense_resample(gpu):
