@@ -76,8 +76,12 @@ struct DCGridSim : dcg_sim {
   size_t sort_tmp_bytes = 0;
   uint32_t n_order = 0;  // padded to a multiple of kBPC
   int order_mode = 1;    // 0 = pool-slot order, 1 = Morton
+  bool use_stencil_pipe = true;  // k_dc_divergence_pipe / k_dc_apply_pipe instead of the one-CTA-per-tile kernels
+  int div_pipe_ctas = 0, apply_pipe_ctas = 0, apply_min_blocks = 3;
+  bool coarse_in_smem = true;
+  static constexpr size_t kCoarseSmemMax = 200 * 1024;
   bool skip_dead_zeroing = true;  // k_dc_divergence4: no pressure clears that project() never reads
-  int advect_min_blocks = 4;  // __launch_bounds__ variant of the advection kernels (3 or 4 CTAs per SM)
+  int advect_min_blocks = 3;  // __launch_bounds__ variant of the advection kernels (3 or 4 CTAs per SM)
   bool use_pipe = true, snake = true;
   unsigned pipe_min_tiles = 0;  // levels with fewer tiles take the one-CTA-per-tile kernel
   int sweep_parity = 0;
@@ -152,7 +156,7 @@ struct DCGridSim : dcg_sim {
     T.M = M; T.levels = levels; T.sparse_levels = sparse;
     for (int l = 0; l < levels; l++) { T.offsets[l] = (uint32_t)offsets[l]; T.max_blocks[l] = (uint32_t)max_blocks[l]; }
     DCG_CUDA_TRY(cudaMalloc(&T.posl, (size_t)M * sizeof(int4)));
-    DCG_CUDA_TRY(cudaMalloc(&T.parent, (size_t)M * 4));
+    DCG_CUDA_TRY(cudaMalloc(&T.parent, ((size_t)M + kB4) * 4));  // padded: the stencil rings stream kB4 entries per tile
     DCG_CUDA_TRY(cudaMalloc(&d_order, ((size_t)M + kBPC) * 4));
     DCG_CUDA_TRY(cudaMalloc(&d_order_keys[0], (size_t)M * 4));
     DCG_CUDA_TRY(cudaMalloc(&d_order_keys[1], (size_t)M * 4));
@@ -206,9 +210,27 @@ struct DCGridSim : dcg_sim {
       jacobi_pipe_ctas = per_sm * sm_count;
       if (const char *e = getenv("DCG_ADVECT")) use_advect_pipe = std::string(e) != "legacy";
       if (const char *e = getenv("DCG_ADVECT_ORDER")) order_mode = std::string(e) == "slot" ? 0 : 1;
+      if (const char *e = getenv("DCG_STENCIL")) use_stencil_pipe = std::string(e) != "legacy";
+      {
+        int per_sm = 0;
+        DCG_CUDA_TRY(cudaFuncSetAttribute(k_dc_divergence_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDivPipeSmem));
+        DCG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_dc_divergence_pipe, kStencilThreads, kDivPipeSmem));
+        if (per_sm < 1) return fail(DCG_ERR_CUDA, "k_dc_divergence_pipe does not fit on an SM");
+        if (const char *e = getenv("DCG_STENCIL_CTAS")) per_sm = std::max(1, std::min(per_sm, atoi(e)));
+        div_pipe_ctas = per_sm * sm_count;
+        if (const char *e = getenv("DCG_APPLY_MINB")) apply_min_blocks = atoi(e) == 2 ? 2 : 3;
+        const void *afn = apply_min_blocks == 2 ? (const void *)k_dc_apply_pipe<2> : (const void *)k_dc_apply_pipe<3>;
+        DCG_CUDA_TRY(cudaFuncSetAttribute(afn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kApplyPipeSmem));
+        DCG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, afn, kStencilThreads, kApplyPipeSmem));
+        if (per_sm < 1) return fail(DCG_ERR_CUDA, "k_dc_apply_pipe does not fit on an SM");
+        if (const char *e = getenv("DCG_STENCIL_CTAS")) per_sm = std::max(1, std::min(per_sm, atoi(e)));
+        apply_pipe_ctas = per_sm * sm_count;
+      }
+      if (const char *e = getenv("DCG_COARSE")) coarse_in_smem = std::string(e) != "gmem";
+      DCG_CUDA_TRY(cudaFuncSetAttribute(k_dc_coarse_cascade<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCoarseSmemMax));
       if (const char *e = getenv("DCG_ZERO_ALL")) skip_dead_zeroing = std::string(e) == "0";
       if (const char *e = getenv("DCG_ADVECT_FUSE")) fuse_advect = std::string(e) != "0";
-      if (const char *e = getenv("DCG_ADVECT_MINB")) advect_min_blocks = atoi(e) == 3 ? 3 : 4;
+      if (const char *e = getenv("DCG_ADVECT_MINB")) advect_min_blocks = atoi(e) == 4 ? 4 : 3;
       for (int mode = 0; mode < 3; mode++) {
         const void *fn = advect_fn(mode);
         DCG_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAdvectPipeSmem));
@@ -244,7 +266,7 @@ struct DCGridSim : dcg_sim {
     spec_velocity = false;
     k_fill_posl<<<blocks_for(M, 256), 256, 0, stream>>>(T.posl, M);
     DCG_CUDA_TRY(cudaMemsetAsync(d_flags, 0, (size_t)M * 4, stream));
-    DCG_CUDA_TRY(cudaMemsetAsync(T.parent, 0xff, (size_t)M * 4, stream));
+    DCG_CUDA_TRY(cudaMemsetAsync(T.parent, 0xff, ((size_t)M + kB4) * 4, stream));
     DCG_CUDA_TRY(cudaMemsetAsync(T.child, 0xff, (size_t)M * 8 * 4, stream));
     DCG_CUDA_TRY(cudaMemsetAsync(T.face, 0, (size_t)M * 96 * 4, stream));
     DCG_CUDA_TRY(cudaMemsetAsync(T.fd, 0, (size_t)M * 12 * 4, stream));
@@ -551,7 +573,7 @@ struct DCGridSim : dcg_sim {
       launches++;
     }
     if (tail < levels - 1) {
-      k_dc_accumulate_coarse<<<1, 1024, 0, stream>>>(T, tail, v, ch);
+      k_dc_accumulate_coarse<<<kAccClusterCTAs, kAccClusterThreads, 0, stream>>>(T, tail, v, ch);
       launches++;
     }
   }
@@ -629,23 +651,50 @@ struct DCGridSim : dcg_sim {
     jacobi_sweep(l, p, tp);
     jacobi_sweep(l, tp, p);
   }
-  void divergence_stage(int zero_from) {
-    k_dc_divergence4<<<blocks_for(M, kB4), kCTA4, 0, stream>>>(T, kp, vw[cur_v], div, p, tp, zero_from);
+  void launch_divergence(int zero_from) {
+    const unsigned tiles = blocks_for(M, kB4);
+    if (use_stencil_pipe)
+      k_dc_divergence_pipe<<<std::min<unsigned>(tiles, (unsigned)div_pipe_ctas), kStencilThreads, kDivPipeSmem, stream>>>(T, kp, vw[cur_v], div, p, tp,
+                                                                                                                          zero_from);
+    else
+      k_dc_divergence4<<<tiles, kCTA4, 0, stream>>>(T, kp, vw[cur_v], div, p, tp, zero_from);
     launches++;
+  }
+  void launch_apply() {
+    const unsigned tiles = blocks_for(M, kB4);
+    if (use_stencil_pipe && apply_min_blocks == 2)
+      k_dc_apply_pipe<2><<<std::min<unsigned>(tiles, (unsigned)apply_pipe_ctas), kStencilThreads, kApplyPipeSmem, stream>>>(T, kp, p, fl, vw[cur_v]);
+    else if (use_stencil_pipe)
+      k_dc_apply_pipe<3><<<std::min<unsigned>(tiles, (unsigned)apply_pipe_ctas), kStencilThreads, kApplyPipeSmem, stream>>>(T, kp, p, fl, vw[cur_v]);
+    else
+      k_dc_apply_pressure4<<<tiles, kCTA4, 0, stream>>>(T, kp, p, fl, vw[cur_v]);
+    launches++;
+  }
+  void divergence_stage(int zero_from) {
+    launch_divergence(zero_from);
     accumulate_scalar(div, true);
   }
   void apply_stage() {
-    k_dc_apply_pressure4<<<blocks_for(M, kB4), kCTA4, 0, stream>>>(T, kp, p, fl, vw[cur_v]);
-    launches++;
+    launch_apply();
     accumulate_velocity(true);
+  }
+  // the coarse tail of the cascade in one single-CTA launch, its fields in shared memory when they fit
+  void launch_coarse_cascade(int cf, int prolong_coarsest, int pairs_coarsest, int pairs_level, int prolong_levels) {
+    const uint64_t end = offsets[levels - 1] + max_blocks[levels - 1];
+    const uint32_t ncell = (uint32_t)((end - offsets[cf]) * kBV);
+    const size_t smem = (size_t)ncell * (3 * 4 + 6 * 2);
+    if (coarse_in_smem && smem <= kCoarseSmemMax && ncell <= 65535)
+      k_dc_coarse_cascade<true><<<1, 1024, smem, stream>>>(T, kp, cf, prolong_coarsest, pairs_coarsest, pairs_level, prolong_levels, p, tp, div, ncell);
+    else
+      k_dc_coarse_cascade<false><<<1, 1024, 0, stream>>>(T, kp, cf, prolong_coarsest, pairs_coarsest, pairs_level, prolong_levels, p, tp, div, 0);
+    launches++;
   }
   int project() override {  // :270-294
     spec_velocity = false;
     divergence_stage(skip_dead_zeroing && project_level_pairs >= 1 ? levels - 1 : 0);
     // levels with <= kCoarseBlocks blocks: the whole coarse part of the cascade in one single-CTA launch
     const int cf = small_levels_from(kCoarseBlocks);
-    k_dc_coarse_cascade<<<1, 1024, 0, stream>>>(T, kp, cf, 0, project_coarsest_pairs, project_level_pairs, 1, p, tp, div);
-    launches++;
+    launch_coarse_cascade(cf, 0, project_coarsest_pairs, project_level_pairs, 1);
     for (int l = cf - 1; l >= 0; l--) {
       if (loads[l] == 0) continue;
       k_dc_prolongate4<<<blocks_for(loads[l], kB4), kCTA4, 0, stream>>>(T, l, p);
@@ -660,8 +709,7 @@ struct DCGridSim : dcg_sim {
     spec_velocity = false;
     divergence_stage(0);
     const int cf = small_levels_from(kCoarseBlocks);
-    k_dc_coarse_cascade<<<1, 1024, 0, stream>>>(T, kp, cf, 0, local_pairs, local_pairs, 0, p, tp, div);
-    launches++;
+    launch_coarse_cascade(cf, 0, local_pairs, local_pairs, 0);
     for (int l = cf - 1; l >= 0; l--)
       for (int i = 0; i < local_pairs; i++) jacobi_pair(l);
     apply_stage();
@@ -743,10 +791,12 @@ struct DCGridSim : dcg_sim {
         cur_q ^= 1;
         bytes = 52.0 * call;
       } else if (st == "divergence") {
-        k_dc_divergence4<<<blocks_for(M, kB4), kCTA4, 0, stream>>>(T, kp, vw[cur_v], div, p, tp, skip_dead_zeroing && project_level_pairs >= 1 ? levels - 1 : 0);
+        launch_divergence(skip_dead_zeroing && project_level_pairs >= 1 ? levels - 1 : 0);
+        launches--;
         bytes = 28.0 * call;
       } else if (st == "apply_pressure") {
-        k_dc_apply_pressure4<<<blocks_for(M, kB4), kCTA4, 0, stream>>>(T, kp, p, fl, vw[cur_v]);
+        launch_apply();
+        launches--;
         bytes = 32.0 * call;
       } else if (st == "accumulate_velocity") {
         k_dc_accumulate_velocity<<<blocks_for(8 * loads[level], 256), 256, 0, stream>>>(T, level, vw[cur_v], 0);

@@ -420,4 +420,276 @@ __global__ void __launch_bounds__(256) k_dc_order_pad(uint32_t *__restrict__ ord
   if (i < padded) order[i] = kNone;
 }
 
+// ---- divergence and pressure gradient (k_dcgrid_calc_divergence / k_dcgrid_apply_pressure), persistent + TMA ring ----
+// The one-CTA-per-tile kernels of dcgrid_stencil.cuh read a quad's four packed velocities with four LDG.128 at a
+// 64-byte lane stride: every request touches 32 half-used sectors and costs 4x the L1 wavefronts of a coalesced
+// one (l1tex data-pipe 78 % busy at 3.5 TB/s, profiles/README.md r1d).  Here a tile's velocities (16 KiB), face
+// descriptors, child links, positions and parent links are contiguous ranges streamed by cp.async.bulk into a
+// 3-stage ring by a producer warp; the consumers read their quads from shared memory in a rotated chunk order
+// (lane t starts at chunk (t >> 1) & 3) that is bank-conflict free, and un-rotate in registers.  Ghosts are
+// still gathered from global memory through the face descriptors; arithmetic and its order are unchanged.
+constexpr int kSStages = 3;
+constexpr int kStencilThreads = kCTA4 + 32;
+struct alignas(128) DivStage {
+  float4 vw[kB4 * kBV];      // 16 KiB
+  uint32_t fd[kB4 * 12];     // 768 B
+  uint32_t child[kB4 * kSV]; // 512 B
+  int4 posl[kB4];            // 256 B
+  uint32_t parent[kB4];      // 64 B (T.parent is padded to a multiple of kB4 entries)
+};
+struct alignas(128) ApplyStage {
+  float4 vw[kB4 * kBV];
+  float p[kB4 * kBV];        // 4 KiB
+  uint32_t fd[kB4 * 12];
+  uint32_t child[kB4 * kSV];
+  int4 posl[kB4];
+  uint32_t parent[kB4];
+};
+constexpr size_t kDivPipeSmem = kSStages * sizeof(DivStage) + 2 * kSStages * sizeof(uint64_t);
+constexpr size_t kApplyPipeSmem = kSStages * sizeof(ApplyStage) + 2 * kSStages * sizeof(uint64_t);
+
+// the quad's four packed velocities from a staged tile: conflict-free rotated reads, then un-rotation
+__device__ __forceinline__ void load_quad_velocities(const float4 *blk, int t, float4 v[4]) {
+  const int r = (t >> 1) & 3;
+  float4 a[4], b[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) a[k] = blk[4 * t + ((k + r) & 3)];  // a[k] = chunk (k + r) & 3
+#pragma unroll
+  for (int c = 0; c < 4; c++) b[c] = (r & 1) ? a[(c + 3) & 3] : a[c];
+#pragma unroll
+  for (int c = 0; c < 4; c++) v[c] = (r & 2) ? b[(c + 2) & 3] : b[c];
+}
+
+template <class Stage>
+__device__ __forceinline__ void stencil_ring_init(uint64_t *full, uint64_t *empty) {
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < kSStages; s++) {
+      pipe::mbar_init(&full[s], 1);
+      pipe::mbar_init(&empty[s], kCTA4 / 32);
+    }
+    pipe::fence_barrier_init();
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kStencilThreads, 3) k_dc_divergence_pipe(Pool T, KParams P, const float4 *__restrict__ vw, float *__restrict__ div,
+                                                                           float *__restrict__ p, float *__restrict__ tp, int zero_from) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  DivStage *st = reinterpret_cast<DivStage *>(smem_raw);
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + kSStages * sizeof(DivStage));
+  uint64_t *empty = full + kSStages;
+  const uint32_t ntiles = (T.M + kB4 - 1) / kB4;
+  stencil_ring_init<DivStage>(full, empty);
+  if (threadIdx.x >= kCTA4) {  // producer warp
+    if (threadIdx.x != kCTA4) return;
+    uint32_t tl = blockIdx.x;
+    for (uint32_t it = 0; tl < ntiles; it++, tl += gridDim.x) {
+      const uint32_t s = it % kSStages;
+      if (it >= (uint32_t)kSStages) pipe::mbar_wait(&empty[s], ((it / kSStages) - 1u) & 1u);
+      const size_t b0 = (size_t)tl * kB4;
+      const uint32_t nv = min((uint32_t)kB4, T.M - (uint32_t)b0);
+      DivStage &S = st[s];
+      pipe::mbar_expect_tx(&full[s], nv * (kBV * 16u + 48u + kSV * 4u + 16u) + kB4 * 4u);
+      pipe::bulk_g2s(S.vw, vw + b0 * kBV, nv * kBV * 16u, &full[s]);
+      pipe::bulk_g2s(S.fd, T.fd + b0 * 12, nv * 48u, &full[s]);
+      pipe::bulk_g2s(S.child, T.child + b0 * kSV, nv * kSV * 4u, &full[s]);
+      pipe::bulk_g2s(S.posl, T.posl + b0, nv * 16u, &full[s]);
+      pipe::bulk_g2s(S.parent, T.parent + b0, kB4 * 4u, &full[s]);
+    }
+    return;
+  }
+  const uint32_t g = threadIdx.x >> 4;
+  const int t = threadIdx.x & 15;
+  int X, Y0, Z0;
+  quad_coords(t, X, Y0, Z0);
+  const int sy = (t >> 2) & 1, sz = (t >> 1) & 1;
+  const unsigned half = 0xFFFFu << (threadIdx.x & 16u);
+  uint32_t tl = blockIdx.x;
+  for (uint32_t it = 0; tl < ntiles; it++, tl += gridDim.x) {
+    const uint32_t s = it % kSStages;
+    pipe::mbar_wait(&full[s], (it / kSStages) & 1u);
+    const DivStage &S = st[s];
+    const uint32_t b = tl * kB4 + g;
+    int4 pl = make_int4(0, 0, 0, kFree);
+    if (b < T.M) pl = S.posl[g];
+    const bool active = pl.w != kFree;
+    float4 v[4];
+    uint32_t child = kNone, ps = kNone;
+    QuadGhosts q;
+    q.has_x = false;
+    if (active) {
+      load_quad_velocities(S.vw + g * kBV, t, v);
+      child = S.child[g * kSV + (t >> 1)];
+      ps = S.parent[g];
+      const uint4 *fdp = reinterpret_cast<const uint4 *>(&S.fd[g * 12]);
+      q = quad_ghosts_from(T, b, t, fdp[0], fdp[1], fdp[2]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; k++) v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncwarp();
+    if ((threadIdx.x & 31u) == 0) pipe::mbar_arrive(&empty[s]);
+    if (!__any_sync(0xFFFFFFFFu, active)) continue;
+    const int scale = 1 << (pl.w & 15);
+    float4 gx = make_float4(0.f, 0.f, 0.f, 0.f);
+    float gy0 = 0.f, gy1 = 0.f, gz0 = 0.f, gz1 = 0.f;
+    if (active) {
+      if (q.has_x) {
+        const int nx = pl.x + (X == 3 ? kBW : -1);
+        gx.x = ghost_product(P, vw, q.x[0], 0, nx, pl.y + Y0, pl.z + Z0, scale);
+        gx.y = ghost_product(P, vw, q.x[1], 0, nx, pl.y + Y0, pl.z + Z0 + 1, scale);
+        gx.z = ghost_product(P, vw, q.x[2], 0, nx, pl.y + Y0 + 1, pl.z + Z0, scale);
+        gx.w = ghost_product(P, vw, q.x[3], 0, nx, pl.y + Y0 + 1, pl.z + Z0 + 1, scale);
+      }
+      const int ny = pl.y + (sy ? kBW : -1), nz = pl.z + (sz ? kBW : -1);
+      gy0 = ghost_product(P, vw, q.y[0], 1, pl.x + X, ny, pl.z + Z0, scale);
+      gy1 = ghost_product(P, vw, q.y[1], 1, pl.x + X, ny, pl.z + Z0 + 1, scale);
+      gz0 = ghost_product(P, vw, q.z[0], 2, pl.x + X, pl.y + Y0, nz, scale);
+      gz1 = ghost_product(P, vw, q.z[1], 2, pl.x + X, pl.y + Y0 + 1, nz, scale);
+    }
+    const float4 px = make_float4(v[0].w * v[0].x, v[1].w * v[1].x, v[2].w * v[2].x, v[3].w * v[3].x);
+    const float4 py = make_float4(v[0].w * v[0].y, v[1].w * v[1].y, v[2].w * v[2].y, v[3].w * v[3].y);
+    const float4 pz = make_float4(v[0].w * v[0].z, v[1].w * v[1].z, v[2].w * v[2].z, v[3].w * v[3].z);
+    QuadNbr nx_, ny_, nz_;
+    quad_exchange_x(nx_, px, t, gx);
+    quad_exchange_y(ny_, py, t, gy0, gy1);
+    quad_exchange_z(nz_, pz, t, gz0, gz1);
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 d = zero;
+    const bool leaf = active && child == kNone;
+    if (leaf) {
+      const float alpha = .5f * P.rdx / (float)scale;
+      d.x = alpha * (nx_.xp.x - nx_.xm.x + py.z - ny_.ym0 + pz.y - nz_.zm0);
+      d.y = alpha * (nx_.xp.y - nx_.xm.y + py.w - ny_.ym1 + nz_.zp0 - pz.x);
+      d.z = alpha * (nx_.xp.z - nx_.xm.z + ny_.yp0 - py.x + pz.w - nz_.zm1);
+      d.w = alpha * (nx_.xp.w - nx_.xm.w + ny_.yp1 - py.y + nz_.zp1 - pz.z);
+    }
+    const bool childless = (__ballot_sync(0xFFFFFFFFu, child != kNone) & half) == 0;
+    float sm = 0.f;
+    sm += d.x; sm += d.y; sm += d.z; sm += d.w;
+    const float lo = __shfl_sync(0xFFFFFFFFu, sm, (threadIdx.x & 31u) ^ 1u);
+    if (!active) continue;
+    const size_t c0 = (size_t)b * kBV + 4 * t;
+    if (pl.w >= zero_from) {
+      __stcs(reinterpret_cast<float4 *>(p + c0), zero);
+      __stcs(reinterpret_cast<float4 *>(tp + c0), zero);
+    }
+    if (leaf) __stcs(reinterpret_cast<float4 *>(div + c0), d);
+    if (childless && (t & 1) && ps != kNone) {
+      float a = lo;
+      a += d.x; a += d.y; a += d.z; a += d.w;
+      div[(size_t)kSV * ps + (t >> 1)] = a * .125f;
+    }
+  }
+}
+
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kStencilThreads, kMinBlocks) k_dc_apply_pipe(Pool T, KParams P, const float *__restrict__ p, const float *__restrict__ fl,
+                                                                      float4 *__restrict__ vw) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  ApplyStage *st = reinterpret_cast<ApplyStage *>(smem_raw);
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + kSStages * sizeof(ApplyStage));
+  uint64_t *empty = full + kSStages;
+  const uint32_t ntiles = (T.M + kB4 - 1) / kB4;
+  stencil_ring_init<ApplyStage>(full, empty);
+  if (threadIdx.x >= kCTA4) {  // producer warp
+    if (threadIdx.x != kCTA4) return;
+    uint32_t tl = blockIdx.x;
+    for (uint32_t it = 0; tl < ntiles; it++, tl += gridDim.x) {
+      const uint32_t s = it % kSStages;
+      if (it >= (uint32_t)kSStages) pipe::mbar_wait(&empty[s], ((it / kSStages) - 1u) & 1u);
+      const size_t b0 = (size_t)tl * kB4;
+      const uint32_t nv = min((uint32_t)kB4, T.M - (uint32_t)b0);
+      ApplyStage &S = st[s];
+      pipe::mbar_expect_tx(&full[s], nv * (kBV * 16u + kBV * 4u + 48u + kSV * 4u + 16u) + kB4 * 4u);
+      pipe::bulk_g2s(S.vw, vw + b0 * kBV, nv * kBV * 16u, &full[s]);
+      pipe::bulk_g2s(S.p, p + b0 * kBV, nv * kBV * 4u, &full[s]);
+      pipe::bulk_g2s(S.fd, T.fd + b0 * 12, nv * 48u, &full[s]);
+      pipe::bulk_g2s(S.child, T.child + b0 * kSV, nv * kSV * 4u, &full[s]);
+      pipe::bulk_g2s(S.posl, T.posl + b0, nv * 16u, &full[s]);
+      pipe::bulk_g2s(S.parent, T.parent + b0, kB4 * 4u, &full[s]);
+    }
+    return;
+  }
+  const uint32_t g = threadIdx.x >> 4;
+  const int t = threadIdx.x & 15;
+  const unsigned half = 0xFFFFu << (threadIdx.x & 16u);
+  uint32_t tl = blockIdx.x;
+  for (uint32_t it = 0; tl < ntiles; it++, tl += gridDim.x) {
+    const uint32_t s = it % kSStages;
+    pipe::mbar_wait(&full[s], (it / kSStages) & 1u);
+    const ApplyStage &S = st[s];
+    const uint32_t b = tl * kB4 + g;
+    int level = kFree;
+    if (b < T.M) level = S.posl[g].w;
+    const bool active = level != kFree;
+    float4 v[4];
+    float4 op = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t child = kNone, ps = kNone;
+    QuadGhosts q;
+    q.has_x = false;
+    if (active) {
+      load_quad_velocities(S.vw + g * kBV, t, v);
+      op = *reinterpret_cast<const float4 *>(&S.p[g * kBV + 4 * t]);
+      child = S.child[g * kSV + (t >> 1)];
+      ps = S.parent[g];
+      const uint4 *fdp = reinterpret_cast<const uint4 *>(&S.fd[g * 12]);
+      q = quad_ghosts_from(T, b, t, fdp[0], fdp[1], fdp[2]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; k++) v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncwarp();
+    if ((threadIdx.x & 31u) == 0) pipe::mbar_arrive(&empty[s]);
+    if (!__any_sync(0xFFFFFFFFu, active)) continue;
+    const float4 ow = make_float4(v[0].w, v[1].w, v[2].w, v[3].w);  // == fl[c0..c0+3]
+    float4 pgx = make_float4(0.f, 0.f, 0.f, 0.f), wgx = pgx;
+    float pg[4] = {0.f, 0.f, 0.f, 0.f}, wg[4] = {0.f, 0.f, 0.f, 0.f};
+    if (active) {
+      if (q.has_x) {
+        pgx = make_float4(p[q.x[0]], p[q.x[1]], p[q.x[2]], p[q.x[3]]);
+        wgx = make_float4(fl[q.x[0]], fl[q.x[1]], fl[q.x[2]], fl[q.x[3]]);
+      }
+      pg[0] = p[q.y[0]]; pg[1] = p[q.y[1]]; pg[2] = p[q.z[0]]; pg[3] = p[q.z[1]];
+      wg[0] = fl[q.y[0]]; wg[1] = fl[q.y[1]]; wg[2] = fl[q.z[0]]; wg[3] = fl[q.z[1]];
+    }
+    const QuadNbr sN = quad_exchange(op, t, pgx, pg[0], pg[1], pg[2], pg[3]);
+    const QuadNbr w = quad_exchange(ow, t, wgx, wg[0], wg[1], wg[2], wg[3]);
+    const unsigned with_child = __ballot_sync(0xFFFFFFFFu, child != kNone);
+    const bool childless = active && (with_child & half) == 0;
+    const bool leaf = active && child == kNone;
+    const float alpha = .5f * P.rdx / (float)(1 << (level & 15));
+    v[0].x -= alpha * (w.xp.x * (sN.xp.x - op.x) + w.xm.x * (op.x - sN.xm.x));
+    v[0].y -= alpha * (ow.z * (op.z - op.x) + w.ym0 * (op.x - sN.ym0));
+    v[0].z -= alpha * (ow.y * (op.y - op.x) + w.zm0 * (op.x - sN.zm0));
+    v[1].x -= alpha * (w.xp.y * (sN.xp.y - op.y) + w.xm.y * (op.y - sN.xm.y));
+    v[1].y -= alpha * (ow.w * (op.w - op.y) + w.ym1 * (op.y - sN.ym1));
+    v[1].z -= alpha * (w.zp0 * (sN.zp0 - op.y) + ow.x * (op.y - op.x));
+    v[2].x -= alpha * (w.xp.z * (sN.xp.z - op.z) + w.xm.z * (op.z - sN.xm.z));
+    v[2].y -= alpha * (w.yp0 * (sN.yp0 - op.z) + ow.x * (op.z - op.x));
+    v[2].z -= alpha * (ow.w * (op.w - op.z) + w.zm1 * (op.z - sN.zm1));
+    v[3].x -= alpha * (w.xp.w * (sN.xp.w - op.w) + w.xm.w * (op.w - sN.xm.w));
+    v[3].y -= alpha * (w.yp1 * (sN.yp1 - op.w) + ow.y * (op.w - op.y));
+    v[3].z -= alpha * (w.zp1 * (sN.zp1 - op.w) + ow.z * (op.w - op.z));
+    const size_t c0 = (size_t)b * kBV + 4 * t;
+    if (leaf) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) vw[c0 + k] = v[k];
+    }
+    float ax = 0.f, ay = 0.f, az = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { ax += v[k].x; ay += v[k].y; az += v[k].z; }
+    const unsigned src = (threadIdx.x & 31u) ^ 1u;
+    const float lx = __shfl_sync(0xFFFFFFFFu, ax, src), ly = __shfl_sync(0xFFFFFFFFu, ay, src), lz = __shfl_sync(0xFFFFFFFFu, az, src);
+    if (childless && (t & 1) && ps != kNone) {
+      ax = lx; ay = ly; az = lz;
+#pragma unroll
+      for (int k = 0; k < 4; k++) { ax += v[k].x; ay += v[k].y; az += v[k].z; }
+      float *dst = reinterpret_cast<float *>(vw + ((size_t)kSV * ps + (t >> 1)));
+      dst[0] = ax * .125f; dst[1] = ay * .125f; dst[2] = az * .125f;
+    }
+  }
+}
+
 }  // namespace dcg

@@ -433,11 +433,11 @@ __global__ void __launch_bounds__(kCTA4) k_dc_apply_pressure4(Pool T, KParams P,
   if (!__any_sync(0xFFFFFFFFu, active)) return;
   const size_t c0 = (size_t)b * kBV + 4 * t;
   const float4 op = *reinterpret_cast<const float4 *>(p + c0);
-  const float4 ow = *reinterpret_cast<const float4 *>(fl + c0);
   const uint32_t child = T.child[(size_t)b * 8 + (t >> 1)];
   float4 v[4];
 #pragma unroll
   for (int k = 0; k < 4; k++) v[k] = vw[c0 + k];
+  const float4 ow = make_float4(v[0].w, v[1].w, v[2].w, v[3].w);  // the cells' own fluidity travels with the velocity (== fl[c0..c0+3])
   const QuadGhosts q = quad_ghosts(T, b, t);
   const QuadNbr s = quad_neighbours(p, op, t, q);
   const QuadNbr w = quad_neighbours(fl, ow, t, q);
@@ -496,29 +496,72 @@ __device__ __forceinline__ uint32_t face_neighbour_cell(const Pool &T, uint32_t 
   if (fd[6] & kFdIrregular) return T.face[(size_t)b * 96 + 16 * f + 4 * a + bb];
   return fd_ghost(fd[f], fd[6 + f], f >> 1, a, bb);
 }
-// value of the neighbour of cell (X,Y,Z) of block b across direction f (-x,+x,-y,+y,-z,+z)
-__device__ __forceinline__ float neighbour_value(const Pool &T, const float *src, uint32_t b, int X, int Y, int Z, int f) {
+// value of the neighbour of cell (X,Y,Z) of block b across direction f (-x,+x,-y,+y,-z,+z); src[0] = cell `base`
+__device__ __forceinline__ float neighbour_value(const Pool &T, const float *src, uint32_t base, uint32_t b, int X, int Y, int Z, int f) {
   int c[3] = {X, Y, Z};
   const int axis = f >> 1;
   c[axis] += (f & 1) ? 1 : -1;
-  if ((unsigned)c[axis] < (unsigned)kBW) return src[b * kBV + cell_bits(c[0], c[1], c[2])];
+  if ((unsigned)c[axis] < (unsigned)kBW) return src[b * kBV + cell_bits(c[0], c[1], c[2]) - base];
   const int a = axis == 0 ? Y : X, bb = axis == 2 ? Y : Z;
-  return src[face_neighbour_cell(T, b, f, a, bb)];
+  return src[face_neighbour_cell(T, b, f, a, bb) - base];
 }
-__device__ __forceinline__ void coarse_sweep(const Pool &T, const KParams &P, int level, const float *in, float *out, const float *div) {
+__device__ __forceinline__ void coarse_sweep(const Pool &T, const KParams &P, int level, const float *in, float *out, const float *div,
+                                             uint32_t base) {
   const float alpha = (float)((1 << level) * (1 << level)) * P.dx * P.dx;
   const uint32_t n = T.loads[level] * kBV;
   for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
     const uint32_t b = T.offsets[level] + (i >> 6), c = i & 63u;
     const int X = cell_x(c), Y = cell_y(c), Z = cell_z(c);
-    const float l = neighbour_value(T, in, b, X, Y, Z, 0), r = neighbour_value(T, in, b, X, Y, Z, 1);
-    const float dn = neighbour_value(T, in, b, X, Y, Z, 2), up = neighbour_value(T, in, b, X, Y, Z, 3);
-    const float bk = neighbour_value(T, in, b, X, Y, Z, 4), fr = neighbour_value(T, in, b, X, Y, Z, 5);
-    out[b * kBV + c] = (l + r + dn + up + bk + fr - alpha * div[b * kBV + c]) / 6.f;
+    const float l = neighbour_value(T, in, base, b, X, Y, Z, 0), r = neighbour_value(T, in, base, b, X, Y, Z, 1);
+    const float dn = neighbour_value(T, in, base, b, X, Y, Z, 2), up = neighbour_value(T, in, base, b, X, Y, Z, 3);
+    const float bk = neighbour_value(T, in, base, b, X, Y, Z, 4), fr = neighbour_value(T, in, base, b, X, Y, Z, 5);
+    out[b * kBV + c - base] = (l + r + dn + up + bk + fr - alpha * div[b * kBV + c - base]) / 6.f;
   }
 }
+// kShared: pressure, t_pressure and divergence of the levels >= finest (the slot range [offsets[finest], end),
+// `ncell` cells; their ghosts never leave it: a ghost lies in the same or a coarser level) live in shared memory
+// for the whole cascade, together with a table of the six neighbour cells of every cell (16-bit offsets into the
+// range, resolved once per launch through the face descriptors).  The single CTA is bound by instruction issue,
+// not by latency: resolving neighbours on every sweep cost ~200 instructions per cell, the table makes a sweep
+// 6 index + 6 value shared-memory loads.  The host falls back to the global-memory instantiation when the range
+// does not fit (ncell > 65535 or 24 B * ncell > kCoarseSmemMax).
+template <bool kShared>
 __global__ void __launch_bounds__(1024) k_dc_coarse_cascade(Pool T, KParams P, int finest, int prolong_coarsest, int pairs_coarsest,
-                                                            int pairs_level, int prolong_levels, float *p, float *tp, const float *div) {
+                                                            int pairs_level, int prolong_levels, float *gp, float *gtp, const float *gdiv,
+                                                            uint32_t ncell) {
+  extern __shared__ __align__(16) float coarse_smem[];
+  const uint32_t base = kShared ? T.offsets[finest] * kBV : 0u;
+  float *p = gp, *tp = gtp;
+  const float *div = gdiv;
+  uint16_t *nb = nullptr;
+  if (kShared) {
+    p = coarse_smem; tp = coarse_smem + ncell;
+    float *sdiv = coarse_smem + 2 * (size_t)ncell;
+    nb = reinterpret_cast<uint16_t *>(coarse_smem + 3 * (size_t)ncell);
+    for (uint32_t i = threadIdx.x; i < ncell; i += blockDim.x) {
+      p[i] = gp[base + i]; tp[i] = gtp[base + i]; sdiv[i] = gdiv[base + i];
+    }
+    div = sdiv;
+    for (int level = T.levels - 1; level >= finest; level--) {
+      const uint32_t n = T.loads[level] * kBV;
+      for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint32_t b = T.offsets[level] + (i >> 6), c = i & 63u;
+        const int X = cell_x(c), Y = cell_y(c), Z = cell_z(c);
+        const uint32_t o = b * kBV + c - base;
+#pragma unroll
+        for (int f = 0; f < 6; f++) {
+          int cc[3] = {X, Y, Z};
+          const int axis = f >> 1;
+          cc[axis] += (f & 1) ? 1 : -1;
+          uint32_t id;
+          if ((unsigned)cc[axis] < (unsigned)kBW) id = b * kBV + cell_bits(cc[0], cc[1], cc[2]);
+          else id = face_neighbour_cell(T, b, f, axis == 0 ? Y : X, axis == 2 ? Y : Z);
+          nb[6 * o + f] = (uint16_t)(id - base);
+        }
+      }
+    }
+    __syncthreads();
+  }
   for (int level = T.levels - 1; level >= finest; level--) {
     const bool top = level == T.levels - 1;
     if (top ? prolong_coarsest : prolong_levels) {  // k_dcgrid_prolongate, dcgrid_multigrid_solver.cu:43-76
@@ -532,49 +575,74 @@ __global__ void __launch_bounds__(1024) k_dc_coarse_cascade(Pool T, KParams P, i
         const int idx = kAA * (1 + (int)((ps >> 2) & 1u) * 2 + (X >> 1)) + kAW * (1 + (int)((ps >> 1) & 1u) * 2 + (Y >> 1)) +
                         (1 + (int)(ps & 1u) * 2 + (Z >> 1));
         const int ii = (X & 1) ? kAA : -kAA, jj = (Y & 1) ? kAW : -kAW, kk = (Z & 1) ? 1 : -1;
-        const float p000 = p[pa[idx]], p001 = p[pa[idx + kk]], p010 = p[pa[idx + jj]], p100 = p[pa[idx + ii]];
-        const float p011 = p[pa[idx + jj + kk]], p101 = p[pa[idx + ii + kk]], p110 = p[pa[idx + ii + jj]], p111 = p[pa[idx + ii + jj + kk]];
-        p[b * kBV + c] = (27.f * p000 + 9.f * (p001 + p010 + p100) + 3.f * (p011 + p101 + p110) + p111) / 64.f;
+        const float p000 = p[pa[idx] - base], p001 = p[pa[idx + kk] - base], p010 = p[pa[idx + jj] - base], p100 = p[pa[idx + ii] - base];
+        const float p011 = p[pa[idx + jj + kk] - base], p101 = p[pa[idx + ii + kk] - base], p110 = p[pa[idx + ii + jj] - base],
+                    p111 = p[pa[idx + ii + jj + kk] - base];
+        p[b * kBV + c - base] = (27.f * p000 + 9.f * (p001 + p010 + p100) + 3.f * (p011 + p101 + p110) + p111) / 64.f;
       }
       __syncthreads();
     }
     const int pairs = top ? pairs_coarsest : pairs_level;
-    for (int s = 0; s < pairs; s++) {
-      coarse_sweep(T, P, level, p, tp, div);
+    for (int s = 0; s < 2 * pairs; s++) {
+      const float *in = (s & 1) ? tp : p;
+      float *out = (s & 1) ? p : tp;
+      if (kShared) {
+        const float alpha = (float)((1 << level) * (1 << level)) * P.dx * P.dx;
+        const uint32_t o0 = T.offsets[level] * kBV - base, n = T.loads[level] * kBV;
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+          const uint32_t o = o0 + i;
+          const uint16_t *q = nb + 6 * o;
+          out[o] = div6(in[q[0]] + in[q[1]] + in[q[2]] + in[q[3]] + in[q[4]] + in[q[5]] - alpha * div[o]);
+        }
+      } else {
+        coarse_sweep(T, P, level, in, out, div, base);
+      }
       __syncthreads();
-      coarse_sweep(T, P, level, tp, p, div);
-      __syncthreads();
+    }
+  }
+  if (kShared) {
+    for (uint32_t i = threadIdx.x; i < ncell; i += blockDim.x) {
+      gp[base + i] = p[i]; gtp[base + i] = tp[i];
     }
   }
 }
 
-// accumulate<T> (dcgrid_structure.cu:188-222) for the small levels first..levels-2, fine -> coarse, one CTA
-__global__ void __launch_bounds__(1024) k_dc_accumulate_coarse(Pool T, int first, float4 *vw, float *ch) {
+// accumulate<T> (dcgrid_structure.cu:188-222) for the small levels first..levels-2, fine -> coarse, in ONE launch:
+// a thread-block cluster of kAccClusterCTAs CTAs (one subblock per thread and level at 512^3), levels separated by
+// the hardware cluster barrier (release/acquire at cluster scope orders the global stores of one level before the
+// loads of the next).
+constexpr int kAccClusterCTAs = 8, kAccClusterThreads = 512;
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__global__ void __cluster_dims__(kAccClusterCTAs, 1, 1) __launch_bounds__(kAccClusterThreads)
+    k_dc_accumulate_coarse(Pool T, int first, float4 *vw, float *ch) {
+  const uint32_t rank = blockIdx.x * kAccClusterThreads + threadIdx.x, stride = kAccClusterCTAs * kAccClusterThreads;
   for (int level = first; level < T.levels - 1; level++) {
     const uint32_t n = 8 * T.loads[level];
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+    for (uint32_t i = rank; i < n; i += stride) {
       const uint32_t sb = 8 * T.offsets[level] + i, b = sb / 8;
       const uint32_t ps = T.parent[b];
       if (ps == kNone) continue;
       if (vw) {
         const float4 *c = vw + (size_t)kSV * sb;
+        float4 v[kSV];
+#pragma unroll
+        for (int k = 0; k < kSV; k++) v[k] = c[k];
         float ax = 0.f, ay = 0.f, az = 0.f;
 #pragma unroll
-        for (int k = 0; k < kSV; k++) {
-          const float4 v = c[k];
-          ax += v.x; ay += v.y; az += v.z;
-        }
+        for (int k = 0; k < kSV; k++) { ax += v[k].x; ay += v[k].y; az += v[k].z; }
         float *dst = reinterpret_cast<float *>(vw + ((size_t)kSV * ps + (sb % 8)));
         dst[0] = ax * .125f; dst[1] = ay * .125f; dst[2] = az * .125f;
       } else {
-        const float *c = ch + (size_t)kSV * sb;
+        const float4 lo = *reinterpret_cast<const float4 *>(ch + (size_t)kSV * sb), hi = *reinterpret_cast<const float4 *>(ch + (size_t)kSV * sb + 4);
         float a = 0.f;
-#pragma unroll
-        for (int k = 0; k < kSV; k++) a += c[k];
+        a += lo.x; a += lo.y; a += lo.z; a += lo.w; a += hi.x; a += hi.y; a += hi.z; a += hi.w;
         ch[(size_t)kSV * ps + (sb % 8)] = a * .125f;
       }
     }
-    __syncthreads();
+    cluster_sync_all();
   }
 }
 

@@ -1,0 +1,5 @@
+set -x
+export LD_LIBRARY_PATH=/usr/local/cuda/lib64:$LD_LIBRARY_PATH
+timeout 300 ncu --profile-from-start off --metrics gpu__time_duration.sum --cache-control none --clock-control none --csv --log-file gpurun_out/r1d_launches_steady_step.csv python tools/trace_step.py --steps 2 > gpurun_out/trace.log 2>&1
+tail -2 gpurun_out/trace.log
+wc -l gpurun_out/r1d_launches_steady_step.csv
