@@ -76,8 +76,10 @@ struct DCGridSim : dcg_sim {
   size_t sort_tmp_bytes = 0;
   uint32_t n_order = 0;  // padded to a multiple of kBPC
   int order_mode = 1;    // 0 = pool-slot order, 1 = Morton
+  uint32_t *d_plist = nullptr, *d_pcount = nullptr, *h_pcount = nullptr;  // blocks with children, per level (k_dc_list_parents)
+  bool prolong_staged = true;
   bool use_stencil_pipe = true;  // k_dc_divergence_pipe / k_dc_apply_pipe instead of the one-CTA-per-tile kernels
-  int div_pipe_ctas = 0, apply_pipe_ctas = 0, apply_min_blocks = 3;
+  int div_pipe_ctas = 0, apply_pipe_ctas = 0, apply_min_blocks = 2;
   bool coarse_in_smem = true;
   static constexpr size_t kCoarseSmemMax = 200 * 1024;
   bool skip_dead_zeroing = true;  // k_dc_divergence4: no pressure clears that project() never reads
@@ -99,6 +101,8 @@ struct DCGridSim : dcg_sim {
     cudaFree(d_flags); cudaFree(d_free); cudaFree(d_touched); cudaFree(d_to_move); cudaFree(d_dest); cudaFree(d_counters); cudaFree(d_flag_bits); cudaFree(d_summary);
     if (h_summary) cudaFreeHost(h_summary);
     cudaFree(d_new_posl); cudaFree(d_sub_scores); cudaFree(d_block_scores);
+    cudaFree(d_plist); cudaFree(d_pcount);
+    if (h_pcount) cudaFreeHost(h_pcount);
     cudaFree(d_order); cudaFree(d_order_keys[0]); cudaFree(d_order_keys[1]); cudaFree(d_order_vals); cudaFree(d_sort_tmp);
     for (int i = 0; i < 2; i++) { cudaFree(vw[i]); cudaFree(q[i]); }
     cudaFree(fl); cudaFree(p); cudaFree(tp); cudaFree(div); cudaFree(scratch); cudaFree(d_partial);
@@ -157,6 +161,9 @@ struct DCGridSim : dcg_sim {
     for (int l = 0; l < levels; l++) { T.offsets[l] = (uint32_t)offsets[l]; T.max_blocks[l] = (uint32_t)max_blocks[l]; }
     DCG_CUDA_TRY(cudaMalloc(&T.posl, (size_t)M * sizeof(int4)));
     DCG_CUDA_TRY(cudaMalloc(&T.parent, ((size_t)M + kB4) * 4));  // padded: the stencil rings stream kB4 entries per tile
+    DCG_CUDA_TRY(cudaMalloc(&d_plist, (size_t)M * 4));
+    DCG_CUDA_TRY(cudaMalloc(&d_pcount, kMaxLevels * 4));
+    DCG_CUDA_TRY(cudaMallocHost(&h_pcount, kMaxLevels * 4));
     DCG_CUDA_TRY(cudaMalloc(&d_order, ((size_t)M + kBPC) * 4));
     DCG_CUDA_TRY(cudaMalloc(&d_order_keys[0], (size_t)M * 4));
     DCG_CUDA_TRY(cudaMalloc(&d_order_keys[1], (size_t)M * 4));
@@ -210,7 +217,7 @@ struct DCGridSim : dcg_sim {
       jacobi_pipe_ctas = per_sm * sm_count;
       if (const char *e = getenv("DCG_ADVECT")) use_advect_pipe = std::string(e) != "legacy";
       if (const char *e = getenv("DCG_ADVECT_ORDER")) order_mode = std::string(e) == "slot" ? 0 : 1;
-      if (const char *e = getenv("DCG_STENCIL")) use_stencil_pipe = std::string(e) != "legacy";
+      if (const char *e = getenv("DCG_STENCIL")) use_stencil_pipe = prolong_staged = std::string(e) != "legacy";
       {
         int per_sm = 0;
         DCG_CUDA_TRY(cudaFuncSetAttribute(k_dc_divergence_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDivPipeSmem));
@@ -218,7 +225,7 @@ struct DCGridSim : dcg_sim {
         if (per_sm < 1) return fail(DCG_ERR_CUDA, "k_dc_divergence_pipe does not fit on an SM");
         if (const char *e = getenv("DCG_STENCIL_CTAS")) per_sm = std::max(1, std::min(per_sm, atoi(e)));
         div_pipe_ctas = per_sm * sm_count;
-        if (const char *e = getenv("DCG_APPLY_MINB")) apply_min_blocks = atoi(e) == 2 ? 2 : 3;
+        if (const char *e = getenv("DCG_APPLY_MINB")) apply_min_blocks = atoi(e) == 3 ? 3 : 2;
         const void *afn = apply_min_blocks == 2 ? (const void *)k_dc_apply_pipe<2> : (const void *)k_dc_apply_pipe<3>;
         DCG_CUDA_TRY(cudaFuncSetAttribute(afn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kApplyPipeSmem));
         DCG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, afn, kStencilThreads, kApplyPipeSmem));
@@ -326,7 +333,11 @@ struct DCGridSim : dcg_sim {
     cub::DeviceRadixSort::SortPairs(d_sort_tmp, bytes, d_order_keys[0], d_order_keys[1], d_order_vals, d_order, (int)M, 0, 32, stream);
     n_order = (uint32_t)((n + kBPC - 1) / kBPC * kBPC);
     if (n_order > n) k_dc_order_pad<<<1, 256, 0, stream>>>(d_order, (uint32_t)n, n_order);
-    launches += 2;
+    cudaMemsetAsync(d_pcount, 0, kMaxLevels * 4, stream);
+    k_dc_list_parents<<<blocks_for(M, 256), 256, 0, stream>>>(T, d_plist, d_pcount);
+    cudaMemcpyAsync(h_pcount, d_pcount, kMaxLevels * 4, cudaMemcpyDeviceToHost, stream);
+    cudaStreamSynchronize(stream);
+    launches += 3;
   }
   uint32_t finer_full_mask() const {
     uint32_t m = 0;
@@ -568,8 +579,16 @@ struct DCGridSim : dcg_sim {
     const int tail = small_levels_from(512);
     for (int l = fused ? 1 : 0; l < levels - 1 && l < tail; l++) {
       if (loads[l] == 0) continue;
-      if (v) k_dc_accumulate_velocity<<<blocks_for(8 * loads[l], 256), 256, 0, stream>>>(T, l, v, fused ? 1 : 0);
-      else k_dc_accumulate_scalar<<<blocks_for(8 * loads[l], 256), 256, 0, stream>>>(T, l, ch, fused ? 1 : 0);
+      if (fused) {  // only blocks with children are left (k_dc_list_parents)
+        const uint32_t n = h_pcount[l];
+        if (n == 0) continue;
+        if (v) k_dc_accumulate_velocity_list<<<blocks_for(8 * (size_t)n, 256), 256, 0, stream>>>(T, d_plist + offsets[l], n, v);
+        else k_dc_accumulate_scalar_list<<<blocks_for(8 * (size_t)n, 256), 256, 0, stream>>>(T, d_plist + offsets[l], n, ch);
+      } else if (v) {
+        k_dc_accumulate_velocity<<<blocks_for(8 * loads[l], 256), 256, 0, stream>>>(T, l, v, 0);
+      } else {
+        k_dc_accumulate_scalar<<<blocks_for(8 * loads[l], 256), 256, 0, stream>>>(T, l, ch, 0);
+      }
       launches++;
     }
     if (tail < levels - 1) {
@@ -651,6 +670,11 @@ struct DCGridSim : dcg_sim {
     jacobi_sweep(l, p, tp);
     jacobi_sweep(l, tp, p);
   }
+  void launch_prolongate(int l) {
+    if (prolong_staged) k_dc_prolongate_staged<<<blocks_for(loads[l], kB4), kCTA4, 0, stream>>>(T, l, p);
+    else k_dc_prolongate4<<<blocks_for(loads[l], kB4), kCTA4, 0, stream>>>(T, l, p);
+    launches++;
+  }
   void launch_divergence(int zero_from) {
     const unsigned tiles = blocks_for(M, kB4);
     if (use_stencil_pipe)
@@ -697,8 +721,7 @@ struct DCGridSim : dcg_sim {
     launch_coarse_cascade(cf, 0, project_coarsest_pairs, project_level_pairs, 1);
     for (int l = cf - 1; l >= 0; l--) {
       if (loads[l] == 0) continue;
-      k_dc_prolongate4<<<blocks_for(loads[l], kB4), kCTA4, 0, stream>>>(T, l, p);
-      launches++;
+      launch_prolongate(l);
       for (int i = 0; i < project_level_pairs; i++) jacobi_pair(l);
     }
     apply_stage();
@@ -802,7 +825,8 @@ struct DCGridSim : dcg_sim {
         k_dc_accumulate_velocity<<<blocks_for(8 * loads[level], 256), 256, 0, stream>>>(T, level, vw[cur_v], 0);
         bytes = 13.5 * cl;
       } else if (st == "prolongate") {
-        k_dc_prolongate4<<<blocks_for(loads[level], kB4), kCTA4, 0, stream>>>(T, level, p);
+        launch_prolongate(level);
+        launches--;
         bytes = 4.5 * cl;
       } else return fail(DCG_ERR_INVALID, "bench_stage: unknown stage %s", stage);
       launches++;

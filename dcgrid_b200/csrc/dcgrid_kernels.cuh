@@ -173,6 +173,44 @@ __global__ void __launch_bounds__(256) k_dc_accumulate_scalar(Pool T, int level,
   ch[(size_t)kSV * ps + (sb % 8)] = a * .125f;
 }
 
+// Blocks that still need a restriction pass when the producing kernel restricted the childless ones itself:
+// the blocks WITH children (and a parent), listed per level at plist[offsets[level] ...) whenever the topology
+// changes, so that a pass costs 8 threads per listed block instead of a child-link probe per pool slot
+// (level 1 at 512^3: 30 k of 243 k blocks).  List order is arbitrary: every subblock is independent.
+__global__ void __launch_bounds__(256) k_dc_list_parents(Pool T, uint32_t *__restrict__ plist, uint32_t *__restrict__ pcount) {
+  const uint32_t b = blockIdx.x * 256 + threadIdx.x;
+  if (b >= T.M) return;
+  const int level = T.posl[b].w;
+  if (level == kFree || T.parent[b] == kNone || !block_has_children(T, b)) return;
+  plist[T.offsets[level] + atomicAdd(&pcount[level], 1u)] = b;
+}
+__global__ void __launch_bounds__(256) k_dc_accumulate_velocity_list(Pool T, const uint32_t *__restrict__ list, uint32_t n, float4 *__restrict__ vw) {
+  const uint32_t t = blockIdx.x * 256 + threadIdx.x;
+  if (t >= 8 * n) return;
+  const uint32_t b = list[t >> 3], sb = 8 * b + (t & 7u);
+  const uint32_t ps = T.parent[b];
+  const float4 *c = vw + (size_t)kSV * sb;
+  float4 v[kSV];
+#pragma unroll
+  for (int i = 0; i < kSV; i++) v[i] = c[i];
+  float ax = 0.f, ay = 0.f, az = 0.f;
+#pragma unroll
+  for (int i = 0; i < kSV; i++) { ax += v[i].x; ay += v[i].y; az += v[i].z; }
+  float *dst = reinterpret_cast<float *>(vw + ((size_t)kSV * ps + (sb % 8)));
+  dst[0] = ax * .125f; dst[1] = ay * .125f; dst[2] = az * .125f;
+}
+__global__ void __launch_bounds__(256) k_dc_accumulate_scalar_list(Pool T, const uint32_t *__restrict__ list, uint32_t n, float *__restrict__ ch) {
+  const uint32_t t = blockIdx.x * 256 + threadIdx.x;
+  if (t >= 8 * n) return;
+  const uint32_t b = list[t >> 3], sb = 8 * b + (t & 7u);
+  const uint32_t ps = T.parent[b];
+  const float4 lo = *reinterpret_cast<const float4 *>(ch + (size_t)kSV * sb);
+  const float4 hi = *reinterpret_cast<const float4 *>(ch + (size_t)kSV * sb + 4);
+  float a = 0.f;
+  a += lo.x; a += lo.y; a += lo.z; a += lo.w; a += hi.x; a += hi.y; a += hi.z; a += hi.w;
+  ch[(size_t)kSV * ps + (sb % 8)] = a * .125f;
+}
+
 // ======================================================================================
 // adaptation (dcgrid_adaptation.cu)
 // ======================================================================================
@@ -544,6 +582,48 @@ __global__ void __launch_bounds__(kCTA4) k_dc_prolongate4(Pool T, int level, flo
   o.z = prolong_one(c, 1, -1);
   o.w = prolong_one(c, 1, 1);
   *reinterpret_cast<float4 *>(p + (size_t)b * kBV + 4 * t) = o;
+}
+
+// Same, with the 4^3 coarse cells a child block interpolates from (its parent subblock's 2^3 cells and their
+// ring) staged once per block in shared memory: 4 index + 4 value loads per thread instead of 18 + 18 — the
+// gather version keeps the L1 data pipe 85 % busy for 4.5 B/cell of useful traffic (profiles/README.md r1d).
+__global__ void __launch_bounds__(kCTA4) k_dc_prolongate_staged(Pool T, int level, float *__restrict__ p) {
+  __shared__ float sc[kB4][64];
+  const uint32_t g = threadIdx.x >> 4;
+  const int t = threadIdx.x & 15;
+  const uint32_t li = blockIdx.x * kB4 + g;
+  const bool active = li < T.loads[level];
+  const uint32_t b = T.offsets[level] + li;
+  const uint32_t ps = active ? T.parent[b] : kNone;
+  const bool ok = active && ps != kNone;
+  if (ok) {
+    const uint32_t *pa = T.apron + (size_t)(ps / 8) * kAV;
+    const int o = kAA * (int)((ps >> 2) & 1u) * 2 + kAW * (int)((ps >> 1) & 1u) * 2 + (int)(ps & 1u) * 2;  // cube origin in the apron
+    uint32_t id[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) id[j] = pa[o + kAA * j + kAW * (t >> 2) + (t & 3)];
+#pragma unroll
+    for (int j = 0; j < 4; j++) sc[g][16 * j + t] = p[id[j]];
+  }
+  __syncthreads();
+  if (!ok) return;
+  int X, Y0, Z0;
+  quad_coords(t, X, Y0, Z0);
+  const int base = 16 * (1 + (X >> 1)) + 4 * (1 + (Y0 >> 1)) + (1 + (Z0 >> 1));
+  const int i = (X & 1) ? 16 : -16;
+  float c[2][3][3];
+#pragma unroll
+  for (int di = 0; di < 2; di++)
+#pragma unroll
+    for (int dj = -1; dj <= 1; dj++)
+#pragma unroll
+      for (int dk = -1; dk <= 1; dk++) c[di][dj + 1][dk + 1] = sc[g][base + di * i + 4 * dj + dk];
+  float4 o4;
+  o4.x = prolong_one(c, -1, -1);
+  o4.y = prolong_one(c, -1, 1);
+  o4.z = prolong_one(c, 1, -1);
+  o4.w = prolong_one(c, 1, 1);
+  *reinterpret_cast<float4 *>(p + (size_t)b * kBV + 4 * t) = o4;
 }
 
 // k_dcgrid_debug_stats, dcgrid_structure.cu:224-251: one thread per block, sequential i,j,k order
