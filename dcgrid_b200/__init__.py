@@ -12,4 +12,4 @@ from .simulation import (  # noqa: F401
     FluidSimulationDCGrid,
     FluidSimulationUniform,
 )
-from .sharding import FluidSimulationUniformSharded  # noqa: F401,E402
+from .sharding import FluidSimulationDCGridSharded, FluidSimulationUniformSharded  # noqa: F401,E402

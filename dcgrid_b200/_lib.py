@@ -50,6 +50,7 @@ SYMBOLS = {
     "dcg_algorithmic_bytes": (_int, [_vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_u64)]),
     "dcg_bench_stage": (_int, [_vp, ctypes.c_char_p, _int, _int, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double)]),
     "dcg_create_uniform_sharded": (_int, [_P, _int, _int, _int, _int, ctypes.POINTER(_vp)]),
+    "dcg_create_dcgrid_sharded": (_int, [_P, ctypes.c_uint64, _int, _int, _int, _int, ctypes.POINTER(_vp)]),
     "dcg_shard_handle_bytes": (_u64, []),
     "dcg_shard_export_handle": (_int, [_vp, _vp, _u64]),
     "dcg_shard_import_handles": (_int, [_vp, _vp, _int]),

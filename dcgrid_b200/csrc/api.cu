@@ -91,6 +91,15 @@ int dcg_create_dcgrid(const dcg_sim_params *params, uint64_t max_num_blocks, int
   return finish_create(dcg_make_dcgrid(max_num_blocks), params, device, out);
 }
 
+int dcg_create_dcgrid_sharded(const dcg_sim_params *params, uint64_t max_num_blocks, int device, int rank, int world, int nlocal,
+                              dcg_sim **out) {
+  if (!params || !out) return DCG_ERR_INVALID;
+  *out = nullptr;
+  int rc = check_device(device);
+  if (rc != DCG_OK) return rc;
+  return finish_create(dcg_make_dcgrid_sharded(max_num_blocks, rank, world, nlocal), params, device, out);
+}
+
 int dcg_destroy(dcg_sim *sim) {
   NEED(sim);
   delete sim;

@@ -26,6 +26,7 @@
 
 #include "dcgrid_kernels.cuh"
 #include "dcgrid_pipe.cuh"
+#include "shard_vmm.h"
 #include "sim.h"
 
 namespace dcg {
@@ -71,12 +72,48 @@ struct DCGridSim : dcg_sim {
   // spec_velocity = that buffer is valid, i.e. nothing has touched velocity, topology or parameters since
   bool fuse_advect = true, spec_velocity = false;
   // processing order of the advection kernels: active slots sorted along a Morton curve (k_dc_order_keys)
-  uint32_t *d_order = nullptr, *d_order_keys[2] = {nullptr, nullptr}, *d_order_vals = nullptr;
+  uint32_t *d_order_keys[2] = {nullptr, nullptr}, *d_order_vals = nullptr;
   void *d_sort_tmp = nullptr;
   size_t sort_tmp_bytes = 0;
-  uint32_t n_order = 0;  // padded to a multiple of kBPC
   int order_mode = 1;    // 0 = pool-slot order, 1 = Morton
-  uint32_t *d_plist = nullptr, *d_pcount = nullptr, *h_pcount = nullptr;  // blocks with children, per level (k_dc_list_parents)
+  uint32_t *d_pcount = nullptr, *h_pcount = nullptr;  // scratch of k_dc_list_parents / k_dc_order_keys counts
+
+  // ---- slab decomposition --------------------------------------------------------------------
+  // The pool is cut into `unit`-slot pieces, each owned by one of `world` ranks (per level: contiguous, equal
+  // shares of the level's slot range).  A rank runs every field kernel on the tiles it owns; cells of other
+  // ranks are read / written in place: one process = all ranks on one device (nlocal == world, plain
+  // cudaMalloc), or one process per GPU (nlocal == 1) with the fields in a virtual range stitched from every
+  // rank's arena (shard_vmm.h), the same cell id addressing the same cell on every GPU over NVLink.  Topology
+  // (block pool, maps, descriptors, adaptation incl. the host selection) is replicated: every process keeps
+  // it and updates it identically.  Ranks run in lock step: a flag barrier over peer memory after each phase.
+  int world = 1, rank0 = 0, nlocal = 1;
+  bool vmm = false, ready = true;
+  uint32_t unit = 0, nunits = 0;
+  std::vector<uint8_t> unit_owner;
+  uint8_t *d_unit_owner = nullptr;
+  struct RankWork {
+    TileRuns all{};                 // absolute tiles (16 slots from slot 0) of the rank's units
+    std::vector<TileRuns> level;    // level-local tiles (16 slots from levelOffsets[l]) inside the active prefix
+    uint32_t *d_order = nullptr;    // Morton-ordered active slots of the rank, padded with kNone
+    uint32_t n_order = 0;
+    uint32_t *d_plist = nullptr;    // blocks with children, per level at [offsets[l] ...)
+    uint32_t pcount[kMaxLevels] = {0};
+  };
+  std::vector<RankWork> work;
+  // cross-process state (vmm)
+  vmm::Driver drv;
+  vmm::FdServer fd_server;
+  CUmemGenericAllocationHandle arena_handle[8] = {0};
+  bool arena_imported[8] = {false};
+  size_t gran = 0, arena_bytes = 0;
+  std::vector<size_t> arena_field_off;           // [rank * kFields + f]
+  std::vector<uint32_t> units_before;            // [unit]: units of the same owner before it
+  std::vector<uint32_t> units_of_rank;
+  static constexpr int kFields = 8;              // vw0 vw1 q0 q1 fl p tp div
+  CUdeviceptr field_va[kFields] = {0}, ctrl_va = 0;
+  size_t field_va_bytes[kFields] = {0};
+  uint32_t *d_epoch = nullptr, *d_barrier_err = nullptr;
+  uint64_t n_barriers = 0;
   bool prolong_staged = true;
   bool use_stencil_pipe = true;  // k_dc_divergence_pipe / k_dc_apply_pipe instead of the one-CTA-per-tile kernels
   int div_pipe_ctas = 0, apply_pipe_ctas = 0, apply_min_blocks = 2;
@@ -101,11 +138,20 @@ struct DCGridSim : dcg_sim {
     cudaFree(d_flags); cudaFree(d_free); cudaFree(d_touched); cudaFree(d_to_move); cudaFree(d_dest); cudaFree(d_counters); cudaFree(d_flag_bits); cudaFree(d_summary);
     if (h_summary) cudaFreeHost(h_summary);
     cudaFree(d_new_posl); cudaFree(d_sub_scores); cudaFree(d_block_scores);
-    cudaFree(d_plist); cudaFree(d_pcount);
+    cudaFree(d_pcount);
     if (h_pcount) cudaFreeHost(h_pcount);
-    cudaFree(d_order); cudaFree(d_order_keys[0]); cudaFree(d_order_keys[1]); cudaFree(d_order_vals); cudaFree(d_sort_tmp);
-    for (int i = 0; i < 2; i++) { cudaFree(vw[i]); cudaFree(q[i]); }
-    cudaFree(fl); cudaFree(p); cudaFree(tp); cudaFree(div); cudaFree(scratch); cudaFree(d_partial);
+    for (auto &w : work) { cudaFree(w.d_order); cudaFree(w.d_plist); }
+    cudaFree(d_unit_owner); cudaFree(d_epoch); cudaFree(d_barrier_err);
+    cudaFree(d_order_keys[0]); cudaFree(d_order_keys[1]); cudaFree(d_order_vals); cudaFree(d_sort_tmp);
+    if (vmm) {
+      cudaDeviceSynchronize();
+      fd_server.finish();
+      release_vmm();
+    } else {
+      for (int i = 0; i < 2; i++) { cudaFree(vw[i]); cudaFree(q[i]); }
+      cudaFree(fl); cudaFree(p); cudaFree(tp); cudaFree(div);
+    }
+    cudaFree(scratch); cudaFree(d_partial);
     if (h_partial) cudaFreeHost(h_partial);
     if (h_sub_scores) cudaFreeHost(h_sub_scores);
     if (h_block_scores) cudaFreeHost(h_block_scores);
@@ -161,15 +207,14 @@ struct DCGridSim : dcg_sim {
     for (int l = 0; l < levels; l++) { T.offsets[l] = (uint32_t)offsets[l]; T.max_blocks[l] = (uint32_t)max_blocks[l]; }
     DCG_CUDA_TRY(cudaMalloc(&T.posl, (size_t)M * sizeof(int4)));
     DCG_CUDA_TRY(cudaMalloc(&T.parent, ((size_t)M + kB4) * 4));  // padded: the stencil rings stream kB4 entries per tile
-    DCG_CUDA_TRY(cudaMalloc(&d_plist, (size_t)M * 4));
-    DCG_CUDA_TRY(cudaMalloc(&d_pcount, kMaxLevels * 4));
-    DCG_CUDA_TRY(cudaMallocHost(&h_pcount, kMaxLevels * 4));
-    DCG_CUDA_TRY(cudaMalloc(&d_order, ((size_t)M + kBPC) * 4));
+    DCG_TRY(setup_sharding());
+    DCG_CUDA_TRY(cudaMalloc(&d_pcount, (kMaxLevels + 1) * 4));
+    DCG_CUDA_TRY(cudaMallocHost(&h_pcount, (kMaxLevels + 1) * 4));
     DCG_CUDA_TRY(cudaMalloc(&d_order_keys[0], (size_t)M * 4));
     DCG_CUDA_TRY(cudaMalloc(&d_order_keys[1], (size_t)M * 4));
     DCG_CUDA_TRY(cudaMalloc(&d_order_vals, (size_t)M * 4));
-    DCG_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp_bytes, d_order_keys[0], d_order_keys[1], d_order_vals, d_order, (int)M, 0, 32,
-                                                 stream));
+    DCG_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp_bytes, d_order_keys[0], d_order_keys[1], d_order_vals, work[0].d_order, (int)M, 0,
+                                                 32, stream));
     DCG_CUDA_TRY(cudaMalloc(&d_sort_tmp, sort_tmp_bytes + 16));
     DCG_CUDA_TRY(cudaMalloc(&T.child, (size_t)M * 8 * 4));
     DCG_CUDA_TRY(cudaMalloc(&T.apron, (size_t)M * kAV * 4));
@@ -192,14 +237,18 @@ struct DCGridSim : dcg_sim {
     DCG_CUDA_TRY(cudaMalloc(&d_new_posl, (size_t)M * sizeof(int4)));
     DCG_CUDA_TRY(cudaMalloc(&d_sub_scores, ((size_t)M * 8 + 1) * 4));
     DCG_CUDA_TRY(cudaMalloc(&d_block_scores, (size_t)M * 4));
-    for (int i = 0; i < 2; i++) {
-      DCG_CUDA_TRY(cudaMalloc(&vw[i], cells * sizeof(float4)));
-      DCG_CUDA_TRY(cudaMalloc(&q[i], cells * 4));
+    if (!vmm) {
+      for (int i = 0; i < 2; i++) {
+        DCG_CUDA_TRY(cudaMalloc(&vw[i], cells * sizeof(float4)));
+        DCG_CUDA_TRY(cudaMalloc(&q[i], cells * 4));
+      }
+      DCG_CUDA_TRY(cudaMalloc(&fl, cells * 4));
+      DCG_CUDA_TRY(cudaMalloc(&p, cells * 4));
+      DCG_CUDA_TRY(cudaMalloc(&tp, cells * 4));
+      DCG_CUDA_TRY(cudaMalloc(&div, cells * 4));
+    } else {
+      DCG_TRY(create_arena());
     }
-    DCG_CUDA_TRY(cudaMalloc(&fl, cells * 4));
-    DCG_CUDA_TRY(cudaMalloc(&p, cells * 4));
-    DCG_CUDA_TRY(cudaMalloc(&tp, cells * 4));
-    DCG_CUDA_TRY(cudaMalloc(&div, cells * 4));
     scratch_floats = 3 * std::max(cells, (size_t)gx * gy * gz);
     DCG_CUDA_TRY(cudaMalloc(&scratch, scratch_floats * 4));
     DCG_CUDA_TRY(cudaMalloc(&d_partial, 1024 * sizeof(double)));
@@ -252,8 +301,217 @@ struct DCGridSim : dcg_sim {
       }
       if (const char *e = getenv("DCG_SNAKE")) snake = std::string(e) != "0";
       if (const char *e = getenv("DCG_JACOBI_CTAS")) jacobi_pipe_ctas = std::max(1, atoi(e)) * sm_count;
+      if (world > 1 && (!use_advect_pipe || !use_stencil_pipe || !use_pipe)) return fail(DCG_ERR_UNSUPPORTED, "the legacy kernel variants are single-GPU only");
     }
+    if (vmm) return DCG_OK;  // the caller exchanges handles; import_handles() maps the peers and resets
     return reset();
+  }
+
+  // ---- sharding: ownership, arenas, barriers ------------------------------------------------------------------
+  int level_of_slot(uint64_t b) const {
+    for (int l = 0; l < levels; l++)
+      if (b >= offsets[l] && b < offsets[l] + max_blocks[l]) return l;
+    return -1;
+  }
+  int setup_sharding() {
+    if (world < 1 || world > 8 || nlocal < 1 || rank0 < 0 || rank0 + nlocal > world) return fail(DCG_ERR_INVALID, "bad rank / world");
+    if (nlocal != 1 && nlocal != world) return fail(DCG_ERR_INVALID, "nlocal must be 1 (one rank per process) or world (all ranks in one process)");
+    vmm = world > 1 && nlocal == 1;
+    // ownership granularity: 2 MiB of the 4-byte fields in the stitched address space, one tile otherwise
+    unit = vmm ? 8192u : (uint32_t)kTile;
+    if (const char *e = getenv("DCG_SHARD_UNIT")) {
+      const uint32_t u = (uint32_t)atoi(e);
+      if (u == 0 || u % kTile || (vmm && u % 8192u)) return fail(DCG_ERR_INVALID, "DCG_SHARD_UNIT must be a multiple of %u", vmm ? 8192u : (uint32_t)kTile);
+      unit = u;
+    }
+    nunits = (uint32_t)((M64 + unit - 1) / unit);
+    unit_owner.assign(nunits, 0);
+    units_before.assign(nunits, 0);
+    units_of_rank.assign(world, 0);
+    for (uint32_t u = 0; u < nunits; u++) {
+      const uint64_t mid = std::min<uint64_t>((uint64_t)u * unit + unit / 2, M64 - 1);
+      const int l = level_of_slot(mid);
+      int r = 0;
+      if (l >= 0 && world > 1) r = (int)std::min<uint64_t>(world - 1, (mid - offsets[l]) * (uint64_t)world / max_blocks[l]);
+      unit_owner[u] = (uint8_t)r;
+      units_before[u] = units_of_rank[r]++;
+    }
+    DCG_CUDA_TRY(cudaMalloc(&d_unit_owner, nunits));
+    DCG_CUDA_TRY(cudaMemcpy(d_unit_owner, unit_owner.data(), nunits, cudaMemcpyHostToDevice));
+    work.resize(nlocal);
+    for (auto &w : work) {
+      DCG_CUDA_TRY(cudaMalloc(&w.d_order, ((size_t)M + kBPC) * 4));
+      DCG_CUDA_TRY(cudaMalloc(&w.d_plist, (size_t)M * 4));
+      w.level.assign(levels, TileRuns{});
+    }
+    return DCG_OK;
+  }
+  // runs of tiles [t0, t1) (tile t = slots base + 16 t ...) whose first slot belongs to a unit of `rank`
+  TileRuns tile_runs(uint64_t base, uint32_t t0, uint32_t t1, int rank) const {
+    TileRuns R{};
+    R.n = 0;
+    R.pre[0] = 0;
+    uint32_t t = t0;
+    while (t < t1) {
+      const uint32_t u = (uint32_t)((base + (uint64_t)t * kTile) / unit);
+      // tiles up to the end of this unit share its owner
+      const uint64_t unit_end = (uint64_t)(u + 1) * unit;
+      uint32_t te = (uint32_t)std::min<uint64_t>(t1, (unit_end - base + kTile - 1) / kTile);
+      if (te <= t) te = t + 1;
+      if (unit_owner[std::min(u, nunits - 1)] == rank) {
+        if (R.n > 0 && R.first[R.n - 1] + (R.pre[R.n] - R.pre[R.n - 1]) == t) {
+          R.pre[R.n] += te - t;  // extends the previous run
+        } else if (R.n < kMaxRuns) {
+          R.first[R.n] = t;
+          R.pre[R.n + 1] = R.pre[R.n] + (te - t);
+          R.n++;
+        }
+      }
+      t = te;
+    }
+    if (R.n == 0) { R.n = 1; R.first[0] = 0; R.pre[1] = 0; }
+    return R;
+  }
+  template <class F>
+  void each_rank(F f) {
+    for (int lr = 0; lr < nlocal; lr++) f(rank0 + lr, work[lr]);
+  }
+  bool has_rank0() const { return rank0 == 0; }
+
+  BarrierPeers peers{};
+  // lock-step barrier over peer memory after a phase whose results other ranks read (no-op inside one process:
+  // stream order is the barrier)
+  void barrier() {
+    if (!vmm) return;
+    k_dcs_barrier<<<1, 32, 0, stream>>>(peers, rank0, world, d_epoch, d_barrier_err);
+    launches++;
+    n_barriers++;
+  }
+
+  int create_arena() {
+    if (!drv.load()) return fail(DCG_ERR_CUDA, "CUDA virtual memory management entry points are not available");
+    CUmemAllocationProp prop = vmm::device_prop(device);
+    if (drv.memGranularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_MINIMUM) != CUDA_SUCCESS || gran == 0) return fail(DCG_ERR_CUDA, "cuMemGetAllocationGranularity failed");
+    if (((size_t)unit * kBV * 4) % gran) return fail(DCG_ERR_UNSUPPORTED, "allocation granularity %zu does not divide a unit", gran);
+    // arena of rank r: [control block: gran][field 0: its units][field 1] ... (identical arithmetic on every rank)
+    arena_field_off.assign((size_t)world * kFields, 0);
+    size_t mine = 0;
+    for (int r = 0; r < world; r++) {
+      size_t o = gran;
+      for (int f = 0; f < kFields; f++) {
+        arena_field_off[(size_t)r * kFields + f] = o;
+        o += (size_t)units_of_rank[r] * unit * kBV * (f < 2 ? 16 : 4);
+      }
+      if (r == rank0) mine = o;
+    }
+    arena_bytes = mine;
+    if (drv.memCreate(&arena_handle[rank0], arena_bytes, &prop, 0) != CUDA_SUCCESS)
+      return fail(DCG_ERR_CUDA, "cuMemCreate(%zu bytes) failed", arena_bytes);
+    arena_imported[rank0] = true;
+    int fd = -1;
+    if (drv.memExport(&fd, arena_handle[rank0], CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0) != CUDA_SUCCESS)
+      return fail(DCG_ERR_CUDA, "cuMemExportToShareableHandle failed");
+    // this rank's control block is mapped and cleared BEFORE the arena is published: a peer may announce its first
+    // barrier epoch as soon as it has imported the arena
+    if (drv.memReserve(&ctrl_va, (size_t)world * gran, gran, 0, 0) != CUDA_SUCCESS) return fail(DCG_ERR_CUDA, "cuMemAddressReserve failed");
+    DCG_TRY(map_piece(ctrl_va + (size_t)rank0 * gran, gran, 0, rank0));
+    {
+      CUmemAccessDesc acc = access_desc();
+      if (drv.memSetAccess(ctrl_va + (size_t)rank0 * gran, gran, &acc, 1) != CUDA_SUCCESS) return fail(DCG_ERR_CUDA, "cuMemSetAccess failed");
+    }
+    DCG_CUDA_TRY(cudaMemset(reinterpret_cast<void *>(ctrl_va + (size_t)rank0 * gran), 0, 4096));
+    DCG_CUDA_TRY(cudaDeviceSynchronize());
+    if (!fd_server.start(fd, world - 1)) return fail(DCG_ERR_CUDA, "cannot open the descriptor socket");
+    ready = false;
+    return DCG_OK;
+  }
+  CUmemAccessDesc access_desc() const {
+    CUmemAccessDesc acc;
+    std::memset(&acc, 0, sizeof acc);
+    acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    acc.location.id = device;
+    acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+    return acc;
+  }
+  int export_handle(void *out, uint64_t cap) override {
+    if (!vmm) return fail(DCG_ERR_INVALID, "not a one-rank-per-process instance");
+    if (cap < vmm::kHandleBytes) return fail(DCG_ERR_INVALID, "handle buffer too small");
+    std::memcpy(out, fd_server.name, vmm::kHandleBytes);
+    return DCG_OK;
+  }
+  int map_piece(CUdeviceptr va, size_t bytes, size_t off, int r) {
+    if (drv.memMap(va, bytes, off, arena_handle[r], 0) != CUDA_SUCCESS) return fail(DCG_ERR_CUDA, "cuMemMap failed (rank %d, %zu bytes)", r, bytes);
+    return DCG_OK;
+  }
+  int import_handles(const void *handles, int count) override {
+    if (!vmm) return fail(DCG_ERR_INVALID, "not a one-rank-per-process instance");
+    if (count != world) return fail(DCG_ERR_INVALID, "expected %d handles, got %d", world, count);
+    DCG_CUDA_TRY(cudaSetDevice(device));
+    for (int r = 0; r < world; r++) {
+      if (r == rank0) continue;
+      char name[vmm::kHandleBytes + 1] = {0};
+      std::memcpy(name, static_cast<const char *>(handles) + (size_t)r * vmm::kHandleBytes, vmm::kHandleBytes);
+      const int fd = vmm::fetch_fd(name);
+      if (fd < 0) return fail(DCG_ERR_CUDA, "could not fetch the arena descriptor of rank %d", r);
+      const CUresult rc = drv.memImport(&arena_handle[r], (void *)(uintptr_t)fd, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR);
+      close(fd);
+      if (rc != CUDA_SUCCESS) return fail(DCG_ERR_CUDA, "cuMemImportFromShareableHandle failed for rank %d", r);
+      arena_imported[r] = true;
+    }
+    fd_server.finish();
+    if (fd_server.served.load() != world - 1) return fail(DCG_ERR_CUDA, "only %d of %d peers fetched this rank's arena", fd_server.served.load(), world - 1);
+    CUmemAccessDesc acc = access_desc();
+    // control blocks: rank r's at ctrl_va + r * gran (this rank's own was mapped at creation)
+    for (int r = 0; r < world; r++) {
+      if (r == rank0) continue;
+      DCG_TRY(map_piece(ctrl_va + (size_t)r * gran, gran, 0, r));
+      if (drv.memSetAccess(ctrl_va + (size_t)r * gran, gran, &acc, 1) != CUDA_SUCCESS)
+        return fail(DCG_ERR_CUDA, "cuMemSetAccess failed: peer access between the GPUs is required");
+    }
+    for (int r = 0; r < world; r++) peers.flags[r] = reinterpret_cast<volatile uint32_t *>(ctrl_va + (size_t)r * gran);
+    // fields: unit u of field f lives in its owner's arena, the k-th of the owner's units
+    for (int f = 0; f < kFields; f++) {
+      const size_t ub = (size_t)unit * kBV * (f < 2 ? 16 : 4);
+      field_va_bytes[f] = (size_t)nunits * ub;
+      if (drv.memReserve(&field_va[f], field_va_bytes[f], gran, 0, 0) != CUDA_SUCCESS) return fail(DCG_ERR_CUDA, "cuMemAddressReserve failed");
+      uint32_t u = 0;
+      while (u < nunits) {
+        uint32_t e = u + 1;
+        while (e < nunits && unit_owner[e] == unit_owner[u]) e++;  // consecutive units of one owner are consecutive in its arena
+        const int r = unit_owner[u];
+        DCG_TRY(map_piece(field_va[f] + (size_t)u * ub, (size_t)(e - u) * ub, arena_field_off[(size_t)r * kFields + f] + (size_t)units_before[u] * ub, r));
+        u = e;
+      }
+      if (drv.memSetAccess(field_va[f], field_va_bytes[f], &acc, 1) != CUDA_SUCCESS) return fail(DCG_ERR_CUDA, "cuMemSetAccess failed");
+    }
+    vw[0] = reinterpret_cast<float4 *>(field_va[0]); vw[1] = reinterpret_cast<float4 *>(field_va[1]);
+    q[0] = reinterpret_cast<float *>(field_va[2]); q[1] = reinterpret_cast<float *>(field_va[3]);
+    fl = reinterpret_cast<float *>(field_va[4]); p = reinterpret_cast<float *>(field_va[5]);
+    tp = reinterpret_cast<float *>(field_va[6]); div = reinterpret_cast<float *>(field_va[7]);
+    DCG_CUDA_TRY(cudaMalloc(&d_epoch, 4));
+    DCG_CUDA_TRY(cudaMalloc(&d_barrier_err, 4));
+    DCG_CUDA_TRY(cudaMemset(d_epoch, 0, 4));
+    DCG_CUDA_TRY(cudaMemset(d_barrier_err, 0, 4));
+    DCG_CUDA_TRY(cudaDeviceSynchronize());
+    ready = true;
+    DCG_TRY(reset());  // starts with a barrier: every rank has mapped every arena before any field is touched
+    return check_barrier_error();
+  }
+  void release_vmm() {
+    if (ctrl_va) { drv.memUnmap(ctrl_va, (size_t)world * gran); drv.memFree(ctrl_va, (size_t)world * gran); }
+    for (int f = 0; f < kFields; f++)
+      if (field_va[f]) { drv.memUnmap(field_va[f], field_va_bytes[f]); drv.memFree(field_va[f], field_va_bytes[f]); }
+    for (int r = 0; r < 8; r++)
+      if (arena_imported[r]) drv.memRelease(arena_handle[r]);
+  }
+  int need_ready() { return ready ? DCG_OK : fail(DCG_ERR_INVALID, "sharded instance not finalized: call dcg_shard_import_handles first"); }
+  int check_barrier_error() {
+    if (!vmm) return DCG_OK;
+    uint32_t e = 0;
+    DCG_CUDA_TRY(cudaMemcpyAsync(&e, d_barrier_err, 4, cudaMemcpyDeviceToHost, stream));
+    DCG_CUDA_TRY(cudaStreamSynchronize(stream));
+    if (e) return fail(DCG_ERR_CUDA, "shard barrier timed out: a peer rank never arrived (ranks must issue identical call sequences)");
+    return DCG_OK;
   }
 
   int on_params_changed() override {
@@ -278,14 +536,33 @@ struct DCGridSim : dcg_sim {
     DCG_CUDA_TRY(cudaMemsetAsync(T.face, 0, (size_t)M * 96 * 4, stream));
     DCG_CUDA_TRY(cudaMemsetAsync(T.fd, 0, (size_t)M * 12 * 4, stream));
     for (int l = 0; l < sparse; l++) DCG_CUDA_TRY(cudaMemsetAsync(T.map[l], 0xff, map_size[l] * 4, stream));
-    for (int i = 0; i < 2; i++) {
-      DCG_CUDA_TRY(cudaMemsetAsync(vw[i], 0, cells * sizeof(float4), stream));
-      DCG_CUDA_TRY(cudaMemsetAsync(q[i], 0, cells * 4, stream));
+    if (!vmm) {
+      for (int i = 0; i < 2; i++) {
+        DCG_CUDA_TRY(cudaMemsetAsync(vw[i], 0, cells * sizeof(float4), stream));
+        DCG_CUDA_TRY(cudaMemsetAsync(q[i], 0, cells * 4, stream));
+      }
+      DCG_CUDA_TRY(cudaMemsetAsync(fl, 0, cells * 4, stream));
+      DCG_CUDA_TRY(cudaMemsetAsync(p, 0, cells * 4, stream));
+      DCG_CUDA_TRY(cudaMemsetAsync(tp, 0, cells * 4, stream));
+      DCG_CUDA_TRY(cudaMemsetAsync(div, 0, cells * 4, stream));
+    } else {
+      // every rank clears its own arena (the fields of the units it owns), then all meet: nobody may start
+      // writing initial values into cells a peer is still clearing
+      DCG_TRY(need_ready());
+      barrier();
+      for (int f = 0; f < kFields; f++) {
+        const size_t ub = (size_t)unit * kBV * (f < 2 ? 16 : 4);
+        uint32_t u = 0;
+        while (u < nunits) {
+          uint32_t e = u + 1;
+          while (e < nunits && unit_owner[e] == unit_owner[u]) e++;
+          if (unit_owner[u] == rank0)
+            DCG_CUDA_TRY(cudaMemsetAsync(reinterpret_cast<void *>(field_va[f] + (size_t)u * ub), 0, (size_t)(e - u) * ub, stream));
+          u = e;
+        }
+      }
+      barrier();
     }
-    DCG_CUDA_TRY(cudaMemsetAsync(fl, 0, cells * 4, stream));
-    DCG_CUDA_TRY(cudaMemsetAsync(p, 0, cells * 4, stream));
-    DCG_CUDA_TRY(cudaMemsetAsync(tp, 0, cells * 4, stream));
-    DCG_CUDA_TRY(cudaMemsetAsync(div, 0, cells * 4, stream));
     DCG_CUDA_TRY(cudaMemsetAsync(d_counters, 0, 2 * 4, stream));
     k_fill_u32<<<blocks_for((size_t)M * 8 + 1, 256), 256, 0, stream>>>(reinterpret_cast<uint32_t *>(d_sub_scores), 0xFF7FFFFFu /* -FLT_MAX */,
                                                                        (size_t)M * 8 + 1);
@@ -306,8 +583,9 @@ struct DCGridSim : dcg_sim {
     launches++;
     for (int l = sparse; l < levels; l++) {
       k_dc_activate_level<<<(unsigned)full_blocks[l], 64, 0, stream>>>(T, kp, l, vw[0], vw[1], q[0], q[1], fl);
-      launches++;
+      launches++;  // (sharded: every process writes the same values into every cell)
     }
+    barrier();
     build_face_descriptors();
     DCG_CUDA_TRY(cudaGetLastError());
     for (int i = 0; i < 5; i++) DCG_TRY(adapt_topology());
@@ -324,20 +602,28 @@ struct DCGridSim : dcg_sim {
     launches++;
     rebuild_order();
   }
-  // called whenever block positions or the set of active blocks changed
+  // called whenever block positions or the set of active blocks changed: per rank, the Morton-ordered list of
+  // its active blocks, the lists of its blocks with children, and the tile runs of every level
   void rebuild_order() {
-    uint64_t n = 0;
-    for (int l = 0; l < levels; l++) n += loads[l];
-    k_dc_order_keys<<<blocks_for(M, 256), 256, 0, stream>>>(T, order_mode, d_order_keys[0], d_order_vals);
-    size_t bytes = sort_tmp_bytes;
-    cub::DeviceRadixSort::SortPairs(d_sort_tmp, bytes, d_order_keys[0], d_order_keys[1], d_order_vals, d_order, (int)M, 0, 32, stream);
-    n_order = (uint32_t)((n + kBPC - 1) / kBPC * kBPC);
-    if (n_order > n) k_dc_order_pad<<<1, 256, 0, stream>>>(d_order, (uint32_t)n, n_order);
-    cudaMemsetAsync(d_pcount, 0, kMaxLevels * 4, stream);
-    k_dc_list_parents<<<blocks_for(M, 256), 256, 0, stream>>>(T, d_plist, d_pcount);
-    cudaMemcpyAsync(h_pcount, d_pcount, kMaxLevels * 4, cudaMemcpyDeviceToHost, stream);
-    cudaStreamSynchronize(stream);
-    launches += 3;
+    for (int lr = 0; lr < nlocal; lr++) {
+      RankWork &w = work[lr];
+      const int rank = rank0 + lr;
+      const uint8_t *own = world > 1 ? d_unit_owner : nullptr;
+      cudaMemsetAsync(d_pcount, 0, (kMaxLevels + 1) * 4, stream);
+      k_dc_order_keys<<<blocks_for(M, 256), 256, 0, stream>>>(T, order_mode, own, unit, rank, d_order_keys[0], d_order_vals, d_pcount + kMaxLevels);
+      size_t bytes = sort_tmp_bytes;
+      cub::DeviceRadixSort::SortPairs(d_sort_tmp, bytes, d_order_keys[0], d_order_keys[1], d_order_vals, w.d_order, (int)M, 0, 32, stream);
+      k_dc_list_parents<<<blocks_for(M, 256), 256, 0, stream>>>(T, own, unit, rank, w.d_plist, d_pcount);
+      cudaMemcpyAsync(h_pcount, d_pcount, (kMaxLevels + 1) * 4, cudaMemcpyDeviceToHost, stream);
+      cudaStreamSynchronize(stream);
+      for (int l = 0; l < kMaxLevels; l++) w.pcount[l] = h_pcount[l];
+      const uint32_t n = h_pcount[kMaxLevels];
+      w.n_order = (n + kBPC - 1) / kBPC * kBPC;
+      if (w.n_order > n) k_dc_order_pad<<<1, 256, 0, stream>>>(w.d_order, n, w.n_order);
+      launches += 4;
+      w.all = tile_runs(0, 0, (uint32_t)((M64 + kTile - 1) / kTile), rank);
+      for (int l = 0; l < levels; l++) w.level[l] = tile_runs(offsets[l], 0, (uint32_t)((loads[l] + kTile - 1) / kTile), rank);
+    }
   }
   uint32_t finer_full_mask() const {
     uint32_t m = 0;
@@ -551,8 +837,11 @@ struct DCGridSim : dcg_sim {
       launches += 2;
       build_face_descriptors();
       for (int l = levels - 2; l >= 0; l--) {
+        // sharded: every process interpolates every new block (identical values); lock step between the levels,
+        // a level reads what the coarser one wrote
         k_dc_propagate<<<num_touched, 64, 0, stream>>>(T, kp, d_touched, l, vw[cur_v], q[cur_q], fl);
         launches++;
+        barrier();
       }
       uint32_t h_cnt[2] = {0, 0};
       DCG_CUDA_TRY(cudaMemcpyAsync(h_cnt, d_counters, 8, cudaMemcpyDeviceToHost, stream));
@@ -580,20 +869,28 @@ struct DCGridSim : dcg_sim {
     for (int l = fused ? 1 : 0; l < levels - 1 && l < tail; l++) {
       if (loads[l] == 0) continue;
       if (fused) {  // only blocks with children are left (k_dc_list_parents)
-        const uint32_t n = h_pcount[l];
-        if (n == 0) continue;
-        if (v) k_dc_accumulate_velocity_list<<<blocks_for(8 * (size_t)n, 256), 256, 0, stream>>>(T, d_plist + offsets[l], n, v);
-        else k_dc_accumulate_scalar_list<<<blocks_for(8 * (size_t)n, 256), 256, 0, stream>>>(T, d_plist + offsets[l], n, ch);
+        each_rank([&](int, RankWork &w) {
+          const uint32_t n = w.pcount[l];
+          if (n == 0) return;
+          if (v) k_dc_accumulate_velocity_list<<<blocks_for(8 * (size_t)n, 256), 256, 0, stream>>>(T, w.d_plist + offsets[l], n, v);
+          else k_dc_accumulate_scalar_list<<<blocks_for(8 * (size_t)n, 256), 256, 0, stream>>>(T, w.d_plist + offsets[l], n, ch);
+          launches++;
+        });
+        barrier();
       } else if (v) {
         k_dc_accumulate_velocity<<<blocks_for(8 * loads[l], 256), 256, 0, stream>>>(T, l, v, 0);
+        launches++;
       } else {
         k_dc_accumulate_scalar<<<blocks_for(8 * loads[l], 256), 256, 0, stream>>>(T, l, ch, 0);
+        launches++;
       }
-      launches++;
     }
     if (tail < levels - 1) {
-      k_dc_accumulate_coarse<<<kAccClusterCTAs, kAccClusterThreads, 0, stream>>>(T, tail, v, ch);
-      launches++;
+      if (has_rank0()) {
+        k_dc_accumulate_coarse<<<kAccClusterCTAs, kAccClusterThreads, 0, stream>>>(T, tail, v, ch);
+        launches++;
+      }
+      barrier();
     }
   }
   void accumulate_velocity(bool fused) { accumulate(vw[cur_v], nullptr, fused); }
@@ -610,13 +907,16 @@ struct DCGridSim : dcg_sim {
   }
   // mode 0: vout <- advected velocity; 1: qout <- advected density; 2: both (k_dc_advect_pipe)
   void launch_advect_pipe(int mode, const float4 *vin, float4 *vout, const float *qi, float *qo) {
-    if (n_order == 0) return;
-    const unsigned grid = std::min<unsigned>(n_order / kBPC, (unsigned)(advect_per_sm[mode] * sm_count));
-    const float *flp = fl;
-    const uint32_t *ord = d_order;
-    void *args[] = {&T, &kp, &ord, &n_order, &vin, &vout, &flp, &qi, &qo};
-    cudaLaunchKernel(advect_fn(mode), dim3(grid), dim3(kAdvectThreads), args, kAdvectPipeSmem, stream);
-    launches++;
+    each_rank([&](int, RankWork &w) {
+      if (w.n_order == 0) return;
+      const unsigned grid = std::min<unsigned>(w.n_order / kBPC, (unsigned)(advect_per_sm[mode] * sm_count));
+      const float *flp = fl;
+      const uint32_t *ord = w.d_order;
+      void *args[] = {&T, &kp, &ord, &w.n_order, &vin, &vout, &flp, &qi, &qo};
+      cudaLaunchKernel(advect_fn(mode), dim3(grid), dim3(kAdvectThreads), args, kAdvectPipeSmem, stream);
+      launches++;
+    });
+    barrier();
   }
   int advect_velocity() override {  // :263-268
     DCG_CUDA_TRY(cudaSetDevice(device));
@@ -656,14 +956,20 @@ struct DCGridSim : dcg_sim {
   }
   // one sweep of a level; persistent TMA-ring kernel for levels with enough tiles to fill the machine
   void jacobi_sweep(int l, const float *in, float *out) {
-    const unsigned tiles = blocks_for(loads[l], kB4);
-    if (use_pipe && tiles >= pipe_min_tiles) {
-      const unsigned grid = std::min<unsigned>(tiles, (unsigned)jacobi_pipe_ctas);
-      k_dc_jacobi_pipe<<<grid, kCTA4, kJacobiPipeSmem, stream>>>(T, kp, l, in, out, div, snake ? (sweep_parity ^= 1) : 0);
-    } else {
-      k_dc_jacobi4<<<tiles, kCTA4, 0, stream>>>(T, kp, l, in, out, div);
-    }
-    launches++;
+    if (snake) sweep_parity ^= 1;
+    each_rank([&](int, RankWork &w) {
+      const TileRuns &R = w.level[l];
+      const unsigned tiles = run_total(R);
+      if (tiles == 0) return;
+      if (use_pipe && blocks_for(loads[l], kB4) >= pipe_min_tiles) {
+        const unsigned grid = std::min<unsigned>(tiles, (unsigned)jacobi_pipe_ctas);
+        k_dc_jacobi_pipe<<<grid, kCTA4, kJacobiPipeSmem, stream>>>(T, kp, R, l, in, out, div, snake ? sweep_parity : 0);
+      } else {
+        k_dc_jacobi4<<<tiles, kCTA4, 0, stream>>>(T, kp, R, l, in, out, div);
+      }
+      launches++;
+    });
+    barrier();
   }
   void jacobi_pair(int l) {
     if (loads[l] == 0) return;
@@ -671,28 +977,42 @@ struct DCGridSim : dcg_sim {
     jacobi_sweep(l, tp, p);
   }
   void launch_prolongate(int l) {
-    if (prolong_staged) k_dc_prolongate_staged<<<blocks_for(loads[l], kB4), kCTA4, 0, stream>>>(T, l, p);
-    else k_dc_prolongate4<<<blocks_for(loads[l], kB4), kCTA4, 0, stream>>>(T, l, p);
-    launches++;
+    each_rank([&](int, RankWork &w) {
+      const TileRuns &R = w.level[l];
+      if (run_total(R) == 0) return;
+      if (prolong_staged) k_dc_prolongate_staged<<<run_total(R), kCTA4, 0, stream>>>(T, R, l, p);
+      else k_dc_prolongate4<<<blocks_for(loads[l], kB4), kCTA4, 0, stream>>>(T, l, p);
+      launches++;
+    });
+    barrier();
   }
   void launch_divergence(int zero_from) {
-    const unsigned tiles = blocks_for(M, kB4);
-    if (use_stencil_pipe)
-      k_dc_divergence_pipe<<<std::min<unsigned>(tiles, (unsigned)div_pipe_ctas), kStencilThreads, kDivPipeSmem, stream>>>(T, kp, vw[cur_v], div, p, tp,
-                                                                                                                          zero_from);
-    else
-      k_dc_divergence4<<<tiles, kCTA4, 0, stream>>>(T, kp, vw[cur_v], div, p, tp, zero_from);
-    launches++;
+    each_rank([&](int, RankWork &w) {
+      const unsigned tiles = run_total(w.all);
+      if (tiles == 0) return;
+      if (use_stencil_pipe)
+        k_dc_divergence_pipe<<<std::min<unsigned>(tiles, (unsigned)div_pipe_ctas), kStencilThreads, kDivPipeSmem, stream>>>(T, kp, w.all, vw[cur_v], div, p,
+                                                                                                                            tp, zero_from);
+      else
+        k_dc_divergence4<<<blocks_for(M, kB4), kCTA4, 0, stream>>>(T, kp, vw[cur_v], div, p, tp, zero_from);
+      launches++;
+    });
+    barrier();
   }
   void launch_apply() {
-    const unsigned tiles = blocks_for(M, kB4);
-    if (use_stencil_pipe && apply_min_blocks == 2)
-      k_dc_apply_pipe<2><<<std::min<unsigned>(tiles, (unsigned)apply_pipe_ctas), kStencilThreads, kApplyPipeSmem, stream>>>(T, kp, p, fl, vw[cur_v]);
-    else if (use_stencil_pipe)
-      k_dc_apply_pipe<3><<<std::min<unsigned>(tiles, (unsigned)apply_pipe_ctas), kStencilThreads, kApplyPipeSmem, stream>>>(T, kp, p, fl, vw[cur_v]);
-    else
-      k_dc_apply_pressure4<<<tiles, kCTA4, 0, stream>>>(T, kp, p, fl, vw[cur_v]);
-    launches++;
+    each_rank([&](int, RankWork &w) {
+      const unsigned tiles = run_total(w.all);
+      if (tiles == 0) return;
+      const unsigned grid = std::min<unsigned>(tiles, (unsigned)apply_pipe_ctas);
+      if (use_stencil_pipe && apply_min_blocks == 2)
+        k_dc_apply_pipe<2><<<grid, kStencilThreads, kApplyPipeSmem, stream>>>(T, kp, w.all, p, fl, vw[cur_v]);
+      else if (use_stencil_pipe)
+        k_dc_apply_pipe<3><<<grid, kStencilThreads, kApplyPipeSmem, stream>>>(T, kp, w.all, p, fl, vw[cur_v]);
+      else
+        k_dc_apply_pressure4<<<blocks_for(M, kB4), kCTA4, 0, stream>>>(T, kp, p, fl, vw[cur_v]);
+      launches++;
+    });
+    barrier();
   }
   void divergence_stage(int zero_from) {
     launch_divergence(zero_from);
@@ -707,11 +1027,14 @@ struct DCGridSim : dcg_sim {
     const uint64_t end = offsets[levels - 1] + max_blocks[levels - 1];
     const uint32_t ncell = (uint32_t)((end - offsets[cf]) * kBV);
     const size_t smem = (size_t)ncell * (3 * 4 + 6 * 2);
-    if (coarse_in_smem && smem <= kCoarseSmemMax && ncell <= 65535)
-      k_dc_coarse_cascade<true><<<1, 1024, smem, stream>>>(T, kp, cf, prolong_coarsest, pairs_coarsest, pairs_level, prolong_levels, p, tp, div, ncell);
-    else
-      k_dc_coarse_cascade<false><<<1, 1024, 0, stream>>>(T, kp, cf, prolong_coarsest, pairs_coarsest, pairs_level, prolong_levels, p, tp, div, 0);
-    launches++;
+    if (has_rank0()) {  // sharded: one rank walks the coarse tail, the others wait at the barrier
+      if (coarse_in_smem && smem <= kCoarseSmemMax && ncell <= 65535)
+        k_dc_coarse_cascade<true><<<1, 1024, smem, stream>>>(T, kp, cf, prolong_coarsest, pairs_coarsest, pairs_level, prolong_levels, p, tp, div, ncell);
+      else
+        k_dc_coarse_cascade<false><<<1, 1024, 0, stream>>>(T, kp, cf, prolong_coarsest, pairs_coarsest, pairs_level, prolong_levels, p, tp, div, 0);
+      launches++;
+    }
+    barrier();
   }
   int project() override {  // :270-294
     spec_velocity = false;
@@ -856,13 +1179,16 @@ struct DCGridSim : dcg_sim {
   }
   int total_density(double *out) override {
     DCG_CUDA_TRY(cudaSetDevice(device));
+    // sum over the cells this instance owns (sharded, one rank per process: the host adds the ranks' partials)
     const int blocks = (int)std::min<size_t>(1024, (cells + 255) / 256);
-    k_dc_total_density<<<blocks, 256, 0, stream>>>(T, q[cur_q], fl, d_partial);
-    launches++;
-    DCG_CUDA_TRY(cudaMemcpyAsync(h_partial, d_partial, blocks * sizeof(double), cudaMemcpyDeviceToHost, stream));
-    DCG_TRY(synchronize());
     double s = 0.0;
-    for (int i = 0; i < blocks; i++) s += h_partial[i];
+    for (int lr = 0; lr < nlocal; lr++) {
+      k_dc_total_density<<<blocks, 256, 0, stream>>>(T, work[lr].all, q[cur_q], fl, d_partial);
+      launches++;
+      DCG_CUDA_TRY(cudaMemcpyAsync(h_partial, d_partial, blocks * sizeof(double), cudaMemcpyDeviceToHost, stream));
+      DCG_TRY(synchronize());
+      for (int i = 0; i < blocks; i++) s += h_partial[i];
+    }
     *out = s;
     return DCG_OK;
   }
@@ -898,6 +1224,10 @@ struct DCGridSim : dcg_sim {
     if (!dst || count < cells * comps) return fail(DCG_ERR_INVALID, "get_field: destination too small");
     if (field == DCG_FIELD_VELOCITY) {
       k_dc_unpack_velocity<<<blocks_for(cells, 256), 256, 0, stream>>>(vw[cur_v], scratch, cells);
+      launches++;
+      src = scratch;
+    } else if (vmm) {  // the field spans every rank's arena: gather it into local memory first
+      k_copy_f32<<<blocks_for(cells, 256), 256, 0, stream>>>(src, scratch, cells);
       launches++;
       src = scratch;
     }
@@ -996,3 +1326,8 @@ struct DCGridSim : dcg_sim {
 }  // namespace dcg
 
 dcg_sim *dcg_make_dcgrid(uint64_t max_num_blocks) { return new dcg::DCGridSim(max_num_blocks); }
+dcg_sim *dcg_make_dcgrid_sharded(uint64_t max_num_blocks, int rank, int world, int nlocal) {
+  auto *s = new dcg::DCGridSim(max_num_blocks);
+  s->world = world; s->rank0 = rank; s->nlocal = nlocal;
+  return s;
+}

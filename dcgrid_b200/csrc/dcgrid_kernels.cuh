@@ -177,9 +177,11 @@ __global__ void __launch_bounds__(256) k_dc_accumulate_scalar(Pool T, int level,
 // the blocks WITH children (and a parent), listed per level at plist[offsets[level] ...) whenever the topology
 // changes, so that a pass costs 8 threads per listed block instead of a child-link probe per pool slot
 // (level 1 at 512^3: 30 k of 243 k blocks).  List order is arbitrary: every subblock is independent.
-__global__ void __launch_bounds__(256) k_dc_list_parents(Pool T, uint32_t *__restrict__ plist, uint32_t *__restrict__ pcount) {
+__global__ void __launch_bounds__(256) k_dc_list_parents(Pool T, const uint8_t *__restrict__ owner, uint32_t unit, int rank,
+                                                         uint32_t *__restrict__ plist, uint32_t *__restrict__ pcount) {
   const uint32_t b = blockIdx.x * 256 + threadIdx.x;
   if (b >= T.M) return;
+  if (owner && owner[b / unit] != rank) return;
   const int level = T.posl[b].w;
   if (level == kFree || T.parent[b] == kNone || !block_has_children(T, b)) return;
   plist[T.offsets[level] + atomicAdd(&pcount[level], 1u)] = b;
@@ -587,11 +589,11 @@ __global__ void __launch_bounds__(kCTA4) k_dc_prolongate4(Pool T, int level, flo
 // Same, with the 4^3 coarse cells a child block interpolates from (its parent subblock's 2^3 cells and their
 // ring) staged once per block in shared memory: 4 index + 4 value loads per thread instead of 18 + 18 — the
 // gather version keeps the L1 data pipe 85 % busy for 4.5 B/cell of useful traffic (profiles/README.md r1d).
-__global__ void __launch_bounds__(kCTA4) k_dc_prolongate_staged(Pool T, int level, float *__restrict__ p) {
+__global__ void __launch_bounds__(kCTA4) k_dc_prolongate_staged(Pool T, TileRuns R, int level, float *__restrict__ p) {
   __shared__ float sc[kB4][64];
   const uint32_t g = threadIdx.x >> 4;
   const int t = threadIdx.x & 15;
-  const uint32_t li = blockIdx.x * kB4 + g;
+  const uint32_t li = run_tile(R, blockIdx.x) * kB4 + g;
   const bool active = li < T.loads[level];
   const uint32_t b = T.offsets[level] + li;
   const uint32_t ps = active ? T.parent[b] : kNone;
@@ -651,16 +653,21 @@ __global__ void __launch_bounds__(256) k_dc_debug_stats(Pool T, KParams P, const
 }
 
 // total smoke over leaf cells, volume weighted (double, fixed reduction tree)
-__global__ void __launch_bounds__(256) k_dc_total_density(Pool T, const float *__restrict__ q, const float *__restrict__ fl,
+__global__ void __launch_bounds__(256) k_dc_total_density(Pool T, TileRuns R, const float *__restrict__ q, const float *__restrict__ fl,
                                                           double *__restrict__ partial) {
   __shared__ double sh[256];
   double s = 0.0;
-  const size_t n = (size_t)T.M * kBV;
-  for (size_t c = (size_t)blockIdx.x * 256 + threadIdx.x; c < n; c += (size_t)gridDim.x * 256) {
-    const int level = T.posl[c >> 6].w;
-    if (level == kFree || T.child[c >> 3] != kNone) continue;
-    const double vol = (double)(1ull << (3 * level));
-    s += vol * (double)(q[c] * fl[c]);
+  const uint32_t total = run_total(R);
+  for (uint32_t j = blockIdx.x; j < total; j += gridDim.x) {
+    const size_t c0 = (size_t)run_tile(R, j) * kTile * kBV;
+    for (uint32_t k = threadIdx.x; k < kTile * kBV; k += 256) {
+      const size_t c = c0 + k;
+      if (c >= (size_t)T.M * kBV) break;
+      const int level = T.posl[c >> 6].w;
+      if (level == kFree || T.child[c >> 3] != kNone) continue;
+      const double vol = (double)(1ull << (3 * level));
+      s += vol * (double)(q[c] * fl[c]);
+    }
   }
   sh[threadIdx.x] = s;
   __syncthreads();
@@ -716,6 +723,44 @@ __global__ void __launch_bounds__(256) k_iota_u32(uint32_t *p, size_t n) {
 __global__ void __launch_bounds__(256) k_fill_posl(int4 *p, size_t n) {
   const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
   if (i < n) p[i] = make_int4(0, 0, 0, kFree);
+}
+
+// ======================================================================================
+// slab decomposition: lock-step barrier over peer memory
+// ======================================================================================
+// flags[r] = rank r's control block (mapped into every process); word j of it = the last epoch rank j announced
+// to r.  The epoch lives in device memory and is advanced by the kernel itself, so the barrier can be replayed
+// from a CUDA graph.  Bounded spin: a rank that never arrives trips *err instead of hanging the GPU.
+struct BarrierPeers {
+  volatile uint32_t *flags[8];
+};
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__global__ void __launch_bounds__(32) k_dcs_barrier(BarrierPeers B, int rank, int world, uint32_t *epoch_counter, uint32_t *err) {
+  const int t = threadIdx.x;
+  uint32_t epoch = 0;
+  if (t == 0) epoch = ++(*epoch_counter);
+  epoch = __shfl_sync(0xFFFFFFFFu, epoch, 0);
+  if (t < world && t != rank) {
+    __threadfence_system();    // everything this rank wrote before the barrier is visible system-wide
+    B.flags[t][rank] = epoch;  // 4-byte store into the peer's control block over NVLink
+    const unsigned long long t0 = global_ns();
+    while ((int32_t)(B.flags[rank][t] - epoch) < 0) {
+      if (global_ns() - t0 > 10000000000ull) {  // 10 s
+        *err = 1;
+        break;
+      }
+    }
+    __threadfence_system();
+  }
+}
+
+__global__ void __launch_bounds__(256) k_copy_f32(const float *__restrict__ src, float *__restrict__ dst, size_t n) {
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (i < n) dst[i] = src[i];
 }
 
 }  // namespace dcg

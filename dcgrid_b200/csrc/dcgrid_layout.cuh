@@ -43,6 +43,21 @@ struct Pool {
   uint32_t *map[kMaxLevels];        // dense block-coordinate -> slot map of each sparse level
 };
 
+// Work partition of the slab-decomposed solver (dcgrid.cu, "sharding"): the tiles (kTile consecutive slots) one
+// rank processes in a launch, as runs of consecutive tiles.  Single GPU: one run covering everything.
+constexpr int kTile = 16, kMaxRuns = 48;
+struct TileRuns {
+  int n;
+  uint32_t first[kMaxRuns];    // first tile of run k
+  uint32_t pre[kMaxRuns + 1];  // tiles in runs 0..k-1; pre[n] = total
+};
+__host__ __device__ __forceinline__ uint32_t run_total(const TileRuns &R) { return R.pre[R.n]; }
+__host__ __device__ __forceinline__ uint32_t run_tile(const TileRuns &R, uint32_t j) {
+  int k = 0;
+  while (k + 1 < R.n && j >= R.pre[k + 1]) k++;
+  return R.first[k] + (j - R.pre[k]);
+}
+
 // in-block cell bits: (sx<<5 | sy<<4 | sz<<3 | cx<<2 | cy<<1 | cz), coordinate = 2*s + c
 // (dcgrid_utils.cuh:50-81)
 __host__ __device__ __forceinline__ int cell_x(uint32_t c) { return (int)((((c >> 5) & 1) << 1) | ((c >> 2) & 1)); }

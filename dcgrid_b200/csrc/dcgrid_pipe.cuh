@@ -89,13 +89,14 @@ constexpr size_t kJacobiPipeSmem = kJStages * sizeof(JacobiStage) + kJStages * s
 
 // tile order: `reverse` walks the level's tiles from the last to the first, so that a sweep starts on the
 // tiles the previous sweep wrote last (still L2-resident: a level-0 field is 62 MB at 512^3, L2 is 126 MB)
-__global__ void __launch_bounds__(kCTA4, 4) k_dc_jacobi_pipe(Pool T, KParams P, int level, const float *__restrict__ in, float *__restrict__ out,
-                                                            const float *__restrict__ div, int reverse) {
+// R: the level-local tiles (tile k = slots offsets[level] + 16k ...) this rank sweeps, clipped to the active prefix
+__global__ void __launch_bounds__(kCTA4, 4) k_dc_jacobi_pipe(Pool T, KParams P, TileRuns R, int level, const float *__restrict__ in,
+                                                            float *__restrict__ out, const float *__restrict__ div, int reverse) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   JacobiStage *st = reinterpret_cast<JacobiStage *>(smem_raw);
   uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + kJStages * sizeof(JacobiStage));
   const uint32_t loads = T.loads[level], off = T.offsets[level];
-  const uint32_t ntiles = (loads + kB4 - 1) / kB4;
+  const uint32_t total = run_total(R), ntiles = 0xFFFFFFFFu;  // ntiles = "no tile"
   const uint32_t g = threadIdx.x >> 4;
   const int t = threadIdx.x & 15;
   if (threadIdx.x == 0) {
@@ -106,9 +107,9 @@ __global__ void __launch_bounds__(kCTA4, 4) k_dc_jacobi_pipe(Pool T, KParams P, 
   __syncthreads();
   const uint64_t pol_stream = pipe::policy_evict_first();
   auto tile_of = [&](uint32_t it) -> uint32_t {  // this CTA's it-th tile, ntiles = none
-    const uint32_t tl = blockIdx.x + it * gridDim.x;
-    if (tl >= ntiles) return ntiles;
-    return reverse ? ntiles - 1 - tl : tl;
+    const uint32_t j = blockIdx.x + it * gridDim.x;
+    if (j >= total) return ntiles;
+    return run_tile(R, reverse ? total - 1 - j : j);
   };
   auto issue_tile = [&](uint32_t it) {  // producer (thread 0): tile `it` of this CTA -> ring slot it % kJStages
     const uint32_t tl = tile_of(it);
@@ -403,12 +404,15 @@ __device__ __forceinline__ uint32_t spread3(uint32_t v) {  // 10 bits -> every t
   return v;
 }
 // mode 0: key = slot (pool order); 1: Morton.  Free slots get key 0xFFFFFFFF and sort to the end.
-__global__ void __launch_bounds__(256) k_dc_order_keys(Pool T, int mode, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+// owner != nullptr: only the blocks of units owned by `rank` (owner[b / unit]) are listed
+__global__ void __launch_bounds__(256) k_dc_order_keys(Pool T, int mode, const uint8_t *__restrict__ owner, uint32_t unit, int rank,
+                                                       uint32_t *__restrict__ keys, uint32_t *__restrict__ vals, uint32_t *__restrict__ count) {
   const uint32_t b = blockIdx.x * 256 + threadIdx.x;
   if (b >= T.M) return;
   const int4 pl = T.posl[b];
   uint32_t key = 0xFFFFFFFFu;
-  if (pl.w != kFree) {
+  if (pl.w != kFree && (!owner || owner[b / unit] == rank)) {
+    atomicAdd(count, 1u);
     if (mode == 0) key = b;
     else key = (spread3((uint32_t)(pl.x << pl.w) >> 2) << 2) | (spread3((uint32_t)(pl.y << pl.w) >> 2) << 1) | spread3((uint32_t)(pl.z << pl.w) >> 2);
   }
@@ -473,21 +477,22 @@ __device__ __forceinline__ void stencil_ring_init(uint64_t *full, uint64_t *empt
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(kStencilThreads, 3) k_dc_divergence_pipe(Pool T, KParams P, const float4 *__restrict__ vw, float *__restrict__ div,
-                                                                           float *__restrict__ p, float *__restrict__ tp, int zero_from) {
+__global__ void __launch_bounds__(kStencilThreads, 3) k_dc_divergence_pipe(Pool T, KParams P, TileRuns R, const float4 *__restrict__ vw,
+                                                                           float *__restrict__ div, float *__restrict__ p, float *__restrict__ tp,
+                                                                           int zero_from) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   DivStage *st = reinterpret_cast<DivStage *>(smem_raw);
   uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + kSStages * sizeof(DivStage));
   uint64_t *empty = full + kSStages;
-  const uint32_t ntiles = (T.M + kB4 - 1) / kB4;
+  const uint32_t ntiles = run_total(R);
   stencil_ring_init<DivStage>(full, empty);
   if (threadIdx.x >= kCTA4) {  // producer warp
     if (threadIdx.x != kCTA4) return;
-    uint32_t tl = blockIdx.x;
-    for (uint32_t it = 0; tl < ntiles; it++, tl += gridDim.x) {
+    uint32_t j = blockIdx.x;
+    for (uint32_t it = 0; j < ntiles; it++, j += gridDim.x) {
       const uint32_t s = it % kSStages;
       if (it >= (uint32_t)kSStages) pipe::mbar_wait(&empty[s], ((it / kSStages) - 1u) & 1u);
-      const size_t b0 = (size_t)tl * kB4;
+      const size_t b0 = (size_t)run_tile(R, j) * kB4;
       const uint32_t nv = min((uint32_t)kB4, T.M - (uint32_t)b0);
       DivStage &S = st[s];
       pipe::mbar_expect_tx(&full[s], nv * (kBV * 16u + 48u + kSV * 4u + 16u) + kB4 * 4u);
@@ -505,12 +510,12 @@ __global__ void __launch_bounds__(kStencilThreads, 3) k_dc_divergence_pipe(Pool 
   quad_coords(t, X, Y0, Z0);
   const int sy = (t >> 2) & 1, sz = (t >> 1) & 1;
   const unsigned half = 0xFFFFu << (threadIdx.x & 16u);
-  uint32_t tl = blockIdx.x;
-  for (uint32_t it = 0; tl < ntiles; it++, tl += gridDim.x) {
+  uint32_t j = blockIdx.x;
+  for (uint32_t it = 0; j < ntiles; it++, j += gridDim.x) {
     const uint32_t s = it % kSStages;
     pipe::mbar_wait(&full[s], (it / kSStages) & 1u);
     const DivStage &S = st[s];
-    const uint32_t b = tl * kB4 + g;
+    const uint32_t b = run_tile(R, j) * kB4 + g;
     int4 pl = make_int4(0, 0, 0, kFree);
     if (b < T.M) pl = S.posl[g];
     const bool active = pl.w != kFree;
@@ -585,21 +590,21 @@ __global__ void __launch_bounds__(kStencilThreads, 3) k_dc_divergence_pipe(Pool 
 }
 
 template <int kMinBlocks>
-__global__ void __launch_bounds__(kStencilThreads, kMinBlocks) k_dc_apply_pipe(Pool T, KParams P, const float *__restrict__ p, const float *__restrict__ fl,
-                                                                      float4 *__restrict__ vw) {
+__global__ void __launch_bounds__(kStencilThreads, kMinBlocks) k_dc_apply_pipe(Pool T, KParams P, TileRuns R, const float *__restrict__ p,
+                                                                               const float *__restrict__ fl, float4 *__restrict__ vw) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   ApplyStage *st = reinterpret_cast<ApplyStage *>(smem_raw);
   uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + kSStages * sizeof(ApplyStage));
   uint64_t *empty = full + kSStages;
-  const uint32_t ntiles = (T.M + kB4 - 1) / kB4;
+  const uint32_t ntiles = run_total(R);
   stencil_ring_init<ApplyStage>(full, empty);
   if (threadIdx.x >= kCTA4) {  // producer warp
     if (threadIdx.x != kCTA4) return;
-    uint32_t tl = blockIdx.x;
-    for (uint32_t it = 0; tl < ntiles; it++, tl += gridDim.x) {
+    uint32_t j = blockIdx.x;
+    for (uint32_t it = 0; j < ntiles; it++, j += gridDim.x) {
       const uint32_t s = it % kSStages;
       if (it >= (uint32_t)kSStages) pipe::mbar_wait(&empty[s], ((it / kSStages) - 1u) & 1u);
-      const size_t b0 = (size_t)tl * kB4;
+      const size_t b0 = (size_t)run_tile(R, j) * kB4;
       const uint32_t nv = min((uint32_t)kB4, T.M - (uint32_t)b0);
       ApplyStage &S = st[s];
       pipe::mbar_expect_tx(&full[s], nv * (kBV * 16u + kBV * 4u + 48u + kSV * 4u + 16u) + kB4 * 4u);
@@ -615,12 +620,12 @@ __global__ void __launch_bounds__(kStencilThreads, kMinBlocks) k_dc_apply_pipe(P
   const uint32_t g = threadIdx.x >> 4;
   const int t = threadIdx.x & 15;
   const unsigned half = 0xFFFFu << (threadIdx.x & 16u);
-  uint32_t tl = blockIdx.x;
-  for (uint32_t it = 0; tl < ntiles; it++, tl += gridDim.x) {
+  uint32_t j = blockIdx.x;
+  for (uint32_t it = 0; j < ntiles; it++, j += gridDim.x) {
     const uint32_t s = it % kSStages;
     pipe::mbar_wait(&full[s], (it / kSStages) & 1u);
     const ApplyStage &S = st[s];
-    const uint32_t b = tl * kB4 + g;
+    const uint32_t b = run_tile(R, j) * kB4 + g;
     int level = kFree;
     if (b < T.M) level = S.posl[g].w;
     const bool active = level != kFree;

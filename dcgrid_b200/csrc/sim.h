@@ -72,6 +72,9 @@ struct dcg_sim {
     out[6] = launches;
     return DCG_OK;
   }
+  // multi-GPU instances, one rank per process: opaque 64-byte handles exchanged through any host channel
+  virtual int export_handle(void *, uint64_t) { return fail(DCG_ERR_UNSUPPORTED, "not a sharded one-rank-per-process instance"); }
+  virtual int import_handles(const void *, int) { return fail(DCG_ERR_UNSUPPORTED, "not a sharded one-rank-per-process instance"); }
   virtual int algorithmic_bytes(double *bytes, uint64_t *active_blocks) = 0;
   virtual int bench_stage(const char *stage, int level, int reps, float *ms_per_launch, double *alg_bytes) = 0;
 
@@ -126,3 +129,4 @@ struct dcg_sim {
 void dcg_set_create_error(const char *msg);  // text returned by dcg_last_error(NULL)
 dcg_sim *dcg_make_uniform();
 dcg_sim *dcg_make_dcgrid(uint64_t max_num_blocks);
+dcg_sim *dcg_make_dcgrid_sharded(uint64_t max_num_blocks, int rank, int world, int nlocal);

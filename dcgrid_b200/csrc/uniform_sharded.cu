@@ -404,14 +404,14 @@ struct UniformShardSim : dcg_sim {
     return DCG_OK;  // the caller exchanges handles, then import_handles() finalizes
   }
 
-  int export_handle(void *out, uint64_t cap) {
+  int export_handle(void *out, uint64_t cap) override {
     if (cap < sizeof(cudaIpcMemHandle_t)) return fail(DCG_ERR_INVALID, "handle buffer too small");
     cudaIpcMemHandle_t h;
     DCG_CUDA_TRY(cudaIpcGetMemHandle(&h, arena[0]));
     std::memcpy(out, &h, sizeof h);
     return DCG_OK;
   }
-  int import_handles(const void *handles, int count) {
+  int import_handles(const void *handles, int count) override {
     if (!ipc) return fail(DCG_ERR_INVALID, "all ranks are local: nothing to import");
     if (count != world) return fail(DCG_ERR_INVALID, "expected %d handles, got %d", world, count);
     DCG_CUDA_TRY(cudaSetDevice(device));
@@ -689,16 +689,14 @@ DCG_API int dcg_create_uniform_sharded(const dcg_sim_params *params, int device,
 DCG_API uint64_t dcg_shard_handle_bytes(void) { return sizeof(cudaIpcMemHandle_t); }
 
 DCG_API int dcg_shard_export_handle(dcg_sim *sim, void *out, uint64_t capacity) {
-  auto *s = dynamic_cast<dcg::UniformShardSim *>(sim);
-  if (!s || !out) return DCG_ERR_INVALID;
-  return s->export_handle(out, capacity);
+  if (!sim || !out) return DCG_ERR_INVALID;
+  return sim->export_handle(out, capacity);
 }
 
 DCG_API int dcg_shard_import_handles(dcg_sim *sim, const void *handles, int count) {
-  auto *s = dynamic_cast<dcg::UniformShardSim *>(sim);
-  if (!s || !handles) return DCG_ERR_INVALID;
-  int rc = s->import_handles(handles, count);
-  if (rc == DCG_OK) rc = s->synchronize();
+  if (!sim || !handles) return DCG_ERR_INVALID;
+  int rc = sim->import_handles(handles, count);
+  if (rc == DCG_OK) rc = sim->synchronize();
   return rc;
 }
 

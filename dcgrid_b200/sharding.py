@@ -13,7 +13,7 @@ import numpy as np
 
 from . import _lib
 from .params import SimParams
-from .simulation import FluidSimulation
+from .simulation import FluidSimulation, FluidSimulationDCGrid
 
 
 def slab_range(gz, world, rank):
@@ -106,4 +106,50 @@ class FluidSimulationUniformSharded(FluidSimulation):
 
     def totalDensity(self):
         """Global smoke total: local partial summed over ranks."""
-        return all_reduce_sum(super().totalDensity(), self.dist if self.nlocal != self.world else None)
+        return all_reduce_sum(FluidSimulation.totalDensity(self), self.dist if self.nlocal != self.world else None)
+
+
+def dcgrid_unit_owner(max_num_blocks, offsets, max_blocks, world, unit):
+    """Owner rank of every ``unit``-slot piece of the block pool: each level's slot range is shared equally and
+    contiguously (same arithmetic as DCGridSim::setup_sharding in csrc/dcgrid.cu)."""
+    M = int(max_num_blocks)
+    n = (M + unit - 1) // unit
+    owner = np.zeros(n, dtype=np.uint8)
+    for u in range(n):
+        mid = min(u * unit + unit // 2, M - 1)
+        for off, mx in zip(offsets, max_blocks):
+            if off <= mid < off + mx:
+                owner[u] = min(world - 1, (mid - off) * world // mx) if world > 1 else 0
+                break
+    return owner
+
+
+class FluidSimulationDCGridSharded(FluidSimulationDCGrid):
+    """Ranks [rank, rank+nlocal) of a ``world``-way slab decomposition of FluidSimulationDCGrid(size, maxNumBlocks).
+
+    nlocal == world: every rank lives in this object on one device (tests the decomposition on one GPU).
+    nlocal == 1: one rank per process; pass ``dist`` (an initialised torch.distributed) to exchange the arena
+    handles.  After construction all ranks must issue the same sequence of solver calls."""
+
+    def __init__(self, size, maxNumBlocks, params: SimParams, world, rank=0, nlocal=None, device=0, dist=None):
+        FluidSimulation.__init__(self)
+        p = SimParams.from_buffer_copy(params)
+        p.gx, p.gy, p.gz = size
+        self.params, self.world, self.rank = p, int(world), int(rank)
+        self.nlocal = self.world if nlocal is None else int(nlocal)
+        self.dist = dist
+        self.maxNumBlocks = int(maxNumBlocks)
+        self._check(self._L.dcg_create_dcgrid_sharded(ctypes.byref(p), self.maxNumBlocks, device, self.rank, self.world, self.nlocal,
+                                                      ctypes.byref(self._h)))
+        if self.nlocal != self.world:
+            n = int(self._L.dcg_shard_handle_bytes())
+            buf = ctypes.create_string_buffer(n)
+            self._check(self._L.dcg_shard_export_handle(self._h, buf, n))
+            blobs = all_gather_bytes(buf.raw, dist)
+            if len(blobs) != self.world:
+                raise ValueError(f"expected {self.world} arena handles, got {len(blobs)}")
+            self._check(self._L.dcg_shard_import_handles(self._h, b"".join(blobs), self.world))
+
+    def totalDensity(self):
+        """Global smoke total: the partial over the cells this instance owns, summed over ranks."""
+        return all_reduce_sum(FluidSimulation.totalDensity(self), self.dist if self.nlocal != self.world else None)

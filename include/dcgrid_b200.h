@@ -206,6 +206,18 @@ DCG_API int dcg_bench_stage(dcg_sim *sim, const char *stage, int level, int reps
  * dcg_get_counters()[7] = number of barriers executed.                                          */
 DCG_API int dcg_create_uniform_sharded(const dcg_sim_params *params, int device, int rank, int world,
                                        int nlocal, dcg_sim **out);
+/* Slab decomposition of the adaptive grid.  The block pool is cut into pieces of 8,192 slots (one tile of 16
+ * slots when nlocal == world), each level's slot range shared equally among the ranks; a rank runs every field
+ * kernel on the tiles it owns.  Block topology is replicated: every process updates its own copy identically
+ * (same kernels, same host selection).  nlocal == 1: one rank per process/GPU; the eight field arrays live in
+ * one virtual range per field stitched from every rank's arena (CUDA VMM, POSIX-fd handles passed over abstract
+ * AF_UNIX sockets), so a cell id addresses the same cell on every GPU and neighbour / gather accesses to cells
+ * of other ranks travel over NVLink inside the kernels; exchange the dcg_shard_export_handle() blobs and call
+ * dcg_shard_import_handles() (maps the peers, then resets in lock step).  nlocal == world: all ranks in this
+ * instance on one device.  Accessors return the WHOLE pool (any rank can read every cell);
+ * dcg_total_density returns the sum over the cells this instance owns.                                      */
+DCG_API int dcg_create_dcgrid_sharded(const dcg_sim_params *params, uint64_t max_num_blocks, int device,
+                                      int rank, int world, int nlocal, dcg_sim **out);
 DCG_API uint64_t dcg_shard_handle_bytes(void);
 DCG_API int dcg_shard_export_handle(dcg_sim *sim, void *out, uint64_t capacity);
 DCG_API int dcg_shard_import_handles(dcg_sim *sim, const void *handles, int count);
