@@ -103,10 +103,11 @@ struct DCGridSim : dcg_sim {
   // cross-process state (vmm)
   vmm::Driver drv;
   vmm::FdServer fd_server;
-  CUmemGenericAllocationHandle arena_handle[8] = {0};
-  bool arena_imported[8] = {false};
-  size_t gran = 0, arena_bytes = 0;
-  std::vector<size_t> arena_field_off;           // [rank * kFields + f]
+  // physical pieces: per rank one control block + one allocation per (run of consecutive owned units, field)
+  struct UnitRun { uint32_t u0, u1; int owner; };
+  std::vector<UnitRun> unit_runs;                        // maximal runs, ascending
+  std::vector<std::vector<CUmemGenericAllocationHandle>> pieces;  // [rank][0] = control, [1 + k * kFields + f] = k-th run of the rank
+  size_t gran = 0;
   std::vector<uint32_t> units_before;            // [unit]: units of the same owner before it
   std::vector<uint32_t> units_of_rank;
   static constexpr int kFields = 8;              // vw0 vw1 q0 q1 fl p tp div
@@ -393,35 +394,35 @@ struct DCGridSim : dcg_sim {
     CUmemAllocationProp prop = vmm::device_prop(device);
     if (drv.memGranularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_MINIMUM) != CUDA_SUCCESS || gran == 0) return fail(DCG_ERR_CUDA, "cuMemGetAllocationGranularity failed");
     if (((size_t)unit * kBV * 4) % gran) return fail(DCG_ERR_UNSUPPORTED, "allocation granularity %zu does not divide a unit", gran);
-    // arena of rank r: [control block: gran][field 0: its units][field 1] ... (identical arithmetic on every rank)
-    arena_field_off.assign((size_t)world * kFields, 0);
-    size_t mine = 0;
-    for (int r = 0; r < world; r++) {
-      size_t o = gran;
-      for (int f = 0; f < kFields; f++) {
-        arena_field_off[(size_t)r * kFields + f] = o;
-        o += (size_t)units_of_rank[r] * unit * kBV * (f < 2 ? 16 : 4);
-      }
-      if (r == rank0) mine = o;
+    unit_runs.clear();
+    for (uint32_t u = 0; u < nunits;) {
+      uint32_t e = u + 1;
+      while (e < nunits && unit_owner[e] == unit_owner[u]) e++;
+      unit_runs.push_back({u, e, (int)unit_owner[u]});
+      u = e;
     }
-    arena_bytes = mine;
-    if (drv.memCreate(&arena_handle[rank0], arena_bytes, &prop, 0) != CUDA_SUCCESS)
-      return fail(DCG_ERR_CUDA, "cuMemCreate(%zu bytes) failed", arena_bytes);
-    arena_imported[rank0] = true;
-    int fd = -1;
-    if (drv.memExport(&fd, arena_handle[rank0], CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0) != CUDA_SUCCESS)
-      return fail(DCG_ERR_CUDA, "cuMemExportToShareableHandle failed");
-    // this rank's control block is mapped and cleared BEFORE the arena is published: a peer may announce its first
-    // barrier epoch as soon as it has imported the arena
+    pieces.assign(world, {});
+    std::vector<int> fds;
+    auto create = [&](size_t bytes) -> int {
+      CUmemGenericAllocationHandle h;
+      if (drv.memCreate(&h, bytes, &prop, 0) != CUDA_SUCCESS) return fail(DCG_ERR_CUDA, "cuMemCreate(%zu bytes) failed", bytes);
+      pieces[rank0].push_back(h);
+      int fd = -1;
+      if (drv.memExport(&fd, h, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0) != CUDA_SUCCESS) return fail(DCG_ERR_CUDA, "cuMemExportToShareableHandle failed");
+      fds.push_back(fd);
+      return DCG_OK;
+    };
+    DCG_TRY(create(gran));  // control block
+    for (const UnitRun &r : unit_runs)
+      if (r.owner == rank0)
+        for (int f = 0; f < kFields; f++) DCG_TRY(create((size_t)(r.u1 - r.u0) * unit * kBV * (f < 2 ? 16 : 4)));
+    // this rank's control block is mapped and cleared BEFORE the pieces are published: a peer may announce its first
+    // barrier epoch as soon as it has imported them
     if (drv.memReserve(&ctrl_va, (size_t)world * gran, gran, 0, 0) != CUDA_SUCCESS) return fail(DCG_ERR_CUDA, "cuMemAddressReserve failed");
-    DCG_TRY(map_piece(ctrl_va + (size_t)rank0 * gran, gran, 0, rank0));
-    {
-      CUmemAccessDesc acc = access_desc();
-      if (drv.memSetAccess(ctrl_va + (size_t)rank0 * gran, gran, &acc, 1) != CUDA_SUCCESS) return fail(DCG_ERR_CUDA, "cuMemSetAccess failed");
-    }
+    DCG_TRY(map_piece(ctrl_va + (size_t)rank0 * gran, gran, pieces[rank0][0]));
     DCG_CUDA_TRY(cudaMemset(reinterpret_cast<void *>(ctrl_va + (size_t)rank0 * gran), 0, 4096));
     DCG_CUDA_TRY(cudaDeviceSynchronize());
-    if (!fd_server.start(fd, world - 1)) return fail(DCG_ERR_CUDA, "cannot open the descriptor socket");
+    if (!fd_server.start(fds, world - 1)) return fail(DCG_ERR_CUDA, "cannot open the descriptor socket");
     ready = false;
     return DCG_OK;
   }
@@ -439,50 +440,50 @@ struct DCGridSim : dcg_sim {
     std::memcpy(out, fd_server.name, vmm::kHandleBytes);
     return DCG_OK;
   }
-  int map_piece(CUdeviceptr va, size_t bytes, size_t off, int r) {
-    if (drv.memMap(va, bytes, off, arena_handle[r], 0) != CUDA_SUCCESS) return fail(DCG_ERR_CUDA, "cuMemMap failed (rank %d, %zu bytes)", r, bytes);
+  // maps one whole physical piece (cuMemMap takes neither offsets nor partial sizes) and opens it to this device
+  int map_piece(CUdeviceptr va, size_t bytes, CUmemGenericAllocationHandle h) {
+    if (drv.memMap(va, bytes, 0, h, 0) != CUDA_SUCCESS) return fail(DCG_ERR_CUDA, "cuMemMap failed (%zu bytes)", bytes);
+    CUmemAccessDesc acc = access_desc();
+    if (drv.memSetAccess(va, bytes, &acc, 1) != CUDA_SUCCESS) return fail(DCG_ERR_CUDA, "cuMemSetAccess failed: peer access between the GPUs is required");
     return DCG_OK;
   }
   int import_handles(const void *handles, int count) override {
     if (!vmm) return fail(DCG_ERR_INVALID, "not a one-rank-per-process instance");
     if (count != world) return fail(DCG_ERR_INVALID, "expected %d handles, got %d", world, count);
     DCG_CUDA_TRY(cudaSetDevice(device));
+    std::vector<int> runs_of(world, 0);
+    for (const UnitRun &r : unit_runs) runs_of[r.owner]++;
     for (int r = 0; r < world; r++) {
       if (r == rank0) continue;
       char name[vmm::kHandleBytes + 1] = {0};
       std::memcpy(name, static_cast<const char *>(handles) + (size_t)r * vmm::kHandleBytes, vmm::kHandleBytes);
-      const int fd = vmm::fetch_fd(name);
-      if (fd < 0) return fail(DCG_ERR_CUDA, "could not fetch the arena descriptor of rank %d", r);
-      const CUresult rc = drv.memImport(&arena_handle[r], (void *)(uintptr_t)fd, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR);
-      close(fd);
-      if (rc != CUDA_SUCCESS) return fail(DCG_ERR_CUDA, "cuMemImportFromShareableHandle failed for rank %d", r);
-      arena_imported[r] = true;
+      std::vector<int> fds;
+      if (!vmm::fetch_fds(name, 1 + runs_of[r] * kFields, fds)) return fail(DCG_ERR_CUDA, "could not fetch the memory descriptors of rank %d", r);
+      for (int fd : fds) {
+        CUmemGenericAllocationHandle h;
+        const CUresult rc = drv.memImport(&h, (void *)(uintptr_t)fd, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR);
+        close(fd);
+        if (rc != CUDA_SUCCESS) return fail(DCG_ERR_CUDA, "cuMemImportFromShareableHandle failed for rank %d", r);
+        pieces[r].push_back(h);
+      }
     }
     fd_server.finish();
-    if (fd_server.served.load() != world - 1) return fail(DCG_ERR_CUDA, "only %d of %d peers fetched this rank's arena", fd_server.served.load(), world - 1);
-    CUmemAccessDesc acc = access_desc();
+    if (fd_server.served.load() != world - 1) return fail(DCG_ERR_CUDA, "only %d of %d peers fetched this rank's memory", fd_server.served.load(), world - 1);
     // control blocks: rank r's at ctrl_va + r * gran (this rank's own was mapped at creation)
     for (int r = 0; r < world; r++) {
-      if (r == rank0) continue;
-      DCG_TRY(map_piece(ctrl_va + (size_t)r * gran, gran, 0, r));
-      if (drv.memSetAccess(ctrl_va + (size_t)r * gran, gran, &acc, 1) != CUDA_SUCCESS)
-        return fail(DCG_ERR_CUDA, "cuMemSetAccess failed: peer access between the GPUs is required");
+      if (r != rank0) DCG_TRY(map_piece(ctrl_va + (size_t)r * gran, gran, pieces[r][0]));
+      peers.flags[r] = reinterpret_cast<volatile uint32_t *>(ctrl_va + (size_t)r * gran);
     }
-    for (int r = 0; r < world; r++) peers.flags[r] = reinterpret_cast<volatile uint32_t *>(ctrl_va + (size_t)r * gran);
-    // fields: unit u of field f lives in its owner's arena, the k-th of the owner's units
+    // fields: the k-th run of rank r, field f = pieces[r][1 + k * kFields + f], mapped at the run's place
     for (int f = 0; f < kFields; f++) {
       const size_t ub = (size_t)unit * kBV * (f < 2 ? 16 : 4);
       field_va_bytes[f] = (size_t)nunits * ub;
       if (drv.memReserve(&field_va[f], field_va_bytes[f], gran, 0, 0) != CUDA_SUCCESS) return fail(DCG_ERR_CUDA, "cuMemAddressReserve failed");
-      uint32_t u = 0;
-      while (u < nunits) {
-        uint32_t e = u + 1;
-        while (e < nunits && unit_owner[e] == unit_owner[u]) e++;  // consecutive units of one owner are consecutive in its arena
-        const int r = unit_owner[u];
-        DCG_TRY(map_piece(field_va[f] + (size_t)u * ub, (size_t)(e - u) * ub, arena_field_off[(size_t)r * kFields + f] + (size_t)units_before[u] * ub, r));
-        u = e;
+      std::vector<int> k_of(world, 0);
+      for (const UnitRun &r : unit_runs) {
+        const int k = k_of[r.owner]++;
+        DCG_TRY(map_piece(field_va[f] + (size_t)r.u0 * ub, (size_t)(r.u1 - r.u0) * ub, pieces[r.owner][1 + (size_t)k * kFields + f]));
       }
-      if (drv.memSetAccess(field_va[f], field_va_bytes[f], &acc, 1) != CUDA_SUCCESS) return fail(DCG_ERR_CUDA, "cuMemSetAccess failed");
     }
     vw[0] = reinterpret_cast<float4 *>(field_va[0]); vw[1] = reinterpret_cast<float4 *>(field_va[1]);
     q[0] = reinterpret_cast<float *>(field_va[2]); q[1] = reinterpret_cast<float *>(field_va[3]);
@@ -494,15 +495,15 @@ struct DCGridSim : dcg_sim {
     DCG_CUDA_TRY(cudaMemset(d_barrier_err, 0, 4));
     DCG_CUDA_TRY(cudaDeviceSynchronize());
     ready = true;
-    DCG_TRY(reset());  // starts with a barrier: every rank has mapped every arena before any field is touched
+    DCG_TRY(reset());  // starts with a barrier: every rank has mapped every piece before any field is touched
     return check_barrier_error();
   }
   void release_vmm() {
     if (ctrl_va) { drv.memUnmap(ctrl_va, (size_t)world * gran); drv.memFree(ctrl_va, (size_t)world * gran); }
     for (int f = 0; f < kFields; f++)
       if (field_va[f]) { drv.memUnmap(field_va[f], field_va_bytes[f]); drv.memFree(field_va[f], field_va_bytes[f]); }
-    for (int r = 0; r < 8; r++)
-      if (arena_imported[r]) drv.memRelease(arena_handle[r]);
+    for (auto &v : pieces)
+      for (auto h : v) drv.memRelease(h);
   }
   int need_ready() { return ready ? DCG_OK : fail(DCG_ERR_INVALID, "sharded instance not finalized: call dcg_shard_import_handles first"); }
   int check_barrier_error() {

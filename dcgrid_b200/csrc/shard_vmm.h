@@ -1,7 +1,8 @@
 // Cross-process unified address space for the slab-decomposed DCGrid solver (host side only).
 //
-// One process per GPU.  Every rank creates ONE physical arena on its device (cuMemCreate), exports it as a POSIX
-// file descriptor, and every process stitches the pieces of all arenas into one virtual range per field
+// One process per GPU.  Every rank creates the physical pieces it owns on its device (cuMemCreate: one per field
+// and run of consecutive owned units — cuMemMap maps whole allocations only), exports them as POSIX file
+// descriptors, and every process stitches the pieces of all ranks into one virtual range per field
 // (cuMemAddressReserve + cuMemMap), so that a pool cell id indexes the same array on every GPU: kernels are the
 // single-GPU kernels, a load or store of a cell another rank owns simply travels over NVLink / NVSwitch.
 // The driver entry points are resolved through cudaGetDriverEntryPoint (no link-time dependency on libcuda, so
@@ -106,14 +107,15 @@ inline int recv_fd(int sock) {
   return fd;
 }
 
-// serves `fd` to `npeers` connecting peers on an abstract socket, in a helper thread
+// serves the descriptors `fds` (all of them, in order) to `npeers` connecting peers on an abstract socket, in a
+// helper thread
 struct FdServer {
   int lfd = -1;
   std::thread th;
   std::atomic<int> served{0};
   char name[kHandleBytes] = {0};
 
-  bool start(int fd, int npeers) {
+  bool start(std::vector<int> fds, int npeers) {
     static std::atomic<int> counter{0};
     std::snprintf(name, sizeof name, "dcgrid-b200-vmm-%d-%d", (int)getpid(), counter.fetch_add(1));
     lfd = socket(AF_UNIX, SOCK_STREAM, 0);
@@ -121,15 +123,18 @@ struct FdServer {
     socklen_t len;
     sockaddr_un a = abstract_addr(name, len);
     if (bind(lfd, reinterpret_cast<sockaddr *>(&a), len) != 0 || listen(lfd, 16) != 0) return false;
-    th = std::thread([this, fd, npeers] {
+    th = std::thread([this, fds, npeers] {
       for (int i = 0; i < npeers; i++) {
         pollfd p = {lfd, POLLIN, 0};
-        if (poll(&p, 1, 120000) <= 0) return;  // a peer never came: give up after two minutes
+        if (poll(&p, 1, 120000) <= 0) break;  // a peer never came: give up after two minutes
         const int c = accept(lfd, nullptr, nullptr);
-        if (c < 0) return;
-        if (send_fd(c, fd)) served.fetch_add(1);
+        if (c < 0) break;
+        bool ok = true;
+        for (int fd : fds) ok = ok && send_fd(c, fd);
+        if (ok) served.fetch_add(1);
         close(c);
       }
+      for (int fd : fds) close(fd);  // the allocations stay alive through their handles
     });
     return true;
   }
@@ -141,21 +146,27 @@ struct FdServer {
   ~FdServer() { finish(); }
 };
 
-inline int fetch_fd(const char *name) {
+// receives `count` descriptors from the peer listening on `name`; false if the peer cannot be reached
+inline bool fetch_fds(const char *name, int count, std::vector<int> &out) {
   for (int attempt = 0; attempt < 1200; attempt++) {  // up to two minutes: the peer may not be listening yet
     const int s = socket(AF_UNIX, SOCK_STREAM, 0);
-    if (s < 0) return -1;
+    if (s < 0) return false;
     socklen_t len;
     sockaddr_un a = abstract_addr(name, len);
     if (connect(s, reinterpret_cast<sockaddr *>(&a), len) == 0) {
-      const int fd = recv_fd(s);
+      out.clear();
+      for (int i = 0; i < count; i++) {
+        const int fd = recv_fd(s);
+        if (fd < 0) break;
+        out.push_back(fd);
+      }
       close(s);
-      return fd;
+      return (int)out.size() == count;
     }
     close(s);
     usleep(100000);
   }
-  return -1;
+  return false;
 }
 
 }  // namespace vmm
