@@ -11,9 +11,11 @@ reference has no terrain SDF), in its DEVELOPED state: after co
 pre-rolled (untimed, --preroll steps, default 140) until the block topology has reached its fixed point,
 because the first ~100 steps after reset() are the adaptation transient, which is a different
 configuration (configs[3], reported here as "transient": reset + the first 20 steps, timed the same
-way before the pre-roll).  Then W warm-up steps, then exactly K timed steps.  N>1: the slab-decomposed
-DCGrid solver is not implemented in this round; each rank runs an independent replica of the same scene
-(weak scaling, no data-path collective) and the JSON says so.
+way before the pre-roll).  Then W warm-up steps, then exactly K timed steps.  N>1 (torchrun, one process
+per GPU): the slab-decomposed solver (dcg_create_dcgrid_sharded) on ONE scene N times as deep — 512 x 512 x
+512N cells, pool N x 524,288 blocks — so the work per GPU is that of the N=1 run ("weak"); every rank owns
+1/N of each level's slots, neighbour and gather accesses to other ranks' cells travel over NVLink inside the
+kernels, ranks meet at a flag barrier after every kernel phase; `value` counts the cells of the whole scene.
 
 --impl reference  times the CPU restatement of the reference's step (oracle/liboracle.so, OpenMP over
 all host cores) on the same scene: the reference itself has no CPU path, its own implementation is
@@ -93,26 +95,36 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
-def make_sim(workload, device):
-    from dcgrid_b200 import FluidSimulationDCGrid, FluidSimulationUniform, scene_params
+def make_sim(workload, device, rank=0, world=1, dist=None):
+    from dcgrid_b200 import (FluidSimulationDCGrid, FluidSimulationDCGridSharded, FluidSimulationUniform,
+                             FluidSimulationUniformSharded, scene_params)
 
     grid, d, M, solids = WORKLOADS[workload]
+    if world > 1:  # one scene, `world` times as deep, slab-decomposed over the ranks
+        size = (d, d, d * world)
+        p = scene_params(*size, solids=solids)
+        if grid == "dcgrid":
+            sim = FluidSimulationDCGridSharded(size, M * world, p, world, rank=rank, nlocal=1, device=device, dist=dist)
+        else:
+            sim = FluidSimulationUniformSharded(size, p, world, rank=rank, nlocal=1, device=device, dist=dist)
+        return sim, p
     p = scene_params(d, solids=solids)
     sim = FluidSimulationDCGrid((d, d, d), M, p, device=device) if grid == "dcgrid" else FluidSimulationUniform((d, d, d), p, device=device)
     return sim, p
 
 
-def cpu_port_step_time(workload, steps, warmup, threads=None):
-    """Times the CPU restatement (oracle) on the host cores.  Returns (seconds per step, cores, create seconds)."""
+def cpu_port_step_time(workload, steps, warmup, threads=None, depth=1):
+    """Times the CPU restatement (oracle) on the host cores.  Returns (seconds per step, cores, create seconds).
+    depth = N of a --gpus N run: the scene is N times as deep (d x d x dN cells, N x M blocks), like the GPU arm's."""
     if threads:
         os.environ["OMP_NUM_THREADS"] = str(threads)
     from dcgrid_b200.params import scene_params
     from tests._oracle import Oracle
 
     grid, d, M, solids = WORKLOADS[workload]
-    p = scene_params(d, solids=solids)
+    p = scene_params(d, d, d * depth, solids=solids)
     t0 = time.perf_counter()
-    o = Oracle(p, M if grid == "dcgrid" else 0)
+    o = Oracle(p, M * depth if grid == "dcgrid" else 0)
     create = time.perf_counter() - t0
     for _ in range(warmup):
         o.step(1)
@@ -150,17 +162,18 @@ def run_reference_arm(args, rank, world):
     grid, d, M, solids = WORKLOADS[args.workload]
     # each oracle step of the 512^3 scene costs seconds; bound the run to a few minutes
     budget_s = 150.0
-    probe, cores, create = cpu_port_step_time(args.workload, 1, 0)
+    depth = max(1, args.gpus)
+    probe, cores, create = cpu_port_step_time(args.workload, 1, 0, depth=depth)
     steps = max(1, min(args.steps, int(budget_s / max(probe, 1e-6))))
     warm = min(args.warmup, 1)
-    dt, cores, _ = cpu_port_step_time(args.workload, steps, warm) if steps > 1 else (probe, cores, create)
-    value = d ** 3 / dt
+    dt, cores, _ = cpu_port_step_time(args.workload, steps, warm, depth=depth) if steps > 1 else (probe, cores, create)
+    value = d ** 3 * depth / dt
     sample = f"{steps} full step(s) of the same scene after reset ({create:.1f} s construction untimed), OpenMP over {cores} threads"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "grid": grid, "effective_cells": d ** 3, "max_num_blocks": M, "solids": bool(solids),
+        "config": {"workload": args.workload, "grid": grid, "effective_cells": d ** 3 * depth, "max_num_blocks": M * depth, "solids": bool(solids),
                    "note": "reference has no CPU path; this is the strict-IEEE CPU restatement (oracle/), pinned bit-exactly to the reference CUDA"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -207,8 +220,9 @@ def main():
         torch.cuda.synchronize()
 
     grid, d, M, solids = WORKLOADS[args.workload]
-    sim, p = make_sim(args.workload, local_rank)
+    sim, p = make_sim(args.workload, local_rank, rank, world, dist if world > 1 else None)
     ctr0 = sim.counters()
+    scene_cells = d ** 3 * world  # N>1: one scene, N times as deep
 
     # ---- configs[3] (adaptation-heavy): reset() + the first 20 steps, topology changing on every step ----
     transient = None
@@ -218,7 +232,7 @@ def main():
         transient = {"steps": 20, "ms_per_step": sim.lastStepMs() / 20, "what": "the first 20 steps after reset(): adaptTopology moves / refines blocks on every step"}
         c = sim.counters()
         transient["calls_that_changed_topology"] = int(c[1] - ctr0[1])
-        transient["value"] = world * d ** 3 / (transient["ms_per_step"] * 1e-3)
+        transient["value"] = scene_cells / (transient["ms_per_step"] * 1e-3)
     # ---- pre-roll: develop the scene (plume + block topology at its fixed point), untimed ----
     done = 20 if transient else 0
     if args.preroll > done:
@@ -242,8 +256,8 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
     ms_per_step = ms_total / args.steps
-    cells = d ** 3
-    value = world * cells / (ms_per_step * 1e-3)
+    cells = scene_cells
+    value = cells / (ms_per_step * 1e-3)
 
     # ---- end-to-end through the C ABI with host buffers: params in (100 B), step, metric out ----
     from dcgrid_b200.params import SimParams
@@ -261,7 +275,7 @@ def main():
     t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * cells / float(t.item())
+    e2e_value = cells / float(t.item())
 
     alg_bytes, active_blocks = sim.algorithmicBytes()
     ctr = sim.counters()
@@ -273,6 +287,8 @@ def main():
         roof = None
         per_stage = {}
         try:
+            if world > 1:
+                raise RuntimeError("stage timings are taken on 1 GPU (a sharded stage needs every rank): see the N=1 line")
             if grid == "dcgrid":
                 tab = sim.levelTable()
                 lvl = int(max(range(len(tab["loads"])), key=lambda l: int(tab["loads"][l])))
@@ -298,13 +314,19 @@ def main():
         except Exception as e:  # noqa: BLE001
             roof = {"error": str(e)[:200]}
         step_ach = alg_bytes / (ms_per_step * 1e-3) / 1e9
+        if world > 1:
+            roof = {"bound": "hbm", "kernel": f"whole step over {world} ranks (per-kernel figures: the N=1 line)", "achieved": step_ach,
+                    "peak": peak * world, "unit": "GB/s", "frac": step_ach / (peak * world), "traffic": None, "peak_source": peak_src}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": args.workload, "grid": grid, "effective_cells": cells, "max_num_blocks": M, "solids": bool(solids),
-                       "active_blocks": active_blocks, "allocated_cell_updates_per_s": world * 64 * active_blocks / (ms_per_step * 1e-3),
-                       "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (slab decomposition not implemented yet)",
+            "config": {"workload": args.workload, "grid": grid, "effective_cells": cells, "max_num_blocks": M * world, "solids": bool(solids),
+                       "active_blocks": active_blocks, "allocated_cell_updates_per_s": 64 * active_blocks / (ms_per_step * 1e-3),
+                       "parallelism": "single GPU" if world == 1 else
+                       f"slab decomposition over {world} ranks of one {d}x{d}x{d * world} scene (pool {M * world} blocks): per-level slot ranges split "
+                       f"{world} ways, peer cells accessed in place over NVLink (one virtual range per field stitched from every GPU's memory), "
+                       "flag barrier after every kernel phase, topology replicated",
                        "l2": "working set (2.5 GB at 512^3) >> 126 MB L2, no flush needed" if cells >= 256 ** 3 else "L2-resident working set (correctness config)",
                        "schedule": "reference project(): 5 Jacobi pairs per level, cascadic",
                        "preroll_steps": args.preroll, "scene_state": "developed (topology at its fixed point)" if bool(ctr[7]) else "transient"},
@@ -314,8 +336,8 @@ def main():
                     "last_total_density": total},
             "gpu_launches": launches,
             "roofline": roof,
-            "step_roofline": {"bound": "hbm", "achieved": step_ach, "peak": peak, "unit": "GB/s", "frac": step_ach / peak,
-                              "alg_bytes_per_step": alg_bytes, "frac_of_8TBps_nominal": step_ach / 8000.0, "peak_source": peak_src},
+            "step_roofline": {"bound": "hbm", "achieved": step_ach, "peak": peak * world, "unit": "GB/s", "frac": step_ach / (peak * world),
+                              "alg_bytes_per_step": alg_bytes, "frac_of_8TBps_nominal": step_ach / (8000.0 * world), "peak_source": peak_src},
             "stages": per_stage,
             "transient": transient,
             "topology": {"adapt_calls": int(ctr[0] - ctr0[0]), "calls_that_changed_topology": int(ctr[1]), "blocks_moved": int(ctr[2]),

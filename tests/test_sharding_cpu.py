@@ -74,3 +74,29 @@ def test_bootstrap_collectives_gloo_world2():
         assert firsts == [1, 2] and lens == [64, 64]       # rank order, fixed size
         assert total == 4.5
         assert zr == (32 * rank, 32 * rank + 32)
+
+
+def test_dcgrid_unit_ownership_is_contiguous_and_balanced_per_level():
+    """Ownership table of the slab-decomposed adaptive solver (dcgrid_unit_owner mirrors
+    DCGridSim::setup_sharding): inside a level the owner never decreases with the slot, and every rank gets
+    its share of a level that spans enough units."""
+    from dcgrid_b200.sharding import dcgrid_unit_owner
+
+    # C3's level table (SURVEY.md App. C): 512^3, M = 524,288
+    max_blocks = [243420, 243419, 32768, 4096, 512, 64, 8, 1]
+    offsets = np.concatenate([[0], np.cumsum(max_blocks)[:-1]]).tolist()
+    M = 524288
+    for world, unit in ((2, 8192), (4, 8192), (8, 8192), (3, 16), (8, 16)):
+        own = dcgrid_unit_owner(M, offsets, max_blocks, world, unit)
+        assert own.shape[0] == (M + unit - 1) // unit and own.max() <= world - 1
+        mids = np.minimum(np.arange(own.shape[0]) * unit + unit // 2, M - 1)
+        for off, mx in zip(offsets, max_blocks):
+            sel = (mids >= off) & (mids < off + mx)
+            o = own[sel]
+            if o.size == 0:
+                continue
+            assert np.all(np.diff(o.astype(int)) >= 0), "owners are contiguous runs inside a level"
+            if o.size >= 4 * world:
+                counts = np.bincount(o, minlength=world)
+                assert counts.min() >= o.size // world - 1 and counts.max() <= o.size // world + 2
+    assert np.all(dcgrid_unit_owner(M, offsets, max_blocks, 1, 8192) == 0)
