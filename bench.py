@@ -40,6 +40,8 @@ WORKLOADS = {
     "dcgrid256": ("dcgrid", 256, 65536, False),   # configs[1] (C2)
     "uniform64": ("uniform", 64, 0, False),       # configs[0] (C1)
     "dcgrid64": ("dcgrid", 64, 4096, False),      # tiny, adaptation never settles (tests)
+    "dcgrid2048": ("dcgrid", 2048, 14000000, True),   # configs[4] (C5d): 2048^3 effective, 70 GB
+    "uniform1024": ("uniform", 1024, 0, True),        # configs[4] (C5u): dense 1024^3, 41 GiB
 }
 METRIC = "effective cell-updates/s per full step"
 UNIT = "cell-updates/s"
@@ -57,25 +59,45 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    """Samples SM clocks / throttle reasons while the timed region runs: NVML every 2 ms when pynvml is there
+    (the timed region of the default run lasts ~0.15 s), else nvidia-smi every 0.2 s."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.stop_flag = index, [], threading.Event()
+        self.nvml = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
 
     def run(self):
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                if self.nvml:
+                    mhz = float(self.nvml.nvmlDeviceGetClockInfo(self.handle, self.nvml.NVML_CLOCK_SM))
+                    try:
+                        mask = int(self.nvml.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                    except Exception:
+                        mask = int(self.nvml.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                    self.samples.append([mhz, self.max_mhz] + ["Active" if mask & bit else "Not Active" for bit, _ in self.REASONS])
+                else:
+                    out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                         capture_output=True, text=True, timeout=5).stdout.strip()
+                    if out:
+                        self.samples.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.002 if self.nvml else 0.2)
 
     def summary(self):
         self.stop_flag.set()
@@ -86,13 +108,13 @@ class ClockSampler(threading.Thread):
                 sm.append(float(s[0]))
                 mx = max(mx, float(s[1]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[2:6]):
-                    if v.lower().startswith("active"):
+                    if str(v).lower().startswith("active"):
                         reasons.add(name)
             except Exception:
                 continue
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
 def make_sim(workload, device, rank=0, world=1, dist=None):
@@ -306,7 +328,7 @@ def main():
             roof = {"bound": "hbm", "kernel": "k_dc_jacobi_pipe" if grid == "dcgrid" else "k_u_jacobi", "level": lvl, "achieved": ach,
                     "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src,
                     "peak_source": peak_src, "ms_per_launch": ms, "alg_bytes_per_launch": b,
-                    "share_of_step": "20 sweeps on the two populated levels + 10 on level 2 = 38 % of the step (profiles/README.md)"}
+                    "share_of_step": "Jacobi sweeps = 37 % of the step at dcgrid512 (profiles/README.md r1d)"}
             for st in (("advect_both",) if grid == "dcgrid" else ()) + ("advect_velocity", "divergence", "apply_pressure", "advect_density"):
                 sim.benchStage(st, 0, 2)
                 ms_s, b_s = sim.benchStage(st, 0, 6)
@@ -327,7 +349,7 @@ def main():
                        f"slab decomposition over {world} ranks of one {d}x{d}x{d * world} scene (pool {M * world} blocks): per-level slot ranges split "
                        f"{world} ways, peer cells accessed in place over NVLink (one virtual range per field stitched from every GPU's memory), "
                        "flag barrier after every kernel phase, topology replicated",
-                       "l2": "working set (2.5 GB at 512^3) >> 126 MB L2, no flush needed" if cells >= 256 ** 3 else "L2-resident working set (correctness config)",
+                       "l2": "working set (2.6 GB at dcgrid512, 0.3 GB at dcgrid256) >> 126 MB L2, no flush needed" if cells >= 256 ** 3 else "L2-resident working set (correctness config)",
                        "schedule": "reference project(): 5 Jacobi pairs per level, cascadic",
                        "preroll_steps": args.preroll, "scene_state": "developed (topology at its fixed point)" if bool(ctr[7]) else "transient"},
             "clocks": clocks,

@@ -123,6 +123,8 @@ struct DCGridSim : dcg_sim {
   bool skip_dead_zeroing = true;  // k_dc_divergence4: no pressure clears that project() never reads
   int advect_min_blocks = 3;  // __launch_bounds__ variant of the advection kernels (3 or 4 CTAs per SM)
   bool use_pipe = true, snake = true;
+  bool jacobi8 = true;  // k_dc_jacobi_pipe8 (8 cells per thread) instead of k_dc_jacobi_pipe (4)
+  int jacobi8_ctas = 0;
   unsigned pipe_min_tiles = 0;  // levels with fewer tiles take the one-CTA-per-tile kernel
   int sweep_parity = 0;
 
@@ -250,7 +252,7 @@ struct DCGridSim : dcg_sim {
     } else {
       DCG_TRY(create_arena());
     }
-    scratch_floats = 3 * std::max(cells, (size_t)gx * gy * gz);
+    scratch_floats = 3 * cells;  // pool-native accessors; the dense level-0 resampling grows it on demand
     DCG_CUDA_TRY(cudaMalloc(&scratch, scratch_floats * 4));
     DCG_CUDA_TRY(cudaMalloc(&d_partial, 1024 * sizeof(double)));
     DCG_CUDA_TRY(cudaMallocHost(&h_partial, 1024 * sizeof(double)));
@@ -296,12 +298,21 @@ struct DCGridSim : dcg_sim {
         if (const char *e = getenv("DCG_ADVECT_CTAS")) advect_per_sm[mode] = std::max(1, atoi(e));
       }
       pipe_min_tiles = 2u * (unsigned)sm_count;
+      {
+        DCG_CUDA_TRY(cudaFuncSetAttribute(k_dc_jacobi_pipe8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kJacobiPipeSmem));
+        int per8 = 0;
+        DCG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per8, k_dc_jacobi_pipe8, kJ8Threads, kJacobiPipeSmem));
+        if (per8 < 1) return fail(DCG_ERR_CUDA, "k_dc_jacobi_pipe8 does not fit on an SM");
+        jacobi8_ctas = per8 * sm_count;
+      }
       if (const char *e = getenv("DCG_JACOBI")) {
-        use_pipe = std::string(e) != "legacy";
-        if (std::string(e) == "pipe_all") pipe_min_tiles = 1;  // tests: exercise the ring on small levels too
+        const std::string v(e);
+        use_pipe = v != "legacy";
+        if (v == "pipe_all" || v == "pipe4_all") pipe_min_tiles = 1;  // tests: exercise the ring on small levels too
+        if (v == "pipe4" || v == "pipe4_all") jacobi8 = false;
       }
       if (const char *e = getenv("DCG_SNAKE")) snake = std::string(e) != "0";
-      if (const char *e = getenv("DCG_JACOBI_CTAS")) jacobi_pipe_ctas = std::max(1, atoi(e)) * sm_count;
+      if (const char *e = getenv("DCG_JACOBI_CTAS")) jacobi_pipe_ctas = jacobi8_ctas = std::max(1, atoi(e)) * sm_count;
       if (world > 1 && (!use_advect_pipe || !use_stencil_pipe || !use_pipe)) return fail(DCG_ERR_UNSUPPORTED, "the legacy kernel variants are single-GPU only");
     }
     if (vmm) return DCG_OK;  // the caller exchanges handles; import_handles() maps the peers and resets
@@ -962,7 +973,10 @@ struct DCGridSim : dcg_sim {
       const TileRuns &R = w.level[l];
       const unsigned tiles = run_total(R);
       if (tiles == 0) return;
-      if (use_pipe && blocks_for(loads[l], kB4) >= pipe_min_tiles) {
+      if (use_pipe && jacobi8 && blocks_for(loads[l], kB4) >= pipe_min_tiles) {
+        const unsigned grid = std::min<unsigned>(tiles, (unsigned)jacobi8_ctas);
+        k_dc_jacobi_pipe8<<<grid, kJ8Threads, kJacobiPipeSmem, stream>>>(T, kp, R, l, in, out, div, snake ? sweep_parity : 0);
+      } else if (use_pipe && blocks_for(loads[l], kB4) >= pipe_min_tiles) {
         const unsigned grid = std::min<unsigned>(tiles, (unsigned)jacobi_pipe_ctas);
         k_dc_jacobi_pipe<<<grid, kCTA4, kJacobiPipeSmem, stream>>>(T, kp, R, l, in, out, div, snake ? sweep_parity : 0);
       } else {
@@ -1216,6 +1230,14 @@ struct DCGridSim : dcg_sim {
     if (layout == DCG_LAYOUT_DENSE_L0) {
       const size_t n = (size_t)gx * gy * gz;
       if (!dst || count < n * comps) return fail(DCG_ERR_INVALID, "get_field: destination too small");
+      if (n * comps > scratch_floats) {  // 8.6 G cells at 2048^3: only allocated when somebody asks for it
+        DCG_CUDA_TRY(cudaStreamSynchronize(stream));
+        cudaFree(scratch);
+        scratch = nullptr;
+        scratch_floats = 0;
+        DCG_CUDA_TRY(cudaMalloc(&scratch, n * comps * 4));
+        scratch_floats = n * comps;
+      }
       k_dc_dense_l0<<<blocks_for(n, 256), 256, 0, stream>>>(T, kp, src, comps, stride, scratch);
       launches++;
       DCG_CUDA_TRY(cudaMemcpyAsync(dst, scratch, n * comps * 4, cudaMemcpyDeviceToHost, stream));

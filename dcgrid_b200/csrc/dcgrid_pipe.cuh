@@ -169,6 +169,171 @@ __global__ void __launch_bounds__(kCTA4, 4) k_dc_jacobi_pipe(Pool T, KParams P, 
   }
 }
 
+// ---- Jacobi sweep, 8 cells per thread --------------------------------------------------------------------------
+// k_dc_jacobi_pipe is bound by instruction issue as much as by DRAM (64 % of the issue slots, 287 warp
+// instructions per tile iteration, profiles/README.md r1d): per 4 cells a thread pays 16 shuffles + 16 selects
+// for the neighbour exchange and the whole per-thread overhead (ring bookkeeping, descriptor decode, ghost
+// addresses).  Here a thread owns one 2x2x2 subblock (8 contiguous cells = two float4), 8 threads per block,
+// 128 threads per 16-block tile: the x/y/z neighbours inside the subblock are the thread's own registers, only
+// one 2x2 face per axis crosses lanes (12 shuffles per 8 cells), and the per-thread overhead is paid once per
+// 8 cells.  Ring, barriers, ghost prefetch, arithmetic and its order are those of k_dc_jacobi_pipe.
+constexpr int kJ8Threads = kB4 * 8;
+struct Ghost12 {
+  float gx[4];  // [cy*2+cz]: the subblock's x face (-x if sx = 0, +x if sx = 1)
+  float gy[4];  // [cx*2+cz]
+  float gz[4];  // [cx*2+cy]
+};
+__device__ __forceinline__ Ghost12 sub_ghost_values(const Pool &T, const float *__restrict__ src, uint32_t b, int t, const uint4 w0,
+                                                    const uint4 w1, const uint4 w2) {
+  Ghost12 g;
+  const int sx = t >> 2, sy = (t >> 1) & 1, sz = t & 1;
+  const int fx = sx, fy = 2 + sy, fz = 4 + sz;
+  if (!(w1.z & kFdIrregular)) {
+    const uint32_t nbx = fx ? w0.y : w0.x, cdx = fx ? w1.w : w1.z;
+    const uint32_t nby = sy ? w0.w : w0.z, cdy = sy ? w2.y : w2.x;
+    const uint32_t nbz = sz ? w1.y : w1.x, cdz = sz ? w2.w : w2.z;
+    if (cdx == 0) {  // same-level neighbour: the facing 2x2 cells are 16 contiguous bytes
+      const float4 v = *reinterpret_cast<const float4 *>(src + nbx + (uint32_t)((sy << 4) | (sz << 3)));
+      g.gx[0] = v.x; g.gx[1] = v.y; g.gx[2] = v.z; g.gx[3] = v.w;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; k++) g.gx[k] = src[fd_ghost(nbx, cdx, 0, 2 * sy + (k >> 1), 2 * sz + (k & 1))];
+    }
+    if (cdy == 0) {  // two 8-byte pairs (cx = 0, 1)
+      const float *a = src + nby + (uint32_t)((sx << 5) | (sz << 3));
+      const float2 v0 = *reinterpret_cast<const float2 *>(a), v1 = *reinterpret_cast<const float2 *>(a + 4);
+      g.gy[0] = v0.x; g.gy[1] = v0.y; g.gy[2] = v1.x; g.gy[3] = v1.y;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; k++) g.gy[k] = src[fd_ghost(nby, cdy, 1, 2 * sx + (k >> 1), 2 * sz + (k & 1))];
+    }
+    if (cdz == 0) {  // elements cz', 2+cz' of the two float4 of the neighbour subblock (cz' = low bit of the base)
+      const uint32_t a = nbz + (uint32_t)((sx << 5) | (sy << 4));
+      const float4 v0 = *reinterpret_cast<const float4 *>(src + (a & ~1u)), v1 = *reinterpret_cast<const float4 *>(src + (a & ~1u) + 4);
+      const bool hi = a & 1u;
+      g.gz[0] = hi ? v0.y : v0.x; g.gz[1] = hi ? v0.w : v0.z; g.gz[2] = hi ? v1.y : v1.x; g.gz[3] = hi ? v1.w : v1.z;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; k++) g.gz[k] = src[fd_ghost(nbz, cdz, 2, 2 * sx + (k >> 1), 2 * sy + (k & 1))];
+    }
+    return g;
+  }
+  const uint32_t *ft = T.face + (size_t)b * 96;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    g.gx[k] = src[ft[16 * fx + 4 * (2 * sy + (k >> 1)) + (2 * sz + (k & 1))]];
+    g.gy[k] = src[ft[16 * fy + 4 * (2 * sx + (k >> 1)) + (2 * sz + (k & 1))]];
+    g.gz[k] = src[ft[16 * fz + 4 * (2 * sx + (k >> 1)) + (2 * sy + (k & 1))]];
+  }
+  return g;
+}
+
+__global__ void __launch_bounds__(kJ8Threads, 5) k_dc_jacobi_pipe8(Pool T, KParams P, TileRuns R, int level, const float *__restrict__ in,
+                                                                  float *__restrict__ out, const float *__restrict__ div, int reverse) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  JacobiStage *st = reinterpret_cast<JacobiStage *>(smem_raw);
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + kJStages * sizeof(JacobiStage));
+  const uint32_t loads = T.loads[level], off = T.offsets[level];
+  const uint32_t total = run_total(R), none = 0xFFFFFFFFu;
+  const uint32_t g = threadIdx.x >> 3;
+  const int t = threadIdx.x & 7;
+  const int sx = t >> 2, sy = (t >> 1) & 1, sz = t & 1;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < kJStages; s++) pipe::mbar_init(&full[s], 1);
+    pipe::fence_barrier_init();
+  }
+  __syncthreads();
+  const uint64_t pol_stream = pipe::policy_evict_first();
+  auto tile_of = [&](uint32_t it) -> uint32_t {
+    const uint32_t j = blockIdx.x + it * gridDim.x;
+    if (j >= total) return none;
+    return run_tile(R, reverse ? total - 1 - j : j);
+  };
+  auto issue_tile = [&](uint32_t it) {
+    const uint32_t tl = tile_of(it);
+    if (tl == none) return;
+    const uint32_t li0 = tl * kB4;
+    const uint32_t nvalid = min((uint32_t)kB4, loads - li0);
+    const size_t b0 = (size_t)off + li0;
+    JacobiStage &S = st[it % kJStages];
+    uint64_t *bar = &full[it % kJStages];
+    pipe::mbar_expect_tx(bar, nvalid * (2u * kBV * 4u + 48u));
+    pipe::bulk_g2s(S.p, in + b0 * kBV, nvalid * kBV * 4u, bar);
+    pipe::bulk_g2s_hint(S.dv, div + b0 * kBV, nvalid * kBV * 4u, bar, pol_stream);
+    pipe::bulk_g2s(S.fd, T.fd + b0 * 12, nvalid * 48u, bar);
+  };
+  auto load_ghosts = [&](uint32_t it) -> Ghost12 {
+    Ghost12 gv;
+#pragma unroll
+    for (int k = 0; k < 4; k++) gv.gx[k] = gv.gy[k] = gv.gz[k] = 0.f;
+    const uint32_t tl = tile_of(it);
+    if (tl != none) {
+      pipe::mbar_wait(&full[it % kJStages], (it / kJStages) & 1u);
+      const uint32_t li = tl * kB4 + g;
+      if (li < loads) {
+        const uint4 *fdp = reinterpret_cast<const uint4 *>(&st[it % kJStages].fd[g * 12]);
+        gv = sub_ghost_values(T, in, off + li, t, fdp[0], fdp[1], fdp[2]);
+      }
+    }
+    return gv;
+  };
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (uint32_t it = 0; it < (uint32_t)kJStages; it++) issue_tile(it);
+  }
+  const float alpha = (float)((1 << level) * (1 << level)) * P.dx * P.dx;
+  Ghost12 gv = load_ghosts(0), g1 = load_ghosts(1);
+  for (uint32_t it = 0;; it++) {
+    const uint32_t tl = tile_of(it);
+    if (tl == none) break;
+    const uint32_t s = it % kJStages;
+    const Ghost12 gn = load_ghosts(it + 2);  // two tiles ahead: in flight while this tile and the next are computed
+    const uint32_t li = tl * kB4 + g;
+    const bool active = li < loads;
+    const JacobiStage &S = st[s];
+    // two float4 per thread at a 32-byte lane stride: the upper four lanes of a block start with the second one,
+    // which makes both requests bank-conflict free
+    float4 a0 = *reinterpret_cast<const float4 *>(&S.p[g * kBV + 8 * t + 4 * sx]);
+    float4 a1 = *reinterpret_cast<const float4 *>(&S.p[g * kBV + 8 * t + 4 * (sx ^ 1)]);
+    float4 d0 = *reinterpret_cast<const float4 *>(&S.dv[g * kBV + 8 * t + 4 * sx]);
+    float4 d1 = *reinterpret_cast<const float4 *>(&S.dv[g * kBV + 8 * t + 4 * (sx ^ 1)]);
+    __syncthreads();  // every thread holds its part of ring slot s in registers: the slot can be refilled
+    if (threadIdx.x == 0) issue_tile(it + kJStages);
+    const float4 lo = sx ? a1 : a0, hi = sx ? a0 : a1, dlo = sx ? d1 : d0, dhi = sx ? d0 : d1;
+    const float own[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};  // k = cx*4 + cy*2 + cz
+    const float dv[8] = {dlo.x, dlo.y, dlo.z, dlo.w, dhi.x, dhi.y, dhi.z, dhi.w};
+    float rx[4], ry[4], rz[4];  // the facing 2x2 cells of the x / y / z sibling subblock
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      rx[j] = __shfl_xor_sync(0xFFFFFFFFu, sx ? own[j] : own[4 + j], 4);                                            // j = cy*2+cz
+      ry[j] = __shfl_xor_sync(0xFFFFFFFFu, sy ? own[(j >> 1) * 4 + (j & 1)] : own[(j >> 1) * 4 + 2 + (j & 1)], 2);  // j = cx*2+cz
+      rz[j] = __shfl_xor_sync(0xFFFFFFFFu, sz ? own[(j >> 1) * 4 + (j & 1) * 2] : own[(j >> 1) * 4 + (j & 1) * 2 + 1], 1);  // j = cx*2+cy
+    }
+    float o[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int cx = k >> 2, cy = (k >> 1) & 1, cz = k & 1;
+      const int jx = cy * 2 + cz, jy = cx * 2 + cz, jz = cx * 2 + cy;
+      // a cell's outward neighbour along an axis: the sibling subblock's facing cell, or the block's ghost
+      const float xm = cx ? own[k - 4] : (sx ? rx[jx] : gv.gx[jx]);
+      const float xp = cx ? (sx ? gv.gx[jx] : rx[jx]) : own[k + 4];
+      const float ym = cy ? own[k - 2] : (sy ? ry[jy] : gv.gy[jy]);
+      const float yp = cy ? (sy ? gv.gy[jy] : ry[jy]) : own[k + 2];
+      const float zm = cz ? own[k - 1] : (sz ? rz[jz] : gv.gz[jz]);
+      const float zp = cz ? (sz ? gv.gz[jz] : rz[jz]) : own[k + 1];
+      o[k] = div6(xm + xp + ym + yp + zm + zp - alpha * dv[k]);
+    }
+    if (active) {
+      float4 *dst = reinterpret_cast<float4 *>(out + ((size_t)off + li) * kBV + 8 * t);
+      dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+      dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+    }
+    gv = g1;
+    g1 = gn;
+  }
+}
+
 // ---- semi-Lagrangian advection (k_dcgrid_advect_velocity / _density, dcgrid_fluid.cu:7-144), persistent ----
 // The one-CTA-per-4-blocks kernels of dcgrid_kernels.cuh spend ~45 % of their stall samples staging the
 // blocks' 6^3 apron maps (LDG -> STS -> barrier) before the first gather can be issued
