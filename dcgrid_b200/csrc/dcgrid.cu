@@ -42,7 +42,18 @@ struct DCGridSim : dcg_sim {
   std::vector<uint64_t> max_blocks, full_blocks, loads, offsets, move_limit;
   std::vector<size_t> map_size;
 
-  Pool T{};
+  Pool T{};   // the reference's numbering: adaptation, accessors
+  Pool Tf{};  // field order (k_dc_resort_keys): what the field kernels see once `mirrored`
+  bool mirrored = false;
+  uint32_t *d_perm = nullptr, *d_perm_new = nullptr;  // reference slot -> field slot
+  unsigned long long *d_sort_keys64[2] = {nullptr, nullptr};
+  void *d_sort_tmp64 = nullptr;
+  size_t sort_tmp64_bytes = 0;
+  bool use_resort = true;
+  int resort_every = 32;      // topology changes between re-sorts during the transient (0 = only at the fixed point)
+  int changes_since_resort = 0;
+  uint64_t n_resorts = 0;
+  const Pool &hot() const { return mirrored ? Tf : T; }
   uint32_t *d_flags = nullptr, *d_free = nullptr, *d_touched = nullptr, *d_to_move = nullptr, *d_dest = nullptr;
   int4 *d_new_posl = nullptr;
   float *d_sub_scores = nullptr, *d_block_scores = nullptr;
@@ -138,6 +149,9 @@ struct DCGridSim : dcg_sim {
     drop_graphs();
     cudaFree(T.posl); cudaFree(T.parent); cudaFree(T.child); cudaFree(T.apron); cudaFree(T.face); cudaFree(T.fd);
     for (int l = 0; l < kMaxLevels; l++) cudaFree(T.map[l]);
+    cudaFree(d_perm); cudaFree(d_perm_new); cudaFree(d_sort_keys64[0]); cudaFree(d_sort_keys64[1]); cudaFree(d_sort_tmp64);
+    cudaFree(Tf.posl); cudaFree(Tf.parent); cudaFree(Tf.child); cudaFree(Tf.apron);
+    for (int l = 0; l < kMaxLevels; l++) cudaFree(Tf.map[l]);
     cudaFree(d_flags); cudaFree(d_free); cudaFree(d_touched); cudaFree(d_to_move); cudaFree(d_dest); cudaFree(d_counters); cudaFree(d_flag_bits); cudaFree(d_summary);
     if (h_summary) cudaFreeHost(h_summary);
     cudaFree(d_new_posl); cudaFree(d_sub_scores); cudaFree(d_block_scores);
@@ -211,6 +225,9 @@ struct DCGridSim : dcg_sim {
     DCG_CUDA_TRY(cudaMalloc(&T.posl, (size_t)M * sizeof(int4)));
     DCG_CUDA_TRY(cudaMalloc(&T.parent, ((size_t)M + kB4) * 4));  // padded: the stencil rings stream kB4 entries per tile
     DCG_TRY(setup_sharding());
+    DCG_CUDA_TRY(cudaMalloc(&d_perm, (size_t)M * 4));
+    if (const char *e = getenv("DCG_RESORT")) use_resort = std::string(e) != "0";
+    if (const char *e = getenv("DCG_RESORT_EVERY")) resort_every = std::max(0, atoi(e));
     DCG_CUDA_TRY(cudaMalloc(&d_pcount, (kMaxLevels + 1) * 4));
     DCG_CUDA_TRY(cudaMallocHost(&h_pcount, (kMaxLevels + 1) * 4));
     DCG_CUDA_TRY(cudaMalloc(&d_order_keys[0], (size_t)M * 4));
@@ -579,7 +596,10 @@ struct DCGridSim : dcg_sim {
     k_fill_u32<<<blocks_for((size_t)M * 8 + 1, 256), 256, 0, stream>>>(reinterpret_cast<uint32_t *>(d_sub_scores), 0xFF7FFFFFu /* -FLT_MAX */,
                                                                        (size_t)M * 8 + 1);
     k_iota_u32<<<blocks_for(M, 256), 256, 0, stream>>>(d_free, M);  // freeBlockIndices[i] = i, :243-249
-    launches += 3;
+    k_iota_u32<<<blocks_for(M, 256), 256, 0, stream>>>(d_perm, M);  // field order = slot order until the first re-sort
+    mirrored = false;
+    changes_since_resort = 0;
+    launches += 4;
     cur_v = cur_q = 0;
     for (int l = 0; l < levels; l++) {  // :232-241
       loads[l] = (max_blocks[l] == full_blocks[l]) ? max_blocks[l] : 0;
@@ -606,14 +626,78 @@ struct DCGridSim : dcg_sim {
 
   // ---- adaptation: fluid_simulation_dcgrid.cu:320-483 --------------------------------------------
   void sync_loads() {
-    for (int l = 0; l < levels; l++) T.loads[l] = (uint32_t)loads[l];
+    for (int l = 0; l < levels; l++) T.loads[l] = Tf.loads[l] = (uint32_t)loads[l];
   }
   void build_face_descriptors() {
     cudaMemsetAsync(d_counters + 1, 0, 4, stream);
-    k_dc_build_fdesc<<<blocks_for((size_t)M * 8, 256), 256, 0, stream>>>(T, d_counters + 1);
+    k_dc_build_fdesc<<<blocks_for((size_t)M * 8, 256), 256, 0, stream>>>(hot(), d_counters + 1);
     launches++;
     rebuild_order();
   }
+  // ---- field order (dcgrid_kernels.cuh, "field order") ----------------------------------------------------
+  int ensure_mirror_storage() {
+    if (Tf.posl) return DCG_OK;
+    DCG_CUDA_TRY(cudaMalloc(&Tf.posl, (size_t)M * sizeof(int4)));
+    DCG_CUDA_TRY(cudaMalloc(&Tf.parent, ((size_t)M + kB4) * 4));
+    DCG_CUDA_TRY(cudaMalloc(&Tf.child, (size_t)M * 8 * 4));
+    DCG_CUDA_TRY(cudaMalloc(&Tf.apron, (size_t)M * kAV * 4));
+    for (int l = 0; l < sparse; l++) DCG_CUDA_TRY(cudaMalloc(&Tf.map[l], map_size[l] * 4));
+    DCG_CUDA_TRY(cudaMalloc(&d_perm_new, (size_t)M * 4));
+    DCG_CUDA_TRY(cudaMalloc(&d_sort_keys64[0], (size_t)M * 8));
+    DCG_CUDA_TRY(cudaMalloc(&d_sort_keys64[1], (size_t)M * 8));
+    DCG_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp64_bytes, d_sort_keys64[0], d_sort_keys64[1], d_order_vals, d_perm_new, (int)M, 0, 64,
+                                                 stream));
+    DCG_CUDA_TRY(cudaMalloc(&d_sort_tmp64, sort_tmp64_bytes + 16));
+    return DCG_OK;
+  }
+  // rebuilds the field-order mirror of the pool from the reference-order pool through d_perm
+  void mirror() {
+    if (!mirrored) return;
+    Tf.M = T.M; Tf.levels = T.levels; Tf.sparse_levels = T.sparse_levels;
+    for (int l = 0; l < kMaxLevels; l++) { Tf.offsets[l] = T.offsets[l]; Tf.max_blocks[l] = T.max_blocks[l]; Tf.loads[l] = T.loads[l]; }
+    Tf.flags = T.flags; Tf.fd = T.fd; Tf.face = T.face;  // descriptors exist once: for whichever pool the field kernels see
+    cudaMemsetAsync(Tf.parent + M, 0xff, kB4 * 4, stream);
+    k_dc_mirror_blocks<<<blocks_for(M, 256), 256, 0, stream>>>(T, Tf, d_perm);
+    k_dc_mirror_apron<<<blocks_for((size_t)M * kAV, 256), 256, 0, stream>>>(T, Tf, d_perm);
+    for (int l = 0; l < sparse; l++) k_dc_mirror_map<<<blocks_for(map_size[l], 256), 256, 0, stream>>>(T.map[l], Tf.map[l], map_size[l], d_perm);
+    launches += 2 + sparse;
+  }
+  // new permutation (active blocks of every sparse level sorted by position), fields moved into the new order
+  int resort() {
+    DCG_TRY(ensure_mirror_storage());
+    k_dc_resort_keys<<<blocks_for(M, 256), 256, 0, stream>>>(T, kp, world, d_sort_keys64[0], d_order_vals);
+    size_t bytes = sort_tmp64_bytes;
+    DCG_CUDA_TRY(cub::DeviceRadixSort::SortPairs(d_sort_tmp64, bytes, d_sort_keys64[0], d_sort_keys64[1], d_order_vals, d_order_keys[0], (int)M, 0, 64,
+                                                 stream));
+    k_dc_perm_from_sorted<<<blocks_for(M, 256), 256, 0, stream>>>(d_order_keys[0], M, d_perm_new);
+    // fields: old field order -> new field order.  The ping-pong pairs move into their idle halves; the four
+    // single buffers go through the accessor scratch.  (Sharded: every process moves the whole pool — the same
+    // values into the same cells — and the ranks meet between reading the old and writing the new order.)
+    spec_velocity = false;
+    barrier();
+    const unsigned gb = blocks_for(cells, 256);
+    k_dc_permute_field<float4><<<gb, 256, 0, stream>>>(vw[cur_v], vw[cur_v ^ 1], d_perm, d_perm_new, cells);
+    k_dc_permute_field<float><<<gb, 256, 0, stream>>>(q[cur_q], q[cur_q ^ 1], d_perm, d_perm_new, cells);
+    barrier();
+    cur_v ^= 1;
+    cur_q ^= 1;
+    float *single[4] = {fl, p, tp, div};
+    for (float *f : single) {
+      k_dc_permute_field<float><<<gb, 256, 0, stream>>>(f, scratch, d_perm, d_perm_new, cells);
+      barrier();
+      k_copy_f32<<<gb, 256, 0, stream>>>(scratch, f, cells);
+      barrier();
+    }
+    launches += 13;
+    std::swap(d_perm, d_perm_new);
+    mirrored = true;
+    mirror();
+    n_resorts++;
+    changes_since_resort = 0;
+    drop_graphs();
+    return DCG_OK;
+  }
+
   // called whenever block positions or the set of active blocks changed: per rank, the Morton-ordered list of
   // its active blocks, the lists of its blocks with children, and the tile runs of every level
   void rebuild_order() {
@@ -622,10 +706,10 @@ struct DCGridSim : dcg_sim {
       const int rank = rank0 + lr;
       const uint8_t *own = world > 1 ? d_unit_owner : nullptr;
       cudaMemsetAsync(d_pcount, 0, (kMaxLevels + 1) * 4, stream);
-      k_dc_order_keys<<<blocks_for(M, 256), 256, 0, stream>>>(T, order_mode, own, unit, rank, d_order_keys[0], d_order_vals, d_pcount + kMaxLevels);
+      k_dc_order_keys<<<blocks_for(M, 256), 256, 0, stream>>>(hot(), order_mode, own, unit, rank, d_order_keys[0], d_order_vals, d_pcount + kMaxLevels);
       size_t bytes = sort_tmp_bytes;
       cub::DeviceRadixSort::SortPairs(d_sort_tmp, bytes, d_order_keys[0], d_order_keys[1], d_order_vals, w.d_order, (int)M, 0, 32, stream);
-      k_dc_list_parents<<<blocks_for(M, 256), 256, 0, stream>>>(T, own, unit, rank, w.d_plist, d_pcount);
+      k_dc_list_parents<<<blocks_for(M, 256), 256, 0, stream>>>(hot(), own, unit, rank, w.d_plist, d_pcount);
       cudaMemcpyAsync(h_pcount, d_pcount, (kMaxLevels + 1) * 4, cudaMemcpyDeviceToHost, stream);
       cudaStreamSynchronize(stream);
       for (int l = 0; l < kMaxLevels; l++) w.pcount[l] = h_pcount[l];
@@ -847,11 +931,16 @@ struct DCGridSim : dcg_sim {
       k_dc_flag_bits<<<blocks_for(M, 256), 256, 0, stream>>>(d_flags, M, d_flag_bits);
       k_dc_refresh_apron<<<blocks_for(M, 8), 256, 0, stream>>>(T, kp, d_flags, d_flag_bits);
       launches += 2;
+      // the field kernels' view of the pool: new blocks take the field slot of their (fresh) reference slot, moved
+      // blocks keep theirs; every `resort_every` changes the sparse levels are re-sorted by position
+      changes_since_resort++;
+      if (use_resort && resort_every > 0 && changes_since_resort >= resort_every) DCG_TRY(resort());
+      else mirror();
       build_face_descriptors();
       for (int l = levels - 2; l >= 0; l--) {
         // sharded: every process interpolates every new block (identical values); lock step between the levels,
         // a level reads what the coarser one wrote
-        k_dc_propagate<<<num_touched, 64, 0, stream>>>(T, kp, d_touched, l, vw[cur_v], q[cur_q], fl);
+        k_dc_propagate<<<num_touched, 64, 0, stream>>>(hot(), kp, d_touched, d_perm, l, vw[cur_v], q[cur_q], fl);
         launches++;
         barrier();
       }
@@ -862,6 +951,10 @@ struct DCGridSim : dcg_sim {
       n_irregular = h_cnt[1];
     } else if (move_limit == limit_before) {
       steady = true;  // nothing changed and the selection state is unchanged: fixed point
+      if (use_resort && changes_since_resort > 0) {  // the layout the steady state will run on, for good
+        DCG_TRY(resort());
+        build_face_descriptors();
+      }
     }
     DCG_CUDA_TRY(cudaGetLastError());
     return DCG_OK;
@@ -884,22 +977,22 @@ struct DCGridSim : dcg_sim {
         each_rank([&](int, RankWork &w) {
           const uint32_t n = w.pcount[l];
           if (n == 0) return;
-          if (v) k_dc_accumulate_velocity_list<<<blocks_for(8 * (size_t)n, 256), 256, 0, stream>>>(T, w.d_plist + offsets[l], n, v);
-          else k_dc_accumulate_scalar_list<<<blocks_for(8 * (size_t)n, 256), 256, 0, stream>>>(T, w.d_plist + offsets[l], n, ch);
+          if (v) k_dc_accumulate_velocity_list<<<blocks_for(8 * (size_t)n, 256), 256, 0, stream>>>(hot(), w.d_plist + offsets[l], n, v);
+          else k_dc_accumulate_scalar_list<<<blocks_for(8 * (size_t)n, 256), 256, 0, stream>>>(hot(), w.d_plist + offsets[l], n, ch);
           launches++;
         });
         barrier();
       } else if (v) {
-        k_dc_accumulate_velocity<<<blocks_for(8 * loads[l], 256), 256, 0, stream>>>(T, l, v, 0);
+        k_dc_accumulate_velocity<<<blocks_for(8 * loads[l], 256), 256, 0, stream>>>(hot(), l, v, 0);
         launches++;
       } else {
-        k_dc_accumulate_scalar<<<blocks_for(8 * loads[l], 256), 256, 0, stream>>>(T, l, ch, 0);
+        k_dc_accumulate_scalar<<<blocks_for(8 * loads[l], 256), 256, 0, stream>>>(hot(), l, ch, 0);
         launches++;
       }
     }
     if (tail < levels - 1) {
       if (has_rank0()) {
-        k_dc_accumulate_coarse<<<kAccClusterCTAs, kAccClusterThreads, 0, stream>>>(T, tail, v, ch);
+        k_dc_accumulate_coarse<<<kAccClusterCTAs, kAccClusterThreads, 0, stream>>>(hot(), tail, v, ch);
         launches++;
       }
       barrier();
@@ -924,7 +1017,8 @@ struct DCGridSim : dcg_sim {
       const unsigned grid = std::min<unsigned>(w.n_order / kBPC, (unsigned)(advect_per_sm[mode] * sm_count));
       const float *flp = fl;
       const uint32_t *ord = w.d_order;
-      void *args[] = {&T, &kp, &ord, &w.n_order, &vin, &vout, &flp, &qi, &qo};
+      Pool hp = hot();
+      void *args[] = {&hp, &kp, &ord, &w.n_order, &vin, &vout, &flp, &qi, &qo};
       cudaLaunchKernel(advect_fn(mode), dim3(grid), dim3(kAdvectThreads), args, kAdvectPipeSmem, stream);
       launches++;
     });
@@ -942,7 +1036,7 @@ struct DCGridSim : dcg_sim {
       cur_v ^= 1;
       accumulate_velocity(true);
     } else {
-      k_dc_advect_velocity<<<blocks_for(M, kBPC), kCTA, 0, stream>>>(T, kp, vw[cur_v], vw[cur_v ^ 1]);
+      k_dc_advect_velocity<<<blocks_for(M, kBPC), kCTA, 0, stream>>>(hot(), kp, vw[cur_v], vw[cur_v ^ 1]);
       launches++;
       cur_v ^= 1;
       accumulate_velocity(false);
@@ -958,7 +1052,7 @@ struct DCGridSim : dcg_sim {
       cur_q ^= 1;
       accumulate_scalar(q[cur_q], true);
     } else {
-      k_dc_advect_density<<<blocks_for(M, kBPC), kCTA, 0, stream>>>(T, kp, vw[cur_v], fl, q[cur_q], q[cur_q ^ 1]);
+      k_dc_advect_density<<<blocks_for(M, kBPC), kCTA, 0, stream>>>(hot(), kp, vw[cur_v], fl, q[cur_q], q[cur_q ^ 1]);
       launches++;
       cur_q ^= 1;
       accumulate_scalar(q[cur_q], false);
@@ -975,12 +1069,12 @@ struct DCGridSim : dcg_sim {
       if (tiles == 0) return;
       if (use_pipe && jacobi8 && blocks_for(loads[l], kB4) >= pipe_min_tiles) {
         const unsigned grid = std::min<unsigned>(tiles, (unsigned)jacobi8_ctas);
-        k_dc_jacobi_pipe8<<<grid, kJ8Threads, kJacobiPipeSmem, stream>>>(T, kp, R, l, in, out, div, snake ? sweep_parity : 0);
+        k_dc_jacobi_pipe8<<<grid, kJ8Threads, kJacobiPipeSmem, stream>>>(hot(), kp, R, l, in, out, div, snake ? sweep_parity : 0);
       } else if (use_pipe && blocks_for(loads[l], kB4) >= pipe_min_tiles) {
         const unsigned grid = std::min<unsigned>(tiles, (unsigned)jacobi_pipe_ctas);
-        k_dc_jacobi_pipe<<<grid, kCTA4, kJacobiPipeSmem, stream>>>(T, kp, R, l, in, out, div, snake ? sweep_parity : 0);
+        k_dc_jacobi_pipe<<<grid, kCTA4, kJacobiPipeSmem, stream>>>(hot(), kp, R, l, in, out, div, snake ? sweep_parity : 0);
       } else {
-        k_dc_jacobi4<<<tiles, kCTA4, 0, stream>>>(T, kp, R, l, in, out, div);
+        k_dc_jacobi4<<<tiles, kCTA4, 0, stream>>>(hot(), kp, R, l, in, out, div);
       }
       launches++;
     });
@@ -995,8 +1089,8 @@ struct DCGridSim : dcg_sim {
     each_rank([&](int, RankWork &w) {
       const TileRuns &R = w.level[l];
       if (run_total(R) == 0) return;
-      if (prolong_staged) k_dc_prolongate_staged<<<run_total(R), kCTA4, 0, stream>>>(T, R, l, p);
-      else k_dc_prolongate4<<<blocks_for(loads[l], kB4), kCTA4, 0, stream>>>(T, l, p);
+      if (prolong_staged) k_dc_prolongate_staged<<<run_total(R), kCTA4, 0, stream>>>(hot(), R, l, p);
+      else k_dc_prolongate4<<<blocks_for(loads[l], kB4), kCTA4, 0, stream>>>(hot(), l, p);
       launches++;
     });
     barrier();
@@ -1006,10 +1100,10 @@ struct DCGridSim : dcg_sim {
       const unsigned tiles = run_total(w.all);
       if (tiles == 0) return;
       if (use_stencil_pipe)
-        k_dc_divergence_pipe<<<std::min<unsigned>(tiles, (unsigned)div_pipe_ctas), kStencilThreads, kDivPipeSmem, stream>>>(T, kp, w.all, vw[cur_v], div, p,
+        k_dc_divergence_pipe<<<std::min<unsigned>(tiles, (unsigned)div_pipe_ctas), kStencilThreads, kDivPipeSmem, stream>>>(hot(), kp, w.all, vw[cur_v], div, p,
                                                                                                                             tp, zero_from);
       else
-        k_dc_divergence4<<<blocks_for(M, kB4), kCTA4, 0, stream>>>(T, kp, vw[cur_v], div, p, tp, zero_from);
+        k_dc_divergence4<<<blocks_for(M, kB4), kCTA4, 0, stream>>>(hot(), kp, vw[cur_v], div, p, tp, zero_from);
       launches++;
     });
     barrier();
@@ -1020,11 +1114,11 @@ struct DCGridSim : dcg_sim {
       if (tiles == 0) return;
       const unsigned grid = std::min<unsigned>(tiles, (unsigned)apply_pipe_ctas);
       if (use_stencil_pipe && apply_min_blocks == 2)
-        k_dc_apply_pipe<2><<<grid, kStencilThreads, kApplyPipeSmem, stream>>>(T, kp, w.all, p, fl, vw[cur_v]);
+        k_dc_apply_pipe<2><<<grid, kStencilThreads, kApplyPipeSmem, stream>>>(hot(), kp, w.all, p, fl, vw[cur_v]);
       else if (use_stencil_pipe)
-        k_dc_apply_pipe<3><<<grid, kStencilThreads, kApplyPipeSmem, stream>>>(T, kp, w.all, p, fl, vw[cur_v]);
+        k_dc_apply_pipe<3><<<grid, kStencilThreads, kApplyPipeSmem, stream>>>(hot(), kp, w.all, p, fl, vw[cur_v]);
       else
-        k_dc_apply_pressure4<<<blocks_for(M, kB4), kCTA4, 0, stream>>>(T, kp, p, fl, vw[cur_v]);
+        k_dc_apply_pressure4<<<blocks_for(M, kB4), kCTA4, 0, stream>>>(hot(), kp, p, fl, vw[cur_v]);
       launches++;
     });
     barrier();
@@ -1044,9 +1138,9 @@ struct DCGridSim : dcg_sim {
     const size_t smem = (size_t)ncell * (3 * 4 + 6 * 2);
     if (has_rank0()) {  // sharded: one rank walks the coarse tail, the others wait at the barrier
       if (coarse_in_smem && smem <= kCoarseSmemMax && ncell <= 65535)
-        k_dc_coarse_cascade<true><<<1, 1024, smem, stream>>>(T, kp, cf, prolong_coarsest, pairs_coarsest, pairs_level, prolong_levels, p, tp, div, ncell);
+        k_dc_coarse_cascade<true><<<1, 1024, smem, stream>>>(hot(), kp, cf, prolong_coarsest, pairs_coarsest, pairs_level, prolong_levels, p, tp, div, ncell);
       else
-        k_dc_coarse_cascade<false><<<1, 1024, 0, stream>>>(T, kp, cf, prolong_coarsest, pairs_coarsest, pairs_level, prolong_levels, p, tp, div, 0);
+        k_dc_coarse_cascade<false><<<1, 1024, 0, stream>>>(hot(), kp, cf, prolong_coarsest, pairs_coarsest, pairs_level, prolong_levels, p, tp, div, 0);
       launches++;
     }
     barrier();
@@ -1136,13 +1230,13 @@ struct DCGridSim : dcg_sim {
         bytes = 12.0 * cl;
       } else if (st == "advect_velocity" || st == "advect_velocity_legacy") {
         if (st == "advect_velocity") launch_advect_pipe(0, vw[cur_v], vw[cur_v ^ 1], nullptr, nullptr);
-        else k_dc_advect_velocity<<<blocks_for(M, kBPC), kCTA, 0, stream>>>(T, kp, vw[cur_v], vw[cur_v ^ 1]), launches++;
+        else k_dc_advect_velocity<<<blocks_for(M, kBPC), kCTA, 0, stream>>>(hot(), kp, vw[cur_v], vw[cur_v ^ 1]), launches++;
         launches--;
         cur_v ^= 1;
         bytes = 28.0 * call;
       } else if (st == "advect_density" || st == "advect_density_legacy") {
         if (st == "advect_density") launch_advect_pipe(1, vw[cur_v], nullptr, q[cur_q], q[cur_q ^ 1]);
-        else k_dc_advect_density<<<blocks_for(M, kBPC), kCTA, 0, stream>>>(T, kp, vw[cur_v], fl, q[cur_q], q[cur_q ^ 1]), launches++;
+        else k_dc_advect_density<<<blocks_for(M, kBPC), kCTA, 0, stream>>>(hot(), kp, vw[cur_v], fl, q[cur_q], q[cur_q ^ 1]), launches++;
         launches--;
         cur_q ^= 1;
         bytes = 24.0 * call;
@@ -1160,7 +1254,7 @@ struct DCGridSim : dcg_sim {
         launches--;
         bytes = 32.0 * call;
       } else if (st == "accumulate_velocity") {
-        k_dc_accumulate_velocity<<<blocks_for(8 * loads[level], 256), 256, 0, stream>>>(T, level, vw[cur_v], 0);
+        k_dc_accumulate_velocity<<<blocks_for(8 * loads[level], 256), 256, 0, stream>>>(hot(), level, vw[cur_v], 0);
         bytes = 13.5 * cl;
       } else if (st == "prolongate") {
         launch_prolongate(level);
@@ -1182,10 +1276,12 @@ struct DCGridSim : dcg_sim {
   // ---- stats / accessors --------------------------------------------------------------------------------
   int debug_stats(float *out) override {  // :517-528 (host sums the per-block partials in slot order)
     DCG_CUDA_TRY(cudaSetDevice(device));
-    k_dc_debug_stats<<<blocks_for(M, 256), 256, 0, stream>>>(T, kp, p, div, scratch);
-    launches++;
+    k_dc_debug_stats<<<blocks_for(M, 256), 256, 0, stream>>>(hot(), kp, p, div, scratch);
+    // per-block partials back in the reference's slot order: the host sum below is order dependent
+    k_dc_gather_u32<<<blocks_for(M, 256), 256, 0, stream>>>(scratch, d_perm, scratch + M, M);
+    launches += 2;
     std::vector<float> h(M);
-    DCG_CUDA_TRY(cudaMemcpyAsync(h.data(), scratch, (size_t)M * 4, cudaMemcpyDeviceToHost, stream));
+    DCG_CUDA_TRY(cudaMemcpyAsync(h.data(), scratch + M, (size_t)M * 4, cudaMemcpyDeviceToHost, stream));
     DCG_CUDA_TRY(cudaStreamSynchronize(stream));
     float sum = 0.f;
     for (uint32_t i = 0; i < M; i++) sum += h[i];
@@ -1198,7 +1294,7 @@ struct DCGridSim : dcg_sim {
     const int blocks = (int)std::min<size_t>(1024, (cells + 255) / 256);
     double s = 0.0;
     for (int lr = 0; lr < nlocal; lr++) {
-      k_dc_total_density<<<blocks, 256, 0, stream>>>(T, work[lr].all, q[cur_q], fl, d_partial);
+      k_dc_total_density<<<blocks, 256, 0, stream>>>(hot(), work[lr].all, q[cur_q], fl, d_partial);
       launches++;
       DCG_CUDA_TRY(cudaMemcpyAsync(h_partial, d_partial, blocks * sizeof(double), cudaMemcpyDeviceToHost, stream));
       DCG_TRY(synchronize());
@@ -1238,22 +1334,18 @@ struct DCGridSim : dcg_sim {
         DCG_CUDA_TRY(cudaMalloc(&scratch, n * comps * 4));
         scratch_floats = n * comps;
       }
-      k_dc_dense_l0<<<blocks_for(n, 256), 256, 0, stream>>>(T, kp, src, comps, stride, scratch);
+      k_dc_dense_l0<<<blocks_for(n, 256), 256, 0, stream>>>(hot(), kp, src, comps, stride, scratch);
       launches++;
       DCG_CUDA_TRY(cudaMemcpyAsync(dst, scratch, n * comps * 4, cudaMemcpyDeviceToHost, stream));
       return synchronize();
     }
     if (layout != DCG_LAYOUT_NATIVE) return fail(DCG_ERR_INVALID, "get_field: unknown layout %d", layout);
     if (!dst || count < cells * comps) return fail(DCG_ERR_INVALID, "get_field: destination too small");
-    if (field == DCG_FIELD_VELOCITY) {
-      k_dc_unpack_velocity<<<blocks_for(cells, 256), 256, 0, stream>>>(vw[cur_v], scratch, cells);
-      launches++;
-      src = scratch;
-    } else if (vmm) {  // the field spans every rank's arena: gather it into local memory first
-      k_copy_f32<<<blocks_for(cells, 256), 256, 0, stream>>>(src, scratch, cells);
-      launches++;
-      src = scratch;
-    }
+    // fields are stored in field order (and, sharded, span every rank's memory): gather into the reference's slot
+    // order in local memory first
+    k_dc_unpermute_f32<<<blocks_for(cells, 256), 256, 0, stream>>>(src, stride, comps, d_perm, scratch, cells);
+    launches++;
+    src = scratch;
     DCG_CUDA_TRY(cudaMemcpyAsync(dst, src, cells * comps * 4, cudaMemcpyDeviceToHost, stream));
     return synchronize();
   }

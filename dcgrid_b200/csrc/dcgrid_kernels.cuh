@@ -365,9 +365,10 @@ __global__ void __launch_bounds__(256) k_dc_refine(Pool T, KParams P, const uint
 }
 
 // k_dcgrid_propagate_values, :92-143: new/moved block <- 27/9/3/1 interpolation of the parent's cells
-__global__ void __launch_bounds__(64) k_dc_propagate(Pool T, KParams P, const uint32_t *__restrict__ touched, int level,
-                                                     float4 *__restrict__ vw, float *__restrict__ q, float *__restrict__ fl) {
-  const uint32_t b = touched[blockIdx.x];
+// T = the pool in field order, touched = reference slots, perm = reference slot -> field slot
+__global__ void __launch_bounds__(64) k_dc_propagate(Pool T, KParams P, const uint32_t *__restrict__ touched, const uint32_t *__restrict__ perm,
+                                                     int level, float4 *__restrict__ vw, float *__restrict__ q, float *__restrict__ fl) {
+  const uint32_t b = perm[touched[blockIdx.x]];
   const int4 pl = T.posl[b];
   if (pl.w != level) return;
   const uint32_t ps = T.parent[b];
@@ -723,6 +724,104 @@ __global__ void __launch_bounds__(256) k_iota_u32(uint32_t *p, size_t n) {
 __global__ void __launch_bounds__(256) k_fill_posl(int4 *p, size_t n) {
   const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
   if (i < n) p[i] = make_int4(0, 0, 0, kFree);
+}
+
+// ======================================================================================
+// field order: a position-sorted renumbering of the sparse levels for the hot kernels
+// ======================================================================================
+// The reference numbers blocks by allocation order and a block keeps its slot when moveBlocks relocates it
+// (dcgrid_adaptation.cu:65-90), so after the adaptation transient slot order says nothing about position on the
+// finest level: a tile of 16 consecutive slots is 16 scattered blocks, their ghost cells miss L1/L2, and a rank
+// of the slab decomposition owning a slot range owns a random half of space (47 % remote face neighbours,
+// profiles/README.md).  The adaptation (scores, selection, moves, refinement, apron refresh) and every accessor
+// stay in the reference's numbering; the field kernels run on a MIRROR of the pool renumbered by
+// perm[reference slot] = field slot, a per-level permutation that sorts the active blocks of each sparse level by
+// position (x-major like the ordered levels, then Morton).  Mirror structures hold field-space ids, the eight field
+// arrays are stored in field order, so the hot kernels are unchanged: they are simply handed the mirrored Pool.
+// Results cannot depend on the numbering: every cell is computed by the same expression from the same values.
+__global__ void __launch_bounds__(256) k_dc_resort_keys(Pool T, KParams P, int world, unsigned long long *__restrict__ keys,
+                                                        uint32_t *__restrict__ vals) {
+  const uint32_t b = blockIdx.x * 256 + threadIdx.x;
+  if (b >= T.M) return;
+  int range = T.levels;  // level whose slot range holds b (slots past the last range stay where they are)
+  for (int l = 0; l < T.levels; l++)
+    if (b >= T.offsets[l] && b < T.offsets[l] + T.max_blocks[l]) range = l;
+  const int4 pl = T.posl[b];
+  unsigned long long k = 0xFFFFFF00000000ull + b;  // free slots: behind the active ones, in slot order
+  if (range >= T.sparse_levels) {
+    k = b;  // ordered levels are addressed arithmetically (ordered_index): identity
+  } else if (pl.w != kFree) {
+    const uint32_t x = (uint32_t)(pl.x << pl.w) >> 2, y = (uint32_t)(pl.y << pl.w) >> 2, z = (uint32_t)(pl.z << pl.w) >> 2;
+    auto spread3 = [](uint32_t v) {
+      v &= 0x3FFu;
+      v = (v | (v << 16)) & 0x030000FFu;
+      v = (v | (v << 8)) & 0x0300F00Fu;
+      v = (v | (v << 4)) & 0x030C30C3u;
+      v = (v | (v << 2)) & 0x09249249u;
+      return v;
+    };
+    const unsigned long long morton = (spread3(x) << 2) | (spread3(y) << 1) | spread3(z);
+    // several ranks: slabs of 8 blocks along x first (the cut direction of the ordered levels), Morton inside
+    k = world > 1 ? ((unsigned long long)(x >> 3) << 32) | morton : morton;
+  }
+  keys[b] = ((unsigned long long)range << 56) | k;
+  vals[b] = b;
+}
+// sorted[i] = reference slot that takes field slot i
+__global__ void __launch_bounds__(256) k_dc_perm_from_sorted(const uint32_t *__restrict__ sorted, uint32_t M, uint32_t *__restrict__ perm) {
+  const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+  if (i < M) perm[sorted[i]] = i;
+}
+// moves one field from the old to the new field order (64 * comps floats per block)
+template <typename V>
+__global__ void __launch_bounds__(256) k_dc_permute_field(const V *__restrict__ src, V *__restrict__ dst, const uint32_t *__restrict__ perm_old,
+                                                          const uint32_t *__restrict__ perm_new, size_t cells) {
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= cells) return;
+  const uint32_t b = (uint32_t)(i >> 6), c = (uint32_t)(i & 63);
+  dst[(size_t)perm_new[b] * kBV + c] = src[(size_t)perm_old[b] * kBV + c];
+}
+__device__ __forceinline__ uint32_t perm_cell(const uint32_t *__restrict__ perm, uint32_t id) {
+  return id == kNone ? kNone : perm[id >> 6] * kBV + (id & 63u);
+}
+__global__ void __launch_bounds__(256) k_dc_mirror_blocks(Pool T, Pool F, const uint32_t *__restrict__ perm) {
+  const uint32_t b = blockIdx.x * 256 + threadIdx.x;
+  if (b >= T.M) return;
+  const uint32_t fb = perm[b];
+  F.posl[fb] = T.posl[b];
+  const uint32_t ps = T.parent[b];
+  F.parent[fb] = ps == kNone ? kNone : 8 * perm[ps >> 3] + (ps & 7u);
+#pragma unroll
+  for (int s = 0; s < kSV; s++) {
+    const uint32_t c = T.child[(size_t)b * kSV + s];
+    F.child[(size_t)fb * kSV + s] = c == kNone ? kNone : perm[c];
+  }
+}
+__global__ void __launch_bounds__(256) k_dc_mirror_apron(Pool T, Pool F, const uint32_t *__restrict__ perm) {
+  const size_t t = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (t >= (size_t)T.M * kAV) return;
+  const uint32_t b = (uint32_t)(t / kAV), i = (uint32_t)(t % kAV);
+  F.apron[(size_t)perm[b] * kAV + i] = perm_cell(perm, T.apron[t]);
+}
+__global__ void __launch_bounds__(256) k_dc_mirror_map(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, size_t n,
+                                                       const uint32_t *__restrict__ perm) {
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t v = src[i];
+  dst[i] = v == kNone ? kNone : perm[v];
+}
+// accessors: field order -> the reference's slot order
+__global__ void __launch_bounds__(256) k_dc_unpermute_f32(const float *__restrict__ src, int stride, int comps, const uint32_t *__restrict__ perm,
+                                                          float *__restrict__ dst, size_t cells) {
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= cells) return;
+  const size_t f = (size_t)perm[i >> 6] * kBV + (i & 63);
+  for (int k = 0; k < comps; k++) dst[comps * i + k] = src[stride * f + k];
+}
+__global__ void __launch_bounds__(256) k_dc_gather_u32(const float *__restrict__ src, const uint32_t *__restrict__ perm, float *__restrict__ dst,
+                                                       uint32_t n) {
+  const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+  if (i < n) dst[i] = src[perm[i]];
 }
 
 // ======================================================================================
