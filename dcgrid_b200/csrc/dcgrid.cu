@@ -651,14 +651,16 @@ struct DCGridSim : dcg_sim {
     return DCG_OK;
   }
   // rebuilds the field-order mirror of the pool from the reference-order pool through d_perm
-  void mirror() {
+  // full = false: after a topology change with an unchanged permutation — k_dc_refresh_apron has already rewritten
+  // the mirrored apron entries it changed, only the small per-block arrays and the level maps are redone
+  void mirror(bool full = true) {
     if (!mirrored) return;
     Tf.M = T.M; Tf.levels = T.levels; Tf.sparse_levels = T.sparse_levels;
     for (int l = 0; l < kMaxLevels; l++) { Tf.offsets[l] = T.offsets[l]; Tf.max_blocks[l] = T.max_blocks[l]; Tf.loads[l] = T.loads[l]; }
     Tf.flags = T.flags; Tf.fd = T.fd; Tf.face = T.face;  // descriptors exist once: for whichever pool the field kernels see
     cudaMemsetAsync(Tf.parent + M, 0xff, kB4 * 4, stream);
     k_dc_mirror_blocks<<<blocks_for(M, 256), 256, 0, stream>>>(T, Tf, d_perm);
-    k_dc_mirror_apron<<<blocks_for((size_t)M * kAV, 256), 256, 0, stream>>>(T, Tf, d_perm);
+    if (full) k_dc_mirror_apron<<<blocks_for((size_t)M * kAV, 256), 256, 0, stream>>>(T, Tf, d_perm);
     for (int l = 0; l < sparse; l++) k_dc_mirror_map<<<blocks_for(map_size[l], 256), 256, 0, stream>>>(T.map[l], Tf.map[l], map_size[l], d_perm);
     launches += 2 + sparse;
   }
@@ -929,13 +931,13 @@ struct DCGridSim : dcg_sim {
       n_changed++;
       drop_graphs();
       k_dc_flag_bits<<<blocks_for(M, 256), 256, 0, stream>>>(d_flags, M, d_flag_bits);
-      k_dc_refresh_apron<<<blocks_for(M, 8), 256, 0, stream>>>(T, kp, d_flags, d_flag_bits);
+      k_dc_refresh_apron<<<blocks_for(M, 8), 256, 0, stream>>>(T, kp, d_flags, d_flag_bits, mirrored ? Tf.apron : nullptr, d_perm);
       launches += 2;
       // the field kernels' view of the pool: new blocks take the field slot of their (fresh) reference slot, moved
       // blocks keep theirs; every `resort_every` changes the sparse levels are re-sorted by position
       changes_since_resort++;
       if (use_resort && resort_every > 0 && changes_since_resort >= resort_every) DCG_TRY(resort());
-      else mirror();
+      else mirror(false);
       build_face_descriptors();
       for (int l = levels - 2; l >= 0; l--) {
         // sharded: every process interpolates every new block (identical values); lock step between the levels,

@@ -89,8 +89,11 @@ __global__ void __launch_bounds__(256) k_dc_flag_bits(const uint32_t *__restrict
 // block walks its 6^3 map in 7 strides of 32 and touches rim entries only; a block whose flag bit and
 // whose neighbours' flag bits are all clear leaves after the bitmap tests.
 __device__ __forceinline__ bool flag_bit(const uint32_t *__restrict__ bits, uint32_t b) { return (bits[b >> 5] >> (b & 31)) & 1u; }
+// fapron / perm: the field-order mirror of the apron map (nullptr while field order = slot order); every entry
+// rewritten here is rewritten there too, translated through perm, so a topology change costs no full re-mirror.
 __global__ void __launch_bounds__(256) k_dc_refresh_apron(Pool T, KParams P, const uint32_t *__restrict__ flags,
-                                                          const uint32_t *__restrict__ flag_bits) {
+                                                          const uint32_t *__restrict__ flag_bits, uint32_t *__restrict__ fapron,
+                                                          const uint32_t *__restrict__ perm) {
   const uint32_t b = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (b >= T.M) return;
   const int4 pl = T.posl[b];
@@ -108,7 +111,9 @@ __global__ void __launch_bounds__(256) k_dc_refresh_apron(Pool T, KParams P, con
       if (nx < 0 || ny < 0 || nz < 0 || nx * scale >= P.gx || ny * scale >= P.gy || nz * scale >= P.gz) {
         // :54-60 feeds APRON coordinates (1..4) to SPREAD where cell coordinates (0..3) are meant
         // (SURVEY App. B-5).  Reproduced on purpose: parity with the reference's Neumann ghosts.
-        *entry = b * kBV + spread(min(max(i, 1), kBW), 2) + spread(min(max(j, 1), kBW), 1) + spread(min(max(k, 1), kBW), 0);
+        const uint32_t e = b * kBV + spread(min(max(i, 1), kBW), 2) + spread(min(max(j, 1), kBW), 1) + spread(min(max(k, 1), kBW), 0);
+        *entry = e;
+        if (fapron) fapron[(size_t)perm[b] * kAV + ai] = perm[b] * kBV + (e & 63u);
         continue;
       }
       int nl = level;
@@ -128,7 +133,9 @@ __global__ void __launch_bounds__(256) k_dc_refresh_apron(Pool T, KParams P, con
     if (nb == kNone) continue;
     const int4 np = T.posl[nb];
     const int s = 1 << (np.w - level);
-    *entry = nb * kBV + cell_bits(nx / s - np.x, ny / s - np.y, nz / s - np.z);
+    const uint32_t cb = cell_bits(nx / s - np.x, ny / s - np.y, nz / s - np.z);
+    *entry = nb * kBV + cb;
+    if (fapron) fapron[(size_t)perm[b] * kAV + ai] = perm[nb] * kBV + cb;
   }
 }
 

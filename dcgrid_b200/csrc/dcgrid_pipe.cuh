@@ -573,11 +573,14 @@ __device__ __forceinline__ uint32_t spread3(uint32_t v) {  // 10 bits -> every t
 __global__ void __launch_bounds__(256) k_dc_order_keys(Pool T, int mode, const uint8_t *__restrict__ owner, uint32_t unit, int rank,
                                                        uint32_t *__restrict__ keys, uint32_t *__restrict__ vals, uint32_t *__restrict__ count) {
   const uint32_t b = blockIdx.x * 256 + threadIdx.x;
-  if (b >= T.M) return;
-  const int4 pl = T.posl[b];
+  const bool in_pool = b < T.M;
+  const int4 pl = in_pool ? T.posl[b] : make_int4(0, 0, 0, kFree);
+  const bool listed = in_pool && pl.w != kFree && (!owner || owner[b / unit] == rank);
+  const unsigned votes = __ballot_sync(0xFFFFFFFFu, listed);  // one atomic per warp, not per block
+  if ((threadIdx.x & 31u) == 0 && votes) atomicAdd(count, (uint32_t)__popc(votes));
+  if (!in_pool) return;
   uint32_t key = 0xFFFFFFFFu;
-  if (pl.w != kFree && (!owner || owner[b / unit] == rank)) {
-    atomicAdd(count, 1u);
+  if (listed) {
     if (mode == 0) key = b;
     else key = (spread3((uint32_t)(pl.x << pl.w) >> 2) << 2) | (spread3((uint32_t)(pl.y << pl.w) >> 2) << 1) | spread3((uint32_t)(pl.z << pl.w) >> 2);
   }

@@ -87,6 +87,7 @@ def test_dcgrid_bit_exact_vs_oracle(gpu, d, M, solids, steps, schedule):
     {"DCG_JACOBI": "pipe_all", "DCG_SNAKE": "0"},
     {"DCG_JACOBI": "pipe4_all"},                           # the 4-cells-per-thread ring kernel
     {"DCG_RESORT_EVERY": "1", "DCG_JACOBI": "pipe_all"},   # field order re-sorted by position after EVERY topology change
+    {"DCG_RESORT_EVERY": "3"},                             # incremental mirror updates between the re-sorts
     {"DCG_RESORT": "0"},                                   # field order = the reference's slot order throughout
     {"DCG_JACOBI": "legacy", "DCG_ADVECT": "legacy"},      # one-CTA-per-tile kernels
     {"DCG_JACOBI_CTAS": "1", "DCG_ADVECT_CTAS": "1"},      # one resident CTA per SM: every CTA walks several tiles
