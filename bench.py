@@ -183,12 +183,25 @@ def run_reference_arm(args, rank, world):
         return
     grid, d, M, solids = WORKLOADS[args.workload]
     # each oracle step of the 512^3 scene costs seconds; bound the run to a few minutes
-    budget_s = 150.0
+    budget_s = 90.0
     depth = max(1, args.gpus)
-    probe, cores, create = cpu_port_step_time(args.workload, 1, 0, depth=depth)
+    from dcgrid_b200.params import scene_params
+    from tests._oracle import Oracle
+
+    cores = os.cpu_count()
+    t0 = time.perf_counter()
+    o = Oracle(scene_params(d, d, d * depth, solids=solids), M * depth if grid == "dcgrid" else 0)
+    create = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    o.step(1)  # warm-up step, also the probe that bounds the sample
+    probe = time.perf_counter() - t0
     steps = max(1, min(args.steps, int(budget_s / max(probe, 1e-6))))
-    warm = min(args.warmup, 1)
-    dt, cores, _ = cpu_port_step_time(args.workload, steps, warm, depth=depth) if steps > 1 else (probe, cores, create)
+    warm = 1
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        o.step(1)
+    dt = (time.perf_counter() - t0) / steps
+    o.close()
     value = d ** 3 * depth / dt
     sample = f"{steps} full step(s) of the same scene after reset ({create:.1f} s construction untimed), OpenMP over {cores} threads"
     line = {
