@@ -185,6 +185,8 @@ def run_reference_arm(args, rank, world):
     # each oracle step of the 512^3 scene costs seconds; bound the run to a few minutes
     budget_s = 90.0
     depth = max(1, args.gpus)
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU arm uses every host core, set before libgomp loads
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count())
     from dcgrid_b200.params import scene_params
     from tests._oracle import Oracle
 

@@ -58,25 +58,27 @@ def main():
         sh.close(); one.close()
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-    # ---- timing of the sharded solver on a larger grid
-    d = args.bench_size
-    p = scene_params(d, solids=True)
-    sh = FluidSimulationUniformSharded((d, d, d), p, world, rank=rank, nlocal=1, device=local, dist=dist)
-    sh.step(3)
-    dist.barrier(); torch.cuda.synchronize()
-    sh.step(args.bench_steps)
-    ms = torch.tensor([sh.lastStepMs()], dtype=torch.float64, device="cuda")
-    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    bytes_local, _ = sh.algorithmicBytes()
-    bt = torch.tensor([bytes_local], dtype=torch.float64, device="cuda")
-    dist.all_reduce(bt)
-    ctr = sh.counters()
-    if rank == 0:
+    # ---- timing of the sharded solver on a larger grid (--bench-size 0: parity only)
+    out = {"check": "mgpu_uniform", "n_gpus": world, "bit_exact_vs_single_gpu": bool(flag.item()), "parity_size": args.size}
+    if args.bench_size > 0:
+        d = args.bench_size
+        p = scene_params(d, solids=True)
+        sh = FluidSimulationUniformSharded((d, d, d), p, world, rank=rank, nlocal=1, device=local, dist=dist)
+        sh.step(3)
+        dist.barrier(); torch.cuda.synchronize()
+        sh.step(args.bench_steps)
+        ms = torch.tensor([sh.lastStepMs()], dtype=torch.float64, device="cuda")
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        bytes_local, _ = sh.algorithmicBytes()
+        bt = torch.tensor([bytes_local], dtype=torch.float64, device="cuda")
+        dist.all_reduce(bt)
+        ctr = sh.counters()
         per = float(ms.item()) / args.bench_steps
-        print(json.dumps({"check": "mgpu_uniform", "n_gpus": world, "bit_exact_vs_single_gpu": bool(flag.item()), "parity_size": args.size,
-                          "bench_size": d, "ms_per_step": per, "cell_updates_per_s": d ** 3 / (per * 1e-3),
-                          "alg_GBps_all_ranks": float(bt.item()) / (per * 1e-3) / 1e9, "barriers": int(ctr[7]), "launches": int(ctr[6])}), flush=True)
-    sh.close()
+        out.update({"bench_size": d, "ms_per_step": per, "cell_updates_per_s": d ** 3 / (per * 1e-3),
+                    "alg_GBps_all_ranks": float(bt.item()) / (per * 1e-3) / 1e9, "barriers": int(ctr[7]), "launches": int(ctr[6])})
+        sh.close()
+    if rank == 0:
+        print(json.dumps(out), flush=True)
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if flag.item() else 1)
