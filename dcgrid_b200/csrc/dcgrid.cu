@@ -111,6 +111,7 @@ struct DCGridSim : dcg_sim {
     uint32_t pcount[kMaxLevels] = {0};
   };
   std::vector<RankWork> work;
+  std::vector<char> level_single;  // the active blocks of the level all belong to one rank: its sweeps need no barrier between them
   // cross-process state (vmm)
   vmm::Driver drv;
   vmm::FdServer fd_server;
@@ -722,6 +723,15 @@ struct DCGridSim : dcg_sim {
       w.all = tile_runs(0, 0, (uint32_t)((M64 + kTile - 1) / kTile), rank);
       for (int l = 0; l < levels; l++) w.level[l] = tile_runs(offsets[l], 0, (uint32_t)((loads[l] + kTile - 1) / kTile), rank);
     }
+    level_single.assign(levels, 0);
+    for (int l = 0; l < levels; l++) {
+      if (loads[l] == 0) { level_single[l] = 1; continue; }
+      // a tile belongs to the owner of its first slot; the last tile may reach into the next unit
+      const uint32_t u0 = (uint32_t)(offsets[l] / unit), u1 = (uint32_t)std::min<uint64_t>(nunits - 1, (offsets[l] + loads[l] - 1) / unit);
+      bool one = true;
+      for (uint32_t u = u0; u <= u1; u++) one = one && unit_owner[u] == unit_owner[u0];
+      level_single[l] = one ? 1 : 0;
+    }
   }
   uint32_t finer_full_mask() const {
     uint32_t m = 0;
@@ -1080,7 +1090,10 @@ struct DCGridSim : dcg_sim {
       }
       launches++;
     });
-    barrier();
+    if (!level_single[l]) barrier();  // a level held by one rank: one barrier after its last sweep (end_level)
+  }
+  void end_level(int l) {
+    if (level_single[l]) barrier();
   }
   void jacobi_pair(int l) {
     if (loads[l] == 0) return;
@@ -1095,7 +1108,7 @@ struct DCGridSim : dcg_sim {
       else k_dc_prolongate4<<<blocks_for(loads[l], kB4), kCTA4, 0, stream>>>(hot(), l, p);
       launches++;
     });
-    barrier();
+    if (!level_single[l]) barrier();  // single-owner level: the same rank sweeps it next
   }
   void launch_divergence(int zero_from) {
     each_rank([&](int, RankWork &w) {
@@ -1157,6 +1170,7 @@ struct DCGridSim : dcg_sim {
       if (loads[l] == 0) continue;
       launch_prolongate(l);
       for (int i = 0; i < project_level_pairs; i++) jacobi_pair(l);
+      end_level(l);
     }
     apply_stage();
     DCG_CUDA_TRY(cudaGetLastError());
@@ -1167,8 +1181,10 @@ struct DCGridSim : dcg_sim {
     divergence_stage(0);
     const int cf = small_levels_from(kCoarseBlocks);
     launch_coarse_cascade(cf, 0, local_pairs, local_pairs, 0);
-    for (int l = cf - 1; l >= 0; l--)
+    for (int l = cf - 1; l >= 0; l--) {
       for (int i = 0; i < local_pairs; i++) jacobi_pair(l);
+      end_level(l);
+    }
     apply_stage();
     DCG_CUDA_TRY(cudaGetLastError());
     return DCG_OK;
