@@ -207,11 +207,12 @@ __device__ __forceinline__ Ghost12 sub_ghost_values(const Pool &T, const float *
 #pragma unroll
       for (int k = 0; k < 4; k++) g.gy[k] = src[fd_ghost(nby, cdy, 1, 2 * sx + (k >> 1), 2 * sz + (k & 1))];
     }
-    if (cdz == 0) {  // elements cz', 2+cz' of the two float4 of the neighbour subblock (cz' = low bit of the base)
-      const uint32_t a = nbz + (uint32_t)((sx << 5) | (sy << 4));
-      const float4 v0 = *reinterpret_cast<const float4 *>(src + (a & ~1u)), v1 = *reinterpret_cast<const float4 *>(src + (a & ~1u) + 4);
-      const bool hi = a & 1u;
-      g.gz[0] = hi ? v0.y : v0.x; g.gz[1] = hi ? v0.w : v0.z; g.gz[2] = hi ? v1.y : v1.x; g.gz[3] = hi ? v1.w : v1.z;
+    if (cdz == 0) {
+      // four 4-byte loads at stride 2 (one sector).  Not two float4 + a select on the base's low bit: the select
+      // would consume the loads where they are issued and turn the two-tiles-ahead prefetch into a blocking wait
+      // (it was the top long-scoreboard stall of the kernel)
+      const float *a = src + nbz + (uint32_t)((sx << 5) | (sy << 4));
+      g.gz[0] = a[0]; g.gz[1] = a[2]; g.gz[2] = a[4]; g.gz[3] = a[6];
     } else {
 #pragma unroll
       for (int k = 0; k < 4; k++) g.gz[k] = src[fd_ghost(nbz, cdz, 2, 2 * sx + (k >> 1), 2 * sy + (k & 1))];
