@@ -315,13 +315,16 @@ struct DCGridSim : dcg_sim {
         if (advect_per_sm[mode] < 1) return fail(DCG_ERR_CUDA, "k_dc_advect_pipe does not fit on an SM");
         if (const char *e = getenv("DCG_ADVECT_CTAS")) advect_per_sm[mode] = std::max(1, atoi(e));
       }
-      pipe_min_tiles = 2u * (unsigned)sm_count;
+      pipe_min_tiles = 2u * (unsigned)sm_count;  // refined below once the resident CTA count of the ring kernel is known
       {
         DCG_CUDA_TRY(cudaFuncSetAttribute(k_dc_jacobi_pipe8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kJacobiPipeSmem));
         int per8 = 0;
         DCG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per8, k_dc_jacobi_pipe8, kJ8Threads, kJacobiPipeSmem));
         if (per8 < 1) return fail(DCG_ERR_CUDA, "k_dc_jacobi_pipe8 does not fit on an SM");
         jacobi8_ctas = per8 * sm_count;
+        // a resident CTA should walk >= 4 tiles to amortise its ring set-up: at 512^3 level 2 (2,048 tiles) takes
+        // 8.3 us with one CTA per tile and 10.3 us with the ring
+        pipe_min_tiles = 4u * (unsigned)jacobi8_ctas;
       }
       if (const char *e = getenv("DCG_JACOBI")) {
         const std::string v(e);
