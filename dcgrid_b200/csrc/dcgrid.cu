@@ -307,7 +307,7 @@ struct DCGridSim : dcg_sim {
       DCG_CUDA_TRY(cudaFuncSetAttribute(k_dc_coarse_cascade<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCoarseSmemMax));
       if (const char *e = getenv("DCG_ZERO_ALL")) skip_dead_zeroing = std::string(e) == "0";
       if (const char *e = getenv("DCG_ADVECT_FUSE")) fuse_advect = std::string(e) != "0";
-      if (const char *e = getenv("DCG_ADVECT_MINB")) advect_min_blocks = atoi(e) == 4 ? 4 : 3;
+      if (const char *e = getenv("DCG_ADVECT_MINB")) advect_min_blocks = (atoi(e) == 4 || atoi(e) == 2) ? atoi(e) : 3;
       for (int mode = 0; mode < 3; mode++) {
         const void *fn = advect_fn(mode);
         DCG_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAdvectPipeSmem));
@@ -1016,6 +1016,11 @@ struct DCGridSim : dcg_sim {
   void accumulate_velocity(bool fused) { accumulate(vw[cur_v], nullptr, fused); }
   void accumulate_scalar(float *ch, bool fused) { accumulate(nullptr, ch, fused); }
   const void *advect_fn(int mode) const {
+    if (advect_min_blocks == 2) {
+      if (mode == 0) return (const void *)k_dc_advect_pipe<0, 2>;
+      if (mode == 1) return (const void *)k_dc_advect_pipe<1, 2>;
+      return (const void *)k_dc_advect_pipe<2, 2>;
+    }
     if (advect_min_blocks == 3) {
       if (mode == 0) return (const void *)k_dc_advect_pipe<0, 3>;
       if (mode == 1) return (const void *)k_dc_advect_pipe<1, 3>;
