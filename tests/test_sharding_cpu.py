@@ -100,3 +100,25 @@ def test_dcgrid_unit_ownership_is_contiguous_and_balanced_per_level():
                 counts = np.bincount(o, minlength=world)
                 assert counts.min() >= o.size // world - 1 and counts.max() <= o.size // world + 2
     assert np.all(dcgrid_unit_owner(M, offsets, max_blocks, 1, 8192) == 0)
+
+
+def test_descriptor_exchange_between_two_processes(tmp_path):
+    """The slab-decomposed DCGrid solver passes its GPU allocations between ranks as POSIX file descriptors over
+    abstract AF_UNIX sockets (dcgrid_b200/csrc/shard_vmm.h: FdServer / fetch_fds).  That plumbing is GPU-free:
+    two processes exchange three descriptors each (pipes carrying a rank-specific message) and check them."""
+    import os
+    import shutil
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cuda_inc = os.environ.get("CUDA_HOME", "/usr/local/cuda") + "/include"
+    if shutil.which("g++") is None or not os.path.exists(os.path.join(cuda_inc, "cuda.h")):
+        import pytest
+
+        pytest.skip("needs g++ and the CUDA headers (types only; nothing is linked)")
+    exe = str(tmp_path / "fd_exchange_test")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-I" + cuda_inc, os.path.join(root, "tests", "native", "fd_exchange_test.cpp"), "-o", exe,
+                           "-pthread"])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "rank0 rc=0 rank1 rc=0" in r.stdout
