@@ -132,6 +132,47 @@ __global__ void __launch_bounds__(256) k_u_advect_density(KParams P, const float
   qout[i] = out;
 }
 
+// advectDensity() of step n and advectVelocity() of step n+1 in one pass: both backtrace every cell through the
+// same velocity field (nothing runs between them, simulation.cpp:104-111) and therefore share the sample — the 8
+// clamped ids and the fluidity-weighted weights.  The advected velocity goes to the idle ping-pong buffer; the
+// host uses it in the next advect_velocity() if nothing touched the state in between (`spec_velocity`).
+__global__ void __launch_bounds__(256) k_u_advect_both(KParams P, const float4 *__restrict__ vin, float4 *__restrict__ vout,
+                                                       const float *__restrict__ qin, float *__restrict__ qout) {
+  const int x = blockIdx.x * BX + threadIdx.x, y = blockIdx.y * BY + threadIdx.y, z = blockIdx.z * BZ + threadIdx.z;
+  if (x >= P.gx || y >= P.gy || z >= P.gz) return;
+  const uint64_t i = lidx(P, x, y, z);
+  const float4 me = vin[i];
+  const float bx = ((float)x + .5f) - me.x * P.dt * P.rdx;
+  const float by = ((float)y + .5f) - me.y * P.dt * P.rdx;
+  const float bz = ((float)z + .5f) - me.z * P.dt * P.rdx;
+  const USample s = u_sample(P, bx, by, bz);
+  float4 c[8];
+  float q[8], f[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    c[k] = vin[s.id[k]];
+    q[k] = qin[s.id[k]];
+    f[k] = c[k].w;
+  }
+  const Weights8 W = corner_weights(f, s.fx, s.fy, s.fz);
+  float3 vo = make_float3(0.f, 0.f, 0.f);
+  float qo = 0.f;
+  if (!(W.acc < 1e-6f)) {
+    float vx[8], vy[8], vz[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int cx = s.x0 + ((k >> 2) & 1), cy = s.y0 + ((k >> 1) & 1), cz = s.z0 + (k & 1);
+      const float3 v = velocity_bc(P, make_float3(c[k].x, c[k].y, c[k].z), cx, cy, cz, 1);
+      vx[k] = v.x; vy[k] = v.y; vz[k] = v.z;
+      q[k] = density_bc(P, q[k], cx, cy, cz, 1);
+    }
+    vo = make_float3(blend8(vx, W.w), blend8(vy, W.w), blend8(vz, W.w));
+    qo = blend8(q, W.w);
+  }
+  vout[i] = make_float4(vo.x, vo.y, vo.z, me.w);
+  qout[i] = qo;
+}
+
 // k_uniform_calc_divergence, uniformgrid_fluid.cu:107-132
 __global__ void __launch_bounds__(256) k_u_divergence(KParams P, const float4 *__restrict__ vw, float *__restrict__ div,
                                                       float *__restrict__ p, float *__restrict__ tp) {
@@ -276,6 +317,9 @@ struct UniformSim : dcg_sim {
   double *h_partial = nullptr;    // pinned
   int cur_v = 0, cur_q = 0;
   bool fluidity_dirty = true;
+  // k_u_advect_both: advect_density() also produces the NEXT step's advected velocity in vw[cur_v ^ 1];
+  // spec_velocity = that buffer is valid (nothing has touched velocity or parameters since)
+  bool fuse_advect = true, spec_velocity = false;
   std::vector<uint64_t> level_off;
 
   // CUDA graph of one full step (advectVelocity, adaptTopology, project, advectDensity)
@@ -327,6 +371,7 @@ struct UniformSim : dcg_sim {
     DCG_CUDA_TRY(cudaMalloc(&scratch, 3 * N * sizeof(float)));
     DCG_CUDA_TRY(cudaMalloc(&d_partial, 1024 * sizeof(double)));
     DCG_CUDA_TRY(cudaMallocHost(&h_partial, 1024 * sizeof(double)));
+    if (const char *e = getenv("DCG_ADVECT_FUSE")) fuse_advect = std::string(e) != "0";
     return reset();
   }
 
@@ -339,6 +384,7 @@ struct UniformSim : dcg_sim {
     if (params.gx != gx || params.gy != gy || params.gz != gz)
       return fail(DCG_ERR_INVALID, "grid size is fixed at construction (the reference sizes its buffers in the ctor)");
     fluidity_dirty = true;
+    spec_velocity = false;
     drop_graphs();
     return DCG_OK;
   }
@@ -350,6 +396,7 @@ struct UniformSim : dcg_sim {
     DCG_CUDA_TRY(cudaMemsetAsync(div, 0, pyr * sizeof(float), stream));
     DCG_CUDA_TRY(cudaMemsetAsync(fluidity, 0, pyr * sizeof(float), stream));
     cur_v = cur_q = 0;
+    spec_velocity = false;
     return init();
   }
   int init() override {  // fluid_simulation_uniform.cu:76-79: adaptTopology + k_uniform_init (zero density, velocity)
@@ -359,6 +406,7 @@ struct UniformSim : dcg_sim {
       DCG_CUDA_TRY(cudaMemsetAsync(q[i], 0, N * sizeof(float), stream));
     }
     fluidity_dirty = true;  // the memset cleared the packed .w lanes
+    spec_velocity = false;
     return adapt_topology();
   }
 
@@ -374,14 +422,23 @@ struct UniformSim : dcg_sim {
   }
 
   int advect_velocity() override {  // fluid_simulation_uniform.cu:90-94
-    k_u_advect_velocity<<<grid_for(0), block(), 0, stream>>>(kp, vw[cur_v], vw[cur_v ^ 1]);
-    launches++;
+    if (spec_velocity) {
+      spec_velocity = false;  // vw[cur_v ^ 1] already holds this step's advected velocity (k_u_advect_both)
+    } else {
+      k_u_advect_velocity<<<grid_for(0), block(), 0, stream>>>(kp, vw[cur_v], vw[cur_v ^ 1]);
+      launches++;
+    }
     cur_v ^= 1;
     DCG_CUDA_TRY(cudaGetLastError());
     return DCG_OK;
   }
   int advect_density() override {  // fluid_simulation_uniform.cu:137-141
-    k_u_advect_density<<<grid_for(0), block(), 0, stream>>>(kp, vw[cur_v], q[cur_q], q[cur_q ^ 1]);
+    if (fuse_advect) {
+      k_u_advect_both<<<grid_for(0), block(), 0, stream>>>(kp, vw[cur_v], vw[cur_v ^ 1], q[cur_q], q[cur_q ^ 1]);
+      spec_velocity = true;
+    } else {
+      k_u_advect_density<<<grid_for(0), block(), 0, stream>>>(kp, vw[cur_v], q[cur_q], q[cur_q ^ 1]);
+    }
     launches++;
     cur_q ^= 1;
     DCG_CUDA_TRY(cudaGetLastError());
@@ -393,6 +450,7 @@ struct UniformSim : dcg_sim {
     launches += 2;
   }
   int project() override {  // fluid_simulation_uniform.cu:96-124
+    spec_velocity = false;
     k_u_divergence<<<grid_for(0), block(), 0, stream>>>(kp, vw[cur_v], div, p, tp);
     launches++;
     for (int l = 1; l < mip_levels; l++) {
@@ -411,6 +469,7 @@ struct UniformSim : dcg_sim {
     return DCG_OK;
   }
   int project_local() override {  // fluid_simulation_uniform.cu:126-135
+    spec_velocity = false;
     k_u_divergence<<<grid_for(0), block(), 0, stream>>>(kp, vw[cur_v], div, p, tp);
     launches++;
     for (int i = 0; i < local_pairs; i++) jacobi_pair(0);
@@ -427,15 +486,20 @@ struct UniformSim : dcg_sim {
     DCG_TRY(adapt_topology());  // flush a pending fluidity rebuild outside the graph
     DCG_CUDA_TRY(cudaEventRecord(ev_begin, stream));
     for (int done = 0; done < n; done++) {
+      if (spec_velocity != fuse_advect) {  // the graphs are captured in the fused steady state only
+        DCG_TRY(dcg_sim::step(1));
+        continue;
+      }
       cudaGraphExec_t &ge = step_graph[cur_v * 2 + cur_q];
       if (!ge) {
         const uint64_t before = launches;
         const int sv = cur_v, sq = cur_q;
+        const bool sspec = spec_velocity;
         cudaGraph_t g = nullptr;
         DCG_CUDA_TRY(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
         const int rc = dcg_sim::step(1);
         const cudaError_t ce = cudaStreamEndCapture(stream, &g);
-        cur_v = sv; cur_q = sq;  // capture records, it does not execute
+        cur_v = sv; cur_q = sq; spec_velocity = sspec;  // capture records, it does not execute
         step_graph_launches = launches - before;
         launches = before;
         if (rc != DCG_OK) return rc;
@@ -497,8 +561,14 @@ struct UniformSim : dcg_sim {
         k_u_jacobi<<<grid_for(level), block(), 0, stream>>>(kp, level, level_off[level], (r & 1) ? tp : p, (r & 1) ? p : tp, div);
         launches++;
         bytes = 12.0 * nl;
-      } else if (st == "advect_velocity") { DCG_TRY(advect_velocity()); bytes = 28.0 * n0; }
-      else if (st == "advect_density") { DCG_TRY(advect_density()); bytes = 24.0 * n0; }
+      } else if (st == "advect_velocity") { spec_velocity = false; DCG_TRY(advect_velocity()); bytes = 28.0 * n0; }
+      else if (st == "advect_density") {
+        const bool saved = fuse_advect;
+        fuse_advect = false;
+        DCG_TRY(advect_density());
+        fuse_advect = saved;
+        bytes = 24.0 * n0;
+      } else if (st == "advect_both") { DCG_TRY(advect_density()); spec_velocity = false; bytes = 52.0 * n0; }
       else if (st == "divergence") {
         k_u_divergence<<<grid_for(0), block(), 0, stream>>>(kp, vw[cur_v], div, p, tp);
         launches++;

@@ -83,3 +83,31 @@ def test_uniform_reset_restores_initial_state(gpu):
     b = FluidSimulationUniform((32, 32, 32), p)
     b.step(5)
     np.testing.assert_array_equal(_bits(a.field("density")), _bits(b.field("density")))
+
+
+@pytest.mark.parametrize("fuse", ["1", "0"])
+def test_uniform_speculative_velocity_any_call_order(gpu, monkeypatch, fuse):
+    """advectDensity() also writes the next step's advected velocity into the idle ping-pong buffer
+    (k_u_advect_both); advectVelocity() may only use it if nothing touched the state in between."""
+    monkeypatch.setenv("DCG_ADVECT_FUSE", fuse)
+    size = (32, 32, 32)
+    p = scene_params(32, solids=True)
+    sim = FluidSimulationUniform(size, p)
+    orc = Oracle(p)
+    sim.step(3); orc.step(3)
+    seq = ["advect_density", "project", "advect_velocity", "advect_density", "advect_velocity", "advect_velocity",
+           "advect_density", "project_local", "advect_density", "advect_velocity", "advect_density", "set_params",
+           "advect_velocity", "project", "advect_density"]
+    names = {"advect_density": "advectDensity", "advect_velocity": "advectVelocity", "project": "project", "project_local": "projectLocal"}
+    for i, op in enumerate(seq):
+        if op == "set_params":
+            p.dt = 2.5
+            sim.setParams(p); orc.set_params(p)
+        else:
+            getattr(sim, names[op])(); getattr(orc, op)()
+        for f in ("density", "velocity"):
+            np.testing.assert_array_equal(np.ascontiguousarray(sim.field(f)).view(np.uint32), np.ascontiguousarray(orc.field(f)).view(np.uint32),
+                                          err_msg=f"{f} after call {i} ({op})")
+    sim.step(4); orc.step(4)
+    for f in ("density", "velocity"):
+        np.testing.assert_array_equal(np.ascontiguousarray(sim.field(f)).view(np.uint32), np.ascontiguousarray(orc.field(f)).view(np.uint32), err_msg=f)
