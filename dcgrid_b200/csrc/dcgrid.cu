@@ -120,8 +120,6 @@ struct DCGridSim : dcg_sim {
   std::vector<UnitRun> unit_runs;                        // maximal runs, ascending
   std::vector<std::vector<CUmemGenericAllocationHandle>> pieces;  // [rank][0] = control, [1 + k * kFields + f] = k-th run of the rank
   size_t gran = 0;
-  std::vector<uint32_t> units_before;            // [unit]: units of the same owner before it
-  std::vector<uint32_t> units_of_rank;
   static constexpr int kFields = 8;              // vw0 vw1 q0 q1 fl p tp div
   CUdeviceptr field_va[kFields] = {0}, ctrl_va = 0;
   size_t field_va_bytes[kFields] = {0};
@@ -359,15 +357,12 @@ struct DCGridSim : dcg_sim {
     }
     nunits = (uint32_t)((M64 + unit - 1) / unit);
     unit_owner.assign(nunits, 0);
-    units_before.assign(nunits, 0);
-    units_of_rank.assign(world, 0);
     for (uint32_t u = 0; u < nunits; u++) {
       const uint64_t mid = std::min<uint64_t>((uint64_t)u * unit + unit / 2, M64 - 1);
       const int l = level_of_slot(mid);
       int r = 0;
       if (l >= 0 && world > 1) r = (int)std::min<uint64_t>(world - 1, (mid - offsets[l]) * (uint64_t)world / max_blocks[l]);
       unit_owner[u] = (uint8_t)r;
-      units_before[u] = units_of_rank[r]++;
     }
     DCG_CUDA_TRY(cudaMalloc(&d_unit_owner, nunits));
     DCG_CUDA_TRY(cudaMemcpy(d_unit_owner, unit_owner.data(), nunits, cudaMemcpyHostToDevice));
