@@ -6,7 +6,7 @@ fails the import raises.
 import ctypes
 import os
 
-from .params import SimParams
+from .params import Options, SimParams
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libdcgrid_b200.so")
@@ -14,12 +14,17 @@ LIB_PATH = os.path.join(HERE, "libdcgrid_b200.so")
 # every symbol include/dcgrid_b200.h declares: name -> (restype, argtypes)
 _vp = ctypes.c_void_p
 _P = ctypes.POINTER(SimParams)
+_O = ctypes.POINTER(Options)
 _u64 = ctypes.c_uint64
 _int = ctypes.c_int
 SYMBOLS = {
     "dcg_default_params": (_int, [_P]),
     "dcg_create_uniform": (_int, [_P, _int, ctypes.POINTER(_vp)]),
     "dcg_create_dcgrid": (_int, [_P, _u64, _int, ctypes.POINTER(_vp)]),
+    "dcg_default_options": (_int, [_O]),
+    "dcg_create_uniform_opt": (_int, [_P, _int, _O, ctypes.POINTER(_vp)]),
+    "dcg_create_dcgrid_opt": (_int, [_P, _u64, _int, _O, ctypes.POINTER(_vp)]),
+    "dcg_create_dcgrid_sharded_opt": (_int, [_P, ctypes.c_uint64, _int, _int, _int, _int, _O, ctypes.POINTER(_vp)]),
     "dcg_destroy": (_int, [_vp]),
     "dcg_set_params": (_int, [_vp, _P]),
     "dcg_get_params": (_int, [_vp, _P]),

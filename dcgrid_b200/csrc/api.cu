@@ -31,7 +31,8 @@ int check_device(int device) {
   return DCG_OK;
 }
 
-int finish_create(dcg_sim *s, const dcg_sim_params *params, int device, dcg_sim **out) {
+int finish_create(dcg_sim *s, const dcg_sim_params *params, int device, dcg_sim **out, const dcg_options *opt = nullptr) {
+  s->set_options(opt);
   int rc = s->construct(params, device);
   if (rc == DCG_OK) rc = s->synchronize();
   if (rc != DCG_OK) {
@@ -75,29 +76,44 @@ int dcg_default_params(dcg_sim_params *p) {  // src/data/sim_params.cpp:4-34 (+ 
   return DCG_OK;
 }
 
-int dcg_create_uniform(const dcg_sim_params *params, int device, dcg_sim **out) {
+int dcg_default_options(dcg_options *o) {
+  if (!o) return DCG_ERR_INVALID;
+  std::memset(o, 0, sizeof *o);
+  o->struct_size = (uint32_t)sizeof *o;
+  return DCG_OK;
+}
+
+int dcg_create_uniform_opt(const dcg_sim_params *params, int device, const dcg_options *opt, dcg_sim **out) {
   if (!params || !out) return DCG_ERR_INVALID;
   *out = nullptr;
   int rc = check_device(device);
   if (rc != DCG_OK) return rc;
-  return finish_create(dcg_make_uniform(), params, device, out);
+  return finish_create(dcg_make_uniform(), params, device, out, opt);
 }
+int dcg_create_uniform(const dcg_sim_params *params, int device, dcg_sim **out) { return dcg_create_uniform_opt(params, device, nullptr, out); }
 
+int dcg_create_dcgrid_opt(const dcg_sim_params *params, uint64_t max_num_blocks, int device, const dcg_options *opt, dcg_sim **out) {
+  if (!params || !out) return DCG_ERR_INVALID;
+  *out = nullptr;
+  int rc = check_device(device);
+  if (rc != DCG_OK) return rc;
+  return finish_create(dcg_make_dcgrid(max_num_blocks), params, device, out, opt);
+}
 int dcg_create_dcgrid(const dcg_sim_params *params, uint64_t max_num_blocks, int device, dcg_sim **out) {
+  return dcg_create_dcgrid_opt(params, max_num_blocks, device, nullptr, out);
+}
+
+int dcg_create_dcgrid_sharded_opt(const dcg_sim_params *params, uint64_t max_num_blocks, int device, int rank, int world, int nlocal,
+                                  const dcg_options *opt, dcg_sim **out) {
   if (!params || !out) return DCG_ERR_INVALID;
   *out = nullptr;
   int rc = check_device(device);
   if (rc != DCG_OK) return rc;
-  return finish_create(dcg_make_dcgrid(max_num_blocks), params, device, out);
+  return finish_create(dcg_make_dcgrid_sharded(max_num_blocks, rank, world, nlocal), params, device, out, opt);
 }
-
 int dcg_create_dcgrid_sharded(const dcg_sim_params *params, uint64_t max_num_blocks, int device, int rank, int world, int nlocal,
                               dcg_sim **out) {
-  if (!params || !out) return DCG_ERR_INVALID;
-  *out = nullptr;
-  int rc = check_device(device);
-  if (rc != DCG_OK) return rc;
-  return finish_create(dcg_make_dcgrid_sharded(max_num_blocks, rank, world, nlocal), params, device, out);
+  return dcg_create_dcgrid_sharded_opt(params, max_num_blocks, device, rank, world, nlocal, nullptr, out);
 }
 
 int dcg_destroy(dcg_sim *sim) {

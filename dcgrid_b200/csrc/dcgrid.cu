@@ -225,8 +225,8 @@ struct DCGridSim : dcg_sim {
     DCG_CUDA_TRY(cudaMalloc(&T.parent, ((size_t)M + kB4) * 4));  // padded: the stencil rings stream kB4 entries per tile
     DCG_TRY(setup_sharding());
     DCG_CUDA_TRY(cudaMalloc(&d_perm, (size_t)M * 4));
-    if (const char *e = getenv("DCG_RESORT")) use_resort = std::string(e) != "0";
-    if (const char *e = getenv("DCG_RESORT_EVERY")) resort_every = std::max(0, atoi(e));
+    use_resort = !opt.no_resort;
+    if (opt.resort_every != 0) resort_every = std::max(0, opt.resort_every);  // -1: only at the fixed point
     DCG_CUDA_TRY(cudaMalloc(&d_pcount, (kMaxLevels + 1) * 4));
     DCG_CUDA_TRY(cudaMallocHost(&h_pcount, (kMaxLevels + 1) * 4));
     DCG_CUDA_TRY(cudaMalloc(&d_order_keys[0], (size_t)M * 4));
@@ -283,35 +283,35 @@ struct DCGridSim : dcg_sim {
       DCG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_dc_jacobi_pipe, kCTA4, kJacobiPipeSmem));
       if (per_sm < 1) return fail(DCG_ERR_CUDA, "k_dc_jacobi_pipe does not fit on an SM");
       jacobi_pipe_ctas = per_sm * sm_count;
-      if (const char *e = getenv("DCG_ADVECT")) use_advect_pipe = std::string(e) != "legacy";
-      if (const char *e = getenv("DCG_ADVECT_ORDER")) order_mode = std::string(e) == "slot" ? 0 : 1;
-      if (const char *e = getenv("DCG_STENCIL")) use_stencil_pipe = prolong_staged = std::string(e) != "legacy";
+      use_advect_pipe = opt.advect != 1;
+      order_mode = opt.advect_slot_order ? 0 : 1;
+      use_stencil_pipe = prolong_staged = opt.stencil != 1;
       {
         int per_sm = 0;
         DCG_CUDA_TRY(cudaFuncSetAttribute(k_dc_divergence_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDivPipeSmem));
         DCG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_dc_divergence_pipe, kStencilThreads, kDivPipeSmem));
         if (per_sm < 1) return fail(DCG_ERR_CUDA, "k_dc_divergence_pipe does not fit on an SM");
-        if (const char *e = getenv("DCG_STENCIL_CTAS")) per_sm = std::max(1, std::min(per_sm, atoi(e)));
+        if (opt.stencil_ctas_per_sm > 0) per_sm = std::max(1, std::min(per_sm, opt.stencil_ctas_per_sm));
         div_pipe_ctas = per_sm * sm_count;
-        if (const char *e = getenv("DCG_APPLY_MINB")) apply_min_blocks = atoi(e) == 3 ? 3 : 2;
+        apply_min_blocks = opt.apply_min_blocks == 3 ? 3 : 2;
         const void *afn = apply_min_blocks == 2 ? (const void *)k_dc_apply_pipe<2> : (const void *)k_dc_apply_pipe<3>;
         DCG_CUDA_TRY(cudaFuncSetAttribute(afn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kApplyPipeSmem));
         DCG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, afn, kStencilThreads, kApplyPipeSmem));
         if (per_sm < 1) return fail(DCG_ERR_CUDA, "k_dc_apply_pipe does not fit on an SM");
-        if (const char *e = getenv("DCG_STENCIL_CTAS")) per_sm = std::max(1, std::min(per_sm, atoi(e)));
+        if (opt.stencil_ctas_per_sm > 0) per_sm = std::max(1, std::min(per_sm, opt.stencil_ctas_per_sm));
         apply_pipe_ctas = per_sm * sm_count;
       }
-      if (const char *e = getenv("DCG_COARSE")) coarse_in_smem = std::string(e) != "gmem";
+      coarse_in_smem = !opt.coarse_in_gmem;
       DCG_CUDA_TRY(cudaFuncSetAttribute(k_dc_coarse_cascade<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCoarseSmemMax));
-      if (const char *e = getenv("DCG_ZERO_ALL")) skip_dead_zeroing = std::string(e) == "0";
-      if (const char *e = getenv("DCG_ADVECT_FUSE")) fuse_advect = std::string(e) != "0";
-      if (const char *e = getenv("DCG_ADVECT_MINB")) advect_min_blocks = (atoi(e) == 4 || atoi(e) == 2) ? atoi(e) : 3;
+      skip_dead_zeroing = !opt.zero_all;
+      fuse_advect = !opt.advect_no_fuse;
+      advect_min_blocks = (opt.advect_min_blocks == 4 || opt.advect_min_blocks == 2) ? opt.advect_min_blocks : 3;
       for (int mode = 0; mode < 3; mode++) {
         const void *fn = advect_fn(mode);
         DCG_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAdvectPipeSmem));
         DCG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&advect_per_sm[mode], fn, kAdvectThreads, kAdvectPipeSmem));
         if (advect_per_sm[mode] < 1) return fail(DCG_ERR_CUDA, "k_dc_advect_pipe does not fit on an SM");
-        if (const char *e = getenv("DCG_ADVECT_CTAS")) advect_per_sm[mode] = std::max(1, atoi(e));
+        if (opt.advect_ctas_per_sm > 0) advect_per_sm[mode] = opt.advect_ctas_per_sm;
       }
       pipe_min_tiles = 2u * (unsigned)sm_count;  // refined below once the resident CTA count of the ring kernel is known
       {
@@ -324,14 +324,11 @@ struct DCGridSim : dcg_sim {
         // 8.3 us with one CTA per tile and 10.3 us with the ring
         pipe_min_tiles = 4u * (unsigned)jacobi8_ctas;
       }
-      if (const char *e = getenv("DCG_JACOBI")) {
-        const std::string v(e);
-        use_pipe = v != "legacy";
-        if (v == "pipe_all" || v == "pipe4_all") pipe_min_tiles = 1;  // tests: exercise the ring on small levels too
-        if (v == "pipe4" || v == "pipe4_all") jacobi8 = false;
-      }
-      if (const char *e = getenv("DCG_SNAKE")) snake = std::string(e) != "0";
-      if (const char *e = getenv("DCG_JACOBI_CTAS")) jacobi_pipe_ctas = jacobi8_ctas = std::max(1, atoi(e)) * sm_count;
+      use_pipe = opt.jacobi != 1;
+      if (opt.jacobi == 2 || opt.jacobi == 4) pipe_min_tiles = 1;  // tests: exercise the ring on small levels too
+      if (opt.jacobi == 3 || opt.jacobi == 4) jacobi8 = false;
+      snake = !opt.no_snake;
+      if (opt.jacobi_ctas_per_sm > 0) jacobi_pipe_ctas = jacobi8_ctas = opt.jacobi_ctas_per_sm * sm_count;
       if (world > 1 && (!use_advect_pipe || !use_stencil_pipe || !use_pipe)) return fail(DCG_ERR_UNSUPPORTED, "the legacy kernel variants are single-GPU only");
     }
     if (vmm) return DCG_OK;  // the caller exchanges handles; import_handles() maps the peers and resets
@@ -350,9 +347,9 @@ struct DCGridSim : dcg_sim {
     vmm = world > 1 && nlocal == 1;
     // ownership granularity: 2 MiB of the 4-byte fields in the stitched address space, one tile otherwise
     unit = vmm ? 8192u : (uint32_t)kTile;
-    if (const char *e = getenv("DCG_SHARD_UNIT")) {
-      const uint32_t u = (uint32_t)atoi(e);
-      if (u == 0 || u % kTile || (vmm && u % 8192u)) return fail(DCG_ERR_INVALID, "DCG_SHARD_UNIT must be a multiple of %u", vmm ? 8192u : (uint32_t)kTile);
+    if (opt.shard_unit) {
+      const uint32_t u = opt.shard_unit;
+      if (u % kTile || (vmm && u % 8192u)) return fail(DCG_ERR_INVALID, "dcg_options.shard_unit must be a multiple of %u", vmm ? 8192u : (uint32_t)kTile);
       unit = u;
     }
     nunits = (uint32_t)((M64 + unit - 1) / unit);
@@ -375,6 +372,7 @@ struct DCGridSim : dcg_sim {
     return DCG_OK;
   }
   // runs of tiles [t0, t1) (tile t = slots base + 16 t ...) whose first slot belongs to a unit of `rank`
+  mutable bool runs_overflow = false;
   TileRuns tile_runs(uint64_t base, uint32_t t0, uint32_t t1, int rank) const {
     TileRuns R{};
     R.n = 0;
@@ -393,6 +391,8 @@ struct DCGridSim : dcg_sim {
           R.first[R.n] = t;
           R.pre[R.n + 1] = R.pre[R.n] + (te - t);
           R.n++;
+        } else {
+          runs_overflow = true;  // rebuild_order() turns this into an error: a dropped run would never be processed
         }
       }
       t = te;
@@ -439,16 +439,25 @@ struct DCGridSim : dcg_sim {
       fds.push_back(fd);
       return DCG_OK;
     };
-    DCG_TRY(create(gran));  // control block
-    for (const UnitRun &r : unit_runs)
-      if (r.owner == rank0)
-        for (int f = 0; f < kFields; f++) DCG_TRY(create((size_t)(r.u1 - r.u0) * unit * kBV * (f < 2 ? 16 : 4)));
-    // this rank's control block is mapped and cleared BEFORE the pieces are published: a peer may announce its first
-    // barrier epoch as soon as it has imported them
-    if (drv.memReserve(&ctrl_va, (size_t)world * gran, gran, 0, 0) != CUDA_SUCCESS) return fail(DCG_ERR_CUDA, "cuMemAddressReserve failed");
-    DCG_TRY(map_piece(ctrl_va + (size_t)rank0 * gran, gran, pieces[rank0][0]));
-    DCG_CUDA_TRY(cudaMemset(reinterpret_cast<void *>(ctrl_va + (size_t)rank0 * gran), 0, 4096));
-    DCG_CUDA_TRY(cudaDeviceSynchronize());
+    // exported descriptors are closed on every early exit (FdServer::start takes them over, also when it fails)
+    auto prepare = [&]() -> int {
+      DCG_TRY(create(gran));  // control block
+      for (const UnitRun &r : unit_runs)
+        if (r.owner == rank0)
+          for (int f = 0; f < kFields; f++) DCG_TRY(create((size_t)(r.u1 - r.u0) * unit * kBV * (f < 2 ? 16 : 4)));
+      // this rank's control block is mapped and cleared BEFORE the pieces are published: a peer may announce its
+      // first barrier epoch as soon as it has imported them
+      if (drv.memReserve(&ctrl_va, (size_t)world * gran, gran, 0, 0) != CUDA_SUCCESS) return fail(DCG_ERR_CUDA, "cuMemAddressReserve failed");
+      DCG_TRY(map_piece(ctrl_va + (size_t)rank0 * gran, gran, pieces[rank0][0]));
+      DCG_CUDA_TRY(cudaMemset(reinterpret_cast<void *>(ctrl_va + (size_t)rank0 * gran), 0, 4096));
+      DCG_CUDA_TRY(cudaDeviceSynchronize());
+      return DCG_OK;
+    };
+    const int rc = prepare();
+    if (rc != DCG_OK) {
+      for (int fd : fds) close(fd);
+      return rc;
+    }
     if (!fd_server.start(fds, world - 1)) return fail(DCG_ERR_CUDA, "cannot open the descriptor socket");
     ready = false;
     return DCG_OK;
@@ -494,7 +503,7 @@ struct DCGridSim : dcg_sim {
         pieces[r].push_back(h);
       }
     }
-    fd_server.finish();
+    fd_server.finish_after_serving(world - 1, 120000);
     if (fd_server.served.load() != world - 1) return fail(DCG_ERR_CUDA, "only %d of %d peers fetched this rank's memory", fd_server.served.load(), world - 1);
     // control blocks: rank r's at ctrl_va + r * gran (this rank's own was mapped at creation)
     for (int r = 0; r < world; r++) {
@@ -533,14 +542,21 @@ struct DCGridSim : dcg_sim {
       for (auto h : v) drv.memRelease(h);
   }
   int need_ready() { return ready ? DCG_OK : fail(DCG_ERR_INVALID, "sharded instance not finalized: call dcg_shard_import_handles first"); }
+  // every public entry point: right device, and (one rank per process) peers mapped — before that the field
+  // pointers, the barrier flags and the epoch counter are null
+  int enter() {
+    DCG_CUDA_TRY(cudaSetDevice(device));
+    return need_ready();
+  }
   int check_barrier_error() {
-    if (!vmm) return DCG_OK;
+    if (!vmm || !d_barrier_err) return DCG_OK;
     uint32_t e = 0;
     DCG_CUDA_TRY(cudaMemcpyAsync(&e, d_barrier_err, 4, cudaMemcpyDeviceToHost, stream));
     DCG_CUDA_TRY(cudaStreamSynchronize(stream));
     if (e) return fail(DCG_ERR_CUDA, "shard barrier timed out: a peer rank never arrived (ranks must issue identical call sequences)");
     return DCG_OK;
   }
+  int health_check() override { return check_barrier_error(); }  // every dcg_synchronize / accessor: a desynchronised peer is an error, not silently wrong fields
 
   int on_params_changed() override {
     if (params.gx != gx || params.gy != gy || params.gz != gz)
@@ -553,7 +569,7 @@ struct DCGridSim : dcg_sim {
 
   // ---- reset / init: fluid_simulation_dcgrid.cu:190-261 -----------------------------------------
   int reset() override {
-    DCG_CUDA_TRY(cudaSetDevice(device));
+    DCG_TRY(enter());
     drop_graphs();
     steady = false;
     spec_velocity = false;
@@ -609,7 +625,7 @@ struct DCGridSim : dcg_sim {
   }
 
   int init() override {  // :190-210
-    DCG_CUDA_TRY(cudaSetDevice(device));
+    DCG_TRY(enter());
     k_dc_init_apron<<<blocks_for((size_t)M * kAV, 256), 256, 0, stream>>>(T);
     launches++;
     for (int l = sparse; l < levels; l++) {
@@ -617,7 +633,7 @@ struct DCGridSim : dcg_sim {
       launches++;  // (sharded: every process writes the same values into every cell)
     }
     barrier();
-    build_face_descriptors();
+    DCG_TRY(build_face_descriptors());
     DCG_CUDA_TRY(cudaGetLastError());
     for (int i = 0; i < 5; i++) DCG_TRY(adapt_topology());
     return DCG_OK;
@@ -627,11 +643,11 @@ struct DCGridSim : dcg_sim {
   void sync_loads() {
     for (int l = 0; l < levels; l++) T.loads[l] = Tf.loads[l] = (uint32_t)loads[l];
   }
-  void build_face_descriptors() {
+  int build_face_descriptors() {
     cudaMemsetAsync(d_counters + 1, 0, 4, stream);
     k_dc_build_fdesc<<<blocks_for((size_t)M * 8, 256), 256, 0, stream>>>(hot(), d_counters + 1);
     launches++;
-    rebuild_order();
+    return rebuild_order();
   }
   // ---- field order (dcgrid_kernels.cuh, "field order") ----------------------------------------------------
   int ensure_mirror_storage() {
@@ -701,7 +717,8 @@ struct DCGridSim : dcg_sim {
 
   // called whenever block positions or the set of active blocks changed: per rank, the Morton-ordered list of
   // its active blocks, the lists of its blocks with children, and the tile runs of every level
-  void rebuild_order() {
+  int rebuild_order() {
+    runs_overflow = false;
     for (int lr = 0; lr < nlocal; lr++) {
       RankWork &w = work[lr];
       const int rank = rank0 + lr;
@@ -730,6 +747,8 @@ struct DCGridSim : dcg_sim {
       for (uint32_t u = u0; u <= u1; u++) one = one && unit_owner[u] == unit_owner[u0];
       level_single[l] = one ? 1 : 0;
     }
+    if (runs_overflow) return fail(DCG_ERR_UNSUPPORTED, "ownership pattern needs more than %d tile runs per launch (dcg_options.shard_unit too small)", kMaxRuns);
+    return DCG_OK;
   }
   uint32_t finer_full_mask() const {
     uint32_t m = 0;
@@ -924,7 +943,7 @@ struct DCGridSim : dcg_sim {
   }
 
   int adapt_topology() override {  // :320-346
-    DCG_CUDA_TRY(cudaSetDevice(device));
+    DCG_TRY(enter());
     n_adapt++;
     spec_velocity = false;
     if (steady) {
@@ -946,7 +965,7 @@ struct DCGridSim : dcg_sim {
       changes_since_resort++;
       if (use_resort && resort_every > 0 && changes_since_resort >= resort_every) DCG_TRY(resort());
       else mirror(false);
-      build_face_descriptors();
+      DCG_TRY(build_face_descriptors());
       for (int l = levels - 2; l >= 0; l--) {
         // sharded: every process interpolates every new block (identical values); lock step between the levels,
         // a level reads what the coarser one wrote
@@ -963,7 +982,7 @@ struct DCGridSim : dcg_sim {
       steady = true;  // nothing changed and the selection state is unchanged: fixed point
       if (use_resort && changes_since_resort > 0) {  // the layout the steady state will run on, for good
         DCG_TRY(resort());
-        build_face_descriptors();
+        DCG_TRY(build_face_descriptors());
       }
     }
     DCG_CUDA_TRY(cudaGetLastError());
@@ -1040,7 +1059,7 @@ struct DCGridSim : dcg_sim {
     barrier();
   }
   int advect_velocity() override {  // :263-268
-    DCG_CUDA_TRY(cudaSetDevice(device));
+    DCG_TRY(enter());
     if (spec_velocity) {
       // vw[cur_v ^ 1] already holds this step's advected velocity (written by the previous advect_density())
       spec_velocity = false;
@@ -1060,7 +1079,7 @@ struct DCGridSim : dcg_sim {
     return DCG_OK;
   }
   int advect_density() override {  // :313-318
-    DCG_CUDA_TRY(cudaSetDevice(device));
+    DCG_TRY(enter());
     if (use_advect_pipe) {
       launch_advect_pipe(fuse_advect ? 2 : 1, vw[cur_v], vw[cur_v ^ 1], q[cur_q], q[cur_q ^ 1]);
       spec_velocity = fuse_advect;
@@ -1164,6 +1183,7 @@ struct DCGridSim : dcg_sim {
     barrier();
   }
   int project() override {  // :270-294
+    DCG_TRY(enter());
     spec_velocity = false;
     divergence_stage(skip_dead_zeroing && project_level_pairs >= 1 ? levels - 1 : 0);
     // levels with <= kCoarseBlocks blocks: the whole coarse part of the cascade in one single-CTA launch
@@ -1180,6 +1200,7 @@ struct DCGridSim : dcg_sim {
     return DCG_OK;
   }
   int project_local() override {  // :296-311
+    DCG_TRY(enter());
     spec_velocity = false;
     divergence_stage(0);
     const int cf = small_levels_from(kCoarseBlocks);
@@ -1194,7 +1215,7 @@ struct DCGridSim : dcg_sim {
   }
 
   int step(int n) override {
-    DCG_CUDA_TRY(cudaSetDevice(device));
+    DCG_TRY(enter());
     DCG_CUDA_TRY(cudaEventRecord(ev_begin, stream));
     for (int done = 0; done < n; done++) {
       if (!steady || spec_velocity != (fuse_advect && use_advect_pipe)) {  // transient: adaptation needs host round trips, run call by call
@@ -1231,7 +1252,7 @@ struct DCGridSim : dcg_sim {
 
   // one launch of a single stage, `reps` times, CUDA-event timed on the instance's stream
   int bench_stage(const char *stage, int level, int reps, float *ms_per_launch, double *alg_bytes) override {
-    DCG_CUDA_TRY(cudaSetDevice(device));
+    DCG_TRY(enter());
     const std::string st(stage);
     spec_velocity = false;
     if (level < 0 || level >= levels) return fail(DCG_ERR_INVALID, "bench_stage: bad level");
@@ -1296,21 +1317,21 @@ struct DCGridSim : dcg_sim {
 
   // ---- stats / accessors --------------------------------------------------------------------------------
   int debug_stats(float *out) override {  // :517-528 (host sums the per-block partials in slot order)
-    DCG_CUDA_TRY(cudaSetDevice(device));
+    DCG_TRY(enter());
     k_dc_debug_stats<<<blocks_for(M, 256), 256, 0, stream>>>(hot(), kp, p, div, scratch);
     // per-block partials back in the reference's slot order: the host sum below is order dependent
     k_dc_gather_u32<<<blocks_for(M, 256), 256, 0, stream>>>(scratch, d_perm, scratch + M, M);
     launches += 2;
     std::vector<float> h(M);
     DCG_CUDA_TRY(cudaMemcpyAsync(h.data(), scratch + M, (size_t)M * 4, cudaMemcpyDeviceToHost, stream));
-    DCG_CUDA_TRY(cudaStreamSynchronize(stream));
+    DCG_TRY(synchronize());
     float sum = 0.f;
     for (uint32_t i = 0; i < M; i++) sum += h[i];
     *out = sum;
     return DCG_OK;
   }
   int total_density(double *out) override {
-    DCG_CUDA_TRY(cudaSetDevice(device));
+    DCG_TRY(enter());
     // sum over the cells this instance owns (sharded, one rank per process: the host adds the ranks' partials)
     const int blocks = (int)std::min<size_t>(1024, (cells + 255) / 256);
     double s = 0.0;
@@ -1331,7 +1352,7 @@ struct DCGridSim : dcg_sim {
   int sparse_levels() const override { return sparse; }
 
   int get_field(int field, int layout, float *dst, uint64_t count) override {
-    DCG_CUDA_TRY(cudaSetDevice(device));
+    DCG_TRY(enter());
     const int comps = field == DCG_FIELD_VELOCITY ? 3 : 1;
     const float *src = nullptr;
     int stride = 1;
@@ -1382,8 +1403,8 @@ struct DCGridSim : dcg_sim {
   }
 
   int get_topology(int32_t *positions, uint8_t *lv, uint64_t *parent, uint64_t *children, uint64_t *apron) override {
-    DCG_CUDA_TRY(cudaSetDevice(device));
-    DCG_CUDA_TRY(cudaStreamSynchronize(stream));
+    DCG_TRY(enter());
+    DCG_TRY(synchronize());
     auto widen = [](const std::vector<uint32_t> &in, uint64_t *out) {
       for (size_t i = 0; i < in.size(); i++) out[i] = in[i] == kNone ? UINT64_MAX : (uint64_t)in[i];
     };
@@ -1414,14 +1435,18 @@ struct DCGridSim : dcg_sim {
   }
 
   int lookup_blocks(const int32_t *positions, uint64_t n, uint64_t *out_slot, uint8_t *out_level) override {
-    DCG_CUDA_TRY(cudaSetDevice(device));
+    DCG_TRY(enter());
     if (n == 0) return DCG_OK;
-    int *d_pos = nullptr;
-    uint32_t *d_slot = nullptr;
-    uint8_t *d_lvl = nullptr;
-    DCG_CUDA_TRY(cudaMalloc(&d_pos, n * 12));
-    DCG_CUDA_TRY(cudaMalloc(&d_slot, n * 4));
-    DCG_CUDA_TRY(cudaMalloc(&d_lvl, n));
+    struct Tmp {  // freed on every exit path
+      void *p = nullptr;
+      ~Tmp() { cudaFree(p); }
+    } t_pos, t_slot, t_lvl;
+    DCG_CUDA_TRY(cudaMalloc(&t_pos.p, n * 12));
+    DCG_CUDA_TRY(cudaMalloc(&t_slot.p, n * 4));
+    DCG_CUDA_TRY(cudaMalloc(&t_lvl.p, n));
+    int *d_pos = static_cast<int *>(t_pos.p);
+    uint32_t *d_slot = static_cast<uint32_t *>(t_slot.p);
+    uint8_t *d_lvl = static_cast<uint8_t *>(t_lvl.p);
     DCG_CUDA_TRY(cudaMemcpyAsync(d_pos, positions, n * 12, cudaMemcpyHostToDevice, stream));
     k_dc_lookup<<<blocks_for(n, 256), 256, 0, stream>>>(T, kp, d_pos, n, d_slot, d_lvl);
     launches++;
@@ -1430,7 +1455,6 @@ struct DCGridSim : dcg_sim {
     DCG_CUDA_TRY(cudaMemcpyAsync(out_level, d_lvl, n, cudaMemcpyDeviceToHost, stream));
     DCG_CUDA_TRY(cudaStreamSynchronize(stream));
     for (uint64_t i = 0; i < n; i++) out_slot[i] = h[i] == kNone ? UINT64_MAX : h[i];
-    cudaFree(d_pos); cudaFree(d_slot); cudaFree(d_lvl);
     return DCG_OK;
   }
 

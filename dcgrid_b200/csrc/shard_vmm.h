@@ -107,28 +107,76 @@ inline int recv_fd(int sock) {
   return fd;
 }
 
-// serves the descriptors `fds` (all of them, in order) to `npeers` connecting peers on an abstract socket, in a
-// helper thread
+// Handle blob (kHandleBytes, exchanged by the ranks through any host channel): bytes [0, 48) = NUL-terminated name
+// of the abstract socket, bytes [48, 64) = a random token.  The server only sends descriptors to a peer that
+// (a) runs under the same effective uid (SO_PEERCRED) and (b) presents the token: an abstract socket has no
+// filesystem permissions, and its name alone is guessable.  Connections that fail either test are dropped
+// without consuming one of the `npeers` slots.
+constexpr size_t kNameBytes = 48, kTokenBytes = 16;
+
+inline bool random_bytes(unsigned char *out, size_t n) {
+  FILE *f = std::fopen("/dev/urandom", "rb");
+  if (!f) return false;
+  const bool ok = std::fread(out, 1, n, f) == n;
+  std::fclose(f);
+  return ok;
+}
+inline bool read_exact(int fd, void *buf, size_t n, int timeout_ms) {
+  size_t got = 0;
+  while (got < n) {
+    pollfd p = {fd, POLLIN, 0};
+    if (poll(&p, 1, timeout_ms) <= 0) return false;
+    const ssize_t r = read(fd, static_cast<char *>(buf) + got, n - got);
+    if (r <= 0) return false;
+    got += (size_t)r;
+  }
+  return true;
+}
+
+// serves the descriptors `fds` (all of them, in order) to `npeers` authenticated peers on an abstract socket, in
+// a helper thread; finish() cancels it
 struct FdServer {
   int lfd = -1;
   std::thread th;
-  std::atomic<int> served{0};
-  char name[kHandleBytes] = {0};
+  std::atomic<int> served{0}, rejected{0};
+  std::atomic<bool> stop{false};
+  char name[kHandleBytes] = {0};  // the whole handle blob: socket name + token
 
   bool start(std::vector<int> fds, int npeers) {
     static std::atomic<int> counter{0};
-    std::snprintf(name, sizeof name, "dcgrid-b200-vmm-%d-%d", (int)getpid(), counter.fetch_add(1));
+    auto close_all = [&fds] { for (int fd : fds) close(fd); };
+    std::memset(name, 0, sizeof name);
+    std::snprintf(name, kNameBytes, "dcgrid-b200-vmm-%d-%d", (int)getpid(), counter.fetch_add(1));
+    if (!random_bytes(reinterpret_cast<unsigned char *>(name) + kNameBytes, kTokenBytes)) { close_all(); return false; }
     lfd = socket(AF_UNIX, SOCK_STREAM, 0);
-    if (lfd < 0) return false;
+    if (lfd < 0) { close_all(); return false; }
     socklen_t len;
     sockaddr_un a = abstract_addr(name, len);
-    if (bind(lfd, reinterpret_cast<sockaddr *>(&a), len) != 0 || listen(lfd, 16) != 0) return false;
+    if (bind(lfd, reinterpret_cast<sockaddr *>(&a), len) != 0 || listen(lfd, 16) != 0) {
+      close(lfd);
+      lfd = -1;
+      close_all();
+      return false;
+    }
     th = std::thread([this, fds, npeers] {
-      for (int i = 0; i < npeers; i++) {
+      int waited_ms = 0;
+      while (served.load() < npeers && !stop.load() && waited_ms < 120000) {  // a peer never came: give up after two minutes
         pollfd p = {lfd, POLLIN, 0};
-        if (poll(&p, 1, 120000) <= 0) break;  // a peer never came: give up after two minutes
+        const int pr = poll(&p, 1, 100);
+        if (pr < 0) break;
+        if (pr == 0) { waited_ms += 100; continue; }
         const int c = accept(lfd, nullptr, nullptr);
         if (c < 0) break;
+        ucred cred;
+        socklen_t cl = sizeof cred;
+        char token[kTokenBytes];
+        const bool trusted = getsockopt(c, SOL_SOCKET, SO_PEERCRED, &cred, &cl) == 0 && cred.uid == geteuid() &&
+                             read_exact(c, token, kTokenBytes, 5000) && std::memcmp(token, name + kNameBytes, kTokenBytes) == 0;
+        if (!trusted) {
+          rejected.fetch_add(1);
+          close(c);
+          continue;
+        }
         bool ok = true;
         for (int fd : fds) ok = ok && send_fd(c, fd);
         if (ok) served.fetch_add(1);
@@ -139,29 +187,41 @@ struct FdServer {
     return true;
   }
   void finish() {
+    stop.store(true);
     if (th.joinable()) th.join();
     if (lfd >= 0) close(lfd);
     lfd = -1;
   }
+  // waits (bounded) until every peer has been served, then stops the thread
+  void finish_after_serving(int npeers, int timeout_ms) {
+    for (int w = 0; served.load() < npeers && w < timeout_ms; w += 10) usleep(10000);
+    finish();
+  }
   ~FdServer() { finish(); }
 };
 
-// receives `count` descriptors from the peer listening on `name`; false if the peer cannot be reached
-inline bool fetch_fds(const char *name, int count, std::vector<int> &out) {
+// receives `count` descriptors from the peer whose handle blob is `handle`; false if the peer cannot be reached
+inline bool fetch_fds(const char *handle, int count, std::vector<int> &out) {
+  char sock_name[kNameBytes + 1] = {0};
+  std::memcpy(sock_name, handle, kNameBytes);
   for (int attempt = 0; attempt < 1200; attempt++) {  // up to two minutes: the peer may not be listening yet
     const int s = socket(AF_UNIX, SOCK_STREAM, 0);
     if (s < 0) return false;
     socklen_t len;
-    sockaddr_un a = abstract_addr(name, len);
+    sockaddr_un a = abstract_addr(sock_name, len);
     if (connect(s, reinterpret_cast<sockaddr *>(&a), len) == 0) {
       out.clear();
-      for (int i = 0; i < count; i++) {
+      bool ok = write(s, handle + kNameBytes, kTokenBytes) == (ssize_t)kTokenBytes;
+      for (int i = 0; ok && i < count; i++) {
         const int fd = recv_fd(s);
         if (fd < 0) break;
         out.push_back(fd);
       }
       close(s);
-      return (int)out.size() == count;
+      if ((int)out.size() == count) return true;
+      for (int fd : out) close(fd);  // partial transfer: do not leak what did arrive
+      out.clear();
+      return false;
     }
     close(s);
     usleep(100000);

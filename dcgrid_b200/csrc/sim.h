@@ -25,6 +25,7 @@
 
 struct dcg_sim {
   dcg_sim_params params{};
+  dcg_options opt{};  // creation-time options (include/dcgrid_b200.h); all-zero = defaults
   dcg::KParams kp{};
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -82,17 +83,34 @@ struct dcg_sim {
     // the reference re-uploads SimParams every frame (src/simulation.cpp:94); identical bytes change
     // nothing here: kernels take the parameters by value and captured graphs stay valid
     if (std::memcmp(&params, p, sizeof params) == 0) return DCG_OK;
+    // a rejected change (grid size is fixed at construction) must leave the instance as it was: the kernels
+    // index their buffers with kp.gx/gy/gz
+    const dcg_sim_params saved = params;
+    const dcg::KParams saved_kp = kp;
     params = *p;
     kp = dcg::make_kparams(params);
-    return on_params_changed();
+    const int rc = on_params_changed();
+    if (rc != DCG_OK) {
+      params = saved;
+      kp = saved_kp;
+    }
+    return rc;
   }
+  void set_options(const dcg_options *o) {
+    opt = dcg_options{};
+    if (!o) return;
+    const size_t n = o->struct_size == 0 || o->struct_size > sizeof(dcg_options) ? sizeof(dcg_options) : o->struct_size;
+    std::memcpy(&opt, o, n);
+  }
+  // errors a kernel can only report through device memory (sharded: a peer that never reached a barrier)
+  virtual int health_check() { return DCG_OK; }
   int synchronize() {
     DCG_CUDA_TRY(cudaStreamSynchronize(stream));
     if (step_timing_pending) {
       DCG_CUDA_TRY(cudaEventElapsedTime(&last_step_ms, ev_begin, ev_end));
       step_timing_pending = false;
     }
-    return DCG_OK;
+    return health_check();
   }
 
   int fail(int code, const char *fmt, ...) {

@@ -371,7 +371,7 @@ struct UniformSim : dcg_sim {
     DCG_CUDA_TRY(cudaMalloc(&scratch, 3 * N * sizeof(float)));
     DCG_CUDA_TRY(cudaMalloc(&d_partial, 1024 * sizeof(double)));
     DCG_CUDA_TRY(cudaMallocHost(&h_partial, 1024 * sizeof(double)));
-    if (const char *e = getenv("DCG_ADVECT_FUSE")) fuse_advect = std::string(e) != "0";
+    fuse_advect = !opt.advect_no_fuse;
     return reset();
   }
 

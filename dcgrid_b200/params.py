@@ -76,3 +76,26 @@ def scene_params(gx: int, gy: int = None, gz: int = None, solids: bool = False) 
     p.rdx = np.float32(1.0) / np.float32(p.dx)
     p.enable_additional_solids = solids
     return p
+
+
+class Options(ctypes.Structure):
+    """``struct dcg_options`` (include/dcgrid_b200.h): creation-time options, every field 0 = default."""
+    _fields_ = [("struct_size", ctypes.c_uint32)] + [(n, ctypes.c_int32) for n in (
+        "jacobi", "jacobi_ctas_per_sm", "no_snake", "advect", "advect_slot_order", "advect_no_fuse", "advect_min_blocks",
+        "advect_ctas_per_sm", "stencil", "stencil_ctas_per_sm", "apply_min_blocks", "coarse_in_gmem", "zero_all", "no_resort",
+        "resort_every")] + [("shard_unit", ctypes.c_uint32), ("no_pdl", ctypes.c_int32), ("host_selection", ctypes.c_int32),
+                            ("reserved", ctypes.c_int32 * 14)]
+
+
+def make_options(options=None) -> Options:
+    """dict (or Options, or None) -> Options with struct_size filled in."""
+    if isinstance(options, Options):
+        o = Options.from_buffer_copy(options)
+    else:
+        o = Options()
+        for k, v in (options or {}).items():
+            if not hasattr(o, k):
+                raise KeyError(f"unknown dcg_options field {k!r}")
+            setattr(o, k, int(v))
+    o.struct_size = ctypes.sizeof(Options)
+    return o

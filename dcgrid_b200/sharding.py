@@ -12,7 +12,7 @@ import ctypes
 import numpy as np
 
 from . import _lib
-from .params import SimParams
+from .params import SimParams, make_options
 from .simulation import FluidSimulation, FluidSimulationDCGrid
 
 
@@ -131,7 +131,7 @@ class FluidSimulationDCGridSharded(FluidSimulationDCGrid):
     nlocal == 1: one rank per process; pass ``dist`` (an initialised torch.distributed) to exchange the arena
     handles.  After construction all ranks must issue the same sequence of solver calls."""
 
-    def __init__(self, size, maxNumBlocks, params: SimParams, world, rank=0, nlocal=None, device=0, dist=None):
+    def __init__(self, size, maxNumBlocks, params: SimParams, world, rank=0, nlocal=None, device=0, dist=None, options=None):
         FluidSimulation.__init__(self)
         p = SimParams.from_buffer_copy(params)
         p.gx, p.gy, p.gz = size
@@ -139,8 +139,9 @@ class FluidSimulationDCGridSharded(FluidSimulationDCGrid):
         self.nlocal = self.world if nlocal is None else int(nlocal)
         self.dist = dist
         self.maxNumBlocks = int(maxNumBlocks)
-        self._check(self._L.dcg_create_dcgrid_sharded(ctypes.byref(p), self.maxNumBlocks, device, self.rank, self.world, self.nlocal,
-                                                      ctypes.byref(self._h)))
+        o = make_options(options)
+        self._check(self._L.dcg_create_dcgrid_sharded_opt(ctypes.byref(p), self.maxNumBlocks, device, self.rank, self.world, self.nlocal,
+                                                          ctypes.byref(o), ctypes.byref(self._h)))
         if self.nlocal != self.world:
             n = int(self._L.dcg_shard_handle_bytes())
             buf = ctypes.create_string_buffer(n)

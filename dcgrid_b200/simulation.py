@@ -17,7 +17,7 @@ import ctypes
 import numpy as np
 
 from . import _lib
-from .params import SimParams
+from .params import SimParams, make_options
 
 FIELDS = {"density": 0, "velocity": 1, "fluidity": 2, "pressure": 3, "divergence": 4, "t_pressure": 5}
 LAYOUT_NATIVE, LAYOUT_DENSE_L0 = 0, 1
@@ -147,24 +147,26 @@ class FluidSimulation:
 class FluidSimulationUniform(FluidSimulation):
     """FluidSimulationUniform(size) — src/uniformgrid/fluid_simulation_uniform.h:5-39."""
 
-    def __init__(self, size, params: SimParams, device=0):
+    def __init__(self, size, params: SimParams, device=0, options=None):
         super().__init__()
         p = SimParams.from_buffer_copy(params)
         p.gx, p.gy, p.gz = size
         self.params = p
-        self._check(self._L.dcg_create_uniform(ctypes.byref(p), device, ctypes.byref(self._h)))
+        o = make_options(options)
+        self._check(self._L.dcg_create_uniform_opt(ctypes.byref(p), device, ctypes.byref(o), ctypes.byref(self._h)))
 
 
 class FluidSimulationDCGrid(FluidSimulation):
     """FluidSimulationDCGrid(size, maxNumBlocks) — src/dcgrid/fluid_simulation_dcgrid.h:5-61."""
 
-    def __init__(self, size, maxNumBlocks, params: SimParams, device=0):
+    def __init__(self, size, maxNumBlocks, params: SimParams, device=0, options=None):
         super().__init__()
         p = SimParams.from_buffer_copy(params)
         p.gx, p.gy, p.gz = size
         self.params = p
         self.maxNumBlocks = int(maxNumBlocks)
-        self._check(self._L.dcg_create_dcgrid(ctypes.byref(p), self.maxNumBlocks, device, ctypes.byref(self._h)))
+        o = make_options(options)
+        self._check(self._L.dcg_create_dcgrid_opt(ctypes.byref(p), self.maxNumBlocks, device, ctypes.byref(o), ctypes.byref(self._h)))
 
     @property
     def sparseLevels(self):

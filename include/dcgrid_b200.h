@@ -12,7 +12,7 @@
  * (the reference prints and exit()s instead, include/cuda/helper_cuda.h:771-781).
  *
  * No torch types, plain pointers and sizes only.  A maintainer binds this from the
- * reference tree with the adapter class in dcgrid_b200/csrc/fluid_simulation_b200.h
+ * reference tree with the adapter class in include/fluid_simulation_b200.h
  * (see INTEGRATION.md).
  */
 #ifndef DCGRID_B200_H
@@ -67,6 +67,40 @@ typedef struct dcg_sim_params {
 
 typedef struct dcg_sim dcg_sim;   /* opaque: one FluidSimulation instance            */
 
+/* ---- creation-time options ----------------------------------------------
+ * Kernel variants, re-sort cadence and sharding granularity of ONE instance, fixed when it is created
+ * (the reference has compile-time constants only).  Every field: 0 = default, so a zeroed struct (or a
+ * NULL pointer) is the default configuration.  Every variant computes bit-identical results
+ * (tests/test_dcgrid_gpu.py runs the combinations against the oracle); they exist for testing small
+ * cases on the code paths big cases take, and for A/B measurements.                              */
+typedef struct dcg_options {
+  uint32_t struct_size;        /* sizeof(dcg_options) of the caller; 0 = this header's                */
+  int32_t jacobi;              /* 0 ring kernel (8 cells/thread) on levels that fill the GPU, one CTA
+                                  per tile below; 1 one CTA per tile everywhere; 2 ring on every level;
+                                  3 / 4 = 0 / 2 with the 4-cells-per-thread ring kernel                 */
+  int32_t jacobi_ctas_per_sm;  /* resident CTAs per SM of the ring kernel (0 = occupancy limit)         */
+  int32_t no_snake;            /* 1: sweeps do not alternate direction                                  */
+  int32_t advect;              /* 0 persistent ring kernel, 1 one CTA per 4 blocks                       */
+  int32_t advect_slot_order;   /* 1: process blocks in pool-slot order instead of Morton order          */
+  int32_t advect_no_fuse;      /* 1: density(n) and velocity(n+1) advection as separate passes          */
+  int32_t advect_min_blocks;   /* __launch_bounds__ variant: 2, 3 (default) or 4 CTAs per SM            */
+  int32_t advect_ctas_per_sm;  /* resident CTAs per SM (0 = occupancy limit)                            */
+  int32_t stencil;             /* divergence / gradient / prolongation: 0 ring + staged, 1 one CTA/tile */
+  int32_t stencil_ctas_per_sm;
+  int32_t apply_min_blocks;    /* 2 (default) or 3                                                      */
+  int32_t coarse_in_gmem;      /* 1: coarse cascade works in global memory instead of shared            */
+  int32_t zero_all;            /* 1: clear pressure / t_pressure of every level like the reference      */
+  int32_t no_resort;           /* 1: field order = the reference's slot order throughout                */
+  int32_t resort_every;        /* topology changes between re-sorts: 0 = 32, -1 = only at the fixed point */
+  uint32_t shard_unit;         /* sharded instances: slots per ownership unit (0 = 8192 / one tile)     */
+  int32_t no_pdl;              /* 1: plain stream order between the kernels of a step (no programmatic
+                                  dependent launch)                                                     */
+  int32_t host_selection;      /* 1: adaptTopology always takes the reference's host selection
+                                  (std::nth_element / std::sort on scores copied D2H)                    */
+  int32_t reserved[14];
+} dcg_options;
+DCG_API int dcg_default_options(dcg_options *out);
+
 /* ---- field / layout selectors for the accessors ------------------------- */
 enum {
   DCG_FIELD_DENSITY = 0,   /* 1 float / cell                                         */
@@ -100,6 +134,11 @@ DCG_API int dcg_create_uniform(const dcg_sim_params *params, int device, dcg_sim
  * (src/dcgrid/fluid_simulation_dcgrid.cu:9-140,190-261).                          */
 DCG_API int dcg_create_dcgrid(const dcg_sim_params *params, uint64_t max_num_blocks,
                               int device, dcg_sim **out);
+
+/* the same with creation-time options (NULL = defaults) */
+DCG_API int dcg_create_uniform_opt(const dcg_sim_params *params, int device, const dcg_options *opt, dcg_sim **out);
+DCG_API int dcg_create_dcgrid_opt(const dcg_sim_params *params, uint64_t max_num_blocks, int device,
+                                  const dcg_options *opt, dcg_sim **out);
 
 DCG_API int dcg_destroy(dcg_sim *sim);
 
@@ -218,6 +257,8 @@ DCG_API int dcg_create_uniform_sharded(const dcg_sim_params *params, int device,
  * dcg_total_density returns the sum over the cells this instance owns.                                      */
 DCG_API int dcg_create_dcgrid_sharded(const dcg_sim_params *params, uint64_t max_num_blocks, int device,
                                       int rank, int world, int nlocal, dcg_sim **out);
+DCG_API int dcg_create_dcgrid_sharded_opt(const dcg_sim_params *params, uint64_t max_num_blocks, int device,
+                                          int rank, int world, int nlocal, const dcg_options *opt, dcg_sim **out);
 DCG_API uint64_t dcg_shard_handle_bytes(void);
 DCG_API int dcg_shard_export_handle(dcg_sim *sim, void *out, uint64_t capacity);
 DCG_API int dcg_shard_import_handles(dcg_sim *sim, const void *handles, int count);

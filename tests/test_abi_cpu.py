@@ -9,7 +9,7 @@ import subprocess
 import pytest
 
 from dcgrid_b200 import _lib
-from dcgrid_b200.params import SimParams, default_params, scene_params
+from dcgrid_b200.params import Options, SimParams, default_params, make_options, scene_params
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HEADER = os.path.join(ROOT, "include", "dcgrid_b200.h")
@@ -68,6 +68,22 @@ def test_default_params_are_the_reference_defaults():
     assert not p.enable_additional_solids
     q = default_params()
     assert bytes(p) == bytes(q)
+
+
+def test_options_struct_matches_the_header():
+    """struct dcg_options: the ctypes mirror has the size the library reports, a zeroed struct is the default."""
+    L = _lib.load()
+    o = Options()
+    assert L.dcg_default_options(ctypes.byref(o)) == 0
+    assert o.struct_size == ctypes.sizeof(Options)
+    assert all(getattr(o, f[0]) == 0 for f in Options._fields_ if f[0] not in ("struct_size", "reserved"))
+    text = open(HEADER).read()
+    body = text[text.index("typedef struct dcg_options {"):text.index("} dcg_options;")]
+    declared = re.findall(r"^\s+u?int32_t\s+(\w+)", body, flags=re.M)
+    assert declared == [f[0] for f in Options._fields_], "field order of Options vs. struct dcg_options"
+    with pytest.raises(KeyError):
+        make_options({"no_such_option": 1})
+    assert make_options({"jacobi": 2}).jacobi == 2
 
 
 def test_null_handles_are_rejected_not_dereferenced():

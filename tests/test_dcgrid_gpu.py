@@ -40,9 +40,9 @@ def assert_same_fields(sim, orc, names, act, where=""):
         np.testing.assert_array_equal(_bits(a), _bits(b), err_msg=f"{f} {where}")
 
 
-def run_pair(d, M, solids, steps, schedule="project", check_every=1):
+def run_pair(d, M, solids, steps, schedule="project", check_every=1, options=None):
     p = scene_params(d, solids=solids)
-    sim = FluidSimulationDCGrid((d, d, d), M, p)
+    sim = FluidSimulationDCGrid((d, d, d), M, p, options=options)
     orc = Oracle(p, M)
     assert sim.levels == orc.levels and sim.sparseLevels == orc.sparse_levels
     act = assert_same_topology(sim, orc, "after reset")
@@ -82,25 +82,26 @@ def test_dcgrid_bit_exact_vs_oracle(gpu, d, M, solids, steps, schedule):
     assert orc.field("density").max() > 0
 
 
-@pytest.mark.parametrize("env", [
-    {"DCG_JACOBI": "pipe_all"},                            # TMA-ring Jacobi on every level, incl. ragged last tiles
-    {"DCG_JACOBI": "pipe_all", "DCG_SNAKE": "0"},
-    {"DCG_JACOBI": "pipe4_all"},                           # the 4-cells-per-thread ring kernel
-    {"DCG_RESORT_EVERY": "1", "DCG_JACOBI": "pipe_all"},   # field order re-sorted by position after EVERY topology change
-    {"DCG_RESORT_EVERY": "3"},                             # incremental mirror updates between the re-sorts
-    {"DCG_RESORT": "0"},                                   # field order = the reference's slot order throughout
-    {"DCG_JACOBI": "legacy", "DCG_ADVECT": "legacy"},      # one-CTA-per-tile kernels
-    {"DCG_JACOBI_CTAS": "1", "DCG_ADVECT_CTAS": "1"},      # one resident CTA per SM: every CTA walks several tiles
-    {"DCG_ADVECT_FUSE": "0", "DCG_ADVECT_ORDER": "slot"},  # density and velocity advection as separate passes, pool order
-    {"DCG_ADVECT_MINB": "3", "DCG_STENCIL": "legacy"},     # 3-CTA/SM advection build; one-CTA-per-tile divergence / gradient
-])
+@pytest.mark.parametrize("options", [
+    {"jacobi": 2},                                         # TMA-ring Jacobi on every level, incl. ragged last tiles
+    {"jacobi": 2, "no_snake": 1},
+    {"jacobi": 4},                                         # the 4-cells-per-thread ring kernel
+    {"resort_every": 1, "jacobi": 2},                      # field order re-sorted by position after EVERY topology change
+    {"resort_every": 3},                                   # incremental mirror updates between the re-sorts
+    {"no_resort": 1},                                      # field order = the reference's slot order throughout
+    {"jacobi": 1, "advect": 1},                            # one-CTA-per-tile kernels
+    {"jacobi_ctas_per_sm": 1, "advect_ctas_per_sm": 1},    # one resident CTA per SM: every CTA walks several tiles
+    {"advect_no_fuse": 1, "advect_slot_order": 1},         # density and velocity advection as separate passes, pool order
+    {"advect_min_blocks": 3, "stencil": 1},                # 3-CTA/SM advection build; one-CTA-per-tile divergence / gradient
+    {"no_pdl": 1, "host_selection": 1},                    # plain stream order; the reference's host selection on every level
+    {"coarse_in_gmem": 1, "zero_all": 1, "apply_min_blocks": 3, "advect_min_blocks": 4},
+], ids=lambda o: ",".join(f"{k}={v}" for k, v in o.items()))
 @pytest.mark.parametrize("d,M,solids,steps", [(64, 2000, True, 8), (32, 301, False, 6), (128, 16384, True, 4)])
-def test_dcgrid_kernel_variants_bit_exact(gpu, monkeypatch, env, d, M, solids, steps):
+def test_dcgrid_kernel_variants_bit_exact(gpu, options, d, M, solids, steps):
     """The persistent cp.async.bulk (TMA ring) kernels and the one-CTA-per-tile kernels are interchangeable:
-    each combination must reproduce the oracle bit for bit (variants are chosen when the instance is created)."""
-    for k, v in env.items():
-        monkeypatch.setenv(k, v)
-    run_pair(d, M, solids, steps, "project", check_every=steps)
+    each combination must reproduce the oracle bit for bit (variants are creation-time options of the instance,
+    struct dcg_options in include/dcgrid_b200.h)."""
+    run_pair(d, M, solids, steps, "project", check_every=steps, options=options)
 
 
 @pytest.mark.parametrize("size,M,steps", [((64, 64, 128), 4000, 10), ((128, 64, 64), 3000, 8), ((32, 64, 96), 1500, 8)])
@@ -207,3 +208,21 @@ def test_dcgrid_reset_is_reproducible(gpu):
     for k in ("pos", "level", "parent", "child", "apron"):
         np.testing.assert_array_equal(t0[k], t1[k], err_msg=k)
     assert np.abs(a.field("velocity")).max() == 0
+
+
+def test_rejected_set_params_leaves_the_instance_intact(gpu):
+    """A grid-size change is rejected (the pool is sized at construction, fluid_simulation_dcgrid.cu:9-140) and must
+    not leave half-applied parameters behind: the next steps still match the oracle, and repeating the rejected
+    call is rejected again (not swallowed by the "identical bytes" shortcut)."""
+    d, M = 32, 300
+    p = scene_params(d, solids=True)
+    sim = FluidSimulationDCGrid((d, d, d), M, p)
+    orc = Oracle(p, M)
+    sim.step(2); orc.step(2)
+    bad = scene_params(64, solids=True)
+    for _ in range(2):
+        with pytest.raises(DcgError):
+            sim.setParams(bad)
+    sim.step(3); orc.step(3)
+    act = assert_same_topology(sim, orc, "after a rejected set_params")
+    assert_same_fields(sim, orc, ("density", "velocity"), act, "after a rejected set_params")

@@ -32,12 +32,10 @@ def _same_state(a, b, fields, where):
     (128, 16384, 8, True, 5, "256"),
     (32, 301, 5, True, 6, None),        # ragged pool, more ranks than some levels have tiles
 ])
-def test_dcgrid_sharded_equals_single_gpu(gpu, monkeypatch, d, M, world, solids, steps, unit):
-    if unit:
-        monkeypatch.setenv("DCG_SHARD_UNIT", unit)
+def test_dcgrid_sharded_equals_single_gpu(gpu, d, M, world, solids, steps, unit):
     p = scene_params(d, solids=solids)
     one = FluidSimulationDCGrid((d, d, d), M, p)
-    sh = FluidSimulationDCGridSharded((d, d, d), M, p, world)
+    sh = FluidSimulationDCGridSharded((d, d, d), M, p, world, options={"shard_unit": int(unit)} if unit else None)
     _same_state(one, sh, ("density", "velocity", "fluidity"), "after reset")
     for s in range(steps):
         for sim in (one, sh):
@@ -52,11 +50,10 @@ def test_dcgrid_sharded_equals_single_gpu(gpu, monkeypatch, d, M, world, solids,
     assert np.abs(one.field("density")).max() > 0
 
 
-def test_dcgrid_sharded_vs_oracle_graph_path(gpu, monkeypatch):
-    monkeypatch.setenv("DCG_RESORT_EVERY", "2")  # x-slab field order re-sorted every other topology change
+def test_dcgrid_sharded_vs_oracle_graph_path(gpu):
     d, M = 64, 2000
     p = scene_params(d, solids=True)
-    sh = FluidSimulationDCGridSharded((d, d, d), M, p, 4)
+    sh = FluidSimulationDCGridSharded((d, d, d), M, p, 4, options={"resort_every": 2})  # slab field order re-sorted every other topology change
     orc = Oracle(p, M)
     sh.step(9); orc.step(9)  # reaches the fixed point: the last steps replay the captured graph
     assert sh.counters()[7] == 1

@@ -85,14 +85,13 @@ def test_uniform_reset_restores_initial_state(gpu):
     np.testing.assert_array_equal(_bits(a.field("density")), _bits(b.field("density")))
 
 
-@pytest.mark.parametrize("fuse", ["1", "0"])
-def test_uniform_speculative_velocity_any_call_order(gpu, monkeypatch, fuse):
+@pytest.mark.parametrize("no_fuse", [0, 1])
+def test_uniform_speculative_velocity_any_call_order(gpu, no_fuse):
     """advectDensity() also writes the next step's advected velocity into the idle ping-pong buffer
     (k_u_advect_both); advectVelocity() may only use it if nothing touched the state in between."""
-    monkeypatch.setenv("DCG_ADVECT_FUSE", fuse)
     size = (32, 32, 32)
     p = scene_params(32, solids=True)
-    sim = FluidSimulationUniform(size, p)
+    sim = FluidSimulationUniform(size, p, options={"advect_no_fuse": no_fuse})
     orc = Oracle(p)
     sim.step(3); orc.step(3)
     seq = ["advect_density", "project", "advect_velocity", "advect_density", "advect_velocity", "advect_velocity",
