@@ -47,6 +47,34 @@ METRIC = "effective cell-updates/s per full step"
 UNIT = "cell-updates/s"
 
 
+def csrc_digest():
+    """SHA-256 over the product sources (dcgrid_b200/csrc + include): ties a committed ncu figure to the code it was taken on."""
+    import hashlib
+
+    h = hashlib.sha256()
+    for d in (os.path.join(ROOT, "dcgrid_b200", "csrc"), os.path.join(ROOT, "include")):
+        for f in sorted(os.listdir(d)):
+            if f.endswith((".cu", ".cuh", ".h")):
+                with open(os.path.join(d, f), "rb") as fh:
+                    h.update(f.encode() + b"\0" + fh.read())
+    return h.hexdigest()[:16]
+
+
+def golden_digest(size, M, solids, steps):
+    """FNV-1a-64 of the reference's raw density + velocity arrays for this scene after `steps` steps, if
+    tests/golden/big/ holds one (made by tests/golden/make_golden_big.py from the reference's own CUDA kernels)."""
+    import glob
+
+    import numpy as np
+
+    for f in sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "big", "*.npz"))):
+        z = np.load(f)
+        m = json.loads(bytes(z["meta"]).decode())
+        if (m["gx"], m["gy"], m["gz"]) == tuple(size) and m["M"] == M and bool(m["solids"]) == bool(solids) and m["steps"] == steps:
+            return os.path.basename(f), int(bytes(z["fnv_raw_density_velocity"]).hex(), 16)
+    return None, None
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -117,7 +145,17 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm), "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
-def make_sim(workload, device, rank=0, world=1, dist=None):
+def parse_options(text):
+    """--opt key=value,key=value -> dict for struct dcg_options (include/dcgrid_b200.h)."""
+    out = {}
+    for kv in (text or "").split(","):
+        if kv.strip():
+            k, v = kv.split("=")
+            out[k.strip()] = int(v)
+    return out
+
+
+def make_sim(workload, device, rank=0, world=1, dist=None, options=None):
     from dcgrid_b200 import (FluidSimulationDCGrid, FluidSimulationDCGridSharded, FluidSimulationUniform,
                              FluidSimulationUniformSharded, scene_params)
 
@@ -126,12 +164,13 @@ def make_sim(workload, device, rank=0, world=1, dist=None):
         size = (d, d, d * world)
         p = scene_params(*size, solids=solids)
         if grid == "dcgrid":
-            sim = FluidSimulationDCGridSharded(size, M * world, p, world, rank=rank, nlocal=1, device=device, dist=dist)
+            sim = FluidSimulationDCGridSharded(size, M * world, p, world, rank=rank, nlocal=1, device=device, dist=dist, options=options)
         else:
             sim = FluidSimulationUniformSharded(size, p, world, rank=rank, nlocal=1, device=device, dist=dist)
         return sim, p
     p = scene_params(d, solids=solids)
-    sim = FluidSimulationDCGrid((d, d, d), M, p, device=device) if grid == "dcgrid" else FluidSimulationUniform((d, d, d), p, device=device)
+    sim = (FluidSimulationDCGrid((d, d, d), M, p, device=device, options=options) if grid == "dcgrid"
+           else FluidSimulationUniform((d, d, d), p, device=device, options=options))
     return sim, p
 
 
@@ -211,6 +250,7 @@ def run_reference_arm(args, rank, world):
         "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "grid": grid, "effective_cells": d ** 3 * depth, "max_num_blocks": M * depth, "solids": bool(solids),
+                   "scene_state": "transient (the first steps after reset; the B200 arm's like-for-like figure is its `transient` object)",
                    "note": "reference has no CPU path; this is the strict-IEEE CPU restatement (oracle/), pinned bit-exactly to the reference CUDA"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -222,13 +262,15 @@ def run_reference_arm(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--preroll", type=int, default=140, help="untimed steps after construction that develop the scene (topology fixed point)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="dcgrid512", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reference-cuda", action="store_true")
+    ap.add_argument("--no-parity-check", action="store_true")
+    ap.add_argument("--opt", default="", help="creation-time options, key=value[,key=value...] (struct dcg_options)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3  # timing rule: W >= 3
@@ -257,7 +299,7 @@ def main():
         torch.cuda.synchronize()
 
     grid, d, M, solids = WORKLOADS[args.workload]
-    sim, p = make_sim(args.workload, local_rank, rank, world, dist if world > 1 else None)
+    sim, p = make_sim(args.workload, local_rank, rank, world, dist if world > 1 else None, parse_options(args.opt))
     ctr0 = sim.counters()
     scene_cells = d ** 3 * world  # N>1: one scene, N times as deep
 
@@ -274,6 +316,22 @@ def main():
     done = 20 if transient else 0
     if args.preroll > done:
         sim.step(args.preroll - done)
+    # ---- parity of the measured configuration: the fields after the pre-roll against the digest of the REFERENCE's
+    # own CUDA run of the same scene and step count (tests/golden/big/, bit-exact: FNV-1a of raw density + velocity) ----
+    parity = {"checked": False, "why": "no committed reference digest for this scene / step count"}
+    if grid == "dcgrid" and not args.no_parity_check:
+        size = (d, d, d * world)
+        case, want = golden_digest(size, M * world, solids, args.preroll)
+        if case is not None:
+            barrier()
+            if rank == 0:
+                from dcgrid_b200 import fnv1a64
+
+                got = fnv1a64(sim.field("density"), sim.field("velocity"))
+                parity = {"checked": True, "ok": bool(got == want), "case": "tests/golden/big/" + case, "steps": args.preroll,
+                          "what": "FNV-1a-64 of the raw density + velocity arrays == the reference's own CUDA kernels (ref_harness_nofma)",
+                          "digest": f"{got:016x}", "reference_digest": f"{want:016x}"}
+            barrier()
     # ---- warm-up: W steps of the developed scene (captures the step graphs) ----
     sim.step(args.warmup)
     barrier()
@@ -334,12 +392,17 @@ def main():
             sim.benchStage("jacobi", lvl, 10)
             ms, b = sim.benchStage("jacobi", lvl, 40)
             ach = b / (ms * 1e-3) / 1e9
+            # DRAM traffic of the dominant kernel from the committed ncu --set full capture — only if that capture was
+            # taken on exactly these sources (csrc_digest recorded beside it), else null
             traffic, traffic_src = None, None
             tpath = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
             if os.path.exists(tpath) and args.workload == "dcgrid512":
                 with open(tpath) as f:
                     tj = json.load(f)
-                traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
+                if tj.get("csrc_digest") == csrc_digest():
+                    traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
+                else:
+                    traffic_src = f"stale: {tj.get('source')} was captured on csrc {tj.get('csrc_digest')}, this is {csrc_digest()}"
             roof = {"bound": "hbm", "kernel": "k_dc_jacobi_pipe" if grid == "dcgrid" else "k_u_jacobi", "level": lvl, "achieved": ach,
                     "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src,
                     "peak_source": peak_src, "ms_per_launch": ms, "alg_bytes_per_launch": b,
@@ -368,9 +431,18 @@ def main():
                        "schedule": "reference project(): 5 Jacobi pairs per level, cascadic",
                        "preroll_steps": args.preroll, "scene_state": "developed (topology at its fixed point)" if bool(ctr[7]) else "transient"},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": ctypes.sizeof(SimParams), "d2h_bytes_per_step": d2h,
-                    "what": "dcg_set_params(host struct) + dcg_step(1) + dcg_total_density (device reduction, partials copied to pinned host memory) per step, host wall clock",
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": d2h,
+                    "what": "dcg_set_params(host struct, 100 B) + dcg_step(1) + dcg_total_density (device reduction, partials copied to pinned "
+                            "host memory) per step, host wall clock.  The solve's only per-step input is SimParams; kernels take it BY VALUE as a "
+                            "launch argument, so an unchanged struct costs no host-to-device copy (the reference re-uploads it to __constant__ "
+                            "memory every frame, src/simulation.cpp:94); the simulation state lives on the device by design, like the reference's",
                     "last_total_density": total},
+            "parity": parity, "parity_checked": bool(parity.get("checked") and parity.get("ok")),
+            "csrc_digest": csrc_digest(),
+            "options": parse_options(args.opt),
+            "diagnostics": ({k: sim.info(k) for k in ("pdl", "pdl_fallbacks", "host_selections", "device_selections", "selection_fallbacks",
+                                                      "levels_shortcut", "resorts", "irregular_blocks", "barriers", "graph_launches_per_step")}
+                            if grid == "dcgrid" else {}),
             "gpu_launches": launches,
             "roofline": roof,
             "step_roofline": {"bound": "hbm", "achieved": step_ach, "peak": peak * world, "unit": "GB/s", "frac": step_ach / (peak * world),
@@ -385,8 +457,10 @@ def main():
         if not args.no_cpu_baseline and world == 1:
             try:
                 dt, cores, create = cpu_port_step_time(args.workload, 2 if cells >= 256 ** 3 else 20, 0)
-                line["cpu_baseline"] = {"value": cells / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                line["cpu_baseline"] = {"value": cells / dt, "unit": UNIT, "cores": cores, "kind": "port", "scene_state": "transient (the first steps after reset)",
                                         "sample": f"{2 if cells >= 256 ** 3 else 20} full steps of the same scene after reset ({create:.1f} s construction untimed), oracle/liboracle.so with OpenMP"}
+                if transient:  # like for like: both arms on the first steps after reset()
+                    transient["vs_cpu_baseline"] = transient["value"] / line["cpu_baseline"]["value"]
             except Exception as e:  # noqa: BLE001
                 line["cpu_baseline"] = {"error": str(e)[:200]}
         print(json.dumps(line), flush=True)

@@ -11,5 +11,6 @@ from .simulation import (  # noqa: F401
     FluidSimulation,
     FluidSimulationDCGrid,
     FluidSimulationUniform,
+    fnv1a64,
 )
 from .sharding import FluidSimulationDCGridSharded, FluidSimulationUniformSharded  # noqa: F401,E402

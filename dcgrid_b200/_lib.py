@@ -51,6 +51,7 @@ SYMBOLS = {
     "dcg_get_topology": (_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "dcg_lookup_blocks": (_int, [_vp, _vp, _u64, _vp, _vp]),
     "dcg_get_counters": (_int, [_vp, _vp]),
+    "dcg_get_info": (_int, [_vp, ctypes.c_char_p, ctypes.POINTER(ctypes.c_double)]),
     "dcg_last_step_ms": (_int, [_vp, ctypes.POINTER(ctypes.c_float)]),
     "dcg_algorithmic_bytes": (_int, [_vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_u64)]),
     "dcg_bench_stage": (_int, [_vp, ctypes.c_char_p, _int, _int, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double)]),
@@ -59,6 +60,7 @@ SYMBOLS = {
     "dcg_shard_handle_bytes": (_u64, []),
     "dcg_shard_export_handle": (_int, [_vp, _vp, _u64]),
     "dcg_shard_import_handles": (_int, [_vp, _vp, _int]),
+    "dcg_fnv1a64": (_u64, [_vp, _u64, _u64]),
     "dcg_last_error": (ctypes.c_char_p, [_vp]),
     "dcg_version": (ctypes.c_char_p, []),
 }

@@ -203,6 +203,11 @@ int dcg_get_counters(dcg_sim *sim, uint64_t out[8]) {
   if (!out) return DCG_ERR_INVALID;
   return sim->get_counters(out);
 }
+int dcg_get_info(dcg_sim *sim, const char *key, double *out) {
+  NEED(sim);
+  if (!key || !out) return DCG_ERR_INVALID;
+  return sim->get_info(key, out);
+}
 int dcg_last_step_ms(dcg_sim *sim, float *out) {
   NEED(sim);
   if (!out) return DCG_ERR_INVALID;
@@ -218,6 +223,16 @@ int dcg_bench_stage(dcg_sim *sim, const char *stage, int level, int reps, float 
   NEED(sim);
   if (!stage || reps <= 0) return sim->fail(DCG_ERR_INVALID, "bench_stage: bad arguments");
   return sim->bench_stage(stage, level, reps, ms_per_launch, alg_bytes);
+}
+
+uint64_t dcg_fnv1a64(const void *data, uint64_t bytes, uint64_t seed) {
+  uint64_t h = seed ? seed : 14695981039346656037ull;
+  const unsigned char *b = static_cast<const unsigned char *>(data);
+  for (uint64_t i = 0; i < bytes; i++) {
+    h ^= b[i];
+    h *= 1099511628211ull;
+  }
+  return h;
 }
 
 const char *dcg_last_error(const dcg_sim *sim) {

@@ -110,6 +110,20 @@ __device__ __forceinline__ float div6(float x) {
   return fmaf(fmaf(-6.f, q, x), r, q);
 }
 
+// ---- programmatic dependent launch (sm_90+) ------------------------------------------------
+// Every kernel of a step starts with pdl_enter(): when the host launched it with
+// cudaLaunchAttributeProgrammaticStreamSerialization its CTAs may become resident while the previous
+// kernel of the stream is still draining (launch latency and CTA ramp-up overlap the predecessor's tail);
+// griddepcontrol.wait then blocks until that kernel has completed and its writes are visible, so the data
+// dependence is exactly that of plain stream order.  launch_dependents lets the NEXT kernel do the same
+// with this one.  Both are no-ops in a launch without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() {
+  pdl_wait();
+  pdl_trigger();
+}
+
 // ---- misc ------------------------------------------------------------------------
 __host__ __device__ __forceinline__ int idiv_up(int a, int b) { return (a + b - 1) / b; }
 

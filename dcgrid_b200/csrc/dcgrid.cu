@@ -60,7 +60,7 @@ struct DCGridSim : dcg_sim {
   ScoreSummary *d_summary = nullptr, *h_summary = nullptr;  // per-level score extrema (device-reduced, 192 B D2H)
   uint32_t *d_flag_bits = nullptr;  // one bit per slot: flags != 0 (k_dc_flag_bits)
   uint32_t *d_counters = nullptr;  // [0] failed allocations, [1] irregular-face blocks (last build)
-  uint64_t n_irregular = 0, n_host_selections = 0, n_levels_shortcut = 0;
+  uint64_t n_irregular = 0, n_host_selections = 0, n_levels_shortcut = 0, n_device_selections = 0, n_selection_fallbacks = 0;
   float4 *vw[2] = {nullptr, nullptr};
   float *q[2] = {nullptr, nullptr};
   float *fl = nullptr, *p = nullptr, *tp = nullptr, *div = nullptr;
@@ -225,6 +225,7 @@ struct DCGridSim : dcg_sim {
     DCG_CUDA_TRY(cudaMalloc(&T.parent, ((size_t)M + kB4) * 4));  // padded: the stencil rings stream kB4 entries per tile
     DCG_TRY(setup_sharding());
     DCG_CUDA_TRY(cudaMalloc(&d_perm, (size_t)M * 4));
+    use_pdl = !opt.no_pdl;
     use_resort = !opt.no_resort;
     if (opt.resort_every != 0) resort_every = std::max(0, opt.resort_every);  // -1: only at the fixed point
     DCG_CUDA_TRY(cudaMalloc(&d_pcount, (kMaxLevels + 1) * 4));
@@ -406,12 +407,28 @@ struct DCGridSim : dcg_sim {
   }
   bool has_rank0() const { return rank0 == 0; }
 
+  // Launch of a step kernel.  use_pdl: programmatic dependent launch — the kernel may become resident before its
+  // predecessor in the stream has drained; every such kernel starts with pdl_enter() (common.cuh), which restores
+  // the full data dependence.  Captured into the step graph as programmatic edges.
+  bool use_pdl = true;
+  uint64_t pdl_fallbacks = 0;
+  template <class... P, class... A>
+  void launch_pdl(void (*k)(P...), dim3 grid, dim3 block, size_t smem, A &&...a) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at{};
+    at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &at;
+    cfg.numAttrs = use_pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, k, P(std::forward<A>(a))...);
+  }
   BarrierPeers peers{};
   // lock-step barrier over peer memory after a phase whose results other ranks read (no-op inside one process:
   // stream order is the barrier)
   void barrier() {
     if (!vmm) return;
-    k_dcs_barrier<<<1, 32, 0, stream>>>(peers, rank0, world, d_epoch, d_barrier_err);
+    launch_pdl(k_dcs_barrier, dim3(1), dim3(32), 0, peers, rank0, world, d_epoch, d_barrier_err);
     launches++;
     n_barriers++;
   }
@@ -1006,22 +1023,22 @@ struct DCGridSim : dcg_sim {
         each_rank([&](int, RankWork &w) {
           const uint32_t n = w.pcount[l];
           if (n == 0) return;
-          if (v) k_dc_accumulate_velocity_list<<<blocks_for(8 * (size_t)n, 256), 256, 0, stream>>>(hot(), w.d_plist + offsets[l], n, v);
-          else k_dc_accumulate_scalar_list<<<blocks_for(8 * (size_t)n, 256), 256, 0, stream>>>(hot(), w.d_plist + offsets[l], n, ch);
+          if (v) launch_pdl(k_dc_accumulate_velocity_list, dim3(blocks_for(8 * (size_t)n, 256)), dim3(256), 0, hot(), w.d_plist + offsets[l], n, v);
+          else launch_pdl(k_dc_accumulate_scalar_list, dim3(blocks_for(8 * (size_t)n, 256)), dim3(256), 0, hot(), w.d_plist + offsets[l], n, ch);
           launches++;
         });
         barrier();
       } else if (v) {
-        k_dc_accumulate_velocity<<<blocks_for(8 * loads[l], 256), 256, 0, stream>>>(hot(), l, v, 0);
+        launch_pdl(k_dc_accumulate_velocity, dim3(blocks_for(8 * loads[l], 256)), dim3(256), 0, hot(), l, v, 0);
         launches++;
       } else {
-        k_dc_accumulate_scalar<<<blocks_for(8 * loads[l], 256), 256, 0, stream>>>(hot(), l, ch, 0);
+        launch_pdl(k_dc_accumulate_scalar, dim3(blocks_for(8 * loads[l], 256)), dim3(256), 0, hot(), l, ch, 0);
         launches++;
       }
     }
     if (tail < levels - 1) {
       if (has_rank0()) {
-        k_dc_accumulate_coarse<<<kAccClusterCTAs, kAccClusterThreads, 0, stream>>>(hot(), tail, v, ch);
+        launch_pdl(k_dc_accumulate_coarse, dim3(kAccClusterCTAs), dim3(kAccClusterThreads), 0, hot(), tail, v, ch);
         launches++;
       }
       barrier();
@@ -1053,7 +1070,14 @@ struct DCGridSim : dcg_sim {
       const uint32_t *ord = w.d_order;
       Pool hp = hot();
       void *args[] = {&hp, &kp, &ord, &w.n_order, &vin, &vout, &flp, &qi, &qo};
-      cudaLaunchKernel(advect_fn(mode), dim3(grid), dim3(kAdvectThreads), args, kAdvectPipeSmem, stream);
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kAdvectThreads); cfg.dynamicSmemBytes = kAdvectPipeSmem; cfg.stream = stream;
+      cudaLaunchAttribute at{};
+      at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at.val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = &at;
+      cfg.numAttrs = use_pdl ? 1 : 0;
+      cudaLaunchKernelExC(&cfg, advect_fn(mode), args);
       launches++;
     });
     barrier();
@@ -1103,12 +1127,12 @@ struct DCGridSim : dcg_sim {
       if (tiles == 0) return;
       if (use_pipe && jacobi8 && blocks_for(loads[l], kB4) >= pipe_min_tiles) {
         const unsigned grid = std::min<unsigned>(tiles, (unsigned)jacobi8_ctas);
-        k_dc_jacobi_pipe8<<<grid, kJ8Threads, kJacobiPipeSmem, stream>>>(hot(), kp, R, l, in, out, div, snake ? sweep_parity : 0);
+        launch_pdl(k_dc_jacobi_pipe8, dim3(grid), dim3(kJ8Threads), kJacobiPipeSmem, hot(), kp, R, l, in, out, div, snake ? sweep_parity : 0);
       } else if (use_pipe && blocks_for(loads[l], kB4) >= pipe_min_tiles) {
         const unsigned grid = std::min<unsigned>(tiles, (unsigned)jacobi_pipe_ctas);
-        k_dc_jacobi_pipe<<<grid, kCTA4, kJacobiPipeSmem, stream>>>(hot(), kp, R, l, in, out, div, snake ? sweep_parity : 0);
+        launch_pdl(k_dc_jacobi_pipe, dim3(grid), dim3(kCTA4), kJacobiPipeSmem, hot(), kp, R, l, in, out, div, snake ? sweep_parity : 0);
       } else {
-        k_dc_jacobi4<<<tiles, kCTA4, 0, stream>>>(hot(), kp, R, l, in, out, div);
+        launch_pdl(k_dc_jacobi4, dim3(tiles), dim3(kCTA4), 0, hot(), kp, R, l, in, out, div);
       }
       launches++;
     });
@@ -1126,8 +1150,8 @@ struct DCGridSim : dcg_sim {
     each_rank([&](int, RankWork &w) {
       const TileRuns &R = w.level[l];
       if (run_total(R) == 0) return;
-      if (prolong_staged) k_dc_prolongate_staged<<<run_total(R), kCTA4, 0, stream>>>(hot(), R, l, p);
-      else k_dc_prolongate4<<<blocks_for(loads[l], kB4), kCTA4, 0, stream>>>(hot(), l, p);
+      if (prolong_staged) launch_pdl(k_dc_prolongate_staged, dim3(run_total(R)), dim3(kCTA4), 0, hot(), R, l, p);
+      else launch_pdl(k_dc_prolongate4, dim3(blocks_for(loads[l], kB4)), dim3(kCTA4), 0, hot(), l, p);
       launches++;
     });
     if (!level_single[l]) barrier();  // single-owner level: the same rank sweeps it next
@@ -1137,10 +1161,10 @@ struct DCGridSim : dcg_sim {
       const unsigned tiles = run_total(w.all);
       if (tiles == 0) return;
       if (use_stencil_pipe)
-        k_dc_divergence_pipe<<<std::min<unsigned>(tiles, (unsigned)div_pipe_ctas), kStencilThreads, kDivPipeSmem, stream>>>(hot(), kp, w.all, vw[cur_v], div, p,
+        launch_pdl(k_dc_divergence_pipe, dim3(std::min<unsigned>(tiles, (unsigned)div_pipe_ctas)), dim3(kStencilThreads), kDivPipeSmem, hot(), kp, w.all, vw[cur_v], div, p,
                                                                                                                             tp, zero_from);
       else
-        k_dc_divergence4<<<blocks_for(M, kB4), kCTA4, 0, stream>>>(hot(), kp, vw[cur_v], div, p, tp, zero_from);
+        launch_pdl(k_dc_divergence4, dim3(blocks_for(M, kB4)), dim3(kCTA4), 0, hot(), kp, vw[cur_v], div, p, tp, zero_from);
       launches++;
     });
     barrier();
@@ -1151,11 +1175,11 @@ struct DCGridSim : dcg_sim {
       if (tiles == 0) return;
       const unsigned grid = std::min<unsigned>(tiles, (unsigned)apply_pipe_ctas);
       if (use_stencil_pipe && apply_min_blocks == 2)
-        k_dc_apply_pipe<2><<<grid, kStencilThreads, kApplyPipeSmem, stream>>>(hot(), kp, w.all, p, fl, vw[cur_v]);
+        launch_pdl(k_dc_apply_pipe<2>, dim3(grid), dim3(kStencilThreads), kApplyPipeSmem, hot(), kp, w.all, p, fl, vw[cur_v]);
       else if (use_stencil_pipe)
-        k_dc_apply_pipe<3><<<grid, kStencilThreads, kApplyPipeSmem, stream>>>(hot(), kp, w.all, p, fl, vw[cur_v]);
+        launch_pdl(k_dc_apply_pipe<3>, dim3(grid), dim3(kStencilThreads), kApplyPipeSmem, hot(), kp, w.all, p, fl, vw[cur_v]);
       else
-        k_dc_apply_pressure4<<<blocks_for(M, kB4), kCTA4, 0, stream>>>(hot(), kp, p, fl, vw[cur_v]);
+        launch_pdl(k_dc_apply_pressure4, dim3(blocks_for(M, kB4)), dim3(kCTA4), 0, hot(), kp, p, fl, vw[cur_v]);
       launches++;
     });
     barrier();
@@ -1175,9 +1199,9 @@ struct DCGridSim : dcg_sim {
     const size_t smem = (size_t)ncell * (3 * 4 + 6 * 2);
     if (has_rank0()) {  // sharded: one rank walks the coarse tail, the others wait at the barrier
       if (coarse_in_smem && smem <= kCoarseSmemMax && ncell <= 65535)
-        k_dc_coarse_cascade<true><<<1, 1024, smem, stream>>>(hot(), kp, cf, prolong_coarsest, pairs_coarsest, pairs_level, prolong_levels, p, tp, div, ncell);
+        launch_pdl(k_dc_coarse_cascade<true>, dim3(1), dim3(1024), smem, hot(), kp, cf, prolong_coarsest, pairs_coarsest, pairs_level, prolong_levels, p, tp, div, ncell);
       else
-        k_dc_coarse_cascade<false><<<1, 1024, 0, stream>>>(hot(), kp, cf, prolong_coarsest, pairs_coarsest, pairs_level, prolong_levels, p, tp, div, 0);
+        launch_pdl(k_dc_coarse_cascade<false>, dim3(1), dim3(1024), 0, hot(), kp, cf, prolong_coarsest, pairs_coarsest, pairs_level, prolong_levels, p, tp, div, 0);
       launches++;
     }
     barrier();
@@ -1223,21 +1247,31 @@ struct DCGridSim : dcg_sim {
         continue;
       }
       cudaGraphExec_t &ge = step_graph[cur_v * 2 + cur_q];
-      if (!ge) {
-        const uint64_t before = launches, adapt_before = n_adapt, skipped_before = n_skipped;
-        const int sv = cur_v, sq = cur_q;
+      for (int attempt = 0; !ge; attempt++) {
+        const uint64_t before = launches, adapt_before = n_adapt, skipped_before = n_skipped, barriers_before = n_barriers;
+        const int sv = cur_v, sq = cur_q, sp = sweep_parity;
         const bool sspec = spec_velocity;
         cudaGraph_t g = nullptr;
         DCG_CUDA_TRY(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
         const int rc = dcg_sim::step(1);  // adapt_topology() is a no-op in the steady state
-        const cudaError_t ce = cudaStreamEndCapture(stream, &g);
+        cudaError_t ce = cudaStreamEndCapture(stream, &g);
         cur_v = sv; cur_q = sq; spec_velocity = sspec;  // capture records, it does not execute
         step_graph_launches = launches - before;
-        launches = before; n_adapt = adapt_before; n_skipped = skipped_before;
-        if (rc != DCG_OK) return rc;
-        DCG_CUDA_TRY(ce);
-        DCG_CUDA_TRY(cudaGraphInstantiate(&ge, g, 0));
-        cudaGraphDestroy(g);
+        launches = before; n_adapt = adapt_before; n_skipped = skipped_before; n_barriers = barriers_before;
+        if (rc != DCG_OK && ce == cudaSuccess) return rc;
+        if (ce == cudaSuccess) ce = cudaGraphInstantiate(&ge, g, 0);
+        if (g) cudaGraphDestroy(g);
+        if (ce != cudaSuccess) {
+          ge = nullptr;
+          cudaGetLastError();
+          if (use_pdl && attempt == 0) {  // programmatic edges not capturable on this driver: plain stream order
+            use_pdl = false;
+            pdl_fallbacks++;
+            sweep_parity = sp;
+            continue;
+          }
+          DCG_CUDA_TRY(ce);
+        }
       }
       DCG_CUDA_TRY(cudaGraphLaunch(ge, stream));
       launches += step_graph_launches;
@@ -1296,7 +1330,7 @@ struct DCGridSim : dcg_sim {
         launches--;
         bytes = 32.0 * call;
       } else if (st == "accumulate_velocity") {
-        k_dc_accumulate_velocity<<<blocks_for(8 * loads[level], 256), 256, 0, stream>>>(hot(), level, vw[cur_v], 0);
+        launch_pdl(k_dc_accumulate_velocity, dim3(blocks_for(8 * loads[level], 256)), dim3(256), 0, hot(), level, vw[cur_v], 0);
         bytes = 13.5 * cl;
       } else if (st == "prolongate") {
         launch_prolongate(level);
@@ -1461,6 +1495,22 @@ struct DCGridSim : dcg_sim {
   int get_counters(uint64_t out[8]) override {
     out[0] = n_adapt; out[1] = n_changed; out[2] = n_moved; out[3] = n_refined;
     out[4] = n_skipped; out[5] = n_failed; out[6] = launches; out[7] = steady ? 1 : 0;
+    return DCG_OK;
+  }
+
+  int get_info(const char *key, double *out) override {
+    const std::string k(key);
+    if (k == "pdl") *out = use_pdl ? 1 : 0;
+    else if (k == "pdl_fallbacks") *out = (double)pdl_fallbacks;
+    else if (k == "host_selections") *out = (double)n_host_selections;
+    else if (k == "device_selections") *out = (double)n_device_selections;
+    else if (k == "selection_fallbacks") *out = (double)n_selection_fallbacks;
+    else if (k == "levels_shortcut") *out = (double)n_levels_shortcut;
+    else if (k == "resorts") *out = (double)n_resorts;
+    else if (k == "irregular_blocks") *out = (double)n_irregular;
+    else if (k == "barriers") *out = (double)n_barriers;
+    else if (k == "graph_launches_per_step") *out = (double)step_graph_launches;
+    else return dcg_sim::get_info(key, out);
     return DCG_OK;
   }
 

@@ -150,6 +150,7 @@ __device__ __forceinline__ bool block_has_children(const Pool &T, uint32_t b) {
   return (c0.x & c0.y & c0.z & c0.w & c1.x & c1.y & c1.z & c1.w) != kNone;
 }
 __global__ void __launch_bounds__(256) k_dc_accumulate_velocity(Pool T, int level, float4 *__restrict__ vw, int skip_childless) {
+  pdl_enter();
   const uint32_t t = blockIdx.x * 256 + threadIdx.x;
   if (t >= 8 * T.loads[level]) return;
   const uint32_t sb = 8 * T.offsets[level] + t, b = sb / 8;
@@ -167,6 +168,7 @@ __global__ void __launch_bounds__(256) k_dc_accumulate_velocity(Pool T, int leve
   dst[0] = ax * .125f; dst[1] = ay * .125f; dst[2] = az * .125f;  // .w (fluidity) untouched
 }
 __global__ void __launch_bounds__(256) k_dc_accumulate_scalar(Pool T, int level, float *__restrict__ ch, int skip_childless) {
+  pdl_enter();
   const uint32_t t = blockIdx.x * 256 + threadIdx.x;
   if (t >= 8 * T.loads[level]) return;
   const uint32_t sb = 8 * T.offsets[level] + t, b = sb / 8;
@@ -194,6 +196,7 @@ __global__ void __launch_bounds__(256) k_dc_list_parents(Pool T, const uint8_t *
   plist[T.offsets[level] + atomicAdd(&pcount[level], 1u)] = b;
 }
 __global__ void __launch_bounds__(256) k_dc_accumulate_velocity_list(Pool T, const uint32_t *__restrict__ list, uint32_t n, float4 *__restrict__ vw) {
+  pdl_enter();
   const uint32_t t = blockIdx.x * 256 + threadIdx.x;
   if (t >= 8 * n) return;
   const uint32_t b = list[t >> 3], sb = 8 * b + (t & 7u);
@@ -209,6 +212,7 @@ __global__ void __launch_bounds__(256) k_dc_accumulate_velocity_list(Pool T, con
   dst[0] = ax * .125f; dst[1] = ay * .125f; dst[2] = az * .125f;
 }
 __global__ void __launch_bounds__(256) k_dc_accumulate_scalar_list(Pool T, const uint32_t *__restrict__ list, uint32_t n, float *__restrict__ ch) {
+  pdl_enter();
   const uint32_t t = blockIdx.x * 256 + threadIdx.x;
   if (t >= 8 * n) return;
   const uint32_t b = list[t >> 3], sb = 8 * b + (t & 7u);
@@ -565,6 +569,7 @@ __device__ __forceinline__ float prolong_one(const float (*c)[3][3], int j, int 
   return (27.f * p000 + 9.f * (p001 + p010 + p100) + 3.f * (p011 + p101 + p110) + p111) / 64.f;
 }
 __global__ void __launch_bounds__(kCTA4) k_dc_prolongate4(Pool T, int level, float *__restrict__ p) {
+  pdl_enter();
   const uint32_t g = threadIdx.x >> 4;
   const int t = threadIdx.x & 15;
   const uint32_t li = blockIdx.x * kB4 + g;
@@ -598,6 +603,7 @@ __global__ void __launch_bounds__(kCTA4) k_dc_prolongate4(Pool T, int level, flo
 // ring) staged once per block in shared memory: 4 index + 4 value loads per thread instead of 18 + 18 — the
 // gather version keeps the L1 data pipe 85 % busy for 4.5 B/cell of useful traffic (profiles/README.md r1d).
 __global__ void __launch_bounds__(kCTA4) k_dc_prolongate_staged(Pool T, TileRuns R, int level, float *__restrict__ p) {
+  pdl_enter();
   __shared__ float sc[kB4][64];
   const uint32_t g = threadIdx.x >> 4;
   const int t = threadIdx.x & 15;
@@ -846,6 +852,7 @@ __device__ __forceinline__ unsigned long long global_ns() {
   return t;
 }
 __global__ void __launch_bounds__(32) k_dcs_barrier(BarrierPeers B, int rank, int world, uint32_t *epoch_counter, uint32_t *err) {
+  pdl_enter();
   const int t = threadIdx.x;
   uint32_t epoch = 0;
   if (t == 0) epoch = ++(*epoch_counter);

@@ -92,6 +92,7 @@ constexpr size_t kJacobiPipeSmem = kJStages * sizeof(JacobiStage) + kJStages * s
 // R: the level-local tiles (tile k = slots offsets[level] + 16k ...) this rank sweeps, clipped to the active prefix
 __global__ void __launch_bounds__(kCTA4, 4) k_dc_jacobi_pipe(Pool T, KParams P, TileRuns R, int level, const float *__restrict__ in,
                                                             float *__restrict__ out, const float *__restrict__ div, int reverse) {
+  pdl_enter();
   extern __shared__ __align__(128) unsigned char smem_raw[];
   JacobiStage *st = reinterpret_cast<JacobiStage *>(smem_raw);
   uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + kJStages * sizeof(JacobiStage));
@@ -231,6 +232,7 @@ __device__ __forceinline__ Ghost12 sub_ghost_values(const Pool &T, const float *
 
 __global__ void __launch_bounds__(kJ8Threads, 5) k_dc_jacobi_pipe8(Pool T, KParams P, TileRuns R, int level, const float *__restrict__ in,
                                                                   float *__restrict__ out, const float *__restrict__ div, int reverse) {
+  pdl_enter();
   extern __shared__ __align__(128) unsigned char smem_raw[];
   JacobiStage *st = reinterpret_cast<JacobiStage *>(smem_raw);
   uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + kJStages * sizeof(JacobiStage));
@@ -426,6 +428,7 @@ __global__ void __launch_bounds__(kAdvectThreads, kMinBlocks) k_dc_advect_pipe(P
                                                                                const float4 *__restrict__ vin, float4 *__restrict__ vout,
                                                                                const float *__restrict__ fl, const float *__restrict__ qin,
                                                                                float *__restrict__ qout) {
+  pdl_enter();
   extern __shared__ __align__(128) unsigned char smem_raw[];
   AdvectStage *st = reinterpret_cast<AdvectStage *>(smem_raw);
   uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + kAStages * sizeof(AdvectStage));
@@ -649,6 +652,7 @@ __device__ __forceinline__ void stencil_ring_init(uint64_t *full, uint64_t *empt
 __global__ void __launch_bounds__(kStencilThreads, 3) k_dc_divergence_pipe(Pool T, KParams P, TileRuns R, const float4 *__restrict__ vw,
                                                                            float *__restrict__ div, float *__restrict__ p, float *__restrict__ tp,
                                                                            int zero_from) {
+  pdl_enter();
   extern __shared__ __align__(128) unsigned char smem_raw[];
   DivStage *st = reinterpret_cast<DivStage *>(smem_raw);
   uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + kSStages * sizeof(DivStage));
@@ -761,6 +765,7 @@ __global__ void __launch_bounds__(kStencilThreads, 3) k_dc_divergence_pipe(Pool 
 template <int kMinBlocks>
 __global__ void __launch_bounds__(kStencilThreads, kMinBlocks) k_dc_apply_pipe(Pool T, KParams P, TileRuns R, const float *__restrict__ p,
                                                                                const float *__restrict__ fl, float4 *__restrict__ vw) {
+  pdl_enter();
   extern __shared__ __align__(128) unsigned char smem_raw[];
   ApplyStage *st = reinterpret_cast<ApplyStage *>(smem_raw);
   uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + kSStages * sizeof(ApplyStage));

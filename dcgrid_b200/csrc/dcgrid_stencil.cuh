@@ -308,6 +308,7 @@ __device__ __forceinline__ GhostVals quad_ghost_values(const Pool &T, const floa
 // Sum order of the reference: left + right + down + up + back + front.
 __global__ void __launch_bounds__(kCTA4) k_dc_jacobi4(Pool T, KParams P, TileRuns R, int level, const float *__restrict__ in,
                                                       float *__restrict__ out, const float *__restrict__ div) {
+  pdl_enter();
   const uint32_t g = threadIdx.x >> 4;
   const int t = threadIdx.x & 15;
   const uint32_t li = run_tile(R, blockIdx.x) * kB4 + g;
@@ -354,6 +355,7 @@ __device__ __forceinline__ float ghost_product(const KParams &P, const float4 *_
 // level from zero and passes 0.
 __global__ void __launch_bounds__(kCTA4) k_dc_divergence4(Pool T, KParams P, const float4 *__restrict__ vw, float *__restrict__ div,
                                                           float *__restrict__ p, float *__restrict__ tp, int zero_from) {
+  pdl_enter();
   const uint32_t g = threadIdx.x >> 4;
   const int t = threadIdx.x & 15;
   const uint32_t b0 = blockIdx.x * kB4 + g;
@@ -430,6 +432,7 @@ __global__ void __launch_bounds__(kCTA4) k_dc_divergence4(Pool T, KParams P, con
 // ---- k_dcgrid_apply_pressure, dcgrid_fluid.cu:232-259 --------------------------------------------------
 __global__ void __launch_bounds__(kCTA4) k_dc_apply_pressure4(Pool T, KParams P, const float *__restrict__ p, const float *__restrict__ fl,
                                                               float4 *__restrict__ vw) {
+  pdl_enter();
   const uint32_t g = threadIdx.x >> 4;
   const int t = threadIdx.x & 15;
   const uint32_t b0 = blockIdx.x * kB4 + g;
@@ -535,6 +538,7 @@ template <bool kShared>
 __global__ void __launch_bounds__(1024) k_dc_coarse_cascade(Pool T, KParams P, int finest, int prolong_coarsest, int pairs_coarsest,
                                                             int pairs_level, int prolong_levels, float *gp, float *gtp, const float *gdiv,
                                                             uint32_t ncell) {
+  pdl_enter();
   extern __shared__ __align__(16) float coarse_smem[];
   const uint32_t base = kShared ? T.offsets[finest] * kBV : 0u;
   float *p = gp, *tp = gtp;
@@ -624,6 +628,7 @@ __device__ __forceinline__ void cluster_sync_all() {
 }
 __global__ void __cluster_dims__(kAccClusterCTAs, 1, 1) __launch_bounds__(kAccClusterThreads)
     k_dc_accumulate_coarse(Pool T, int first, float4 *vw, float *ch) {
+  pdl_enter();
   const uint32_t rank = blockIdx.x * kAccClusterThreads + threadIdx.x, stride = kAccClusterCTAs * kAccClusterThreads;
   for (int level = first; level < T.levels - 1; level++) {
     const uint32_t n = 8 * T.loads[level];

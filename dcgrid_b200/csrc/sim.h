@@ -73,6 +73,10 @@ struct dcg_sim {
     out[6] = launches;
     return DCG_OK;
   }
+  virtual int get_info(const char *key, double *out) {
+    if (std::strcmp(key, "launches") == 0) { *out = (double)launches; return DCG_OK; }
+    return fail(DCG_ERR_INVALID, "get_info: unknown key %s", key);
+  }
   // multi-GPU instances, one rank per process: opaque 64-byte handles exchanged through any host channel
   virtual int export_handle(void *, uint64_t) { return fail(DCG_ERR_UNSUPPORTED, "not a sharded one-rank-per-process instance"); }
   virtual int import_handles(const void *, int) { return fail(DCG_ERR_UNSUPPORTED, "not a sharded one-rank-per-process instance"); }

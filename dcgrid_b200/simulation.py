@@ -31,6 +31,16 @@ def _ptr(a):
     return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
 
 
+def fnv1a64(*arrays):
+    """FNV-1a-64 over the bytes of the given arrays, in order (dcg_fnv1a64): the digest the reference harness prints."""
+    L = _lib.load()
+    h = 0
+    for a in arrays:
+        a = np.ascontiguousarray(a)
+        h = int(L.dcg_fnv1a64(_ptr(a), a.nbytes, h))
+    return h
+
+
 class FluidSimulation:
     """Base: one opaque ``dcg_sim*``."""
 
@@ -122,6 +132,11 @@ class FluidSimulation:
         b = ctypes.c_double()
         self._check(self._L.dcg_bench_stage(self._h, stage.encode(), level, reps, ctypes.byref(ms), ctypes.byref(b)))
         return float(ms.value), float(b.value)
+
+    def info(self, key):
+        out = ctypes.c_double()
+        self._check(self._L.dcg_get_info(self._h, key.encode(), ctypes.byref(out)))
+        return float(out.value)
 
     def counters(self):
         out = np.zeros(8, dtype=np.uint64)

@@ -213,6 +213,13 @@ DCG_API int dcg_lookup_blocks(dcg_sim *sim, const int32_t *positions, uint64_t n
  * dcgrid_utils.cuh:120-124), [6] kernel launches issued so far, [7] reserved.     */
 DCG_API int dcg_get_counters(dcg_sim *sim, uint64_t out[8]);
 
+/* Named diagnostics (what the instance did, not part of the result): "pdl" (1 = kernels of a step are chained by
+ * programmatic dependent launch), "pdl_fallbacks", "host_selections" (levels that took the reference's host
+ * selection in adaptTopology), "device_selections", "selection_fallbacks" (levels where the device selection found a
+ * tie group straddling the cut and handed over to the host selection), "levels_shortcut", "resorts",
+ * "irregular_blocks", "barriers", "graph_launches_per_step".  Unknown key: DCG_ERR_INVALID.                  */
+DCG_API int dcg_get_info(dcg_sim *sim, const char *key, double *out);
+
 /* Device time (ms, CUDA events on the instance's stream) of the last dcg_step
  * batch; valid after dcg_synchronize().                                            */
 DCG_API int dcg_last_step_ms(dcg_sim *sim, float *out);
@@ -262,6 +269,11 @@ DCG_API int dcg_create_dcgrid_sharded_opt(const dcg_sim_params *params, uint64_t
 DCG_API uint64_t dcg_shard_handle_bytes(void);
 DCG_API int dcg_shard_export_handle(dcg_sim *sim, void *out, uint64_t capacity);
 DCG_API int dcg_shard_import_handles(dcg_sim *sim, const void *handles, int count);
+
+/* FNV-1a (64-bit, offset basis 14695981039346656037 when seed == 0) of a HOST buffer; chain calls by passing the
+ * previous result as `seed`.  The digest oracle/ref_harness prints for the reference's raw density + velocity
+ * arrays: bench.py and the tests compare fields of the big scenes with committed reference digests through it. */
+DCG_API uint64_t dcg_fnv1a64(const void *data, uint64_t bytes, uint64_t seed);
 
 /* Last error text of this instance (or of creation when sim == NULL). */
 DCG_API const char *dcg_last_error(const dcg_sim *sim);
