@@ -330,6 +330,10 @@ struct DCGridSim : dcg_sim {
       if (opt.jacobi == 3 || opt.jacobi == 4) jacobi8 = false;
       snake = !opt.no_snake;
       if (opt.jacobi_ctas_per_sm > 0) jacobi_pipe_ctas = jacobi8_ctas = opt.jacobi_ctas_per_sm * sm_count;
+      if (opt.jacobi_max_ctas > 0) {
+        jacobi_pipe_ctas = std::min(jacobi_pipe_ctas, opt.jacobi_max_ctas);
+        jacobi8_ctas = std::min(jacobi8_ctas, opt.jacobi_max_ctas);
+      }
       if (world > 1 && (!use_advect_pipe || !use_stencil_pipe || !use_pipe)) return fail(DCG_ERR_UNSUPPORTED, "the legacy kernel variants are single-GPU only");
     }
     if (vmm) return DCG_OK;  // the caller exchanges handles; import_handles() maps the peers and resets

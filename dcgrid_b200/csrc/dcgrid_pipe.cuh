@@ -23,6 +23,12 @@ __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
+// Orders this thread's earlier generic-proxy accesses to shared memory (LD.SHARED of a ring slot) before later
+// async-proxy accesses (the cp.async.bulk that refills the slot).  A CTA barrier or an mbarrier arrival alone does
+// NOT order the two proxies: without this fence a refill occasionally overtook reads of the slot still in flight —
+// never on the small test scenes, on ~0.1 % of the tiles of the 512^3 scene (profiles/README.md r2b: the ring Jacobi
+// kernels differed from the reference at the first step; found by tests/test_golden_big_gpu.py).
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(saddr(bar)), "r"(bytes) : "memory");
 }
@@ -157,7 +163,8 @@ __global__ void __launch_bounds__(kCTA4, 4) k_dc_jacobi_pipe(Pool T, KParams P, 
     const JacobiStage &S = st[s];  // its barrier was waited for by load_ghosts(it)
     const float4 own = *reinterpret_cast<const float4 *>(&S.p[g * kBV + 4 * t]);
     const float4 dv = *reinterpret_cast<const float4 *>(&S.dv[g * kBV + 4 * t]);
-    __syncthreads();  // every thread holds its part of ring slot s in registers: the slot can be refilled
+    pipe::fence_proxy_async();  // the reads above, before the async-proxy refill issued after the barrier
+    __syncthreads();            // every thread holds its part of ring slot s in registers: the slot can be refilled
     if (threadIdx.x == 0) issue_tile(it + kJStages);
     const QuadNbr n = quad_exchange(own, t, gv.gx, gv.gy0, gv.gy1, gv.gz0, gv.gz1);
     float4 o;
@@ -301,7 +308,8 @@ __global__ void __launch_bounds__(kJ8Threads, 5) k_dc_jacobi_pipe8(Pool T, KPara
     float4 a1 = *reinterpret_cast<const float4 *>(&S.p[g * kBV + 8 * t + 4 * (sx ^ 1)]);
     float4 d0 = *reinterpret_cast<const float4 *>(&S.dv[g * kBV + 8 * t + 4 * sx]);
     float4 d1 = *reinterpret_cast<const float4 *>(&S.dv[g * kBV + 8 * t + 4 * (sx ^ 1)]);
-    __syncthreads();  // every thread holds its part of ring slot s in registers: the slot can be refilled
+    pipe::fence_proxy_async();  // the reads above, before the async-proxy refill issued after the barrier
+    __syncthreads();            // every thread holds its part of ring slot s in registers: the slot can be refilled
     if (threadIdx.x == 0) issue_tile(it + kJStages);
     const float4 lo = sx ? a1 : a0, hi = sx ? a0 : a1, dlo = sx ? d1 : d0, dhi = sx ? d0 : d1;
     const float own[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};  // k = cx*4 + cy*2 + cz
@@ -503,6 +511,7 @@ __global__ void __launch_bounds__(kAdvectThreads, kMinBlocks) k_dc_advect_pipe(P
         smp = d_sample_pipe(T, P, S.apron + g * kAV, S.child + g * kSV, pl, bx, by, bz);
       }
     }
+    pipe::fence_proxy_async();
     __syncwarp();  // every lane is done with ring slot s (positions, velocities, apron ids)
     if ((threadIdx.x & 31u) == 0) pipe::mbar_arrive(&empty[s]);
     if (!live) continue;
@@ -706,6 +715,7 @@ __global__ void __launch_bounds__(kStencilThreads, 3) k_dc_divergence_pipe(Pool 
 #pragma unroll
       for (int k = 0; k < 4; k++) v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    pipe::fence_proxy_async();
     __syncwarp();
     if ((threadIdx.x & 31u) == 0) pipe::mbar_arrive(&empty[s]);
     if (!__any_sync(0xFFFFFFFFu, active)) continue;
@@ -819,6 +829,7 @@ __global__ void __launch_bounds__(kStencilThreads, kMinBlocks) k_dc_apply_pipe(P
 #pragma unroll
       for (int k = 0; k < 4; k++) v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    pipe::fence_proxy_async();
     __syncwarp();
     if ((threadIdx.x & 31u) == 0) pipe::mbar_arrive(&empty[s]);
     if (!__any_sync(0xFFFFFFFFu, active)) continue;

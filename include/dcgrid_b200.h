@@ -97,9 +97,73 @@ typedef struct dcg_options {
                                   dependent launch)                                                     */
   int32_t host_selection;      /* 1: adaptTopology always takes the reference's host selection
                                   (std::nth_element / std::sort on scores copied D2H)                    */
-  int32_t reserved[14];
+  int32_t jacobi_max_ctas;     /* > 0: cap on the resident CTAs of the ring kernel (tests: few CTAs walk many
+                                  tiles each, the regime of the big scenes, on a small one)               */
+  int32_t reserved[13];
 } dcg_options;
 DCG_API int dcg_default_options(dcg_options *out);
+
+
+/* ---- extensions beyond the reference snapshot ------------------------------------
+ * BASELINE.json's north_star names features the snapshot under /root/reference does not contain:
+ * a flow-driven refinement score, MacCormack advection, temperature / vapor fields with buoyancy, vorticity
+ * confinement and condensation source terms, a terrain SDF.  They are specified by the CPU oracle
+ * (oracle/dcgrid_oracle.cpp, "extensions") — the ONLY pin there is: "parity unpinned" against the reference — and
+ * switched on per instance through this struct.  All zero (the default) = the reference snapshot's behaviour, bit for
+ * bit.  Arithmetic uses + - * / sqrtf floorf fminf fmaxf only, in a fixed order, so CPU spec and CUDA agree bitwise.
+ * DCGrid instances only (the uniform solver ignores everything but `terrain`).                                   */
+typedef struct dcg_ext_params {
+  uint32_t struct_size;          /* sizeof(dcg_ext_params) of the caller; 0 = this header's                  */
+  int32_t score_mode;            /* 0: geometric score of the snapshot (dcgrid_adaptation.cu:26-34);
+                                    1: flow-driven = sum over the subblock's 8 cells of |vorticity|, the code the
+                                       reference carries commented out (dcgrid_adaptation.cu:6-8,36-39) fed by
+                                       k_dcgrid_calc_vorticity (dcgrid_fluid.cu:146-172)                      */
+  int32_t advection;             /* 0: semi-Lagrangian (reference); 1: MacCormack (forward SL, backward SL of the
+                                       result, half the difference added back, clamped to the 8 corners of the
+                                       forward sample; velocity, density, temperature and vapor)              */
+  int32_t sources;               /* 1: temperature / vapor are advected with the density and dcg_apply_sources()
+                                       (called by dcg_step between adaptTopology and project) adds buoyancy,
+                                       vorticity confinement and condensation in ONE fused pass               */
+  int32_t terrain;               /* 1: solids = height-field terrain instead of the sphere (src/sdf.cuh:20);
+                                       needs SimParams.enable_additional_solids                               */
+  float buoyancy;                /* m/s^2 per unit of (theta - theta_ambient(h)) / ambient_temperature       */
+  float vapor_buoyancy;          /* m/s^2 per unit of vapor mixing ratio                                     */
+  float smoke_weight;            /* m/s^2 per unit of density (condensed water / smoke loading)              */
+  float ambient_temperature;     /* potential temperature at the floor, K                                    */
+  float ambient_lapse;           /* d(theta_ambient)/dh, K per world unit                                    */
+  float adiabatic_lapse;         /* T = theta - adiabatic_lapse * h, K per world unit                        */
+  float vorticity_confinement;   /* epsilon of the confinement force eps * dx * (N x omega)                  */
+  float saturation_base;         /* qs(T) = max(0, saturation_base + saturation_slope * (T - ambient_temperature)) */
+  float saturation_slope;
+  float condensation_rate;       /* fraction of (qv - qs) exchanged per step, 0..1                           */
+  float latent_heat;             /* K of theta per unit of condensed vapor                                   */
+  float temperature_emission;    /* inlet: theta = theta_ambient(0) + temperature_emission                   */
+  float vapor_emission;          /* inlet: vapor mixing ratio                                                */
+  float ambient_vapor;           /* initial / far-field vapor mixing ratio                                   */
+  float terrain_height;          /* peak height of the terrain, level-0 cells                                */
+  float terrain_wavelength;      /* hill spacing, level-0 cells                                              */
+  int32_t reserved[11];
+} dcg_ext_params;
+DCG_API int dcg_default_ext_params(dcg_ext_params *out);   /* all switches off, plausible coefficients       */
+/* Takes effect at the next call; changing `terrain`, `sources` or the ambient profile re-initialises nothing by
+ * itself: call dcg_reset() afterwards for a consistent start.                                                 */
+DCG_API int dcg_set_ext_params(dcg_sim *sim, const dcg_ext_params *ext);
+DCG_API int dcg_get_ext_params(const dcg_sim *sim, dcg_ext_params *out);
+/* The fused source pass (sources == 1), on leaf cells, followed by the restriction of the touched fields. */
+DCG_API int dcg_apply_sources(dcg_sim *sim);
+
+/* Point samples of a field at `n` positions (3*n floats, level-0 cell units): mode 0 = value of the finest
+ * covering cell (sampleCoarse, src/dcgrid/dcgrid_rendering.cu:6-24), mode 1 = trilinear through the covering
+ * block's apron map (samplePrecise, :26-58, interpolate() of src/raymarching.cuh:26-40).  `out`: n floats
+ * (3*n for the velocity).  Uniform instances: mode 0 only.                                                  */
+DCG_API int dcg_sample_field(dcg_sim *sim, int field, int mode, const float *positions, uint64_t n, float *out);
+
+/* State dump / load: the whole simulation state (block pool, level tables, move limits, every field, the
+ * extension parameters) in the reference's slot order, little-endian, format documented in DESIGN.md.  A run
+ * continued from a loaded state is bit-identical to the uninterrupted run.  The target of dcg_load_state must
+ * have been created with the same grid size and pool size.                                                  */
+DCG_API int dcg_save_state(dcg_sim *sim, const char *path);
+DCG_API int dcg_load_state(dcg_sim *sim, const char *path);
 
 /* ---- field / layout selectors for the accessors ------------------------- */
 enum {
@@ -110,7 +174,10 @@ enum {
                               advectVelocity() (buffers alias in the reference,
                               src/dcgrid/dcgrid_structure.cu:94-102)                 */
   DCG_FIELD_DIVERGENCE = 4,/* same validity window as pressure                       */
-  DCG_FIELD_T_PRESSURE = 5 /* the penultimate Jacobi iterate                         */
+  DCG_FIELD_T_PRESSURE = 5,/* the penultimate Jacobi iterate                         */
+  DCG_FIELD_TEMPERATURE = 6,/* extension (dcg_ext_params.sources): potential temperature, 1 float / cell */
+  DCG_FIELD_VAPOR = 7,     /* extension: vapor mixing ratio, 1 float / cell          */
+  DCG_FIELD_VORTICITY = 8  /* extension: 3 floats / cell, as of the last adaptTopology() / dcg_apply_sources() */
 };
 enum {
   DCG_LAYOUT_NATIVE = 0,   /* reference memory order: uniform idx=(z*gy+y)*gx+x
@@ -271,8 +338,9 @@ DCG_API int dcg_shard_export_handle(dcg_sim *sim, void *out, uint64_t capacity);
 DCG_API int dcg_shard_import_handles(dcg_sim *sim, const void *handles, int count);
 
 /* FNV-1a (64-bit, offset basis 14695981039346656037 when seed == 0) of a HOST buffer; chain calls by passing the
- * previous result as `seed`.  The digest oracle/ref_harness prints for the reference's raw density + velocity
- * arrays: bench.py and the tests compare fields of the big scenes with committed reference digests through it. */
+ * previous result as `seed`.  oracle/ref_harness prints this digest of the reference's raw density + velocity
+ * arrays, started from ITS offset basis 1469598103934665603 (pass that as `seed`; dcgrid_b200.fnv1a64 does):
+ * bench.py and the tests compare fields of the big scenes with committed reference digests through it.       */
 DCG_API uint64_t dcg_fnv1a64(const void *data, uint64_t bytes, uint64_t seed);
 
 /* Last error text of this instance (or of creation when sim == NULL). */

@@ -63,6 +63,40 @@ inline float cell_fluidity(const dcg_sim_params &P, int x, int y, int z, int sca
   return 1.f - overlap;
 }
 
+// ---------------------------------------------------------------------------
+// EXTENSIONS (include/dcgrid_b200.h "extensions").  Nothing below this banner exists in the
+// reference snapshot: THIS FILE IS THE SPECIFICATION, parity against the reference is unpinned.  Only
+// + - * / sqrtf floorf fminf fmaxf, in the order written, so the CUDA kernels can match bit for bit.
+// ---------------------------------------------------------------------------
+// terrain height field replacing sceneSDF (src/sdf.cuh:20): parabolic hills of period `terrain_wavelength` in x and
+// z (valleys along the lines x, z = k * wavelength, so the inlet disc in the domain centre stays open when the
+// wavelength divides half the domain); signed distance = height above the surface (vertical, conservative)
+inline float terrain_sdf(const dcg_ext_params &E, float px, float py, float pz) {
+  float ux = px / E.terrain_wavelength;
+  ux = ux - floorf(ux);
+  const float wx = 2.f * ux - 1.f;
+  const float hx = 1.f - wx * wx;
+  float uz = pz / E.terrain_wavelength;
+  uz = uz - floorf(uz);
+  const float wz = 2.f * uz - 1.f;
+  const float hz = 1.f - wz * wz;
+  return py - E.terrain_height * hx * hz;
+}
+inline float cell_fluidity(const dcg_sim_params &P, const dcg_ext_params &E, int x, int y, int z, int scale) {
+  if (!E.terrain) return cell_fluidity(P, x, y, z, scale);
+  if (!P.enable_additional_solids) return 1.f;
+  const float sqrt3 = 1.73205f;
+  const float px = ((float)x + .5f) * (float)scale;
+  const float py = ((float)y + .5f) * (float)scale;
+  const float pz = ((float)z + .5f) * (float)scale;
+  const float d = terrain_sdf(E, px, py, pz);
+  const float overlap = fmaxf(0.f, fminf(.5f - d / ((float)scale * sqrt3), 1.f));
+  return 1.f - overlap;
+}
+// height of a cell centre above the floor, world units; y in cells of size `scale`
+inline float cell_height(const dcg_sim_params &P, int y, int scale) { return ((float)y + .5f) * (float)scale * P.dx; }
+inline float ambient_theta(const dcg_ext_params &E, float h) { return E.ambient_temperature + E.ambient_lapse * h; }
+
 inline bool in_inlet(const dcg_sim_params &P, int x, int y, int z, int scale) {
   if (!(y < 0)) return false;                                      // sim_utils.cu:28,44
   const float a = (float)(x * scale) - .5f * (float)P.gx;
@@ -81,6 +115,18 @@ inline float density_bc(const dcg_sim_params &P, float q, int x, int y, int z, i
   if (in_inlet(P, x, y, z, scale)) return P.density_emission_rate;
   if (out_of_domain(P, x, y, z, scale)) return 0.f;
   return q;
+}
+
+// extension scalars: inlet -> emission value, any other outside cell -> the ambient profile, else pass-through
+inline float temperature_bc(const dcg_sim_params &P, const dcg_ext_params &E, float t, int x, int y, int z, int scale) {
+  if (in_inlet(P, x, y, z, scale)) return E.ambient_temperature + E.temperature_emission;
+  if (out_of_domain(P, x, y, z, scale)) return ambient_theta(E, cell_height(P, y, scale));
+  return t;
+}
+inline float vapor_bc(const dcg_sim_params &P, const dcg_ext_params &E, float v, int x, int y, int z, int scale) {
+  if (in_inlet(P, x, y, z, scale)) return E.vapor_emission;
+  if (out_of_domain(P, x, y, z, scale)) return E.ambient_vapor;
+  return v;
 }
 
 // grid_math.cuh:24-30 (3-D mipmapCells) and :42-52 (3-D mipmapIdx offset part)
@@ -126,7 +172,9 @@ inline float blend8(const float q[8], const float w[8]) {
 // ===========================================================================
 struct orc_sim {
   dcg_sim_params P{};
+  dcg_ext_params E{};  // extensions, all zero = the reference snapshot
   bool is_dcgrid = false;
+  virtual void apply_sources() {}
   int coarse_pairs = 0, level_pairs = 0, local_pairs = 0;
   virtual ~orc_sim() {}
   virtual void reset() = 0;
@@ -435,6 +483,8 @@ struct DCGridOracle : orc_sim {
   std::vector<uint8_t> lvl, flags;
   std::vector<u64> apron, free_idx, parent, child;
   std::vector<float> density, velocity /*3*64M*/, fluidity, temp /*3*64M*/;
+  // extensions: potential temperature, vapor, vorticity (3 floats / cell), MacCormack scratch
+  std::vector<float> temperature, vapor, vort, mc_hat, mc_out;
   std::vector<float> block_scores, sub_scores;
   std::vector<u64> to_move, dest, touched;
   bool pool_error = false;
@@ -488,6 +538,7 @@ struct DCGridOracle : orc_sim {
     apron.assign(M * AV, 0); free_idx.assign(M, 0); parent.assign(M, kNone); child.assign(8 * M, kNone);
     density.assign(num_cells_, 0.f); velocity.assign(3 * num_cells_, 0.f);
     fluidity.assign(num_cells_, 0.f); temp.assign(3 * num_cells_, 0.f);
+    temperature.assign(num_cells_, 0.f); vapor.assign(num_cells_, 0.f); vort.assign(3 * num_cells_, 0.f);
     block_scores.assign(M, 0.f);
     sub_scores.assign(8 * M + 1, -FLT_MAX);  // +1: the reference reads one float past the end for slot M-1 (App. B-1)
     to_move.assign(M, 0); dest.assign(8 * M, 0); touched.assign(M, 0);
@@ -632,7 +683,9 @@ struct DCGridOracle : orc_sim {
                 const u64 c = a[AA * i + AW * j + k];
                 density[c] = 0.f;
                 velocity[3 * c] = velocity[3 * c + 1] = velocity[3 * c + 2] = 0.f;
-                fluidity[c] = cell_fluidity(P, px + i - 1, py + j - 1, pz + k - 1, scale);
+                fluidity[c] = cell_fluidity(P, E, px + i - 1, py + j - 1, pz + k - 1, scale);
+                temperature[c] = ambient_theta(E, cell_height(P, py + j - 1, scale));  // extension: the ambient profile
+                vapor[c] = E.ambient_vapor;
               }
         }
   }
@@ -728,70 +781,144 @@ struct DCGridOracle : orc_sim {
     return s;
   }
 
-  void advect_velocity() override {  // fluid_simulation_dcgrid.cu:263-268, dcgrid_fluid.cu:74-91,112-127
-    float *tv = t_velocity();
+  // backtraced (sign = -1) or forward-traced (sign = +1) position of cell c of block b along the cell's own velocity
+  void trace(u64 b, u64 c, float sign, float &bx, float &by, float &bz) const {
+    const float scale = (float)(1 << lvl[b]);
     const float alpha = P.dt * P.rdx;
+    const float fx = (float)(pos[3 * b] | cell_x(c)), fy = (float)(pos[3 * b + 1] | cell_y(c)), fz = (float)(pos[3 * b + 2] | cell_z(c));
+    if (sign < 0.f) {  // the reference's expression, dcgrid_fluid.cu:119-123
+      bx = (fx + .5f) * scale - velocity[3 * c] * alpha;
+      by = (fy + .5f) * scale - velocity[3 * c + 1] * alpha;
+      bz = (fz + .5f) * scale - velocity[3 * c + 2] * alpha;
+    } else {
+      bx = (fx + .5f) * scale + velocity[3 * c] * alpha;
+      by = (fy + .5f) * scale + velocity[3 * c + 1] * alpha;
+      bz = (fz + .5f) * scale + velocity[3 * c + 2] * alpha;
+    }
+  }
+  // semi-Lagrangian gather of a `comps`-component field through the cell's own velocity (k_dcgrid_advect_velocity /
+  // _density, dcgrid_fluid.cu:74-144): out[c] for every cell of every active block, 0 for non-leaf cells.
+  // bc(values[comps], x, y, z, scale) substitutes boundary values per corner.
+  template <class BC>
+  void gather_sl(const float *phi, int comps, float *out, BC bc) const {
 #pragma omp parallel for schedule(dynamic, 64)
     for (u64 b = 0; b < M; b++) {
       if (lvl[b] == 0xFF) continue;
-      const float scale = (float)(1 << lvl[b]);
       for (u64 c = b * BV; c < (b + 1) * BV; c++) {
-        V3 out{0.f, 0.f, 0.f};
+        float o[3] = {0.f, 0.f, 0.f};
         if (child[c >> 3] == kNone) {
-          const float fx = (float)(pos[3 * b] | cell_x(c)), fy = (float)(pos[3 * b + 1] | cell_y(c)), fz = (float)(pos[3 * b + 2] | cell_z(c));
-          const float bx = (fx + .5f) * scale - velocity[3 * c] * alpha;
-          const float by = (fy + .5f) * scale - velocity[3 * c + 1] * alpha;
-          const float bz = (fz + .5f) * scale - velocity[3 * c + 2] * alpha;
+          float bx, by, bz;
+          trace(b, c, -1.f, bx, by, bz);
           const Sample s = sample(bx, by, bz);
           if (!(s.c.acc < 1e-6f)) {
-            float vx[8], vy[8], vz[8];
+            float v8[3][8];
             for (int q = 0; q < 8; q++) {
-              const V3 v = velocity_bc(P, V3{velocity[3 * s.id[q]], velocity[3 * s.id[q] + 1], velocity[3 * s.id[q] + 2]},
-                                       s.x0 + ((q >> 2) & 1), s.y0 + ((q >> 1) & 1), s.z0 + (q & 1), s.scale);
-              vx[q] = v.x; vy[q] = v.y; vz[q] = v.z;
+              float v[3] = {0.f, 0.f, 0.f};
+              for (int k = 0; k < comps; k++) v[k] = phi[comps * s.id[q] + k];
+              bc(v, s.x0 + ((q >> 2) & 1), s.y0 + ((q >> 1) & 1), s.z0 + (q & 1), s.scale);
+              for (int k = 0; k < comps; k++) v8[k][q] = v[k];
             }
-            out = V3{blend8(vx, s.c.w), blend8(vy, s.c.w), blend8(vz, s.c.w)};
+            for (int k = 0; k < comps; k++) o[k] = blend8(v8[k], s.c.w);
           }
         }
-        tv[3 * c] = out.x; tv[3 * c + 1] = out.y; tv[3 * c + 2] = out.z;
+        for (int k = 0; k < comps; k++) out[comps * c + k] = o[k];
       }
     }
+  }
+  void accumulate_all(float *ch, int comps) { for (int l = 0; l < levels - 1; l++) accumulate(ch, comps, l); }
+
+  // EXTENSION (dcg_ext_params.advection == 1): MacCormack on top of the semi-Lagrangian gather.
+  //   hat  = SL(phi)                                   (then restricted, like every advected field)
+  //   back = SL of `hat` along the REVERSED trajectory (cell centre + v dt)
+  //   out  = clamp(hat + .5 (phi - back), min, max of the 8 boundary-substituted corners of the forward sample)
+  // falling back to hat where either sample has no fluid weight.  Trajectories use the pre-advection velocity.
+  template <class BC>
+  void maccormack(float *phi, int comps, BC bc) {
+    mc_hat.resize(3 * num_cells_); mc_out.resize(3 * num_cells_);
+    float *hat = mc_hat.data(), *out = mc_out.data();
+    std::fill(mc_hat.begin(), mc_hat.end(), 0.f);
+    gather_sl(phi, comps, hat, bc);
+    accumulate_all(hat, comps);
+#pragma omp parallel for schedule(dynamic, 64)
+    for (u64 b = 0; b < M; b++) {
+      if (lvl[b] == 0xFF) continue;
+      for (u64 c = b * BV; c < (b + 1) * BV; c++) {
+        float o[3] = {0.f, 0.f, 0.f};
+        if (child[c >> 3] == kNone) {
+          float bx, by, bz;
+          trace(b, c, -1.f, bx, by, bz);
+          const Sample s = sample(bx, by, bz);
+          if (!(s.c.acc < 1e-6f)) {
+            float mn[3], mx[3];
+            for (int q = 0; q < 8; q++) {
+              float v[3] = {0.f, 0.f, 0.f};
+              for (int k = 0; k < comps; k++) v[k] = phi[comps * s.id[q] + k];
+              bc(v, s.x0 + ((q >> 2) & 1), s.y0 + ((q >> 1) & 1), s.z0 + (q & 1), s.scale);
+              for (int k = 0; k < comps; k++) {
+                mn[k] = q == 0 ? v[k] : fminf(mn[k], v[k]);
+                mx[k] = q == 0 ? v[k] : fmaxf(mx[k], v[k]);
+              }
+            }
+            for (int k = 0; k < comps; k++) o[k] = hat[comps * c + k];
+            float fx, fy, fz;
+            trace(b, c, 1.f, fx, fy, fz);
+            const Sample sf = sample(fx, fy, fz);
+            if (!(sf.c.acc < 1e-6f)) {
+              float v8[3][8];
+              for (int q = 0; q < 8; q++) {
+                float v[3] = {0.f, 0.f, 0.f};
+                for (int k = 0; k < comps; k++) v[k] = hat[comps * sf.id[q] + k];
+                bc(v, sf.x0 + ((q >> 2) & 1), sf.y0 + ((q >> 1) & 1), sf.z0 + (q & 1), sf.scale);
+                for (int k = 0; k < comps; k++) v8[k][q] = v[k];
+              }
+              for (int k = 0; k < comps; k++) {
+                const float back = blend8(v8[k], sf.c.w);
+                const float r = hat[comps * c + k] + .5f * (phi[comps * c + k] - back);
+                o[k] = fminf(fmaxf(r, mn[k]), mx[k]);
+              }
+            }
+          }
+        }
+        for (int k = 0; k < comps; k++) out[comps * c + k] = o[k];
+      }
+    }
+    for (u64 b = 0; b < M; b++)
+      if (lvl[b] != 0xFF) std::memcpy(phi + comps * b * BV, out + comps * b * BV, comps * BV * sizeof(float));
+    accumulate_all(phi, comps);
+  }
+
+  void advect_velocity() override {  // fluid_simulation_dcgrid.cu:263-268, dcgrid_fluid.cu:74-91,112-127
+    auto bc = [this](float *v, int x, int y, int z, int scale) {
+      const V3 r = velocity_bc(P, V3{v[0], v[1], v[2]}, x, y, z, scale);
+      v[0] = r.x; v[1] = r.y; v[2] = r.z;
+    };
+    if (E.advection == 1) { maccormack(velocity.data(), 3, bc); return; }
+    float *tv = t_velocity();
+    gather_sl(velocity.data(), 3, tv, bc);
     std::memcpy(velocity.data(), tv, 3 * num_cells_ * sizeof(float));  // whole-pool D2D copy, :265-266
     accumulate_velocity();
   }
 
-  void advect_density() override {  // fluid_simulation_dcgrid.cu:313-318, dcgrid_fluid.cu:93-110,129-144
+  template <class BC>
+  void advect_scalar(std::vector<float> &phi, BC bc) {
+    if (E.advection == 1) { maccormack(phi.data(), 1, bc); return; }
     float *tq = t_density();
-    const float alpha = P.dt * P.rdx;
-#pragma omp parallel for schedule(dynamic, 64)
-    for (u64 b = 0; b < M; b++) {
-      if (lvl[b] == 0xFF) continue;
-      const float scale = (float)(1 << lvl[b]);
-      for (u64 c = b * BV; c < (b + 1) * BV; c++) {
-        float out = 0.f;
-        if (child[c >> 3] == kNone) {
-          const float fx = (float)(pos[3 * b] | cell_x(c)), fy = (float)(pos[3 * b + 1] | cell_y(c)), fz = (float)(pos[3 * b + 2] | cell_z(c));
-          const float bx = (fx + .5f) * scale - velocity[3 * c] * alpha;
-          const float by = (fy + .5f) * scale - velocity[3 * c + 1] * alpha;
-          const float bz = (fz + .5f) * scale - velocity[3 * c + 2] * alpha;
-          const Sample s = sample(bx, by, bz);
-          if (!(s.c.acc < 1e-6f)) {
-            float q8[8];
-            for (int q = 0; q < 8; q++)
-              q8[q] = density_bc(P, density[s.id[q]], s.x0 + ((q >> 2) & 1), s.y0 + ((q >> 1) & 1), s.z0 + (q & 1), s.scale);
-            out = blend8(q8, s.c.w);
-          }
-        }
-        tq[c] = out;
-      }
+    gather_sl(phi.data(), 1, tq, bc);
+    std::memcpy(phi.data(), tq, num_cells_ * sizeof(float));  // :315-316
+    accumulate_all(phi.data(), 1);
+  }
+  void advect_density() override {  // fluid_simulation_dcgrid.cu:313-318, dcgrid_fluid.cu:93-110,129-144
+    advect_scalar(density, [this](float *v, int x, int y, int z, int scale) { v[0] = density_bc(P, v[0], x, y, z, scale); });
+    if (E.sources) {  // extension: temperature and vapor ride along (same trajectories, same weights)
+      advect_scalar(temperature, [this](float *v, int x, int y, int z, int scale) { v[0] = temperature_bc(P, E, v[0], x, y, z, scale); });
+      advect_scalar(vapor, [this](float *v, int x, int y, int z, int scale) { v[0] = vapor_bc(P, E, v[0], x, y, z, scale); });
     }
-    std::memcpy(density.data(), tq, num_cells_ * sizeof(float));  // :315-316
-    accumulate_density();
   }
 
   void calc_vorticity() {  // dcgrid_fluid.cu:146-172 — result is dead in this snapshot (overwritten by divergence),
                            // kept because it scribbles over `temporary` exactly like the reference
-    float *vo = temp.data();
+    // extensions that consume the vorticity keep it in a buffer of its own (the reference's aliases `temporary`)
+    float *vo = (E.score_mode == 1 || E.sources) ? vort.data() : temp.data();
     for (u64 b = 0; b < M; b++) {
       if (lvl[b] == 0xFF) continue;
       const u64 *a = &apron[AV * b];
@@ -930,6 +1057,15 @@ struct DCGridOracle : orc_sim {
         sub_scores[sb] = -FLT_MAX;
         continue;
       }
+      if (E.score_mode == 1) {  // EXTENSION: the commented-out lines :36-39 with calcCellScore (:6-8) = |vorticity|
+        float acc = 0.f;
+        for (int i = 0; i < SV; i++) {
+          const float *w = &vort[3 * (SV * sb + i)];
+          acc += sqrtf(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+        }
+        sub_scores[sb] = acc;
+        continue;
+      }
       const float s = (float)(1 << level);
       const float px = s * ((float)pos[3 * b] + 2.f * (float)((sb >> 2) & 1) + 1.f);
       const float py = s * ((float)pos[3 * b + 1] + 2.f * (float)((sb >> 1) & 1) + 1.f);
@@ -1020,9 +1156,121 @@ struct DCGridOracle : orc_sim {
           velocity[3 * c + q] = ((27.f / 64.f) * v[3 * i000] + (9.f / 64.f) * (v[3 * i001] + v[3 * i010] + v[3 * i100]) +
                                  (3.f / 64.f) * (v[3 * i011] + v[3 * i101] + v[3 * i110]) + (1.f / 64.f) * v[3 * i111]);
         }
-        fluidity[c] = cell_fluidity(P, x, y, z, scale);
+        fluidity[c] = cell_fluidity(P, E, x, y, z, scale);
+        for (std::vector<float> *f : {&temperature, &vapor}) {  // extension scalars: interpolated like the density
+          const float *a = f->data();
+          (*f)[c] = ((27.f / 64.f) * a[i000] + (9.f / 64.f) * (a[i001] + a[i010] + a[i100]) + (3.f / 64.f) * (a[i011] + a[i101] + a[i110]) +
+                     (1.f / 64.f) * a[i111]);
+        }
       }
     }
+  }
+
+  // EXTENSION (dcg_ext_params.sources): condensation, buoyancy and vorticity confinement in one pass over the
+  // leaf cells, between adaptTopology and project; then the touched fields are restricted.
+  void apply_sources() override {
+    if (!E.sources) return;
+    calc_vorticity();  // on the topology the projection will see
+    auto wlen = [this](u64 i) { const float *w = &vort[3 * i]; return sqrtf(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]); };
+#pragma omp parallel for schedule(dynamic, 64)
+    for (u64 b = 0; b < M; b++) {
+      if (lvl[b] == 0xFF) continue;
+      const u64 *a = &apron[AV * b];
+      const int scale = 1 << lvl[b];
+      const float alpha = .5f * P.rdx / scale;
+      for (u64 c = b * BV; c < (b + 1) * BV; c++) {
+        if (child[c >> 3] != kNone) continue;
+        const int y = pos[3 * b + 1] | cell_y(c);
+        const float h = cell_height(P, y, scale);
+        float th = temperature[c], qv = vapor[c], qc = density[c];
+        // condensation (dq > 0) / evaporation (dq < 0, limited by the condensed water present)
+        const float tabs = th - E.adiabatic_lapse * h;
+        const float qs = fmaxf(0.f, E.saturation_base + E.saturation_slope * (tabs - E.ambient_temperature));
+        float dq = E.condensation_rate * (qv - qs);
+        dq = fmaxf(dq, -qc);
+        qv = qv - dq;
+        qc = qc + dq;
+        th = th + E.latent_heat * dq;
+        // buoyancy
+        const float tha = ambient_theta(E, h);
+        const float lift = E.buoyancy * ((th - tha) / E.ambient_temperature) + E.vapor_buoyancy * qv - E.smoke_weight * qc;
+        // vorticity confinement: eps * cell size * (N x omega), N = grad|omega| / |grad|omega||
+        const int ai = apron_of(c);
+        const float gx_ = alpha * (wlen(a[ai + AA]) - wlen(a[ai - AA]));
+        const float gy_ = alpha * (wlen(a[ai + AW]) - wlen(a[ai - AW]));
+        const float gz_ = alpha * (wlen(a[ai + 1]) - wlen(a[ai - 1]));
+        const float glen = sqrtf(gx_ * gx_ + gy_ * gy_ + gz_ * gz_);
+        float fx = 0.f, fy = 0.f, fz = 0.f;
+        if (glen > 1e-12f) {
+          const float inv = 1.f / glen;
+          const float nx = gx_ * inv, ny = gy_ * inv, nz = gz_ * inv;
+          const float *w = &vort[3 * c];
+          const float k = E.vorticity_confinement * (P.dx * (float)scale);
+          fx = k * (ny * w[2] - nz * w[1]);
+          fy = k * (nz * w[0] - nx * w[2]);
+          fz = k * (nx * w[1] - ny * w[0]);
+        }
+        const float g = P.dt * fluidity[c];
+        velocity[3 * c] = velocity[3 * c] + g * fx;
+        velocity[3 * c + 1] = velocity[3 * c + 1] + g * (fy + lift);
+        velocity[3 * c + 2] = velocity[3 * c + 2] + g * fz;
+        temperature[c] = th;
+        vapor[c] = qv;
+        density[c] = qc;
+      }
+    }
+    accumulate_velocity();
+    accumulate_density();
+    accumulate_all(temperature.data(), 1);
+    accumulate_all(vapor.data(), 1);
+  }
+
+  // sampleCoarse / samplePrecise, dcgrid_rendering.cu:6-58 + interpolate(), raymarching.cuh:26-40 (clampPos: the
+  // integer position clamped to the domain)
+  void sample_field(const float *f, int comps, int mode, const float *xyz, u64 n, float *out) const {
+    for (u64 i = 0; i < n; i++) {
+      const float px = xyz[3 * i], py = xyz[3 * i + 1], pz = xyz[3 * i + 2];
+      const int ix = iclamp((int)floorf(px), 0, gx - 1), iy = iclamp((int)floorf(py), 0, gy - 1), iz = iclamp((int)floorf(pz), 0, gz - 1);
+      int level = 0;
+      const u64 b = block_index_deep(ix, iy, iz, level);
+      if (mode == 0) {
+        const u64 c = BV * b + spread((ix >> level) % BW, 2) + spread((iy >> level) % BW, 1) + spread((iz >> level) % BW, 0);
+        for (int k = 0; k < comps; k++) out[comps * i + k] = f[comps * c + k];
+        continue;
+      }
+      const float inv = 1.f / (float)(1 << level);
+      const float x = px * inv - .5f, y = py * inv - .5f, z = pz * inv - .5f;
+      const float xf = floorf(x), yf = floorf(y), zf = floorf(z);
+      const float dx = x - xf, dy = y - yf, dz = z - zf;
+      // (the reference does not clamp the apron offset; positions within the domain keep it inside 0..4)
+      const int ai = iclamp((int)xf + 1 - pos[3 * b], 0, AW - 2), aj = iclamp((int)yf + 1 - pos[3 * b + 1], 0, AW - 2),
+                ak = iclamp((int)zf + 1 - pos[3 * b + 2], 0, AW - 2);
+      const u64 *a = &apron[AV * b + AA * ai + AW * aj + ak];
+      const u64 id[8] = {a[0], a[1], a[AW], a[AW + 1], a[AA], a[AA + 1], a[AA + AW], a[AA + AW + 1]};
+      for (int k = 0; k < comps; k++) {
+        auto v = [&](int q) { return f[comps * id[q] + k]; };
+        const float dxi = 1.f - dx;
+        const float c00 = v(0) * dxi + v(4) * dx, c01 = v(1) * dxi + v(5) * dx, c10 = v(2) * dxi + v(6) * dx, c11 = v(3) * dxi + v(7) * dx;
+        const float dyi = 1.f - dy;
+        const float c0 = c00 * dyi + c10 * dy, c1 = c01 * dyi + c11 * dy;
+        out[comps * i + k] = c0 * (1.f - dz) + c1 * dz;
+      }
+    }
+  }
+  const float *field_ptr(int field, int &comps) {
+    comps = 1;
+    switch (field) {
+      case DCG_FIELD_DENSITY: return density.data();
+      case DCG_FIELD_VELOCITY: comps = 3; return velocity.data();
+      case DCG_FIELD_FLUIDITY: return fluidity.data();
+      case DCG_FIELD_PRESSURE: return pressure();
+      case DCG_FIELD_DIVERGENCE: return divergence();
+      case DCG_FIELD_T_PRESSURE: return t_pressure();
+      case DCG_FIELD_TEMPERATURE: return temperature.data();
+      case DCG_FIELD_VAPOR: return vapor.data();
+      case DCG_FIELD_VORTICITY: comps = 3; return vort.data();
+    }
+    return nullptr;
   }
 
   // ---- host orchestration: fluid_simulation_dcgrid.cu ---------------------------
@@ -1129,6 +1377,9 @@ struct DCGridOracle : orc_sim {
     std::fill(velocity.begin(), velocity.end(), 0.f);
     std::fill(fluidity.begin(), fluidity.end(), 0.f);
     std::fill(temp.begin(), temp.end(), 0.f);
+    std::fill(temperature.begin(), temperature.end(), 0.f);
+    std::fill(vapor.begin(), vapor.end(), 0.f);
+    std::fill(vort.begin(), vort.end(), 0.f);
     for (int l = 0; l < levels; l++) {
       loads[l] = (max_blocks[l] == full_blocks[l]) ? max_blocks[l] : 0;
       move_limit[l] = 0;
@@ -1171,6 +1422,9 @@ struct DCGridOracle : orc_sim {
       case DCG_FIELD_PRESSURE: std::memcpy(dst, pressure(), n * 4); return 0;
       case DCG_FIELD_DIVERGENCE: std::memcpy(dst, divergence(), n * 4); return 0;
       case DCG_FIELD_T_PRESSURE: std::memcpy(dst, t_pressure(), n * 4); return 0;
+      case DCG_FIELD_TEMPERATURE: std::memcpy(dst, temperature.data(), n * 4); return 0;
+      case DCG_FIELD_VAPOR: std::memcpy(dst, vapor.data(), n * 4); return 0;
+      case DCG_FIELD_VORTICITY: std::memcpy(dst, vort.data(), 3 * n * 4); return 0;
     }
     return 1;
   }
@@ -1204,9 +1458,21 @@ ORC_API void orc_step(orc_sim *s, int n) {  // src/simulation.cpp:104-111
   for (int i = 0; i < n; i++) {
     s->advect_velocity();
     s->adapt_topology();
+    s->apply_sources();  // extension; no-op unless dcg_ext_params.sources
     s->project();
     s->advect_density();
   }
+}
+ORC_API void orc_set_ext_params(orc_sim *s, const dcg_ext_params *e) { s->E = *e; }
+ORC_API void orc_apply_sources(orc_sim *s) { s->apply_sources(); }
+ORC_API int orc_sample_field(orc_sim *s, int field, int mode, const float *positions, uint64_t n, float *out) {
+  if (!s->is_dcgrid) return 1;
+  DCGridOracle *g = static_cast<DCGridOracle *>(s);
+  int comps = 1;
+  const float *f = g->field_ptr(field, comps);
+  if (!f) return 1;
+  g->sample_field(f, comps, mode, positions, n, out);
+  return 0;
 }
 ORC_API float orc_debug_stats(orc_sim *s) { return s->debug_stats(); }
 ORC_API uint64_t orc_num_cells(orc_sim *s) { return s->num_cells(); }
