@@ -5,7 +5,7 @@ include/dcgrid_b200.h) and this thin host-side mirror of the reference's FluidSi
 interface.  Importing the package does not load CUDA; constructing a simulation does and
 fails loudly when the extension or a GPU is missing.
 """
-from .params import SimParams, default_params, scene_params  # noqa: F401
+from .params import ExtParams, SimParams, default_params, make_ext, scene_params  # noqa: F401
 from .simulation import (  # noqa: F401
     DcgError,
     FluidSimulation,

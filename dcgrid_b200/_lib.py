@@ -6,7 +6,7 @@ fails the import raises.
 import ctypes
 import os
 
-from .params import Options, SimParams
+from .params import ExtParams, Options, SimParams
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libdcgrid_b200.so")
@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(HERE, "libdcgrid_b200.so")
 _vp = ctypes.c_void_p
 _P = ctypes.POINTER(SimParams)
 _O = ctypes.POINTER(Options)
+_E = ctypes.POINTER(ExtParams)
 _u64 = ctypes.c_uint64
 _int = ctypes.c_int
 SYMBOLS = {
@@ -61,6 +62,13 @@ SYMBOLS = {
     "dcg_shard_export_handle": (_int, [_vp, _vp, _u64]),
     "dcg_shard_import_handles": (_int, [_vp, _vp, _int]),
     "dcg_fnv1a64": (_u64, [_vp, _u64, _u64]),
+    "dcg_default_ext_params": (_int, [_E]),
+    "dcg_set_ext_params": (_int, [_vp, _E]),
+    "dcg_get_ext_params": (_int, [_vp, _E]),
+    "dcg_apply_sources": (_int, [_vp]),
+    "dcg_sample_field": (_int, [_vp, _int, _int, _vp, _u64, _vp]),
+    "dcg_save_state": (_int, [_vp, ctypes.c_char_p]),
+    "dcg_load_state": (_int, [_vp, ctypes.c_char_p]),
     "dcg_last_error": (ctypes.c_char_p, [_vp]),
     "dcg_version": (ctypes.c_char_p, []),
 }

@@ -168,6 +168,59 @@ int dcg_set_jacobi_schedule(dcg_sim *sim, int coarsest, int level, int local) {
   return DCG_OK;
 }
 
+int dcg_default_ext_params(dcg_ext_params *e) {
+  if (!e) return DCG_ERR_INVALID;
+  std::memset(e, 0, sizeof *e);
+  e->struct_size = (uint32_t)sizeof *e;
+  // switches off; coefficients of a plausible moist plume (world units as in SimParams: dx = 10000 / gx)
+  e->buoyancy = 9.81f;
+  e->vapor_buoyancy = 5.9f;       // 0.61 g
+  e->smoke_weight = 9.81f;
+  e->ambient_temperature = 290.f;
+  e->ambient_lapse = 0.003f;
+  e->adiabatic_lapse = 0.0098f;
+  e->vorticity_confinement = 0.05f;
+  e->saturation_base = 0.012f;
+  e->saturation_slope = 0.0001f;
+  e->condensation_rate = 0.5f;
+  e->latent_heat = 2500.f;
+  e->temperature_emission = 8.f;
+  e->vapor_emission = 0.02f;
+  e->ambient_vapor = 0.004f;
+  e->terrain_height = 24.f;
+  e->terrain_wavelength = 32.f;
+  return DCG_OK;
+}
+int dcg_set_ext_params(dcg_sim *sim, const dcg_ext_params *e) {
+  NEED(sim);
+  if (!e) return DCG_ERR_INVALID;
+  return sim->set_ext(e);
+}
+int dcg_get_ext_params(const dcg_sim *sim, dcg_ext_params *out) {
+  NEED(sim);
+  if (!out) return DCG_ERR_INVALID;
+  *out = sim->ext;
+  out->struct_size = (uint32_t)sizeof *out;
+  return DCG_OK;
+}
+int dcg_apply_sources(dcg_sim *sim) { NEED(sim); return sim->apply_sources(); }
+int dcg_sample_field(dcg_sim *sim, int field, int mode, const float *positions, uint64_t n, float *out) {
+  NEED(sim);
+  if ((!positions || !out) && n > 0) return DCG_ERR_INVALID;
+  if (mode != 0 && mode != 1) return sim->fail(DCG_ERR_INVALID, "sample_field: mode must be 0 (coarse) or 1 (precise)");
+  return sim->sample_field(field, mode, positions, n, out);
+}
+int dcg_save_state(dcg_sim *sim, const char *path) {
+  NEED(sim);
+  if (!path) return DCG_ERR_INVALID;
+  return sim->save_state(path);
+}
+int dcg_load_state(dcg_sim *sim, const char *path) {
+  NEED(sim);
+  if (!path) return DCG_ERR_INVALID;
+  return sim->load_state(path);
+}
+
 int dcg_total_density(dcg_sim *sim, double *out) {
   NEED(sim);
   if (!out) return DCG_ERR_INVALID;

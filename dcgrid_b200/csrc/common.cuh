@@ -21,9 +21,12 @@ struct KParams {
   float vel_rate, dens_rate, emit_radius;
   int gx, gy, gz;
   int solids;
+  // extension (dcg_ext_params.terrain): height-field terrain instead of the sphere; 0 = the reference's scene
+  int terrain;
+  float terrain_height, terrain_wavelength;
 };
 
-inline KParams make_kparams(const dcg_sim_params &p) {
+inline KParams make_kparams(const dcg_sim_params &p, const dcg_ext_params &e = dcg_ext_params{}) {
   KParams k;
   k.dt = p.dt; k.dx = p.dx; k.rdx = p.rdx;
   k.vel_rate = p.velocity_emission_rate;
@@ -31,6 +34,9 @@ inline KParams make_kparams(const dcg_sim_params &p) {
   k.emit_radius = p.emission_radius;
   k.gx = p.gx; k.gy = p.gy; k.gz = p.gz;
   k.solids = p.enable_additional_solids ? 1 : 0;
+  k.terrain = e.terrain ? 1 : 0;
+  k.terrain_height = e.terrain_height;
+  k.terrain_wavelength = e.terrain_wavelength;
   return k;
 }
 
@@ -39,8 +45,21 @@ __device__ __forceinline__ float cell_fluidity(const KParams &P, int x, int y, i
   if (!P.solids) return 1.f;
   const float fs = (float)scale;
   const float px = ((float)x + .5f) * fs, py = ((float)y + .5f) * fs, pz = ((float)z + .5f) * fs;
-  const float ex = px - (float)P.gx * .5f, ey = py - (float)P.gy * .45f, ez = pz - (float)P.gz * .5f;
-  const float d = sqrtf(ex * ex + ey * ey + ez * ez) - 2000.f * P.rdx;
+  float d;
+  if (P.terrain) {  // extension, specified by oracle/dcgrid_oracle.cpp terrain_sdf()
+    float ux = px / P.terrain_wavelength;
+    ux = ux - floorf(ux);
+    const float wx = 2.f * ux - 1.f;
+    const float hx = 1.f - wx * wx;
+    float uz = pz / P.terrain_wavelength;
+    uz = uz - floorf(uz);
+    const float wz = 2.f * uz - 1.f;
+    const float hz = 1.f - wz * wz;
+    d = py - P.terrain_height * hx * hz;
+  } else {
+    const float ex = px - (float)P.gx * .5f, ey = py - (float)P.gy * .45f, ez = pz - (float)P.gz * .5f;
+    d = sqrtf(ex * ex + ey * ey + ez * ez) - 2000.f * P.rdx;
+  }
   const float overlap = fmaxf(0.f, fminf(.5f - d / (fs * 1.73205f), 1.f));
   return 1.f - overlap;
 }

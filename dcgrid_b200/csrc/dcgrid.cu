@@ -17,6 +17,7 @@
 //  * in the steady state a 2-step CUDA graph replaces ~270 launches.
 #include <algorithm>
 #include <cfloat>
+#include <chrono>
 #include <functional>
 #include <numeric>
 #include <string>
@@ -24,6 +25,7 @@
 
 #include <cub/device/device_radix_sort.cuh>
 
+#include "dcgrid_ext.cuh"
 #include "dcgrid_kernels.cuh"
 #include "dcgrid_pipe.cuh"
 #include "shard_vmm.h"
@@ -68,11 +70,21 @@ struct DCGridSim : dcg_sim {
   size_t scratch_floats = 0;
   double *d_partial = nullptr, *h_partial = nullptr;
   int cur_v = 0, cur_q = 0;
+  // extensions (dcgrid_ext.cuh): temperature / vapor ping-pong pairs, vorticity (+ |omega| in .w), MacCormack scratch;
+  // allocated when an extension that needs them is switched on
+  float *th[2] = {nullptr, nullptr}, *qvp[2] = {nullptr, nullptr}, *s_mc = nullptr;
+  float4 *vort = nullptr, *vw_mc = nullptr;
+  int cur_s = 0;
+  bool ext_on() const { return ext.score_mode || ext.advection || ext.sources; }
 
   // pinned host mirrors for the selection
   float *h_sub_scores = nullptr, *h_block_scores = nullptr;
   uint32_t *h_to_move = nullptr, *h_dest = nullptr;
 
+  // host wall time spent in the phases of adaptTopology() (incl. their stream synchronisations): dcg_get_info "adapt_*_ms"
+  double t_move_ms = 0, t_refine_ms = 0, t_apron_ms = 0, t_layout_ms = 0, t_propagate_ms = 0;
+  static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+  bool timing_sync = false;  // diagnostics: synchronise between the phases so that the split above is exact
   bool steady = false;
   uint64_t n_adapt = 0, n_changed = 0, n_moved = 0, n_refined = 0, n_skipped = 0, n_failed = 0;
 
@@ -138,7 +150,7 @@ struct DCGridSim : dcg_sim {
   unsigned pipe_min_tiles = 0;  // levels with fewer tiles take the one-CTA-per-tile kernel
   int sweep_parity = 0;
 
-  cudaGraphExec_t step_graph[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaGraphExec_t step_graph[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   uint64_t step_graph_launches = 0;
 
   explicit DCGridSim(uint64_t m) : M64(m) { dcgrid = true; }
@@ -167,6 +179,8 @@ struct DCGridSim : dcg_sim {
       for (int i = 0; i < 2; i++) { cudaFree(vw[i]); cudaFree(q[i]); }
       cudaFree(fl); cudaFree(p); cudaFree(tp); cudaFree(div);
     }
+    for (int i = 0; i < 2; i++) { cudaFree(th[i]); cudaFree(qvp[i]); }
+    cudaFree(s_mc); cudaFree(vort); cudaFree(vw_mc);
     cudaFree(scratch); cudaFree(d_partial);
     if (h_partial) cudaFreeHost(h_partial);
     if (h_sub_scores) cudaFreeHost(h_sub_scores);
@@ -367,7 +381,8 @@ struct DCGridSim : dcg_sim {
       unit_owner[u] = (uint8_t)r;
     }
     DCG_CUDA_TRY(cudaMalloc(&d_unit_owner, nunits));
-    DCG_CUDA_TRY(cudaMemcpy(d_unit_owner, unit_owner.data(), nunits, cudaMemcpyHostToDevice));
+    DCG_CUDA_TRY(cudaMemcpyAsync(d_unit_owner, unit_owner.data(), nunits, cudaMemcpyHostToDevice, stream));
+    DCG_CUDA_TRY(cudaStreamSynchronize(stream));
     work.resize(nlocal);
     for (auto &w : work) {
       DCG_CUDA_TRY(cudaMalloc(&w.d_order, ((size_t)M + kBPC) * 4));
@@ -588,6 +603,93 @@ struct DCGridSim : dcg_sim {
     return DCG_OK;
   }
 
+  // ---- extensions ------------------------------------------------------------------------------------
+  int on_ext_changed() override {
+    if (ext_on() && world > 1) return fail(DCG_ERR_UNSUPPORTED, "the extensions are single-GPU only");
+    DCG_CUDA_TRY(cudaSetDevice(device));
+    DCG_TRY(ensure_ext_storage());
+    steady = false;
+    spec_velocity = false;
+    drop_graphs();
+    return DCG_OK;
+  }
+  int ensure_ext_storage() {
+    if (ext.sources && !th[0]) {
+      for (int i = 0; i < 2; i++) {
+        DCG_CUDA_TRY(cudaMalloc(&th[i], cells * 4));
+        DCG_CUDA_TRY(cudaMalloc(&qvp[i], cells * 4));
+        DCG_CUDA_TRY(cudaMemsetAsync(th[i], 0, cells * 4, stream));
+        DCG_CUDA_TRY(cudaMemsetAsync(qvp[i], 0, cells * 4, stream));
+      }
+    }
+    if ((ext.sources || ext.score_mode) && !vort) {
+      DCG_CUDA_TRY(cudaMalloc(&vort, cells * sizeof(float4)));
+      DCG_CUDA_TRY(cudaMemsetAsync(vort, 0, cells * sizeof(float4), stream));
+    }
+    if (ext.advection && !vw_mc) {
+      DCG_CUDA_TRY(cudaMalloc(&vw_mc, cells * sizeof(float4)));
+      DCG_CUDA_TRY(cudaMalloc(&s_mc, cells * 4));
+      DCG_CUDA_TRY(cudaMemsetAsync(vw_mc, 0, cells * sizeof(float4), stream));
+      DCG_CUDA_TRY(cudaMemsetAsync(s_mc, 0, cells * 4, stream));
+    }
+    return DCG_OK;
+  }
+  void launch_vorticity() {
+    ext::k_dc_ext_vorticity<<<blocks_for(M, kBPC), kCTA, 0, stream>>>(hot(), kp, vw[cur_v], vort);
+    launches++;
+  }
+  // the fused source pass + restriction of what it touched (oracle apply_sources)
+  int apply_sources() override {
+    DCG_TRY(enter());
+    if (!ext.sources) return DCG_OK;
+    spec_velocity = false;
+    launch_vorticity();
+    ext::k_dc_ext_sources<<<blocks_for(M, kBPC), kCTA, 0, stream>>>(hot(), kp, ext, vw[cur_v], q[cur_q], th[cur_s], qvp[cur_s], vort);
+    launches++;
+    accumulate(vw[cur_v], nullptr, false);
+    accumulate(nullptr, q[cur_q], false);
+    accumulate(nullptr, th[cur_s], false);
+    accumulate(nullptr, qvp[cur_s], false);
+    DCG_CUDA_TRY(cudaGetLastError());
+    return DCG_OK;
+  }
+  // semi-Lagrangian gather + restriction of the velocity / of one scalar (kind 0 density, 1 temperature, 2 vapor)
+  void sl_velocity(const float4 *in, float4 *out) {
+    if (use_advect_pipe) {
+      launch_advect_pipe(0, in, out, nullptr, nullptr);
+      accumulate(out, nullptr, true);
+    } else {
+      k_dc_advect_velocity<<<blocks_for(M, kBPC), kCTA, 0, stream>>>(hot(), kp, in, out);
+      launches++;
+      accumulate(out, nullptr, false);
+    }
+  }
+  void sl_scalar(int kind, const float *in, float *out) {
+    const unsigned gb = blocks_for(M, kBPC);
+    if (kind == 0 && use_advect_pipe) {
+      launch_advect_pipe(1, vw[cur_v], nullptr, in, out);
+      accumulate(nullptr, out, true);
+      return;
+    }
+    if (kind == 0) k_dc_advect_density<<<gb, kCTA, 0, stream>>>(hot(), kp, vw[cur_v], fl, in, out);
+    else if (kind == 1) ext::k_dc_ext_advect_scalar<1, false><<<gb, kCTA, 0, stream>>>(hot(), kp, ext, vw[cur_v], fl, in, nullptr, out);
+    else ext::k_dc_ext_advect_scalar<2, false><<<gb, kCTA, 0, stream>>>(hot(), kp, ext, vw[cur_v], fl, in, nullptr, out);
+    launches++;
+    accumulate(nullptr, out, false);
+  }
+  // MacCormack (oracle maccormack()): `cur` holds phi, `other` receives hat, the result lands in s_mc and the
+  // buffers rotate so that `cur` holds the result
+  void maccormack_scalar(int kind, float *&cur, float *other) {
+    sl_scalar(kind, cur, other);
+    const unsigned gb = blocks_for(M, kBPC);
+    if (kind == 0) ext::k_dc_ext_advect_scalar<0, true><<<gb, kCTA, 0, stream>>>(hot(), kp, ext, vw[cur_v], fl, cur, other, s_mc);
+    else if (kind == 1) ext::k_dc_ext_advect_scalar<1, true><<<gb, kCTA, 0, stream>>>(hot(), kp, ext, vw[cur_v], fl, cur, other, s_mc);
+    else ext::k_dc_ext_advect_scalar<2, true><<<gb, kCTA, 0, stream>>>(hot(), kp, ext, vw[cur_v], fl, cur, other, s_mc);
+    launches++;
+    std::swap(cur, s_mc);
+    accumulate(nullptr, cur, false);
+  }
+
   // ---- reset / init: fluid_simulation_dcgrid.cu:190-261 -----------------------------------------
   int reset() override {
     DCG_TRY(enter());
@@ -628,6 +730,13 @@ struct DCGridSim : dcg_sim {
       }
       barrier();
     }
+    DCG_TRY(ensure_ext_storage());
+    for (int i = 0; i < 2; i++) {
+      if (th[i]) DCG_CUDA_TRY(cudaMemsetAsync(th[i], 0, cells * 4, stream));
+      if (qvp[i]) DCG_CUDA_TRY(cudaMemsetAsync(qvp[i], 0, cells * 4, stream));
+    }
+    if (vort) DCG_CUDA_TRY(cudaMemsetAsync(vort, 0, cells * sizeof(float4), stream));
+    cur_s = 0;
     DCG_CUDA_TRY(cudaMemsetAsync(d_counters, 0, 2 * 4, stream));
     k_fill_u32<<<blocks_for((size_t)M * 8 + 1, 256), 256, 0, stream>>>(reinterpret_cast<uint32_t *>(d_sub_scores), 0xFF7FFFFFu /* -FLT_MAX */,
                                                                        (size_t)M * 8 + 1);
@@ -654,6 +763,10 @@ struct DCGridSim : dcg_sim {
       launches++;  // (sharded: every process writes the same values into every cell)
     }
     barrier();
+    if (ext.sources) {  // extension: temperature / vapor start from the ambient profile
+      ext::k_dc_ext_init_scalars<<<blocks_for(M, kBPC), kCTA, 0, stream>>>(T, kp, ext, th[0], th[1], qvp[0], qvp[1]);
+      launches++;
+    }
     DCG_TRY(build_face_descriptors());
     DCG_CUDA_TRY(cudaGetLastError());
     for (int i = 0; i < 5; i++) DCG_TRY(adapt_topology());
@@ -719,6 +832,12 @@ struct DCGridSim : dcg_sim {
     barrier();
     cur_v ^= 1;
     cur_q ^= 1;
+    if (th[0]) {  // extension scalars travel with the density
+      k_dc_permute_field<float><<<gb, 256, 0, stream>>>(th[cur_s], th[cur_s ^ 1], d_perm, d_perm_new, cells);
+      k_dc_permute_field<float><<<gb, 256, 0, stream>>>(qvp[cur_s], qvp[cur_s ^ 1], d_perm, d_perm_new, cells);
+      cur_s ^= 1;
+      launches += 2;
+    }
     float *single[4] = {fl, p, tp, div};
     for (float *f : single) {
       k_dc_permute_field<float><<<gb, 256, 0, stream>>>(f, scratch, d_perm, d_perm_new, cells);
@@ -785,7 +904,8 @@ struct DCGridSim : dcg_sim {
     for (int l = 0; l < kMaxLevels; l++) { init.max_ss[l] = -1; init.min_bs[l] = 0xFFFFFFFFu; init.n_refine[l] = 0; }
     *h_summary = init;
     DCG_CUDA_TRY(cudaMemcpyAsync(d_summary, h_summary, sizeof(ScoreSummary), cudaMemcpyHostToDevice, stream));
-    k_dc_subblock_scores<<<blocks_for((size_t)M * 8, 256), 256, 0, stream>>>(T, kp, mask, d_sub_scores, d_summary);
+    k_dc_subblock_scores<<<blocks_for((size_t)M * 8, 256), 256, 0, stream>>>(T, kp, mask, d_sub_scores, d_summary, ext.score_mode == 1 ? vort : nullptr,
+                                                                             d_perm);
     launches++;
     if (with_block_scores) {
       k_dc_block_scores<<<blocks_for(M, 256), 256, 0, stream>>>(T, mask, d_sub_scores, d_block_scores, d_summary);
@@ -973,8 +1093,14 @@ struct DCGridSim : dcg_sim {
     }
     const std::vector<uint64_t> limit_before = move_limit;
     uint32_t num_touched = 0;
+    if (ext.score_mode == 1) launch_vorticity();  // k_dcgrid_calc_vorticity at the head of adaptTopology (:321): live with the flow-driven score
+    double t0 = now_ms();
     DCG_TRY(move_blocks(num_touched));
+    double t1 = now_ms();
+    t_move_ms += t1 - t0;
     DCG_TRY(refine_subblocks(num_touched));
+    t0 = now_ms();
+    t_refine_ms += t0 - t1;
     if (num_touched > 0) {
       n_changed++;
       drop_graphs();
@@ -984,14 +1110,23 @@ struct DCGridSim : dcg_sim {
       // the field kernels' view of the pool: new blocks take the field slot of their (fresh) reference slot, moved
       // blocks keep theirs; every `resort_every` changes the sparse levels are re-sorted by position
       changes_since_resort++;
+      if (timing_sync) cudaStreamSynchronize(stream);
+      t1 = now_ms();
+      t_apron_ms += t1 - t0;
       if (use_resort && resort_every > 0 && changes_since_resort >= resort_every) DCG_TRY(resort());
       else mirror(false);
       DCG_TRY(build_face_descriptors());
+      t0 = now_ms();
+      t_layout_ms += t0 - t1;
       for (int l = levels - 2; l >= 0; l--) {
         // sharded: every process interpolates every new block (identical values); lock step between the levels,
         // a level reads what the coarser one wrote
         k_dc_propagate<<<num_touched, 64, 0, stream>>>(hot(), kp, d_touched, d_perm, l, vw[cur_v], q[cur_q], fl);
         launches++;
+        if (ext.sources) {
+          ext::k_dc_ext_propagate<<<num_touched, 64, 0, stream>>>(hot(), d_touched, d_perm, l, th[cur_s], qvp[cur_s]);
+          launches++;
+        }
         barrier();
       }
       uint32_t h_cnt[2] = {0, 0};
@@ -999,7 +1134,8 @@ struct DCGridSim : dcg_sim {
       DCG_CUDA_TRY(cudaStreamSynchronize(stream));
       n_failed = h_cnt[0];
       n_irregular = h_cnt[1];
-    } else if (move_limit == limit_before) {
+      t_propagate_ms += now_ms() - t0;
+    } else if (move_limit == limit_before && ext.score_mode == 0) {  // (flow-driven scores change with the fields: never a fixed point)
       steady = true;  // nothing changed and the selection state is unchanged: fixed point
       if (use_resort && changes_since_resort > 0) {  // the layout the steady state will run on, for good
         DCG_TRY(resort());
@@ -1088,6 +1224,16 @@ struct DCGridSim : dcg_sim {
   }
   int advect_velocity() override {  // :263-268
     DCG_TRY(enter());
+    if (ext.advection == 1) {  // extension: MacCormack
+      spec_velocity = false;
+      sl_velocity(vw[cur_v], vw[cur_v ^ 1]);
+      ext::k_dc_ext_maccormack_velocity<<<blocks_for(M, kBPC), kCTA, 0, stream>>>(hot(), kp, vw[cur_v], vw[cur_v ^ 1], vw_mc);
+      launches++;
+      std::swap(vw[cur_v], vw_mc);
+      accumulate(vw[cur_v], nullptr, false);
+      DCG_CUDA_TRY(cudaGetLastError());
+      return DCG_OK;
+    }
     if (spec_velocity) {
       // vw[cur_v ^ 1] already holds this step's advected velocity (written by the previous advect_density())
       spec_velocity = false;
@@ -1108,6 +1254,21 @@ struct DCGridSim : dcg_sim {
   }
   int advect_density() override {  // :313-318
     DCG_TRY(enter());
+    if (ext.advection == 1) {  // extension: MacCormack, every advected scalar
+      spec_velocity = false;
+      maccormack_scalar(0, q[cur_q], q[cur_q ^ 1]);
+      if (ext.sources) {
+        maccormack_scalar(1, th[cur_s], th[cur_s ^ 1]);
+        maccormack_scalar(2, qvp[cur_s], qvp[cur_s ^ 1]);
+      }
+      DCG_CUDA_TRY(cudaGetLastError());
+      return DCG_OK;
+    }
+    if (ext.sources) {  // extension: temperature and vapor ride along (same trajectories; before the velocity buffer flips)
+      sl_scalar(1, th[cur_s], th[cur_s ^ 1]);
+      sl_scalar(2, qvp[cur_s], qvp[cur_s ^ 1]);
+      cur_s ^= 1;
+    }
     if (use_advect_pipe) {
       launch_advect_pipe(fuse_advect ? 2 : 1, vw[cur_v], vw[cur_v ^ 1], q[cur_q], q[cur_q ^ 1]);
       spec_velocity = fuse_advect;
@@ -1246,20 +1407,21 @@ struct DCGridSim : dcg_sim {
     DCG_TRY(enter());
     DCG_CUDA_TRY(cudaEventRecord(ev_begin, stream));
     for (int done = 0; done < n; done++) {
-      if (!steady || spec_velocity != (fuse_advect && use_advect_pipe)) {  // transient: adaptation needs host round trips, run call by call
+      // transient: adaptation needs host round trips, run call by call (MacCormack rotates buffers: never replayed)
+      if (!steady || ext.advection || spec_velocity != (fuse_advect && use_advect_pipe)) {
         DCG_TRY(dcg_sim::step(1));
         continue;
       }
-      cudaGraphExec_t &ge = step_graph[cur_v * 2 + cur_q];
+      cudaGraphExec_t &ge = step_graph[cur_v * 4 + cur_q * 2 + cur_s];
       for (int attempt = 0; !ge; attempt++) {
         const uint64_t before = launches, adapt_before = n_adapt, skipped_before = n_skipped, barriers_before = n_barriers;
-        const int sv = cur_v, sq = cur_q, sp = sweep_parity;
+        const int sv = cur_v, sq = cur_q, ss = cur_s, sp = sweep_parity;
         const bool sspec = spec_velocity;
         cudaGraph_t g = nullptr;
         DCG_CUDA_TRY(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
         const int rc = dcg_sim::step(1);  // adapt_topology() is a no-op in the steady state
         cudaError_t ce = cudaStreamEndCapture(stream, &g);
-        cur_v = sv; cur_q = sq; spec_velocity = sspec;  // capture records, it does not execute
+        cur_v = sv; cur_q = sq; cur_s = ss; spec_velocity = sspec;  // capture records, it does not execute
         step_graph_launches = launches - before;
         launches = before; n_adapt = adapt_before; n_skipped = skipped_before; n_barriers = barriers_before;
         if (rc != DCG_OK && ce == cudaSuccess) return rc;
@@ -1282,6 +1444,7 @@ struct DCGridSim : dcg_sim {
       n_adapt++; n_skipped++;
       cur_v ^= 1;
       cur_q ^= 1;
+      if (ext.sources) cur_s ^= 1;
     }
     DCG_CUDA_TRY(cudaEventRecord(ev_end, stream));
     step_timing_pending = true;
@@ -1391,7 +1554,7 @@ struct DCGridSim : dcg_sim {
 
   int get_field(int field, int layout, float *dst, uint64_t count) override {
     DCG_TRY(enter());
-    const int comps = field == DCG_FIELD_VELOCITY ? 3 : 1;
+    const int comps = (field == DCG_FIELD_VELOCITY || field == DCG_FIELD_VORTICITY) ? 3 : 1;
     const float *src = nullptr;
     int stride = 1;
     switch (field) {
@@ -1401,8 +1564,12 @@ struct DCGridSim : dcg_sim {
       case DCG_FIELD_PRESSURE: src = p; break;
       case DCG_FIELD_DIVERGENCE: src = div; break;
       case DCG_FIELD_T_PRESSURE: src = tp; break;
+      case DCG_FIELD_TEMPERATURE: src = th[cur_s]; break;
+      case DCG_FIELD_VAPOR: src = qvp[cur_s]; break;
+      case DCG_FIELD_VORTICITY: src = reinterpret_cast<const float *>(vort); stride = 4; break;
       default: return fail(DCG_ERR_INVALID, "get_field: unknown field %d", field);
     }
+    if (!src) return fail(DCG_ERR_INVALID, "get_field: field %d belongs to an extension that is not switched on (dcg_set_ext_params)", field);
     if (layout == DCG_LAYOUT_DENSE_L0) {
       const size_t n = (size_t)gx * gy * gz;
       if (!dst || count < n * comps) return fail(DCG_ERR_INVALID, "get_field: destination too small");
@@ -1427,6 +1594,178 @@ struct DCGridSim : dcg_sim {
     launches++;
     src = scratch;
     DCG_CUDA_TRY(cudaMemcpyAsync(dst, src, cells * comps * 4, cudaMemcpyDeviceToHost, stream));
+    return synchronize();
+  }
+
+  // field pointer (field order), components and float stride of an accessor field; nullptr = not available
+  const float *field_src(int field, int &comps, int &stride) const {
+    comps = 1; stride = 1;
+    switch (field) {
+      case DCG_FIELD_DENSITY: return q[cur_q];
+      case DCG_FIELD_VELOCITY: comps = 3; stride = 4; return reinterpret_cast<const float *>(vw[cur_v]);
+      case DCG_FIELD_FLUIDITY: return fl;
+      case DCG_FIELD_PRESSURE: return p;
+      case DCG_FIELD_DIVERGENCE: return div;
+      case DCG_FIELD_T_PRESSURE: return tp;
+      case DCG_FIELD_TEMPERATURE: return th[cur_s];
+      case DCG_FIELD_VAPOR: return qvp[cur_s];
+      case DCG_FIELD_VORTICITY: comps = 3; stride = 4; return reinterpret_cast<const float *>(vort);
+    }
+    return nullptr;
+  }
+  int sample_field(int field, int mode, const float *positions, uint64_t n, float *out) override {
+    DCG_TRY(enter());
+    int comps, stride;
+    const float *src = field_src(field, comps, stride);
+    if (!src) return fail(DCG_ERR_INVALID, "sample_field: field %d is unknown or belongs to an extension that is not switched on", field);
+    if (n == 0) return DCG_OK;
+    struct Tmp {
+      void *p = nullptr;
+      ~Tmp() { cudaFree(p); }
+    } t_pos, t_out;
+    DCG_CUDA_TRY(cudaMalloc(&t_pos.p, n * 12));
+    DCG_CUDA_TRY(cudaMalloc(&t_out.p, n * comps * 4));
+    DCG_CUDA_TRY(cudaMemcpyAsync(t_pos.p, positions, n * 12, cudaMemcpyHostToDevice, stream));
+    ext::k_dc_ext_sample<<<blocks_for(n, 256), 256, 0, stream>>>(hot(), kp, src, comps, stride, mode, static_cast<const float *>(t_pos.p), n,
+                                                                 static_cast<float *>(t_out.p));
+    launches++;
+    DCG_CUDA_TRY(cudaMemcpyAsync(out, t_out.p, n * comps * 4, cudaMemcpyDeviceToHost, stream));
+    return synchronize();
+  }
+
+  // ---- state dump / load (format: DESIGN.md "State file") ------------------------------------------------------
+  struct StateHeader {
+    char magic[8];  // "DCGB200S"
+    uint32_t version, header_bytes;
+    int32_t gx, gy, gz, levels, sparse, has_scalars;
+    uint64_t M;
+    uint64_t counters[8];
+    uint64_t loads[kMaxLevels], move_limit[kMaxLevels];
+    dcg_sim_params params;
+    dcg_ext_params ext;
+    int32_t pairs[3];
+  };
+  int save_state(const char *path) override {
+    DCG_TRY(enter());
+    if (world > 1) return fail(DCG_ERR_UNSUPPORTED, "save_state: single-GPU instances only");
+    DCG_TRY(synchronize());
+    FILE *f = std::fopen(path, "wb");
+    if (!f) return fail(DCG_ERR_INVALID, "save_state: cannot open %s", path);
+    struct Closer {
+      FILE *f;
+      ~Closer() { std::fclose(f); }
+    } closer{f};
+    StateHeader H{};
+    std::memcpy(H.magic, "DCGB200S", 8);
+    H.version = 1; H.header_bytes = (uint32_t)sizeof H;
+    H.gx = gx; H.gy = gy; H.gz = gz; H.levels = levels; H.sparse = sparse; H.has_scalars = th[0] ? 1 : 0;
+    H.M = M;
+    get_counters(H.counters);
+    for (int l = 0; l < levels; l++) { H.loads[l] = loads[l]; H.move_limit[l] = move_limit[l]; }
+    H.params = params; H.ext = ext;
+    H.pairs[0] = project_coarsest_pairs; H.pairs[1] = project_level_pairs; H.pairs[2] = local_pairs;
+    bool ok = std::fwrite(&H, sizeof H, 1, f) == 1;
+    std::vector<unsigned char> h;
+    auto put_dev = [&](const void *dev, size_t bytes) {
+      h.resize(bytes);
+      if (cudaMemcpyAsync(h.data(), dev, bytes, cudaMemcpyDeviceToHost, stream) != cudaSuccess || cudaStreamSynchronize(stream) != cudaSuccess) { ok = false; return; }
+      ok = ok && std::fwrite(h.data(), 1, bytes, f) == bytes;
+    };
+    // block pool, reference numbering
+    put_dev(T.posl, (size_t)M * sizeof(int4));
+    put_dev(T.parent, (size_t)M * 4);
+    put_dev(T.child, (size_t)M * 8 * 4);
+    put_dev(T.apron, (size_t)M * kAV * 4);
+    // fields, reference slot order (through the accessor path)
+    const int fields[] = {DCG_FIELD_VELOCITY, DCG_FIELD_DENSITY, DCG_FIELD_FLUIDITY, DCG_FIELD_PRESSURE, DCG_FIELD_T_PRESSURE, DCG_FIELD_DIVERGENCE,
+                          DCG_FIELD_TEMPERATURE, DCG_FIELD_VAPOR};
+    for (int fi = 0; fi < (H.has_scalars ? 8 : 6) && ok; fi++) {
+      int comps, stride;
+      const float *src = field_src(fields[fi], comps, stride);
+      k_dc_unpermute_f32<<<blocks_for(cells, 256), 256, 0, stream>>>(src, stride, comps, d_perm, scratch, cells);
+      launches++;
+      if (cudaStreamSynchronize(stream) != cudaSuccess) { ok = false; break; }
+      put_dev(scratch, cells * comps * 4);
+    }
+    if (!ok) return fail(DCG_ERR_CUDA, "save_state: write to %s failed", path);
+    return DCG_OK;
+  }
+  int load_state(const char *path) override {
+    DCG_TRY(enter());
+    if (world > 1) return fail(DCG_ERR_UNSUPPORTED, "load_state: single-GPU instances only");
+    FILE *f = std::fopen(path, "rb");
+    if (!f) return fail(DCG_ERR_INVALID, "load_state: cannot open %s", path);
+    struct Closer {
+      FILE *f;
+      ~Closer() { std::fclose(f); }
+    } closer{f};
+    StateHeader H{};
+    if (std::fread(&H, sizeof H, 1, f) != 1 || std::memcmp(H.magic, "DCGB200S", 8) != 0 || H.version != 1 || H.header_bytes != sizeof H)
+      return fail(DCG_ERR_INVALID, "load_state: %s is not a dcgrid_b200 state file of this version", path);
+    if (H.gx != gx || H.gy != gy || H.gz != gz || H.M != M || H.levels != levels || H.sparse != sparse)
+      return fail(DCG_ERR_INVALID, "load_state: the file holds a %dx%dx%d grid with %llu blocks, this instance %dx%dx%d with %u", H.gx, H.gy, H.gz,
+                  (unsigned long long)H.M, gx, gy, gz, M);
+    DCG_TRY(synchronize());
+    drop_graphs();
+    params = H.params;
+    ext = H.ext;
+    kp = make_kparams(params, ext);
+    DCG_TRY(ensure_ext_storage());
+    if (H.has_scalars && !th[0]) return fail(DCG_ERR_INVALID, "load_state: the file carries temperature / vapor but its parameters do not enable them");
+    project_coarsest_pairs = H.pairs[0]; project_level_pairs = H.pairs[1]; local_pairs = H.pairs[2];
+    for (int l = 0; l < levels; l++) { loads[l] = H.loads[l]; move_limit[l] = H.move_limit[l]; }
+    n_adapt = H.counters[0]; n_changed = H.counters[1]; n_moved = H.counters[2]; n_refined = H.counters[3]; n_skipped = H.counters[4];
+    n_failed = H.counters[5];
+    sync_loads();
+    std::vector<unsigned char> h;
+    bool ok = true;
+    auto get_dev = [&](void *dev, size_t bytes) {
+      h.resize(bytes);
+      if (std::fread(h.data(), 1, bytes, f) != bytes) { ok = false; return; }
+      // on the instance's stream: a blocking cudaMemcpy from pageable memory may return before its DMA has landed, and
+      // the non-blocking stream the kernels run on is not ordered behind it
+      ok = ok && cudaMemcpyAsync(dev, h.data(), bytes, cudaMemcpyHostToDevice, stream) == cudaSuccess && cudaStreamSynchronize(stream) == cudaSuccess;
+    };
+    get_dev(T.posl, (size_t)M * sizeof(int4));
+    get_dev(T.parent, (size_t)M * 4);
+    get_dev(T.child, (size_t)M * 8 * 4);
+    get_dev(T.apron, (size_t)M * kAV * 4);
+    if (!ok) return fail(DCG_ERR_INVALID, "load_state: %s is truncated", path);
+    // field order = slot order until the next re-sort; level maps rebuilt from the positions
+    mirrored = false;
+    changes_since_resort = 1;
+    steady = false;
+    spec_velocity = false;
+    cur_v = cur_q = cur_s = 0;
+    k_iota_u32<<<blocks_for(M, 256), 256, 0, stream>>>(d_perm, M);
+    DCG_CUDA_TRY(cudaMemsetAsync(d_flags, 0, (size_t)M * 4, stream));
+    for (int l = 0; l < sparse; l++) DCG_CUDA_TRY(cudaMemsetAsync(T.map[l], 0xff, map_size[l] * 4, stream));
+    ext::k_dc_ext_rebuild_maps<<<blocks_for(M, 256), 256, 0, stream>>>(T, kp);
+    launches += 2;
+    DCG_CUDA_TRY(cudaStreamSynchronize(stream));
+    // velocity (3 floats / cell) and fluidity arrive separately and are packed; scratch holds 3 * cells floats
+    get_dev(scratch, cells * 3 * 4);
+    get_dev(q[0], cells * 4);
+    get_dev(fl, cells * 4);
+    if (!ok) return fail(DCG_ERR_INVALID, "load_state: %s is truncated", path);
+    ext::k_dc_ext_pack_vw<<<blocks_for(cells, 256), 256, 0, stream>>>(scratch, fl, vw[0], vw[1], cells);
+    launches++;
+    DCG_CUDA_TRY(cudaMemcpyAsync(q[1], q[0], cells * 4, cudaMemcpyDeviceToDevice, stream));
+    DCG_CUDA_TRY(cudaStreamSynchronize(stream));
+    get_dev(p, cells * 4);
+    get_dev(tp, cells * 4);
+    get_dev(div, cells * 4);
+    if (H.has_scalars) {
+      get_dev(th[0], cells * 4);
+      get_dev(qvp[0], cells * 4);
+      if (ok) {
+        DCG_CUDA_TRY(cudaMemcpyAsync(th[1], th[0], cells * 4, cudaMemcpyDeviceToDevice, stream));
+        DCG_CUDA_TRY(cudaMemcpyAsync(qvp[1], qvp[0], cells * 4, cudaMemcpyDeviceToDevice, stream));
+      }
+    }
+    if (!ok) return fail(DCG_ERR_INVALID, "load_state: %s is truncated", path);
+    DCG_TRY(build_face_descriptors());
+    DCG_CUDA_TRY(cudaGetLastError());
     return synchronize();
   }
 
@@ -1514,6 +1853,12 @@ struct DCGridSim : dcg_sim {
     else if (k == "irregular_blocks") *out = (double)n_irregular;
     else if (k == "barriers") *out = (double)n_barriers;
     else if (k == "graph_launches_per_step") *out = (double)step_graph_launches;
+    else if (k == "adapt_move_ms") *out = t_move_ms;
+    else if (k == "adapt_refine_ms") *out = t_refine_ms;
+    else if (k == "adapt_apron_ms") *out = t_apron_ms;
+    else if (k == "adapt_layout_ms") *out = t_layout_ms;
+    else if (k == "adapt_propagate_ms") *out = t_propagate_ms;
+    else if (k == "timing_sync") { timing_sync = !timing_sync; *out = timing_sync ? 1 : 0; }
     else return dcg_sim::get_info(key, out);
     return DCG_OK;
   }

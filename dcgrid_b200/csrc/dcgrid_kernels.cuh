@@ -242,15 +242,23 @@ __device__ __forceinline__ bool warp_uniform(int v) {
 
 // k_dcgrid_calc_subblock_scores, :10-40.  finer_full bit l = "level l cannot be refined further"
 // ((l==0 && loads[0]==full[0]) || (l>0 && loads[l-1]==full[l-1]), :19-21).
+// vort != nullptr: the flow-driven score (extension, dcg_ext_params.score_mode == 1) — the lines the reference carries
+// commented out, :36-39, with calcCellScore (:6-8) = |vorticity|, stored in .w of vort (field order: perm maps slots)
 __global__ void __launch_bounds__(256) k_dc_subblock_scores(Pool T, KParams P, uint32_t finer_full, float *__restrict__ sub_scores,
-                                                            ScoreSummary *__restrict__ sum) {
+                                                            ScoreSummary *__restrict__ sum, const float4 *__restrict__ vort,
+                                                            const uint32_t *__restrict__ perm) {
   const uint32_t sb = blockIdx.x * 256 + threadIdx.x;
   int level = kFree;
   float score = -FLT_MAX;
   if (sb < 8 * T.M) {
     const int4 pl = T.posl[sb / 8];
     level = pl.w;
-    if (!(T.child[sb] != kNone || pl.w == kFree || ((finer_full >> pl.w) & 1))) {
+    if (!(T.child[sb] != kNone || pl.w == kFree || ((finer_full >> pl.w) & 1)) && vort) {
+      const float4 *w = vort + ((size_t)perm[sb / 8] * kBV + (size_t)kSV * (sb & 7u));
+      score = 0.f;
+#pragma unroll
+      for (int i = 0; i < kSV; i++) score += w[i].w;
+    } else if (!(T.child[sb] != kNone || pl.w == kFree || ((finer_full >> pl.w) & 1))) {
       const float s = (float)(1 << pl.w);
       const float px = s * ((float)pl.x + 2.f * (float)((sb >> 2) & 1) + 1.f);
       const float py = s * ((float)pl.y + 2.f * (float)((sb >> 1) & 1) + 1.f);

@@ -26,6 +26,7 @@
 struct dcg_sim {
   dcg_sim_params params{};
   dcg_options opt{};  // creation-time options (include/dcgrid_b200.h); all-zero = defaults
+  dcg_ext_params ext{};  // extensions beyond the reference snapshot; all-zero = the snapshot's behaviour
   dcg::KParams kp{};
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -58,6 +59,34 @@ struct dcg_sim {
 
   // additions
   virtual int step(int n);
+  // extensions (include/dcgrid_b200.h, "extensions"): DCGrid instances implement them
+  virtual int on_ext_changed() {
+    if (ext.score_mode || ext.advection || ext.sources || ext.terrain) return fail(DCG_ERR_UNSUPPORTED, "extensions are implemented for DCGrid instances only");
+    return DCG_OK;
+  }
+  virtual int apply_sources() { return DCG_OK; }
+  virtual int sample_field(int, int, const float *, uint64_t, float *) { return fail(DCG_ERR_UNSUPPORTED, "sample_field: DCGrid instances only"); }
+  virtual int save_state(const char *) { return fail(DCG_ERR_UNSUPPORTED, "save_state: DCGrid instances only"); }
+  virtual int load_state(const char *) { return fail(DCG_ERR_UNSUPPORTED, "load_state: DCGrid instances only"); }
+  int set_ext(const dcg_ext_params *e) {
+    dcg_ext_params n{};
+    const size_t bytes = e->struct_size == 0 || e->struct_size > sizeof(dcg_ext_params) ? sizeof(dcg_ext_params) : e->struct_size;
+    std::memcpy(&n, e, bytes);
+    n.struct_size = (uint32_t)sizeof(dcg_ext_params);
+    if (n.score_mode < 0 || n.score_mode > 1 || n.advection < 0 || n.advection > 1) return fail(DCG_ERR_INVALID, "ext: score_mode and advection must be 0 or 1");
+    if (n.sources && !(n.ambient_temperature > 0.f)) return fail(DCG_ERR_INVALID, "ext: sources need ambient_temperature > 0");
+    if (n.terrain && !(n.terrain_wavelength > 0.f)) return fail(DCG_ERR_INVALID, "ext: terrain needs terrain_wavelength > 0");
+    const dcg_ext_params saved = ext;
+    const dcg::KParams saved_kp = kp;
+    ext = n;
+    kp = dcg::make_kparams(params, ext);
+    const int rc = on_ext_changed();
+    if (rc != DCG_OK) {
+      ext = saved;
+      kp = saved_kp;
+    }
+    return rc;
+  }
   virtual int on_params_changed() = 0;
   virtual int total_density(double *out) = 0;
   virtual uint64_t num_cells() const = 0;
@@ -92,7 +121,7 @@ struct dcg_sim {
     const dcg_sim_params saved = params;
     const dcg::KParams saved_kp = kp;
     params = *p;
-    kp = dcg::make_kparams(params);
+    kp = dcg::make_kparams(params, ext);
     const int rc = on_params_changed();
     if (rc != DCG_OK) {
       params = saved;
@@ -131,7 +160,7 @@ struct dcg_sim {
   }
   int base_setup(const dcg_sim_params *p, int dev) {
     params = *p;
-    kp = dcg::make_kparams(params);
+    kp = dcg::make_kparams(params, ext);
     device = dev;
     DCG_CUDA_TRY(cudaSetDevice(device));
     DCG_CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));

@@ -636,6 +636,7 @@ int dcg_sim::step(int n) {
   for (int i = 0; i < n; i++) {
     DCG_TRY(advect_velocity());
     DCG_TRY(adapt_topology());
+    if (ext.sources) DCG_TRY(apply_sources());  // extension: the fused source pass
     DCG_TRY(project());
     DCG_TRY(advect_density());
   }

@@ -99,3 +99,26 @@ def make_options(options=None) -> Options:
             setattr(o, k, int(v))
     o.struct_size = ctypes.sizeof(Options)
     return o
+
+
+class ExtParams(ctypes.Structure):
+    """``struct dcg_ext_params`` (include/dcgrid_b200.h): extensions beyond the reference snapshot; all zero = off."""
+    _fields_ = [("struct_size", ctypes.c_uint32)] + [(n, ctypes.c_int32) for n in ("score_mode", "advection", "sources", "terrain")] + [
+        (n, ctypes.c_float) for n in (
+            "buoyancy", "vapor_buoyancy", "smoke_weight", "ambient_temperature", "ambient_lapse", "adiabatic_lapse", "vorticity_confinement",
+            "saturation_base", "saturation_slope", "condensation_rate", "latent_heat", "temperature_emission", "vapor_emission", "ambient_vapor",
+            "terrain_height", "terrain_wavelength")] + [("reserved", ctypes.c_int32 * 11)]
+
+
+def make_ext(**kw) -> ExtParams:
+    """dcg_default_ext_params() (plausible coefficients, every switch off) with the given fields overridden."""
+    e = ExtParams()
+    from . import _lib
+
+    _lib.load().dcg_default_ext_params(ctypes.byref(e))
+    for k, v in kw.items():
+        if not hasattr(e, k):
+            raise KeyError(f"unknown dcg_ext_params field {k!r}")
+        setattr(e, k, v)
+    e.struct_size = ctypes.sizeof(ExtParams)
+    return e

@@ -19,7 +19,8 @@ import numpy as np
 from . import _lib
 from .params import SimParams, make_options
 
-FIELDS = {"density": 0, "velocity": 1, "fluidity": 2, "pressure": 3, "divergence": 4, "t_pressure": 5}
+FIELDS = {"density": 0, "velocity": 1, "fluidity": 2, "pressure": 3, "divergence": 4, "t_pressure": 5, "temperature": 6, "vapor": 7,
+          "vorticity": 8}
 LAYOUT_NATIVE, LAYOUT_DENSE_L0 = 0, 1
 
 
@@ -113,6 +114,33 @@ class FluidSimulation:
     def synchronize(self):
         self._check(self._L.dcg_synchronize(self._h))
 
+    # -- extensions beyond the reference snapshot (include/dcgrid_b200.h, "extensions") ----------------
+    def setExt(self, ext):
+        self._check(self._L.dcg_set_ext_params(self._h, ctypes.byref(ext)))
+
+    def getExt(self):
+        from .params import ExtParams
+
+        e = ExtParams()
+        self._check(self._L.dcg_get_ext_params(self._h, ctypes.byref(e)))
+        return e
+
+    def applySources(self):
+        self._check(self._L.dcg_apply_sources(self._h))
+
+    def sampleField(self, name, positions, precise=False):
+        positions = np.ascontiguousarray(positions, dtype=np.float32).reshape(-1, 3)
+        comps = 3 if name in ("velocity", "vorticity") else 1
+        out = np.empty(positions.shape[0] * comps, dtype=np.float32)
+        self._check(self._L.dcg_sample_field(self._h, FIELDS[name], 1 if precise else 0, _ptr(positions), positions.shape[0], _ptr(out)))
+        return out.reshape(-1, 3) if comps == 3 else out
+
+    def saveState(self, path):
+        self._check(self._L.dcg_save_state(self._h, str(path).encode()))
+
+    def loadState(self, path):
+        self._check(self._L.dcg_load_state(self._h, str(path).encode()))
+
     def setJacobiSchedule(self, project_coarsest_pairs, project_level_pairs, local_pairs):
         self._check(self._L.dcg_set_jacobi_schedule(self._h, project_coarsest_pairs, project_level_pairs, local_pairs))
 
@@ -158,7 +186,7 @@ class FluidSimulation:
         return int(self._L.dcg_num_levels(self._h))
 
     def field(self, name, layout=LAYOUT_NATIVE, count=None):
-        comps = 3 if name == "velocity" else 1
+        comps = 3 if name in ("velocity", "vorticity") else 1
         n = self.numCells if count is None else count
         out = np.empty(n * comps, dtype=np.float32)
         self._check(self._L.dcg_get_field(self._h, FIELDS[name], layout, _ptr(out), out.size))

@@ -798,15 +798,17 @@ struct DCGridOracle : orc_sim {
   }
   // semi-Lagrangian gather of a `comps`-component field through the cell's own velocity (k_dcgrid_advect_velocity /
   // _density, dcgrid_fluid.cu:74-144): out[c] for every cell of every active block, 0 for non-leaf cells.
-  // bc(values[comps], x, y, z, scale) substitutes boundary values per corner.
-  template <class BC>
-  void gather_sl(const float *phi, int comps, float *out, BC bc) const {
+  // bc(values[comps], x, y, z, scale) substitutes boundary values per corner; fb(values, y, scale) is what a leaf cell
+  // gets when its sample has no fluid weight (the reference: 0; the extension scalars: their ambient value).
+  template <class BC, class FB>
+  void gather_sl(const float *phi, int comps, float *out, BC bc, FB fb) const {
 #pragma omp parallel for schedule(dynamic, 64)
     for (u64 b = 0; b < M; b++) {
       if (lvl[b] == 0xFF) continue;
       for (u64 c = b * BV; c < (b + 1) * BV; c++) {
         float o[3] = {0.f, 0.f, 0.f};
         if (child[c >> 3] == kNone) {
+          fb(o, pos[3 * b + 1] | cell_y(c), 1 << lvl[b]);
           float bx, by, bz;
           trace(b, c, -1.f, bx, by, bz);
           const Sample s = sample(bx, by, bz);
@@ -832,12 +834,12 @@ struct DCGridOracle : orc_sim {
   //   back = SL of `hat` along the REVERSED trajectory (cell centre + v dt)
   //   out  = clamp(hat + .5 (phi - back), min, max of the 8 boundary-substituted corners of the forward sample)
   // falling back to hat where either sample has no fluid weight.  Trajectories use the pre-advection velocity.
-  template <class BC>
-  void maccormack(float *phi, int comps, BC bc) {
+  template <class BC, class FB>
+  void maccormack(float *phi, int comps, BC bc, FB fb) {
     mc_hat.resize(3 * num_cells_); mc_out.resize(3 * num_cells_);
     float *hat = mc_hat.data(), *out = mc_out.data();
     std::fill(mc_hat.begin(), mc_hat.end(), 0.f);
-    gather_sl(phi, comps, hat, bc);
+    gather_sl(phi, comps, hat, bc, fb);
     accumulate_all(hat, comps);
 #pragma omp parallel for schedule(dynamic, 64)
     for (u64 b = 0; b < M; b++) {
@@ -845,6 +847,7 @@ struct DCGridOracle : orc_sim {
       for (u64 c = b * BV; c < (b + 1) * BV; c++) {
         float o[3] = {0.f, 0.f, 0.f};
         if (child[c >> 3] == kNone) {
+          fb(o, pos[3 * b + 1] | cell_y(c), 1 << lvl[b]);
           float bx, by, bz;
           trace(b, c, -1.f, bx, by, bz);
           const Sample s = sample(bx, by, bz);
@@ -892,26 +895,30 @@ struct DCGridOracle : orc_sim {
       const V3 r = velocity_bc(P, V3{v[0], v[1], v[2]}, x, y, z, scale);
       v[0] = r.x; v[1] = r.y; v[2] = r.z;
     };
-    if (E.advection == 1) { maccormack(velocity.data(), 3, bc); return; }
+    auto zero = [](float *, int, int) {};
+    if (E.advection == 1) { maccormack(velocity.data(), 3, bc, zero); return; }
     float *tv = t_velocity();
-    gather_sl(velocity.data(), 3, tv, bc);
+    gather_sl(velocity.data(), 3, tv, bc, zero);
     std::memcpy(velocity.data(), tv, 3 * num_cells_ * sizeof(float));  // whole-pool D2D copy, :265-266
     accumulate_velocity();
   }
 
-  template <class BC>
-  void advect_scalar(std::vector<float> &phi, BC bc) {
-    if (E.advection == 1) { maccormack(phi.data(), 1, bc); return; }
+  template <class BC, class FB>
+  void advect_scalar(std::vector<float> &phi, BC bc, FB fb) {
+    if (E.advection == 1) { maccormack(phi.data(), 1, bc, fb); return; }
     float *tq = t_density();
-    gather_sl(phi.data(), 1, tq, bc);
+    gather_sl(phi.data(), 1, tq, bc, fb);
     std::memcpy(phi.data(), tq, num_cells_ * sizeof(float));  // :315-316
     accumulate_all(phi.data(), 1);
   }
   void advect_density() override {  // fluid_simulation_dcgrid.cu:313-318, dcgrid_fluid.cu:93-110,129-144
-    advect_scalar(density, [this](float *v, int x, int y, int z, int scale) { v[0] = density_bc(P, v[0], x, y, z, scale); });
-    if (E.sources) {  // extension: temperature and vapor ride along (same trajectories, same weights)
-      advect_scalar(temperature, [this](float *v, int x, int y, int z, int scale) { v[0] = temperature_bc(P, E, v[0], x, y, z, scale); });
-      advect_scalar(vapor, [this](float *v, int x, int y, int z, int scale) { v[0] = vapor_bc(P, E, v[0], x, y, z, scale); });
+    advect_scalar(density, [this](float *v, int x, int y, int z, int scale) { v[0] = density_bc(P, v[0], x, y, z, scale); }, [](float *, int, int) {});
+    if (E.sources) {  // extension: temperature and vapor ride along (same trajectories, same weights); a cell whose
+                      // sample has no fluid weight (inside a solid) takes the ambient value instead of the reference's 0
+      advect_scalar(temperature, [this](float *v, int x, int y, int z, int scale) { v[0] = temperature_bc(P, E, v[0], x, y, z, scale); },
+                    [this](float *o, int y, int scale) { o[0] = ambient_theta(E, cell_height(P, y, scale)); });
+      advect_scalar(vapor, [this](float *v, int x, int y, int z, int scale) { v[0] = vapor_bc(P, E, v[0], x, y, z, scale); },
+                    [this](float *o, int, int) { o[0] = E.ambient_vapor; });
     }
   }
 

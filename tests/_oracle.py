@@ -8,12 +8,12 @@ import subprocess
 
 import numpy as np
 
-from dcgrid_b200.params import SimParams
+from dcgrid_b200.params import ExtParams, SimParams
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "oracle", "liboracle.so")
 
-FIELD = {"density": 0, "velocity": 1, "fluidity": 2, "pressure": 3, "divergence": 4, "t_pressure": 5}
+FIELD = {"density": 0, "velocity": 1, "fluidity": 2, "pressure": 3, "divergence": 4, "t_pressure": 5, "temperature": 6, "vapor": 7, "vorticity": 8}
 
 
 def build():
@@ -54,6 +54,9 @@ def lib():
         L.orc_lookup_blocks.argtypes = [vp, vp, ctypes.c_uint64, vp, vp]
         L.orc_get_counters.argtypes = [vp, vp]
         L.orc_get_move_limits.argtypes = [vp, vp]
+        L.orc_set_ext_params.argtypes = [vp, ctypes.POINTER(ExtParams)]
+        L.orc_apply_sources.argtypes = [vp]
+        L.orc_sample_field.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, ctypes.c_uint64, vp]
         _lib = L
     return _lib
 
@@ -92,6 +95,22 @@ class Oracle:
         self.params = params
         self.L.orc_set_params(self.h, ctypes.byref(params))
 
+    def set_ext(self, ext: ExtParams):
+        """extensions: this oracle is their specification"""
+        self.ext = ext
+        self.L.orc_set_ext_params(self.h, ctypes.byref(ext))
+
+    def apply_sources(self):
+        self.L.orc_apply_sources(self.h)
+
+    def sample_field(self, name, positions, precise=False):
+        positions = np.ascontiguousarray(positions, dtype=np.float32).reshape(-1, 3)
+        comps = 3 if name in ("velocity", "vorticity") else 1
+        out = np.empty(positions.shape[0] * comps, dtype=np.float32)
+        rc = self.L.orc_sample_field(self.h, FIELD[name], 1 if precise else 0, _ptr(positions), positions.shape[0], _ptr(out))
+        assert rc == 0
+        return out.reshape(-1, 3) if comps == 3 else out
+
     def reset(self):
         self.L.orc_reset(self.h)
 
@@ -129,11 +148,12 @@ class Oracle:
         return int(self.L.orc_sparse_levels(self.h))
 
     def field(self, name):
-        n = self.num_cells * (3 if name == "velocity" else 1)
+        vec = name in ("velocity", "vorticity")
+        n = self.num_cells * (3 if vec else 1)
         out = np.empty(n, dtype=np.float32)
         rc = self.L.orc_get_field(self.h, FIELD[name], _ptr(out))
         assert rc == 0
-        return out.reshape(-1, 3) if name == "velocity" else out
+        return out.reshape(-1, 3) if vec else out
 
     def level_table(self):
         L = self.levels
