@@ -75,7 +75,12 @@ struct DCGridSim : dcg_sim {
   float *th[2] = {nullptr, nullptr}, *qvp[2] = {nullptr, nullptr}, *s_mc = nullptr;
   float4 *vort = nullptr, *vw_mc = nullptr;
   int cur_s = 0;
-  bool ext_on() const { return ext.score_mode || ext.advection || ext.sources; }
+  bool ext_on() const { return ext.score_mode || ext.advection || ext.sources || ext.selection; }
+  // device-side selection (dcgrid_ext.cuh, namespace sel): sort keys, per-level scalars, compaction scratch
+  unsigned long long *d_sel_keys[2] = {nullptr, nullptr};
+  void *d_sel_tmp = nullptr;
+  size_t sel_tmp_bytes = 0, sel_max_n = 0;
+  uint32_t *d_sel_sc = nullptr, *h_sel_sc = nullptr, *d_sel_cta = nullptr, *d_sel_mc = nullptr, *d_sel_dc = nullptr;
 
   // pinned host mirrors for the selection
   float *h_sub_scores = nullptr, *h_block_scores = nullptr;
@@ -181,6 +186,9 @@ struct DCGridSim : dcg_sim {
     }
     for (int i = 0; i < 2; i++) { cudaFree(th[i]); cudaFree(qvp[i]); }
     cudaFree(s_mc); cudaFree(vort); cudaFree(vw_mc);
+    cudaFree(sel_mc_keys);
+    cudaFree(d_sel_keys[0]); cudaFree(d_sel_keys[1]); cudaFree(d_sel_tmp); cudaFree(d_sel_sc); cudaFree(d_sel_cta); cudaFree(d_sel_mc); cudaFree(d_sel_dc);
+    if (h_sel_sc) cudaFreeHost(h_sel_sc);
     cudaFree(scratch); cudaFree(d_partial);
     if (h_partial) cudaFreeHost(h_partial);
     if (h_sub_scores) cudaFreeHost(h_sub_scores);
@@ -634,6 +642,20 @@ struct DCGridSim : dcg_sim {
     }
     return DCG_OK;
   }
+  int ensure_sel_storage() {
+    if (d_sel_keys[0]) return DCG_OK;
+    sel_max_n = max_blocks[0];
+    for (int l = 1; l < levels; l++) sel_max_n = std::max<size_t>(sel_max_n, 8 * max_blocks[l]);
+    for (int i = 0; i < 2; i++) DCG_CUDA_TRY(cudaMalloc(&d_sel_keys[i], sel_max_n * 8));
+    DCG_CUDA_TRY(cub::DeviceRadixSort::SortKeys(nullptr, sel_tmp_bytes, d_sel_keys[0], d_sel_keys[1], (int)sel_max_n, 0, 64, stream));
+    DCG_CUDA_TRY(cudaMalloc(&d_sel_tmp, sel_tmp_bytes + 16));
+    DCG_CUDA_TRY(cudaMalloc(&d_sel_sc, 4 * kMaxLevels * 4));
+    DCG_CUDA_TRY(cudaMallocHost(&h_sel_sc, 4 * kMaxLevels * 4));
+    DCG_CUDA_TRY(cudaMalloc(&d_sel_cta, (sel_max_n / sel::kSelCta + 2) * 4));
+    DCG_CUDA_TRY(cudaMalloc(&d_sel_mc, (size_t)M * 4));
+    DCG_CUDA_TRY(cudaMalloc(&d_sel_dc, (size_t)M * 4));
+    return DCG_OK;
+  }
   void launch_vorticity() {
     ext::k_dc_ext_vorticity<<<blocks_for(M, kBPC), kCTA, 0, stream>>>(hot(), kp, vw[cur_v], vort);
     launches++;
@@ -816,7 +838,8 @@ struct DCGridSim : dcg_sim {
   // new permutation (active blocks of every sparse level sorted by position), fields moved into the new order
   int resort() {
     DCG_TRY(ensure_mirror_storage());
-    k_dc_resort_keys<<<blocks_for(M, 256), 256, 0, stream>>>(T, kp, world, d_sort_keys64[0], d_order_vals);
+    const int slab_axis = (gz > gx && gz >= gy) ? 2 : (gy > gx ? 1 : 0);  // longest axis; x on ties (the order of the ordered levels)
+    k_dc_resort_keys<<<blocks_for(M, 256), 256, 0, stream>>>(T, kp, world, slab_axis, d_sort_keys64[0], d_order_vals);
     size_t bytes = sort_tmp64_bytes;
     DCG_CUDA_TRY(cub::DeviceRadixSort::SortPairs(d_sort_tmp64, bytes, d_sort_keys64[0], d_sort_keys64[1], d_order_vals, d_order_keys[0], (int)M, 0, 64,
                                                  stream));
@@ -957,6 +980,7 @@ struct DCGridSim : dcg_sim {
         if (move_candidates(level) > 0) move_limit[level] = 0;  // matches == 0 => moveLimit = 0 (:420)
       return DCG_OK;
     }
+    if (ext.selection == 1) return move_blocks_device(need, num_touched);
     // slices the host selection reads: block scores of level l and l+1 (the protect-next-parent write,
     // :417, lands in level l+1), subblock scores of level l+1
     std::vector<char> got_bs(levels, 0), got_ss(levels, 0);
@@ -1031,6 +1055,111 @@ struct DCGridSim : dcg_sim {
     return DCG_OK;
   }
 
+  // moveBlocks with the total-order selection (dcg_ext_params.selection == 1; oracle move_blocks, "EXTENSION"): keys,
+  // two radix sorts, the monotone greedy rule and the protection of the receiving parents, level after level on the
+  // stream; ONE 4-byte-per-level read-back (the match counts feed moveLimit and the list sizes).
+  int move_blocks_device(const std::vector<char> &need, uint32_t &num_touched) {
+    DCG_TRY(ensure_sel_storage());
+    DCG_CUDA_TRY(cudaMemsetAsync(d_sel_sc, 0, 4 * kMaxLevels * 4, stream));
+    std::vector<uint64_t> base(levels, 0), lim(levels, 0);
+    uint64_t upper = 0;
+    for (int level = 0; level < levels - 1; level++) {
+      const uint64_t l = move_candidates(level);
+      lim[level] = l;
+      base[level] = upper;
+      if (l == 0 || !need[level]) continue;
+      n_device_selections++;
+      const uint32_t d0 = (uint32_t)max_blocks[level], d1 = (uint32_t)(8 * max_blocks[level + 1]);
+      uint32_t *sc = d_sel_sc + 4 * level;
+      // movable blocks of the level, ascending
+      sel::k_sel_keys<false><<<blocks_for(d0, 256), 256, 0, stream>>>(d_block_scores, (uint32_t)offsets[level], d0, d_sel_keys[0], sc + 0);
+      size_t bytes = sel_tmp_bytes;
+      DCG_CUDA_TRY(cub::DeviceRadixSort::SortKeys(d_sel_tmp, bytes, d_sel_keys[0], d_sel_keys[1], (int)d0, 0, 64, stream));
+      // only the first l entries of the sorted block list are needed: keep them in the tail of buffer 0's space? no —
+      // copy them aside (l <= d0 <= M)
+      DCG_CUDA_TRY(cudaMemcpyAsync(d_sort_keys64_sel(), d_sel_keys[1], std::min<uint64_t>(l, d0) * 8, cudaMemcpyDeviceToDevice, stream));
+      // destinations of level + 1, descending
+      sel::k_sel_keys<true><<<blocks_for(d1, 256), 256, 0, stream>>>(d_sub_scores, (uint32_t)(8 * offsets[level + 1]), d1, d_sel_keys[0], sc + 1);
+      bytes = sel_tmp_bytes;
+      DCG_CUDA_TRY(cub::DeviceRadixSort::SortKeys(d_sel_tmp, bytes, d_sel_keys[0], d_sel_keys[1], (int)d1, 0, 64, stream));
+      sel::k_sel_match_init<<<1, 1, 0, stream>>>(sc, (uint32_t)l);
+      sel::k_sel_match<<<blocks_for(l, 256), 256, 0, stream>>>(d_block_scores, d_sub_scores, d_sort_keys64_sel(), d_sel_keys[1], sc);
+      sel::k_sel_apply<<<blocks_for(l, 256), 256, 0, stream>>>(d_block_scores, d_sort_keys64_sel(), d_sel_keys[1], sc, d_sel_mc + upper, d_sel_dc + upper);
+      launches += 7;
+      upper += l;
+    }
+    DCG_CUDA_TRY(cudaMemcpyAsync(h_sel_sc, d_sel_sc, 4 * kMaxLevels * 4, cudaMemcpyDeviceToHost, stream));
+    DCG_CUDA_TRY(cudaStreamSynchronize(stream));
+    uint64_t n_move = 0;
+    for (int level = 0; level < levels - 1; level++) {
+      if (lim[level] == 0) continue;
+      const uint64_t matches = need[level] ? h_sel_sc[4 * level + 3] : 0;
+      move_limit[level] = (uint64_t)(matches * 1.2f);  // :420
+      if (matches == 0) continue;
+      DCG_CUDA_TRY(cudaMemcpyAsync(d_to_move + n_move, d_sel_mc + base[level], matches * 4, cudaMemcpyDeviceToDevice, stream));
+      DCG_CUDA_TRY(cudaMemcpyAsync(d_dest + n_move, d_sel_dc + base[level], matches * 4, cudaMemcpyDeviceToDevice, stream));
+      n_move += matches;
+    }
+    if (n_move > 0) {
+      const uint32_t n = (uint32_t)n_move;
+      k_dc_move_prepare<<<blocks_for(n, 256), 256, 0, stream>>>(T, d_to_move, d_dest, n, d_new_posl);
+      k_dc_move_commit<<<blocks_for(n, 256), 256, 0, stream>>>(T, kp, d_to_move, d_dest, n, d_new_posl, d_flags);
+      k_dc_map_insert<<<blocks_for(n, 256), 256, 0, stream>>>(T, kp, d_to_move, n);
+      launches += 3;
+      DCG_CUDA_TRY(cudaMemcpyAsync(d_touched, d_to_move, (size_t)n * 4, cudaMemcpyDeviceToDevice, stream));  // :433-434
+      num_touched += n;
+      n_moved += n;
+    }
+    return DCG_OK;
+  }
+  // the first l sorted block keys of a level, kept while buffer 1 is reused for the destinations (8 B x M)
+  unsigned long long *sel_mc_keys = nullptr;
+  unsigned long long *d_sort_keys64_sel() {
+    if (!sel_mc_keys) cudaMalloc(&sel_mc_keys, (size_t)M * 8);
+    return sel_mc_keys;
+  }
+
+  // Candidate lists of refineSubblocks, compacted on the device (sel::k_sel_*): for every level with room and
+  // candidates, the ids with score > 1e-4 in ascending order — the exact sequence of the reference's host scan (:455-463).
+  // Where the list fits the room (n <= limit) it IS the reference's result; where it does not, the reference keeps the
+  // `limit` largest ids in the order std::nth_element leaves them (libstdc++-specific): that level's compact list goes
+  // to the host for the same call on the same sequence (selection == 0), or its tail is taken in ascending order
+  // (selection == 1).  No score array crosses PCIe either way.
+  int refine_lists_device(const std::vector<uint64_t> &limits, uint64_t &n_ref, RefineGroups &G, std::vector<uint64_t> &added) {
+    DCG_TRY(ensure_sel_storage());
+    uint32_t *cand = reinterpret_cast<uint32_t *>(d_sel_keys[0]);
+    for (int level = 1; level < levels; level++) {
+      const uint64_t limit = limits[level];
+      G.start[level - 1] = (uint32_t)n_ref;
+      G.base[level - 1] = (uint32_t)(offsets[level - 1] + loads[level - 1]);
+      const uint64_t n = h_summary->n_refine[level];
+      if (limit == 0 || n == 0) continue;
+      const uint32_t first = (uint32_t)(8 * offsets[level]), cnt = (uint32_t)(8 * max_blocks[level]);
+      const unsigned nct = blocks_for(cnt, sel::kSelCta);
+      sel::k_sel_count<<<nct, sel::kSelCta, 0, stream>>>(d_sub_scores, first, cnt, 1e-4f, d_sel_cta);
+      sel::k_sel_scan<<<1, sel::kSelCta, 0, stream>>>(d_sel_cta, nct, d_sel_cta + nct);
+      sel::k_sel_scatter<<<nct, sel::kSelCta, 0, stream>>>(d_sub_scores, first, cnt, 1e-4f, d_sel_cta, cand);
+      launches += 3;
+      const uint64_t take = std::min(n, limit);
+      if (n <= limit || ext.selection == 1) {
+        n_device_selections++;
+        DCG_CUDA_TRY(cudaMemcpyAsync(d_dest + n_ref, cand + (n - take), take * 4, cudaMemcpyDeviceToDevice, stream));
+      } else {
+        n_selection_fallbacks++;
+        n_host_selections++;
+        uint32_t *di = h_dest + n_ref;
+        DCG_CUDA_TRY(cudaMemcpyAsync(di, cand, n * 4, cudaMemcpyDeviceToHost, stream));
+        DCG_CUDA_TRY(cudaStreamSynchronize(stream));
+        std::nth_element(di, di + limit, di + n, std::greater<uint32_t>{});  // keeps the LARGEST ids (App. B-4)
+        DCG_CUDA_TRY(cudaMemcpyAsync(d_dest + n_ref, di, take * 4, cudaMemcpyHostToDevice, stream));
+        DCG_CUDA_TRY(cudaStreamSynchronize(stream));  // h_dest is reused by the next level
+      }
+      added[level - 1] = take;
+      n_ref += take;
+    }
+    return DCG_OK;
+  }
+
   // refineSubblocks, :439-483.  Levels with no room (limit == 0, the normal case once the pool is
   // full) or no candidate (device-counted) are skipped without copying scores.
   int refine_subblocks(uint32_t &num_touched) {
@@ -1043,13 +1172,30 @@ struct DCGridSim : dcg_sim {
     if (!any) return DCG_OK;
     DCG_TRY(compute_scores(false));
     any = false;
+    for (int level = 1; level < levels; level++) any = any || (limits[level] > 0 && h_summary->n_refine[level] > 0);
+    if (!any) return DCG_OK;
+    if (!opt.host_selection || ext.selection == 1) {  // candidate lists compacted on the device
+      uint64_t n_ref = 0;
+      RefineGroups G{};
+      std::vector<uint64_t> added(levels, 0);
+      DCG_TRY(refine_lists_device(limits, n_ref, G, added));
+      if (n_ref > 0) {
+        const uint32_t n = (uint32_t)n_ref;
+        if ((size_t)num_touched + n > (size_t)2 * M) return fail(DCG_ERR_POOL, "touched list overflow");
+        k_dc_refine<<<blocks_for(n, 256), 256, 0, stream>>>(T, kp, d_dest, n, G, d_free, d_flags, d_touched, num_touched, d_counters);
+        launches++;
+        for (int l = 0; l < levels; l++) loads[l] += added[l];
+        sync_loads();
+        num_touched += n;
+        n_refined += n;
+      }
+      return DCG_OK;
+    }
     for (int level = 1; level < levels; level++) {
       if (limits[level] == 0 || h_summary->n_refine[level] == 0) continue;
-      any = true;
       DCG_CUDA_TRY(cudaMemcpyAsync(h_sub_scores + 8 * offsets[level], d_sub_scores + 8 * offsets[level], 8 * max_blocks[level] * 4,
                                    cudaMemcpyDeviceToHost, stream));
     }
-    if (!any) return DCG_OK;
     DCG_CUDA_TRY(cudaStreamSynchronize(stream));
     const float *ss = h_sub_scores;
     uint64_t n_ref = 0;

@@ -357,3 +357,127 @@ __global__ void __launch_bounds__(256) k_dc_ext_rebuild_maps(Pool T, KParams P) 
 
 }  // namespace ext
 }  // namespace dcg
+
+// ======================================================================================================================
+// Device-side selection of adaptTopology (north_star (1): warp-ballot and prefix-sum compaction; SURVEY App. B-8 stage 2)
+// ======================================================================================================================
+namespace dcg {
+namespace sel {
+
+constexpr int kSelCta = 1024;  // one element per thread: a CTA covers 1024 consecutive ids, a warp 32
+
+// Order-preserving compaction of the ids i in [first, first + n) with score[i] > thresh — the candidate scan of
+// refineSubblocks (fluid_simulation_dcgrid.cu:455-463: `if (subblockScores[i] > 1e-4f) list[n++] = i`) — in three
+// passes: per-CTA counts from warp ballots, an exclusive scan of the counts, and the scatter at
+// CTA offset + warp prefix + popc(ballot below the lane).  The output is in ascending id order, exactly the sequence the
+// reference's host loop produces.
+__device__ __forceinline__ uint32_t cta_rank(bool pred, uint32_t &cta_total) {
+  __shared__ uint32_t warp_sum[kSelCta / 32];
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const unsigned votes = __ballot_sync(0xFFFFFFFFu, pred);
+  if (lane == 0) warp_sum[warp] = __popc(votes);
+  __syncthreads();
+  uint32_t before = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < kSelCta / 32; w++) {
+    const uint32_t v = warp_sum[w];
+    before += w < (int)warp ? v : 0u;
+    total += v;
+  }
+  cta_total = total;
+  return before + __popc(votes & ((1u << lane) - 1u));
+}
+__global__ void __launch_bounds__(kSelCta) k_sel_count(const float *__restrict__ score, uint32_t first, uint32_t n, float thresh,
+                                                       uint32_t *__restrict__ cta_counts) {
+  const uint32_t i = blockIdx.x * kSelCta + threadIdx.x;
+  uint32_t total;
+  cta_rank(i < n && score[first + i] > thresh, total);
+  if (threadIdx.x == 0) cta_counts[blockIdx.x] = total;
+}
+// in-place exclusive scan of `n` counts by one CTA (n <= a few 10^4: chunks of 1024 with a running carry); total -> *sum
+__global__ void __launch_bounds__(kSelCta) k_sel_scan(uint32_t *__restrict__ counts, uint32_t n, uint32_t *__restrict__ sum) {
+  __shared__ uint32_t part[kSelCta / 32];
+  __shared__ uint32_t carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  for (uint32_t base = 0; base < n; base += kSelCta) {
+    const uint32_t i = base + threadIdx.x;
+    const uint32_t v = i < n ? counts[i] : 0u;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+      if ((int)lane >= o) incl += t;
+    }
+    if (lane == 31) part[warp] = incl;
+    __syncthreads();
+    uint32_t wbefore = 0, chunk = 0;
+#pragma unroll
+    for (int w = 0; w < kSelCta / 32; w++) {
+      const uint32_t pv = part[w];
+      wbefore += w < (int)warp ? pv : 0u;
+      chunk += pv;
+    }
+    const uint32_t carry = carry_s;
+    if (i < n) counts[i] = carry + wbefore + incl - v;
+    __syncthreads();
+    if (threadIdx.x == 0) carry_s = carry + chunk;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *sum = carry_s;
+}
+__global__ void __launch_bounds__(kSelCta) k_sel_scatter(const float *__restrict__ score, uint32_t first, uint32_t n, float thresh,
+                                                         const uint32_t *__restrict__ cta_offsets, uint32_t *__restrict__ out) {
+  const uint32_t i = blockIdx.x * kSelCta + threadIdx.x;
+  const bool pred = i < n && score[first + i] > thresh;
+  uint32_t total;
+  const uint32_t r = cta_rank(pred, total);
+  if (pred) out[cta_offsets[blockIdx.x] + r] = first + i;
+}
+
+// Sort keys of the total-order selection (dcg_ext_params.selection == 1).  Non-negative floats order like their bit
+// patterns: blocks ascending by (score, slot) -> key = bits << 32 | slot; destinations descending by score, ascending by
+// id -> key = ~bits << 32 | id.  Negative scores (unmovable / unusable) get the all-ones key and sort behind everything.
+// counts[0] += number of valid keys (one atomic per warp).
+template <bool kDescending>
+__global__ void __launch_bounds__(256) k_sel_keys(const float *__restrict__ score, uint32_t first, uint32_t n, unsigned long long *__restrict__ keys,
+                                                  uint32_t *__restrict__ count) {
+  const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+  bool valid = false;
+  if (i < n) {
+    const float s = score[first + i];
+    valid = s >= 0.f;
+    const uint32_t bits = __float_as_uint(s);
+    keys[i] = valid ? ((unsigned long long)(kDescending ? ~bits : bits) << 32) | (unsigned long long)(first + i) : ~0ull;
+  }
+  const unsigned votes = __ballot_sync(0xFFFFFFFFu, valid);
+  if ((threadIdx.x & 31u) == 0 && votes) atomicAdd(count, (uint32_t)__popc(votes));
+}
+// sc[0] = valid blocks, sc[1] = valid destinations, -> sc[2] = K = min(l, sc[0], sc[1]), sc[3] = matches (starts at K)
+__global__ void k_sel_match_init(uint32_t *__restrict__ sc, uint32_t l) {
+  const uint32_t K = min(l, min(sc[0], sc[1]));
+  sc[2] = K;
+  sc[3] = K;
+}
+// the greedy rule (:410-418) on the two sorted lists: matches = first m with !(bs[mc[m]] < ss[dc[m]]) — block scores
+// ascend and destination scores descend along the lists, so the condition is monotone and the first failure is a minimum
+__global__ void __launch_bounds__(256) k_sel_match(const float *__restrict__ bs, const float *__restrict__ ss, const unsigned long long *__restrict__ mc,
+                                                   const unsigned long long *__restrict__ dc, uint32_t *__restrict__ sc) {
+  const uint32_t m = blockIdx.x * 256 + threadIdx.x;
+  if (m >= sc[2]) return;
+  if (!(bs[(uint32_t)mc[m]] < ss[(uint32_t)dc[m]])) atomicMin(&sc[3], m);
+}
+// the matched pairs -> lists; the parents that receive a block are protected for the next level's selection
+__global__ void __launch_bounds__(256) k_sel_apply(float *__restrict__ bs, const unsigned long long *__restrict__ mc, const unsigned long long *__restrict__ dc,
+                                                   const uint32_t *__restrict__ sc, uint32_t *__restrict__ to_move, uint32_t *__restrict__ dest) {
+  const uint32_t m = blockIdx.x * 256 + threadIdx.x;
+  if (m >= sc[3]) return;
+  const uint32_t b = (uint32_t)mc[m], d = (uint32_t)dc[m];
+  bs[d >> 3] = -FLT_MAX;
+  to_move[m] = b;
+  dest[m] = d;
+}
+
+}  // namespace sel
+}  // namespace dcg

@@ -760,7 +760,9 @@ __global__ void __launch_bounds__(256) k_fill_posl(int4 *p, size_t n) {
 // position (x-major like the ordered levels, then Morton).  Mirror structures hold field-space ids, the eight field
 // arrays are stored in field order, so the hot kernels are unchanged: they are simply handed the mirrored Pool.
 // Results cannot depend on the numbering: every cell is computed by the same expression from the same values.
-__global__ void __launch_bounds__(256) k_dc_resort_keys(Pool T, KParams P, int world, unsigned long long *__restrict__ keys,
+// slab_axis: the axis the ranks' slabs are stacked along (the longest axis of the domain: the cut surfaces are the
+// smallest cross-sections; x-slabs of a 512 x 512 x 4096 scene would have 8 x larger surfaces than z-slabs)
+__global__ void __launch_bounds__(256) k_dc_resort_keys(Pool T, KParams P, int world, int slab_axis, unsigned long long *__restrict__ keys,
                                                         uint32_t *__restrict__ vals) {
   const uint32_t b = blockIdx.x * 256 + threadIdx.x;
   if (b >= T.M) return;
@@ -782,8 +784,9 @@ __global__ void __launch_bounds__(256) k_dc_resort_keys(Pool T, KParams P, int w
       return v;
     };
     const unsigned long long morton = (spread3(x) << 2) | (spread3(y) << 1) | spread3(z);
-    // several ranks: slabs of 8 blocks along x first (the cut direction of the ordered levels), Morton inside
-    k = world > 1 ? ((unsigned long long)(x >> 3) << 32) | morton : morton;
+    // several ranks: slabs of 8 blocks along the stacking axis first, Morton inside
+    const uint32_t along = slab_axis == 0 ? x : (slab_axis == 1 ? y : z);
+    k = world > 1 ? ((unsigned long long)(along >> 3) << 32) | morton : morton;
   }
   keys[b] = ((unsigned long long)range << 56) | k;
   vals[b] = b;

@@ -103,11 +103,11 @@ def make_options(options=None) -> Options:
 
 class ExtParams(ctypes.Structure):
     """``struct dcg_ext_params`` (include/dcgrid_b200.h): extensions beyond the reference snapshot; all zero = off."""
-    _fields_ = [("struct_size", ctypes.c_uint32)] + [(n, ctypes.c_int32) for n in ("score_mode", "advection", "sources", "terrain")] + [
+    _fields_ = [("struct_size", ctypes.c_uint32)] + [(n, ctypes.c_int32) for n in ("score_mode", "advection", "sources", "terrain", "selection")] + [
         (n, ctypes.c_float) for n in (
             "buoyancy", "vapor_buoyancy", "smoke_weight", "ambient_temperature", "ambient_lapse", "adiabatic_lapse", "vorticity_confinement",
             "saturation_base", "saturation_slope", "condensation_rate", "latent_heat", "temperature_emission", "vapor_emission", "ambient_vapor",
-            "terrain_height", "terrain_wavelength")] + [("reserved", ctypes.c_int32 * 11)]
+            "terrain_height", "terrain_wavelength")] + [("reserved", ctypes.c_int32 * 10)]
 
 
 def make_ext(**kw) -> ExtParams:

@@ -126,6 +126,16 @@ typedef struct dcg_ext_params {
                                        vorticity confinement and condensation in ONE fused pass               */
   int32_t terrain;               /* 1: solids = height-field terrain instead of the sphere (src/sdf.cuh:20);
                                        needs SimParams.enable_additional_solids                               */
+  int32_t selection;             /* move / refine selection of adaptTopology.
+                                    0: the reference's, verbatim (std::nth_element / std::sort with its comparators on
+                                       the host, fluid_simulation_dcgrid.cu:348-483: the outcome depends on libstdc++'s
+                                       treatment of ties and of a comparator that is not a strict weak order, so only the
+                                       same algorithm on the same sequence reproduces it);
+                                    1: a TOTAL order, evaluated entirely on the device: blocks by (score ascending, slot
+                                       ascending), destinations by (score descending, subblock id ascending), negative
+                                       scores excluded, the parents of ALL matched destinations protected, refinement
+                                       candidates in ascending id order keeping the largest ids.  Same greedy rule and
+                                       limits; a different, well-defined topology evolution                       */
   float buoyancy;                /* m/s^2 per unit of (theta - theta_ambient(h)) / ambient_temperature       */
   float vapor_buoyancy;          /* m/s^2 per unit of vapor mixing ratio                                     */
   float smoke_weight;            /* m/s^2 per unit of density (condensed water / smoke loading)              */
@@ -142,7 +152,7 @@ typedef struct dcg_ext_params {
   float ambient_vapor;           /* initial / far-field vapor mixing ratio                                   */
   float terrain_height;          /* peak height of the terrain, level-0 cells                                */
   float terrain_wavelength;      /* hill spacing, level-0 cells                                              */
-  int32_t reserved[11];
+  int32_t reserved[10];
 } dcg_ext_params;
 DCG_API int dcg_default_ext_params(dcg_ext_params *out);   /* all switches off, plausible coefficients       */
 /* Takes effect at the next call; changing `terrain`, `sources` or the ambient profile re-initialises nothing by

@@ -1293,6 +1293,29 @@ struct DCGridOracle : orc_sim {
       u64 l = std::min({d0, d1, loads[level], full_blocks[level] - loads[level]});
       if (move_limit[level] > 0) l = std::min(l, move_limit[level]);
       if (l == 0) continue;
+      if (E.selection == 1) {
+        // EXTENSION (dcg_ext_params.selection == 1): the same greedy rule on a TOTAL order — movable blocks by (score
+        // ascending, slot ascending), destinations by (score descending, id ascending), negative scores excluded —
+        // so that the outcome does not depend on how a sort library treats ties and a non-strict-weak comparator
+        std::vector<u64> mcv, dcv;
+        for (u64 b = offsets[level]; b < offsets[level] + d0; b++)
+          if (block_scores[b] >= 0.f) mcv.push_back(b);
+        std::stable_sort(mcv.begin(), mcv.end(), [this](u64 a, u64 b) { return block_scores[a] < block_scores[b]; });
+        for (u64 sb = 8 * offsets[level + 1]; sb < 8 * offsets[level + 1] + d1; sb++)
+          if (sub_scores[sb] >= 0.f) dcv.push_back(sb);
+        std::stable_sort(dcv.begin(), dcv.end(), [this](u64 a, u64 b) { return sub_scores[a] > sub_scores[b]; });
+        const u64 K = std::min<u64>({l, mcv.size(), dcv.size()});
+        u64 matches = 0;
+        while (matches < K && block_scores[mcv[matches]] < sub_scores[dcv[matches]]) matches++;
+        for (u64 i = 0; i < matches; i++) {
+          block_scores[dcv[i] / 8] = -FLT_MAX;  // the parents that receive a block stay where they are in this pass
+          to_move[n_move + i] = mcv[i];
+          dest[n_move + i] = dcv[i];
+        }
+        move_limit[level] = (u64)(matches * 1.2f);
+        n_move += matches;
+        continue;
+      }
       u64 *mc = to_move.data() + n_move;
       std::iota(mc, mc + d0, offsets[level]);
       if (d0 <= l)
@@ -1337,7 +1360,10 @@ struct DCGridOracle : orc_sim {
       u64 n = 0;
       for (u64 i = start; i < end; i++)
         if (sub_scores[i] > 1e-4f) di[n++] = i;
-      if (n > limit) std::nth_element(di, di + limit, di + n, std::greater<u64>{});
+      if (n > limit) {
+        if (E.selection == 1) std::copy(di + (n - limit), di + n, di);  // EXTENSION: the largest ids, in ascending order
+        else std::nth_element(di, di + limit, di + n, std::greater<u64>{});
+      }
       n_ref += std::min(n, limit);
     }
     if (n_ref > 0) {

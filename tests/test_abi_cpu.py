@@ -86,6 +86,22 @@ def test_options_struct_matches_the_header():
     assert make_options({"jacobi": 2}).jacobi == 2
 
 
+def test_ext_params_struct_matches_the_header():
+    """struct dcg_ext_params: same field order and types as the ctypes mirror; the defaults switch every extension off."""
+    from dcgrid_b200.params import ExtParams, make_ext
+
+    e = make_ext()
+    assert e.struct_size == ctypes.sizeof(ExtParams)
+    assert (e.score_mode, e.advection, e.sources, e.terrain, e.selection) == (0, 0, 0, 0, 0)
+    assert e.ambient_temperature > 0 and e.terrain_wavelength > 0
+    text = open(HEADER).read()
+    body = text[text.index("typedef struct dcg_ext_params {"):text.index("} dcg_ext_params;")]
+    declared = re.findall(r"^\s+(?:u?int32_t|float)\s+(\w+)", body, flags=re.M)
+    assert declared == [f[0] for f in ExtParams._fields_], "field order of ExtParams vs. struct dcg_ext_params"
+    with pytest.raises(KeyError):
+        make_ext(no_such_field=1)
+
+
 def test_null_handles_are_rejected_not_dereferenced():
     L = _lib.load()
     assert L.dcg_step(None, 1) != 0

@@ -20,6 +20,10 @@ CASES = {
     "terrain": dict(TERRAIN),
     "sources_maccormack": dict(sources=1, advection=1),
     "cloud_scene": dict(sources=1, advection=1, score_mode=1, **TERRAIN),  # BASELINE configs[2]/[3] in small
+    # total-order selection evaluated entirely on the device (radix sorts + ballot / prefix-sum compaction)
+    "device_selection_geometric": dict(selection=1),
+    "device_selection_flow": dict(selection=1, score_mode=1),
+    "wildfire_scene": dict(selection=1, score_mode=1, sources=1, advection=1),  # BASELINE configs[3] in small
 }
 
 
@@ -48,6 +52,7 @@ def make_pair(d, M, kw, options=None):
 def test_extension_matches_its_cpu_specification(gpu, case):
     kw = CASES[case]
     sim, orc = make_pair(64, 4096, kw)
+    host0 = sim.info("host_selections")  # (the constructor's own reset ran before the extension was switched on)
     act = assert_same_topology(sim, orc, "after reset")
     assert_same_fields(sim, orc, [f for f in fields_of(kw) if f != "vorticity"], act, "after reset")
     for s in range(8):
@@ -62,6 +67,8 @@ def test_extension_matches_its_cpu_specification(gpu, case):
         assert_same_fields(sim, orc, fields_of(kw), act, f"step {s}")
     if kw.get("score_mode"):
         assert orc.level_table()["loads"][0] > 0 and sim.counters()[7] == 0, "flow-driven refinement follows the plume and never reaches a fixed point"
+    if kw.get("selection"):
+        assert sim.info("device_selections") > 0 and sim.info("host_selections") == host0 and sim.counters()[2] > 0, "blocks moved, no host selection"
     if kw.get("sources"):
         assert orc.field("density").max() > 0 and float(np.ptp(orc.field("temperature")[np.repeat(act, 64)])) > 1.0
 
