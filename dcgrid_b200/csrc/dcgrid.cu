@@ -52,6 +52,7 @@ struct DCGridSim : dcg_sim {
   void *d_sort_tmp64 = nullptr;
   size_t sort_tmp64_bytes = 0;
   bool use_resort = true;
+  bool sort_ordered = false;  // several ranks stacked along y or z: the ordered levels are renumbered along that axis too
   int resort_every = 32;      // topology changes between re-sorts during the transient (0 = only at the fixed point)
   int changes_since_resort = 0;
   uint64_t n_resorts = 0;
@@ -813,6 +814,8 @@ struct DCGridSim : dcg_sim {
     DCG_CUDA_TRY(cudaMalloc(&Tf.child, (size_t)M * 8 * 4));
     DCG_CUDA_TRY(cudaMalloc(&Tf.apron, (size_t)M * kAV * 4));
     for (int l = 0; l < sparse; l++) DCG_CUDA_TRY(cudaMalloc(&Tf.map[l], map_size[l] * 4));
+    if (sort_ordered)
+      for (int l = sparse; l < levels; l++) DCG_CUDA_TRY(cudaMalloc(&Tf.map[l], full_blocks[l] * 4));
     DCG_CUDA_TRY(cudaMalloc(&d_perm_new, (size_t)M * 4));
     DCG_CUDA_TRY(cudaMalloc(&d_sort_keys64[0], (size_t)M * 8));
     DCG_CUDA_TRY(cudaMalloc(&d_sort_keys64[1], (size_t)M * 8));
@@ -834,12 +837,22 @@ struct DCGridSim : dcg_sim {
     if (full) k_dc_mirror_apron<<<blocks_for((size_t)M * kAV, 256), 256, 0, stream>>>(T, Tf, d_perm);
     for (int l = 0; l < sparse; l++) k_dc_mirror_map<<<blocks_for(map_size[l], 256), 256, 0, stream>>>(T.map[l], Tf.map[l], map_size[l], d_perm);
     launches += 2 + sparse;
+    if (sort_ordered) {  // the mirror looks every level up through a dense map
+      Tf.sparse_levels = levels;
+      if (full) {
+        for (int l = sparse; l < levels; l++) cudaMemsetAsync(Tf.map[l], 0xff, full_blocks[l] * 4, stream);
+        ext::k_dc_ext_rebuild_maps<<<blocks_for(M, 256), 256, 0, stream>>>(Tf, kp);
+        launches++;
+      }
+    }
   }
   // new permutation (active blocks of every sparse level sorted by position), fields moved into the new order
+  int slab_axis = 0;
   int resort() {
+    slab_axis = (gz > gx && gz >= gy) ? 2 : (gy > gx ? 1 : 0);  // longest axis; x on ties (the construction order of the ordered levels)
+    sort_ordered = world > 1 && slab_axis != 0;
     DCG_TRY(ensure_mirror_storage());
-    const int slab_axis = (gz > gx && gz >= gy) ? 2 : (gy > gx ? 1 : 0);  // longest axis; x on ties (the order of the ordered levels)
-    k_dc_resort_keys<<<blocks_for(M, 256), 256, 0, stream>>>(T, kp, world, slab_axis, d_sort_keys64[0], d_order_vals);
+    k_dc_resort_keys<<<blocks_for(M, 256), 256, 0, stream>>>(T, kp, world, slab_axis, sort_ordered ? 1 : 0, d_sort_keys64[0], d_order_vals);
     size_t bytes = sort_tmp64_bytes;
     DCG_CUDA_TRY(cub::DeviceRadixSort::SortPairs(d_sort_tmp64, bytes, d_sort_keys64[0], d_sort_keys64[1], d_order_vals, d_order_keys[0], (int)M, 0, 64,
                                                  stream));
@@ -1436,10 +1449,11 @@ struct DCGridSim : dcg_sim {
       const TileRuns &R = w.level[l];
       const unsigned tiles = run_total(R);
       if (tiles == 0) return;
-      if (use_pipe && jacobi8 && blocks_for(loads[l], kB4) >= pipe_min_tiles) {
+      // (the tiles THIS rank sweeps decide: half of a level that fills one GPU does not fill two)
+      if (use_pipe && jacobi8 && tiles >= pipe_min_tiles) {
         const unsigned grid = std::min<unsigned>(tiles, (unsigned)jacobi8_ctas);
         launch_pdl(k_dc_jacobi_pipe8, dim3(grid), dim3(kJ8Threads), kJacobiPipeSmem, hot(), kp, R, l, in, out, div, snake ? sweep_parity : 0);
-      } else if (use_pipe && blocks_for(loads[l], kB4) >= pipe_min_tiles) {
+      } else if (use_pipe && tiles >= pipe_min_tiles) {
         const unsigned grid = std::min<unsigned>(tiles, (unsigned)jacobi_pipe_ctas);
         launch_pdl(k_dc_jacobi_pipe, dim3(grid), dim3(kCTA4), kJacobiPipeSmem, hot(), kp, R, l, in, out, div, snake ? sweep_parity : 0);
       } else {

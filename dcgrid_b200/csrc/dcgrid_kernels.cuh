@@ -762,8 +762,11 @@ __global__ void __launch_bounds__(256) k_fill_posl(int4 *p, size_t n) {
 // Results cannot depend on the numbering: every cell is computed by the same expression from the same values.
 // slab_axis: the axis the ranks' slabs are stacked along (the longest axis of the domain: the cut surfaces are the
 // smallest cross-sections; x-slabs of a 512 x 512 x 4096 scene would have 8 x larger surfaces than z-slabs)
-__global__ void __launch_bounds__(256) k_dc_resort_keys(Pool T, KParams P, int world, int slab_axis, unsigned long long *__restrict__ keys,
-                                                        uint32_t *__restrict__ vals) {
+// sort_ordered: the fully allocated ("ordered") levels are renumbered too — their slot order is x-major by
+// construction (dcgrid_utils.cuh:172-183), i.e. x-slabs; with another stacking axis the mirror addresses them through
+// dense maps like the sparse levels (Tf.sparse_levels = levels) so that every level is cut along the same axis
+__global__ void __launch_bounds__(256) k_dc_resort_keys(Pool T, KParams P, int world, int slab_axis, int sort_ordered,
+                                                        unsigned long long *__restrict__ keys, uint32_t *__restrict__ vals) {
   const uint32_t b = blockIdx.x * 256 + threadIdx.x;
   if (b >= T.M) return;
   int range = T.levels;  // level whose slot range holds b (slots past the last range stay where they are)
@@ -771,7 +774,7 @@ __global__ void __launch_bounds__(256) k_dc_resort_keys(Pool T, KParams P, int w
     if (b >= T.offsets[l] && b < T.offsets[l] + T.max_blocks[l]) range = l;
   const int4 pl = T.posl[b];
   unsigned long long k = 0xFFFFFF00000000ull + b;  // free slots: behind the active ones, in slot order
-  if (range >= T.sparse_levels) {
+  if (range >= T.sparse_levels && !sort_ordered) {
     k = b;  // ordered levels are addressed arithmetically (ordered_index): identity
   } else if (pl.w != kFree) {
     const uint32_t x = (uint32_t)(pl.x << pl.w) >> 2, y = (uint32_t)(pl.y << pl.w) >> 2, z = (uint32_t)(pl.z << pl.w) >> 2;

@@ -50,6 +50,21 @@ def test_dcgrid_sharded_equals_single_gpu(gpu, d, M, world, solids, steps, unit)
     assert np.abs(one.field("density")).max() > 0
 
 
+@pytest.mark.parametrize("size,M,world", [((32, 32, 128), 1500, 4), ((32, 96, 32), 1200, 3), ((128, 32, 32), 1500, 2)])
+def test_dcgrid_sharded_slabs_follow_the_longest_axis(gpu, size, M, world):
+    """Non-cubic domains: the ranks' slabs are stacked along the longest axis; for y / z stacking the ordered levels
+    are renumbered too (dense maps in the mirror).  Results must not depend on any of it."""
+    p = scene_params(*size, solids=size[0] <= 32)  # (the sphere's radius scales with gx: it would fill a 128 x 32 x 32 domain)
+    one = FluidSimulationDCGrid(size, M, p)
+    sh = FluidSimulationDCGridSharded(size, M, p, world, options={"resort_every": 2})
+    one.step(9)
+    sh.step(9)
+    _same_state(one, sh, ("density", "velocity", "fluidity"), f"{size} world {world}")
+    assert sh.info("resorts") > 0 and np.abs(one.field("density")).max() > 0
+    pos = np.random.default_rng(5).uniform(0, 1, size=(500, 3)).astype(np.float32) * np.float32(size)
+    np.testing.assert_array_equal(_bits(one.sampleField("velocity", pos, True)), _bits(sh.sampleField("velocity", pos, True)))
+
+
 def test_dcgrid_sharded_vs_oracle_graph_path(gpu):
     d, M = 64, 2000
     p = scene_params(d, solids=True)
