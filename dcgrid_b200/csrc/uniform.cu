@@ -65,11 +65,19 @@ __device__ __forceinline__ USample u_sample(const KParams &P, float px, float py
   const int xa = clampi(s.x0, 0, P.gx - 1), xb = clampi(s.x0 + 1, 0, P.gx - 1);
   const int ya = clampi(s.y0, 0, P.gy - 1), yb = clampi(s.y0 + 1, 0, P.gy - 1);
   const int za = clampi(s.z0, 0, P.gz - 1), zb = clampi(s.z0 + 1, 0, P.gz - 1);
-  s.id[0] = lidx(P, xa, ya, za); s.id[1] = lidx(P, xa, ya, zb);
-  s.id[2] = lidx(P, xa, yb, za); s.id[3] = lidx(P, xa, yb, zb);
-  s.id[4] = lidx(P, xb, ya, za); s.id[5] = lidx(P, xb, ya, zb);
-  s.id[6] = lidx(P, xb, yb, za); s.id[7] = lidx(P, xb, yb, zb);
+  // one full index, the other seven by adding the (0 or 1 cell) steps: the kernels that gather are bound by instruction
+  // issue, not by memory (ncu: 71 % of the issue slots, 500 warp instructions per 32 cells)
+  const uint64_t base = lidx(P, xa, ya, za);
+  const uint64_t ox = (uint64_t)(xb - xa), oy = (uint64_t)(yb - ya) * P.gx, oz = (uint64_t)(zb - za) * P.gx * P.gy;
+  s.id[0] = base; s.id[1] = base + oz;
+  s.id[2] = base + oy; s.id[3] = base + oy + oz;
+  s.id[4] = base + ox; s.id[5] = base + ox + oz;
+  s.id[6] = base + ox + oy; s.id[7] = base + ox + oy + oz;
   return s;
+}
+// true iff all 8 corners lie inside the domain: the boundary conditions are the identity there (sim_utils.cu:24-55)
+__device__ __forceinline__ bool u_inside(const KParams &P, const USample &s) {
+  return s.x0 >= 0 && s.y0 >= 0 && s.z0 >= 0 && s.x0 + 1 < P.gx && s.y0 + 1 < P.gy && s.z0 + 1 < P.gz;
 }
 
 // k_uniform_advect_velocity, uniformgrid_fluid.cu:50-67,88-95
@@ -93,10 +101,11 @@ __global__ void __launch_bounds__(256) k_u_advect_velocity(KParams P, const floa
   float3 out = make_float3(0.f, 0.f, 0.f);
   if (!(W.acc < 1e-6f)) {
     float vx[8], vy[8], vz[8];
+    const bool inside = u_inside(P, s);
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-      const float3 v = velocity_bc(P, make_float3(c[k].x, c[k].y, c[k].z), s.x0 + ((k >> 2) & 1), s.y0 + ((k >> 1) & 1),
-                                   s.z0 + (k & 1), 1);
+      float3 v = make_float3(c[k].x, c[k].y, c[k].z);
+      if (!inside) v = velocity_bc(P, v, s.x0 + ((k >> 2) & 1), s.y0 + ((k >> 1) & 1), s.z0 + (k & 1), 1);
       vx[k] = v.x; vy[k] = v.y; vz[k] = v.z;
     }
     out = make_float3(blend8(vx, W.w), blend8(vy, W.w), blend8(vz, W.w));
@@ -124,9 +133,11 @@ __global__ void __launch_bounds__(256) k_u_advect_density(KParams P, const float
   const Weights8 W = corner_weights(f, s.fx, s.fy, s.fz);
   float out = 0.f;
   if (!(W.acc < 1e-6f)) {
+    if (!u_inside(P, s)) {
 #pragma unroll
-    for (int k = 0; k < 8; k++)
-      q[k] = density_bc(P, q[k], s.x0 + ((k >> 2) & 1), s.y0 + ((k >> 1) & 1), s.z0 + (k & 1), 1);
+      for (int k = 0; k < 8; k++)
+        q[k] = density_bc(P, q[k], s.x0 + ((k >> 2) & 1), s.y0 + ((k >> 1) & 1), s.z0 + (k & 1), 1);
+    }
     out = blend8(q, W.w);
   }
   qout[i] = out;
@@ -159,12 +170,16 @@ __global__ void __launch_bounds__(256) k_u_advect_both(KParams P, const float4 *
   float qo = 0.f;
   if (!(W.acc < 1e-6f)) {
     float vx[8], vy[8], vz[8];
+    const bool inside = u_inside(P, s);
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-      const int cx = s.x0 + ((k >> 2) & 1), cy = s.y0 + ((k >> 1) & 1), cz = s.z0 + (k & 1);
-      const float3 v = velocity_bc(P, make_float3(c[k].x, c[k].y, c[k].z), cx, cy, cz, 1);
+      float3 v = make_float3(c[k].x, c[k].y, c[k].z);
+      if (!inside) {
+        const int cx = s.x0 + ((k >> 2) & 1), cy = s.y0 + ((k >> 1) & 1), cz = s.z0 + (k & 1);
+        v = velocity_bc(P, v, cx, cy, cz, 1);
+        q[k] = density_bc(P, q[k], cx, cy, cz, 1);
+      }
       vx[k] = v.x; vy[k] = v.y; vz[k] = v.z;
-      q[k] = density_bc(P, q[k], cx, cy, cz, 1);
     }
     vo = make_float3(blend8(vx, W.w), blend8(vy, W.w), blend8(vz, W.w));
     qo = blend8(q, W.w);
@@ -222,6 +237,91 @@ __global__ void __launch_bounds__(256) k_u_jacobi(KParams P, int level, uint64_t
   const float pd = in[y > 0 ? i - sy : i], pu = in[y < h - 1 ? i + sy : i];
   const float pb = in[z > 0 ? i - sz : i], pf = in[z < d - 1 ? i + sz : i];
   out[i] = (pl + pr + pd + pu + pb + pf - alpha * div[i]) / 6.f;
+}
+
+// ---- z-marching variants (sm_100a tuning; profiles/README.md r2h) --------------------------------------------------
+// ncu on the one-thread-per-cell kernels above: the Jacobi sweep issues 120 warp instructions per 32 cells (64-bit index
+// arithmetic, boundary selects, the generic division) and sits at 79 % of the issue slots with DRAM traffic exactly at
+// its 12 B/cell; the divergence keeps the L1 data pipe 99 % busy with six 16-byte neighbour loads per cell.  Here a
+// thread marches along z and keeps its column's three planes in registers, so that the z neighbours cost nothing, the x
+// neighbours come from the adjacent lanes by shuffle (only the two edge lanes of a warp load), and the index arithmetic
+// is paid once per thread: 4 cells per thread and plane for the scalar fields (one float4), 1 cell for the packed
+// velocity.  Same expressions in the same order; x / 6.f through div6() (bit-identical, common.cuh).
+constexpr int ZTX = 32, ZTY = 8;  // 256 threads: a warp covers one x row of the tile
+
+__global__ void __launch_bounds__(ZTX * ZTY) k_u_jacobi_zm(KParams P, int level, uint64_t off, const float *__restrict__ in, float *__restrict__ out,
+                                                           const float *__restrict__ div, int zc) {
+  const int w = P.gx >> level, h = P.gy >> level, d = P.gz >> level;
+  const int x = 4 * (blockIdx.x * ZTX + threadIdx.x), y = blockIdx.y * ZTY + threadIdx.y;
+  const int z0 = blockIdx.z * zc, z1 = min(z0 + zc, d);
+  const int scale = 1 << level;
+  const float alpha = P.dx * P.dx * scale * scale;
+  const size_t sy = (size_t)w, sz = (size_t)w * h;
+  const size_t col = off + (size_t)y * w + x;  // + z * sz
+  const size_t dnrow = y > 0 ? col - sy : col, uprow = y < h - 1 ? col + sy : col;
+  const unsigned lane = threadIdx.x;
+  const bool left_edge = lane == 0, right_edge = lane == ZTX - 1;
+  auto ld4 = [&](size_t i) { return *reinterpret_cast<const float4 *>(in + i); };
+  float4 cur = ld4(col + (size_t)z0 * sz);
+  float4 prev = z0 > 0 ? ld4(col + (size_t)(z0 - 1) * sz) : cur;
+  for (int z = z0; z < z1; z++) {
+    const size_t zo = (size_t)z * sz;
+    const float4 next = z < d - 1 ? ld4(col + zo + sz) : cur;
+    const float4 dn = ld4(dnrow + zo), up = ld4(uprow + zo);
+    const float4 dv = *reinterpret_cast<const float4 *>(div + col + zo);
+    float xl = __shfl_up_sync(0xFFFFFFFFu, cur.w, 1), xr = __shfl_down_sync(0xFFFFFFFFu, cur.x, 1);
+    if (left_edge) xl = x > 0 ? in[col + zo - 1] : cur.x;
+    if (right_edge) xr = x + 4 < w ? in[col + zo + 4] : cur.w;
+    float4 o;
+    o.x = div6(xl + cur.y + dn.x + up.x + prev.x + next.x - alpha * dv.x);
+    o.y = div6(cur.x + cur.z + dn.y + up.y + prev.y + next.y - alpha * dv.y);
+    o.z = div6(cur.y + cur.w + dn.z + up.z + prev.z + next.z - alpha * dv.z);
+    o.w = div6(cur.z + xr + dn.w + up.w + prev.w + next.w - alpha * dv.w);
+    *reinterpret_cast<float4 *>(out + col + zo) = o;
+    prev = cur;
+    cur = next;
+  }
+}
+
+__global__ void __launch_bounds__(ZTX * ZTY) k_u_divergence_zm(KParams P, const float4 *__restrict__ vw, float *__restrict__ div, float *__restrict__ p,
+                                                               float *__restrict__ tp, int zc) {
+  const int x = blockIdx.x * ZTX + threadIdx.x, y = blockIdx.y * ZTY + threadIdx.y;
+  const int z0 = blockIdx.z * zc, z1 = min(z0 + zc, P.gz);
+  const size_t sy = (size_t)P.gx, sz = (size_t)P.gx * P.gy;
+  const size_t col = (size_t)y * P.gx + x;
+  const size_t dnrow = y > 0 ? col - sy : col, uprow = y < P.gy - 1 ? col + sy : col;
+  const unsigned lane = threadIdx.x;
+  const bool left_edge = lane == 0, right_edge = lane == ZTX - 1;
+  // boundary conditions only substitute values of neighbours OUTSIDE the domain (sim_utils.cu:24-39)
+  const bool xy_inner = x > 0 && x < P.gx - 1 && y > 0 && y < P.gy - 1;
+  float4 cur = vw[col + (size_t)z0 * sz];
+  float4 prev = z0 > 0 ? vw[col + (size_t)(z0 - 1) * sz] : cur;
+  for (int z = z0; z < z1; z++) {
+    const size_t zo = (size_t)z * sz;
+    const float4 next = z < P.gz - 1 ? vw[col + zo + sz] : cur;
+    const float4 dn = vw[dnrow + zo], up = vw[uprow + zo];
+    float4 l, r;
+    l.x = __shfl_up_sync(0xFFFFFFFFu, cur.x, 1); l.w = __shfl_up_sync(0xFFFFFFFFu, cur.w, 1);
+    r.x = __shfl_down_sync(0xFFFFFFFFu, cur.x, 1); r.w = __shfl_down_sync(0xFFFFFFFFu, cur.w, 1);
+    l.y = l.z = r.y = r.z = 0.f;
+    if (left_edge) l = x > 0 ? vw[col + zo - 1] : cur;
+    if (right_edge) r = x < P.gx - 1 ? vw[col + zo + 1] : cur;
+    float lx = l.x, rx = r.x, dy = dn.y, uy = up.y, bz = prev.z, fz = next.z;
+    if (!(xy_inner && z > 0 && z < P.gz - 1)) {
+      lx = velocity_bc(P, make_float3(l.x, l.y, l.z), x - 1, y, z, 1).x;
+      rx = velocity_bc(P, make_float3(r.x, r.y, r.z), x + 1, y, z, 1).x;
+      dy = velocity_bc(P, make_float3(dn.x, dn.y, dn.z), x, y - 1, z, 1).y;
+      uy = velocity_bc(P, make_float3(up.x, up.y, up.z), x, y + 1, z, 1).y;
+      bz = velocity_bc(P, make_float3(prev.x, prev.y, prev.z), x, y, z - 1, 1).z;
+      fz = velocity_bc(P, make_float3(next.x, next.y, next.z), x, y, z + 1, 1).z;
+    }
+    const size_t i = col + zo;
+    p[i] = 0.f;
+    tp[i] = 0.f;
+    div[i] = .5f * P.rdx * (r.w * rx - l.w * lx + up.w * uy - dn.w * dy + next.w * fz - prev.w * bz);
+    prev = cur;
+    cur = next;
+  }
 }
 
 // k_uniform_prolongate, uniformgrid_fluid.cu:206-237
@@ -444,15 +544,37 @@ struct UniformSim : dcg_sim {
     DCG_CUDA_TRY(cudaGetLastError());
     return DCG_OK;
   }
+  // z-marching kernels: the level's x extent in whole warps of float4 (128 cells), y in tiles of 8, 16-byte aligned rows
+  bool zm_ok(int l) const {
+    const int w = gx >> l, h = gy >> l;
+    return !opt.stencil && w % (4 * ZTX) == 0 && h % ZTY == 0 && level_off[l] % 4 == 0;
+  }
+  static int zm_chunk(int d) { return d >= 256 ? 32 : (d >= 32 ? 16 : d); }
+  void jacobi_sweep(int l, const float *in, float *out) {
+    if (zm_ok(l)) {
+      const int d = gz >> l, zc = zm_chunk(d);
+      k_u_jacobi_zm<<<dim3((gx >> l) / (4 * ZTX), (gy >> l) / ZTY, idiv_up(d, zc)), dim3(ZTX, ZTY), 0, stream>>>(kp, l, level_off[l], in, out, div, zc);
+    } else {
+      k_u_jacobi<<<grid_for(l), block(), 0, stream>>>(kp, l, level_off[l], in, out, div);
+    }
+    launches++;
+  }
   void jacobi_pair(int l) {
-    k_u_jacobi<<<grid_for(l), block(), 0, stream>>>(kp, l, level_off[l], p, tp, div);
-    k_u_jacobi<<<grid_for(l), block(), 0, stream>>>(kp, l, level_off[l], tp, p, div);
-    launches += 2;
+    jacobi_sweep(l, p, tp);
+    jacobi_sweep(l, tp, p);
+  }
+  void launch_divergence() {
+    if (!opt.stencil && gx % ZTX == 0 && gy % ZTY == 0) {
+      const int zc = zm_chunk(gz);
+      k_u_divergence_zm<<<dim3(gx / ZTX, gy / ZTY, idiv_up(gz, zc)), dim3(ZTX, ZTY), 0, stream>>>(kp, vw[cur_v], div, p, tp, zc);
+    } else {
+      k_u_divergence<<<grid_for(0), block(), 0, stream>>>(kp, vw[cur_v], div, p, tp);
+    }
+    launches++;
   }
   int project() override {  // fluid_simulation_uniform.cu:96-124
     spec_velocity = false;
-    k_u_divergence<<<grid_for(0), block(), 0, stream>>>(kp, vw[cur_v], div, p, tp);
-    launches++;
+    launch_divergence();
     for (int l = 1; l < mip_levels; l++) {
       k_u_restrict<<<grid_for(l), block(), 0, stream>>>(kp, l, level_off[l], level_off[l - 1], div, p, tp);
       launches++;
@@ -470,8 +592,7 @@ struct UniformSim : dcg_sim {
   }
   int project_local() override {  // fluid_simulation_uniform.cu:126-135
     spec_velocity = false;
-    k_u_divergence<<<grid_for(0), block(), 0, stream>>>(kp, vw[cur_v], div, p, tp);
-    launches++;
+    launch_divergence();
     for (int i = 0; i < local_pairs; i++) jacobi_pair(0);
     k_u_apply_pressure<<<grid_for(0), block(), 0, stream>>>(kp, p, fluidity, vw[cur_v]);
     launches++;
@@ -558,8 +679,7 @@ struct UniformSim : dcg_sim {
     DCG_CUDA_TRY(cudaEventRecord(ev_begin, stream));
     for (int r = 0; r < reps; r++) {
       if (st == "jacobi") {
-        k_u_jacobi<<<grid_for(level), block(), 0, stream>>>(kp, level, level_off[level], (r & 1) ? tp : p, (r & 1) ? p : tp, div);
-        launches++;
+        jacobi_sweep(level, (r & 1) ? tp : p, (r & 1) ? p : tp);
         bytes = 12.0 * nl;
       } else if (st == "advect_velocity") { spec_velocity = false; DCG_TRY(advect_velocity()); bytes = 28.0 * n0; }
       else if (st == "advect_density") {
@@ -570,8 +690,7 @@ struct UniformSim : dcg_sim {
         bytes = 24.0 * n0;
       } else if (st == "advect_both") { DCG_TRY(advect_density()); spec_velocity = false; bytes = 52.0 * n0; }
       else if (st == "divergence") {
-        k_u_divergence<<<grid_for(0), block(), 0, stream>>>(kp, vw[cur_v], div, p, tp);
-        launches++;
+        launch_divergence();
         bytes = 28.0 * n0;
       } else if (st == "apply_pressure") {
         k_u_apply_pressure<<<grid_for(0), block(), 0, stream>>>(kp, p, fluidity, vw[cur_v]);

@@ -59,6 +59,31 @@ def test_uniform_non_cubic(gpu):
         np.testing.assert_array_equal(_bits(sim.field(f)), _bits(orc.field(f)), err_msg=f)
 
 
+@pytest.mark.parametrize("size,solids,schedule,options", [
+    ((256, 16, 32), False, "project", None),    # levels 0 and 1 take the z-marching kernels (x extent in whole warps of float4)
+    ((128, 64, 72), True, "local", None),       # z extent not a multiple of the chunk; solids; projectLocal's 5 pairs
+    ((256, 16, 32), False, "project", {"stencil": 1}),  # the one-thread-per-cell kernels at the same size
+])
+def test_uniform_z_marching_kernels(gpu, size, solids, schedule, options):
+    """k_u_jacobi_zm / k_u_divergence_zm only engage from 128 cells in x: sizes the other cases never reach."""
+    p = scene_params(*size, solids=solids)
+    sim = FluidSimulationUniform(size, p, options=options)
+    orc = Oracle(p)
+    for s in range(6):
+        sim.advectVelocity(); orc.advect_velocity()
+        sim.adaptTopology(); orc.adapt_topology()
+        if schedule == "project":
+            sim.project(); orc.project()
+        else:
+            sim.projectLocal(); orc.project_local()
+        for f in FIELDS_AFTER_PROJECT + ("velocity",):
+            np.testing.assert_array_equal(_bits(sim.field(f)), _bits(orc.field(f)), err_msg=f"{f} after project, step {s}")
+        sim.advectDensity(); orc.advect_density()
+    for f in ("density", "velocity"):
+        np.testing.assert_array_equal(_bits(sim.field(f)), _bits(orc.field(f)), err_msg=f)
+    assert orc.field("density").max() > 0
+
+
 def test_uniform_step_graph_equals_calls(gpu):
     """dcg_step (CUDA-graph replay of the 4-call sequence) == the four calls issued one by one."""
     p = scene_params(32)
