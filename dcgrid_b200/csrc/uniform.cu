@@ -188,9 +188,64 @@ __global__ void __launch_bounds__(256) k_u_advect_both(KParams P, const float4 *
   qout[i] = qo;
 }
 
+// The same, marching along z: the cell's own velocity — the first of the two dependent load rounds of a gather — is
+// fetched one plane ahead, so that only the corner loads are on a thread's critical path, and the index set-up is paid
+// once per column.
+__global__ void __launch_bounds__(256) k_u_advect_both_zm(KParams P, const float4 *__restrict__ vin, float4 *__restrict__ vout,
+                                                          const float *__restrict__ qin, float *__restrict__ qout, int zc) {
+  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+  const int z0 = blockIdx.z * zc, z1 = min(z0 + zc, P.gz);
+  if (x >= P.gx || y >= P.gy) return;
+  const uint64_t sz = (uint64_t)P.gx * P.gy;
+  const uint64_t col = (uint64_t)y * P.gx + x;
+  const float alpha = P.dt * P.rdx;  // (me.x * P.dt * P.rdx evaluates as (me.x * dt) * rdx in the reference: kept below)
+  (void)alpha;
+  float4 nxt = vin[col + (uint64_t)z0 * sz];
+  for (int z = z0; z < z1; z++) {
+    const uint64_t i = col + (uint64_t)z * sz;
+    const float4 me = nxt;
+    if (z + 1 < z1) nxt = vin[i + sz];
+    const float bx = ((float)x + .5f) - me.x * P.dt * P.rdx;
+    const float by = ((float)y + .5f) - me.y * P.dt * P.rdx;
+    const float bz = ((float)z + .5f) - me.z * P.dt * P.rdx;
+    const USample s = u_sample(P, bx, by, bz);
+    float4 c[8];
+    float q[8], f[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      c[k] = vin[s.id[k]];
+      q[k] = qin[s.id[k]];
+      f[k] = c[k].w;
+    }
+    const Weights8 W = corner_weights(f, s.fx, s.fy, s.fz);
+    float3 vo = make_float3(0.f, 0.f, 0.f);
+    float qo = 0.f;
+    if (!(W.acc < 1e-6f)) {
+      float vx[8], vy[8], vz[8];
+      const bool inside = u_inside(P, s);
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        float3 v = make_float3(c[k].x, c[k].y, c[k].z);
+        if (!inside) {
+          const int cx = s.x0 + ((k >> 2) & 1), cy = s.y0 + ((k >> 1) & 1), cz = s.z0 + (k & 1);
+          v = velocity_bc(P, v, cx, cy, cz, 1);
+          q[k] = density_bc(P, q[k], cx, cy, cz, 1);
+        }
+        vx[k] = v.x; vy[k] = v.y; vz[k] = v.z;
+      }
+      vo = make_float3(blend8(vx, W.w), blend8(vy, W.w), blend8(vz, W.w));
+      qo = blend8(q, W.w);
+    }
+    vout[i] = make_float4(vo.x, vo.y, vo.z, me.w);
+    qout[i] = qo;
+  }
+}
+
 // k_uniform_calc_divergence, uniformgrid_fluid.cu:107-132
+// zero: bit 0 = clear p, bit 1 = clear t_p like the reference does here; project() skips the level-0 clears it provably
+// never reads (the prolongation rewrites every p of the level, the first sweep every t_p, before either is read)
 __global__ void __launch_bounds__(256) k_u_divergence(KParams P, const float4 *__restrict__ vw, float *__restrict__ div,
-                                                      float *__restrict__ p, float *__restrict__ tp) {
+                                                      float *__restrict__ p, float *__restrict__ tp, int zero) {
   const int x = blockIdx.x * BX + threadIdx.x, y = blockIdx.y * BY + threadIdx.y, z = blockIdx.z * BZ + threadIdx.z;
   if (x >= P.gx || y >= P.gy || z >= P.gz) return;
   const uint64_t i = lidx(P, x, y, z);
@@ -204,8 +259,8 @@ __global__ void __launch_bounds__(256) k_u_divergence(KParams P, const float4 *_
   const float3 vu = velocity_bc(P, make_float3(up.x, up.y, up.z), x, y + 1, z, 1);
   const float3 vb = velocity_bc(P, make_float3(b.x, b.y, b.z), x, y, z - 1, 1);
   const float3 vf = velocity_bc(P, make_float3(f.x, f.y, f.z), x, y, z + 1, 1);
-  p[i] = 0.f;
-  tp[i] = 0.f;
+  if (zero & 1) p[i] = 0.f;
+  if (zero & 2) tp[i] = 0.f;
   div[i] = .5f * P.rdx * (r.w * vr.x - l.w * vl.x + up.w * vu.y - dn.w * vd.y + f.w * vf.z - b.w * vb.z);
 }
 
@@ -284,7 +339,7 @@ __global__ void __launch_bounds__(ZTX * ZTY) k_u_jacobi_zm(KParams P, int level,
 }
 
 __global__ void __launch_bounds__(ZTX * ZTY) k_u_divergence_zm(KParams P, const float4 *__restrict__ vw, float *__restrict__ div, float *__restrict__ p,
-                                                               float *__restrict__ tp, int zc) {
+                                                               float *__restrict__ tp, int zc, int zero) {
   const int x = blockIdx.x * ZTX + threadIdx.x, y = blockIdx.y * ZTY + threadIdx.y;
   const int z0 = blockIdx.z * zc, z1 = min(z0 + zc, P.gz);
   const size_t sy = (size_t)P.gx, sz = (size_t)P.gx * P.gy;
@@ -316,8 +371,8 @@ __global__ void __launch_bounds__(ZTX * ZTY) k_u_divergence_zm(KParams P, const 
       fz = velocity_bc(P, make_float3(next.x, next.y, next.z), x, y, z + 1, 1).z;
     }
     const size_t i = col + zo;
-    p[i] = 0.f;
-    tp[i] = 0.f;
+    if (zero & 1) p[i] = 0.f;
+    if (zero & 2) tp[i] = 0.f;
     div[i] = .5f * P.rdx * (r.w * rx - l.w * lx + up.w * uy - dn.w * dy + next.w * fz - prev.w * bz);
     prev = cur;
     cur = next;
@@ -341,6 +396,48 @@ __global__ void __launch_bounds__(256) k_u_prolongate(KParams P, int level, uint
   p[i] = (27.f * p000 + 9.f * (p001 + p010 + p100) + 3.f * (p011 + p101 + p110) + p111) / 64.f;
 }
 
+// z-marching prolongation: 4 fine cells (one float4 store) per thread and plane.  The one-thread-per-cell kernel above
+// took 4.5 ms at 1024^3 for 4.8 GB of traffic (8 coarse loads and a page of 64-bit index arithmetic per cell); here the
+// four cells x = 4k .. 4k+3 share the coarse cells 2k-1 .. 2k+2 of four coarse rows.  Same expression per cell.
+__global__ void __launch_bounds__(ZTX * ZTY) k_u_prolongate_zm(KParams P, int level, uint64_t off, uint64_t poff, float *__restrict__ p, int zc) {
+  const int w = P.gx >> level, h = P.gy >> level, d = P.gz >> level;
+  const int x = 4 * (blockIdx.x * ZTX + threadIdx.x), y = blockIdx.y * ZTY + threadIdx.y;
+  const int z0 = blockIdx.z * zc, z1 = min(z0 + zc, d);
+  const int pw = w / 2, ph = h / 2;
+  const int sy = (y == 0 || y == h - 1) ? 0 : 2 * (y % 2) - 1;
+  const float *c = p + poff;
+  // coarse columns 2k-1 .. 2k+2; the outer two are only used by cells whose x step is not suppressed at a wall
+  const int X = x / 2;
+  const int xm = x == 0 ? X : X - 1, xp = x + 4 >= w ? X + 1 : X + 2;
+  const size_t row0 = (size_t)(y / 2) * pw, row1 = (size_t)(y / 2 + sy) * pw;
+  for (int z = z0; z < z1; z++) {
+    const int sz = (z == 0 || z == d - 1) ? 0 : 2 * (z % 2) - 1;
+    const size_t pl0 = (size_t)(z / 2) * pw * ph, pl1 = (size_t)(z / 2 + sz) * pw * ph;
+    float v[4][4];  // [row: (y0,z0) (y1,z0) (y0,z1) (y1,z1)][coarse column xm, X, X+1, xp]
+    const size_t r[4] = {pl0 + row0, pl0 + row1, pl1 + row0, pl1 + row1};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const float2 mid = *reinterpret_cast<const float2 *>(c + r[k] + X);
+      v[k][0] = c[r[k] + xm];
+      v[k][1] = mid.x;
+      v[k][2] = mid.y;
+      v[k][3] = c[r[k] + xp];
+    }
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int a = 1 + (j >> 1);  // own coarse column: X for j = 0, 1; X + 1 for j = 2, 3
+      // x step: -1 for even x, +1 for odd x, 0 on the two wall cells (uniformgrid_fluid.cu:218)
+      const int b = (j & 1) ? a + 1 : a - 1;
+      const bool wall = (x + j == 0) || (x + j == w - 1);
+      const float p000 = v[0][a], p010 = v[1][a], p100 = v[2][a], p110 = v[3][a];
+      const float p001 = wall ? p000 : v[0][b], p011 = wall ? p010 : v[1][b], p101 = wall ? p100 : v[2][b], p111 = wall ? p110 : v[3][b];
+      o[j] = (27.f * p000 + 9.f * (p001 + p010 + p100) + 3.f * (p011 + p101 + p110) + p111) / 64.f;
+    }
+    *reinterpret_cast<float4 *>(p + off + ((size_t)z * h + y) * w + x) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 // k_uniform_apply_pressure, uniformgrid_fluid.cu:239-260
 __global__ void __launch_bounds__(256) k_u_apply_pressure(KParams P, const float *__restrict__ p, const float *__restrict__ fl,
                                                           float4 *__restrict__ vw) {
@@ -361,6 +458,38 @@ __global__ void __launch_bounds__(256) k_u_apply_pressure(KParams P, const float
   v.y -= alpha * (wu * (p[iu] - pc) + wd * (pc - p[id]));
   v.z -= alpha * (wf * (p[iff] - pc) + wb * (pc - p[ib]));
   vw[i] = v;
+}
+
+// z-marching pressure gradient: the column's pressure and fluidity planes in registers, x neighbours by shuffle
+__global__ void __launch_bounds__(ZTX * ZTY) k_u_apply_zm(KParams P, const float *__restrict__ p, const float *__restrict__ fl, float4 *__restrict__ vw,
+                                                          int zc) {
+  const int x = blockIdx.x * ZTX + threadIdx.x, y = blockIdx.y * ZTY + threadIdx.y;
+  const int z0 = blockIdx.z * zc, z1 = min(z0 + zc, P.gz);
+  const size_t sy = (size_t)P.gx, sz = (size_t)P.gx * P.gy;
+  const size_t col = (size_t)y * P.gx + x;
+  const size_t dnrow = y > 0 ? col - sy : col, uprow = y < P.gy - 1 ? col + sy : col;
+  const bool left_edge = threadIdx.x == 0, right_edge = threadIdx.x == ZTX - 1;
+  const float alpha = .5f * P.rdx;
+  float pc = p[col + (size_t)z0 * sz], wc = fl[col + (size_t)z0 * sz];
+  float pb = pc, wb = wc;
+  if (z0 > 0) { pb = p[col + (size_t)(z0 - 1) * sz]; wb = fl[col + (size_t)(z0 - 1) * sz]; }
+  for (int z = z0; z < z1; z++) {
+    const size_t zo = (size_t)z * sz, i = col + zo;
+    float pf = pc, wf = wc;
+    if (z < P.gz - 1) { pf = p[i + sz]; wf = fl[i + sz]; }
+    const float pd = p[dnrow + zo], pu = p[uprow + zo], wd = fl[dnrow + zo], wu = fl[uprow + zo];
+    float4 v = vw[i];
+    float pl = __shfl_up_sync(0xFFFFFFFFu, pc, 1), wl = __shfl_up_sync(0xFFFFFFFFu, wc, 1);
+    float pr = __shfl_down_sync(0xFFFFFFFFu, pc, 1), wr = __shfl_down_sync(0xFFFFFFFFu, wc, 1);
+    if (left_edge) { pl = x > 0 ? p[i - 1] : pc; wl = x > 0 ? fl[i - 1] : wc; }
+    if (right_edge) { pr = x < P.gx - 1 ? p[i + 1] : pc; wr = x < P.gx - 1 ? fl[i + 1] : wc; }
+    v.x -= alpha * (wr * (pr - pc) + wl * (pc - pl));
+    v.y -= alpha * (wu * (pu - pc) + wd * (pc - pd));
+    v.z -= alpha * (wf * (pf - pc) + wb * (pc - pb));
+    vw[i] = v;
+    pb = pc; wb = wc;
+    pc = pf; wc = wf;
+  }
 }
 
 // k_uniform_debug_stats, uniformgrid_structure.cu:33-43: per-256-cell bins, sequential sums
@@ -533,7 +662,12 @@ struct UniformSim : dcg_sim {
     return DCG_OK;
   }
   int advect_density() override {  // fluid_simulation_uniform.cu:137-141
-    if (fuse_advect) {
+    if (fuse_advect && !opt.advect && gz >= 64) {
+      const int zc = opt.advect_ctas_per_sm > 0 ? opt.advect_ctas_per_sm : 16;  // (option reused: planes per thread)
+      k_u_advect_both_zm<<<dim3(idiv_up(gx, 32), idiv_up(gy, 8), idiv_up(gz, zc)), dim3(32, 8), 0, stream>>>(kp, vw[cur_v], vw[cur_v ^ 1], q[cur_q],
+                                                                                                           q[cur_q ^ 1], zc);
+      spec_velocity = true;
+    } else if (fuse_advect) {
       k_u_advect_both<<<grid_for(0), block(), 0, stream>>>(kp, vw[cur_v], vw[cur_v ^ 1], q[cur_q], q[cur_q ^ 1]);
       spec_velocity = true;
     } else {
@@ -563,30 +697,44 @@ struct UniformSim : dcg_sim {
     jacobi_sweep(l, p, tp);
     jacobi_sweep(l, tp, p);
   }
-  void launch_divergence() {
+  void launch_apply() {
     if (!opt.stencil && gx % ZTX == 0 && gy % ZTY == 0) {
       const int zc = zm_chunk(gz);
-      k_u_divergence_zm<<<dim3(gx / ZTX, gy / ZTY, idiv_up(gz, zc)), dim3(ZTX, ZTY), 0, stream>>>(kp, vw[cur_v], div, p, tp, zc);
+      k_u_apply_zm<<<dim3(gx / ZTX, gy / ZTY, idiv_up(gz, zc)), dim3(ZTX, ZTY), 0, stream>>>(kp, p, fluidity, vw[cur_v], zc);
     } else {
-      k_u_divergence<<<grid_for(0), block(), 0, stream>>>(kp, vw[cur_v], div, p, tp);
+      k_u_apply_pressure<<<grid_for(0), block(), 0, stream>>>(kp, p, fluidity, vw[cur_v]);
+    }
+    launches++;
+  }
+  void launch_divergence(int zero = 3) {
+    if (opt.zero_all) zero = 3;
+    if (!opt.stencil && gx % ZTX == 0 && gy % ZTY == 0) {
+      const int zc = zm_chunk(gz);
+      k_u_divergence_zm<<<dim3(gx / ZTX, gy / ZTY, idiv_up(gz, zc)), dim3(ZTX, ZTY), 0, stream>>>(kp, vw[cur_v], div, p, tp, zc, zero);
+    } else {
+      k_u_divergence<<<grid_for(0), block(), 0, stream>>>(kp, vw[cur_v], div, p, tp, zero);
     }
     launches++;
   }
   int project() override {  // fluid_simulation_uniform.cu:96-124
     spec_velocity = false;
-    launch_divergence();
+    launch_divergence(mip_levels > 1 && project_level_pairs >= 1 ? 0 : 3);
     for (int l = 1; l < mip_levels; l++) {
       k_u_restrict<<<grid_for(l), block(), 0, stream>>>(kp, l, level_off[l], level_off[l - 1], div, p, tp);
       launches++;
     }
     for (int i = 0; i < project_coarsest_pairs; i++) jacobi_pair(mip_levels - 1);
     for (int l = mip_levels - 2; l >= 0; l--) {
-      k_u_prolongate<<<grid_for(l), block(), 0, stream>>>(kp, l, level_off[l], level_off[l + 1], p);
+      if (zm_ok(l) && level_off[l + 1] % 2 == 0) {
+        const int d = gz >> l, zc = zm_chunk(d);
+        k_u_prolongate_zm<<<dim3((gx >> l) / (4 * ZTX), (gy >> l) / ZTY, idiv_up(d, zc)), dim3(ZTX, ZTY), 0, stream>>>(kp, l, level_off[l], level_off[l + 1], p, zc);
+      } else {
+        k_u_prolongate<<<grid_for(l), block(), 0, stream>>>(kp, l, level_off[l], level_off[l + 1], p);
+      }
       launches++;
       for (int i = 0; i < project_level_pairs; i++) jacobi_pair(l);
     }
-    k_u_apply_pressure<<<grid_for(0), block(), 0, stream>>>(kp, p, fluidity, vw[cur_v]);
-    launches++;
+    launch_apply();
     DCG_CUDA_TRY(cudaGetLastError());
     return DCG_OK;
   }
@@ -594,8 +742,7 @@ struct UniformSim : dcg_sim {
     spec_velocity = false;
     launch_divergence();
     for (int i = 0; i < local_pairs; i++) jacobi_pair(0);
-    k_u_apply_pressure<<<grid_for(0), block(), 0, stream>>>(kp, p, fluidity, vw[cur_v]);
-    launches++;
+    launch_apply();
     DCG_CUDA_TRY(cudaGetLastError());
     return DCG_OK;
   }
@@ -693,8 +840,7 @@ struct UniformSim : dcg_sim {
         launch_divergence();
         bytes = 28.0 * n0;
       } else if (st == "apply_pressure") {
-        k_u_apply_pressure<<<grid_for(0), block(), 0, stream>>>(kp, p, fluidity, vw[cur_v]);
-        launches++;
+        launch_apply();
         bytes = 32.0 * n0;
       } else return fail(DCG_ERR_INVALID, "bench_stage: unknown stage %s", stage);
     }
