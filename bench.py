@@ -155,16 +155,17 @@ def parse_options(text):
     return out
 
 
-def make_sim(workload, device, rank=0, world=1, dist=None, options=None):
+def make_sim(workload, device, rank=0, world=1, dist=None, options=None, depth=None):
     from dcgrid_b200 import (FluidSimulationDCGrid, FluidSimulationDCGridSharded, FluidSimulationUniform,
                              FluidSimulationUniformSharded, scene_params)
 
     grid, d, M, solids = WORKLOADS[workload]
-    if world > 1:  # one scene, `world` times as deep, slab-decomposed over the ranks
-        size = (d, d, d * world)
+    if world > 1:  # one scene, `depth` (= world: weak; 1: strong, --strong) times as deep, slab-decomposed over the ranks
+        depth = world if depth is None else depth
+        size = (d, d, d * depth)
         p = scene_params(*size, solids=solids)
         if grid == "dcgrid":
-            sim = FluidSimulationDCGridSharded(size, M * world, p, world, rank=rank, nlocal=1, device=device, dist=dist, options=options)
+            sim = FluidSimulationDCGridSharded(size, M * depth, p, world, rank=rank, nlocal=1, device=device, dist=dist, options=options)
         else:
             sim = FluidSimulationUniformSharded(size, p, world, rank=rank, nlocal=1, device=device, dist=dist)
         return sim, p
@@ -270,6 +271,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reference-cuda", action="store_true")
     ap.add_argument("--no-parity-check", action="store_true")
+    ap.add_argument("--strong", action="store_true", help="N > 1: the workload's own scene (e.g. BASELINE configs[4]: uniform1024, dcgrid2048) sharded over the "
+                    "ranks instead of a scene N times as deep")
+    ap.add_argument("--no-named-configs", action="store_true", help="skip the extension scenes (cloud scene, adaptation-heavy scene)")
     ap.add_argument("--opt", default="", help="creation-time options, key=value[,key=value...] (struct dcg_options)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
@@ -299,9 +303,10 @@ def main():
         torch.cuda.synchronize()
 
     grid, d, M, solids = WORKLOADS[args.workload]
-    sim, p = make_sim(args.workload, local_rank, rank, world, dist if world > 1 else None, parse_options(args.opt))
+    depth = 1 if (args.strong or world == 1) else world
+    sim, p = make_sim(args.workload, local_rank, rank, world, dist if world > 1 else None, parse_options(args.opt), depth=depth)
     ctr0 = sim.counters()
-    scene_cells = d ** 3 * world  # N>1: one scene, N times as deep
+    scene_cells = d ** 3 * depth  # N>1: one scene, N times as deep (weak) or the workload's own scene (--strong)
 
     # ---- configs[3] (adaptation-heavy): reset() + the first 20 steps, topology changing on every step ----
     transient = None
@@ -312,6 +317,33 @@ def main():
         c = sim.counters()
         transient["calls_that_changed_topology"] = int(c[1] - ctr0[1])
         transient["value"] = scene_cells / (transient["ms_per_step"] * 1e-3)
+    # ---- the configurations BASELINE.json names beyond what the reference snapshot contains, on the extensions of
+    # SURVEY 8(f) (parity unpinned: CPU specification only, tests/test_ext_gpu.py), each on an instance of its own:
+    #   configs[2] as worded: cloud scene over a terrain SDF with temperature + vapor (fused source pass);
+    #   configs[3]: rapidly changing refinement — flow-driven (vorticity) score, selection entirely on the device ----
+    named = None
+    if grid == "dcgrid" and world == 1 and args.workload == "dcgrid512" and not args.no_named_configs:
+        from dcgrid_b200 import FluidSimulationDCGrid, make_ext
+
+        named = {}
+        for name, kw, pre in (("cloud_scene_terrain_temperature_vapor", dict(terrain=1, terrain_height=96.0, terrain_wavelength=128.0, sources=1), 140),
+                              ("adaptation_heavy_flow_driven", dict(score_mode=1, selection=1, sources=1), 60)):
+            try:
+                s2 = FluidSimulationDCGrid((d, d, d), M, p, device=local_rank, options=parse_options(args.opt))
+                s2.setExt(make_ext(**kw))
+                s2.reset()
+                s2.step(pre)
+                c0 = s2.counters().copy()
+                s2.step(20, sync=True)
+                c1 = s2.counters()
+                ms2 = s2.lastStepMs() / 20
+                named[name] = {"ext": kw, "preroll_steps": pre, "steps": 20, "ms_per_step": ms2, "value": scene_cells / (ms2 * 1e-3), "unit": UNIT,
+                               "calls_that_changed_topology": int(c1[1] - c0[1]), "blocks_moved": int(c1[2] - c0[2]), "subblocks_refined": int(c1[3] - c0[3]),
+                               "host_selections": s2.info("host_selections"), "device_selections": s2.info("device_selections"), "steady": bool(c1[7]),
+                               "parity": "unpinned (extension: bit-exact against its CPU specification on small scenes, tests/test_ext_gpu.py)"}
+                s2.close()
+            except Exception as e:  # noqa: BLE001
+                named[name] = {"error": str(e)[:200]}
     # ---- pre-roll: develop the scene (plume + block topology at its fixed point), untimed ----
     done = 20 if transient else 0
     if args.preroll > done:
@@ -320,8 +352,8 @@ def main():
     # own CUDA run of the same scene and step count (tests/golden/big/, bit-exact: FNV-1a of raw density + velocity) ----
     parity = {"checked": False, "why": "no committed reference digest for this scene / step count"}
     if grid == "dcgrid" and not args.no_parity_check:
-        size = (d, d, d * world)
-        case, want = golden_digest(size, M * world, solids, args.preroll)
+        size = (d, d, d * depth)
+        case, want = golden_digest(size, M * depth, solids, args.preroll)
         if case is not None:
             barrier()
             if rank == 0:
@@ -403,10 +435,17 @@ def main():
                     traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
                 else:
                     traffic_src = f"stale: {tj.get('source')} was captured on csrc {tj.get('csrc_digest')}, this is {csrc_digest()}"
-            roof = {"bound": "hbm", "kernel": "k_dc_jacobi_pipe" if grid == "dcgrid" else "k_u_jacobi", "level": lvl, "achieved": ach,
+            sweeps_big = 0  # sweeps per step that run this kernel on a level of this size (levels 0 and 1 at dcgrid512)
+            if grid == "dcgrid":
+                big = int(tab["loads"][lvl])
+                sweeps_big = sum(10 for l in range(len(tab["loads"])) if int(tab["loads"][l]) * 10 >= big * 9)
+            else:
+                sweeps_big = 2
+            roof = {"bound": "hbm", "kernel": "k_dc_jacobi_pipe8" if grid == "dcgrid" else "k_u_jacobi_zm", "level": lvl, "achieved": ach,
                     "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src,
                     "peak_source": peak_src, "ms_per_launch": ms, "alg_bytes_per_launch": b,
-                    "share_of_step": "Jacobi sweeps = 37 % of the step at dcgrid512 (profiles/README.md r1d)"}
+                    "share_of_step": sweeps_big * ms / ms_per_step,
+                    "share_of_step_what": f"{sweeps_big} launches of this size per step x ms_per_launch / ms_per_step (the kernel family with the largest share)"}
             for st in (("advect_both",) if grid == "dcgrid" else ()) + ("advect_velocity", "divergence", "apply_pressure", "advect_density"):
                 sim.benchStage(st, 0, 2)
                 ms_s, b_s = sim.benchStage(st, 0, 6)
@@ -419,12 +458,12 @@ def main():
                     "peak": peak * world, "unit": "GB/s", "frac": step_ach / (peak * world), "traffic": None, "peak_source": peak_src}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if (args.strong and world > 1) else "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": args.workload, "grid": grid, "effective_cells": cells, "max_num_blocks": M * world, "solids": bool(solids),
+            "config": {"workload": args.workload, "grid": grid, "effective_cells": cells, "max_num_blocks": M * depth, "solids": bool(solids),
                        "active_blocks": active_blocks, "allocated_cell_updates_per_s": 64 * active_blocks / (ms_per_step * 1e-3),
                        "parallelism": "single GPU" if world == 1 else
-                       f"slab decomposition over {world} ranks of one {d}x{d}x{d * world} scene (pool {M * world} blocks): per-level slot ranges split "
+                       f"slab decomposition over {world} ranks of one {d}x{d}x{d * depth} scene (pool {M * depth} blocks): per-level slot ranges split "
                        f"{world} ways, peer cells accessed in place over NVLink (one virtual range per field stitched from every GPU's memory), "
                        "flag barrier after every kernel phase, topology replicated",
                        "l2": "working set (2.6 GB at dcgrid512, 0.3 GB at dcgrid256) >> 126 MB L2, no flush needed" if cells >= 256 ** 3 else "L2-resident working set (correctness config)",
@@ -449,6 +488,7 @@ def main():
                               "alg_bytes_per_step": alg_bytes, "frac_of_8TBps_nominal": step_ach / (8000.0 * world), "peak_source": peak_src},
             "stages": per_stage,
             "transient": transient,
+            "named_configs": named,
             "topology": {"adapt_calls": int(ctr[0] - ctr0[0]), "calls_that_changed_topology": int(ctr[1]), "blocks_moved": int(ctr[2]),
                          "subblocks_refined": int(ctr[3]), "calls_skipped_at_fixed_point": int(ctr[4]), "steady": bool(ctr[7])},
         }
