@@ -17,13 +17,13 @@ for name, kw, pre in (("geometric", {}, 0), ("geometric_device", dict(selection=
             sim.step(pre)
         if sync:
             sim.info("timing_sync")
-        keys = ("adapt_move_ms", "adapt_refine_ms", "adapt_apron_ms", "adapt_layout_ms", "adapt_propagate_ms")
+        keys = ("adapt_move_ms", "adapt_refine_ms", "adapt_apron_ms", "adapt_layout_ms", "adapt_propagate_ms", "select_scores_ms", "select_d2h_ms", "select_host_ms")
         t0 = {k: sim.info(k) for k in keys}
         c0 = sim.counters().copy()
         w = time.time()
         sim.step(20)
         wall = (time.time() - w) * 1e3 / 20
         c = sim.counters()
-        print(name, "sync" if sync else "async", "ms/step dev %.3f wall %.3f" % (sim.lastStepMs() / 20, wall), {k[6:]: round((sim.info(k) - t0[k]) / 20, 3) for k in keys},
+        print(name, "sync" if sync else "async", "ms/step dev %.3f wall %.3f" % (sim.lastStepMs() / 20, wall), {k.split('_', 1)[1]: round((sim.info(k) - t0[k]) / 20, 3) for k in keys},
               "changed", int(c[1] - c0[1]), "moved", int(c[2] - c0[2]), "refined", int(c[3] - c0[3]), "host_sel", sim.info("host_selections"), "dev_sel", sim.info("device_selections"), "shortcut", sim.info("levels_shortcut"), flush=True)
         del sim
