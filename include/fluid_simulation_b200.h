@@ -93,6 +93,15 @@ public:
   void velocity(float *dst, size_t count, int layout = DCG_LAYOUT_NATIVE) { getField(DCG_FIELD_VELOCITY, layout, dst, count); }
   void pressure(float *dst, size_t count, int layout = DCG_LAYOUT_NATIVE) { getField(DCG_FIELD_PRESSURE, layout, dst, count); }
   void fluidity(float *dst, size_t count, int layout = DCG_LAYOUT_NATIVE) { getField(DCG_FIELD_FLUIDITY, layout, dst, count); }
+  // extensions beyond the reference snapshot (dcg_ext_params: flow-driven score, MacCormack, temperature / vapor +
+  // the fused source pass, terrain, device-side selection); off unless switched on here
+  void temperature(float *dst, size_t count, int layout = DCG_LAYOUT_NATIVE) { getField(DCG_FIELD_TEMPERATURE, layout, dst, count); }
+  void vapor(float *dst, size_t count, int layout = DCG_LAYOUT_NATIVE) { getField(DCG_FIELD_VAPOR, layout, dst, count); }
+  void setExtensions(const dcg_ext_params &e) { check(dcg_set_ext_params(m_sim, &e)); }
+  void applySources() { check(dcg_apply_sources(m_sim)); }
+  void sample(int field, bool precise, const float *positions, size_t n, float *out) { check(dcg_sample_field(m_sim, field, precise ? 1 : 0, positions, n, out)); }
+  void saveState(const char *path) { check(dcg_save_state(m_sim, path)); }
+  void loadState(const char *path) { check(dcg_load_state(m_sim, path)); }
   dcg_sim *handle() const { return m_sim; }
 
   void setParams(const dcg_sim_params &p) { check(dcg_set_params(m_sim, &p)); }
