@@ -43,6 +43,7 @@ struct DCGridSim : dcg_sim {
   size_t cells = 0;
   std::vector<uint64_t> max_blocks, full_blocks, loads, offsets, move_limit;
   std::vector<size_t> map_size;
+  size_t fmap_size = 0;
 
   Pool T{};   // the reference's numbering: adaptation, accessors
   Pool Tf{};  // field order (k_dc_resort_keys): what the field kernels see once `mirrored`
@@ -167,7 +168,7 @@ struct DCGridSim : dcg_sim {
   ~DCGridSim() override {
     cudaSetDevice(device);
     drop_graphs();
-    cudaFree(T.posl); cudaFree(T.parent); cudaFree(T.child); cudaFree(T.apron); cudaFree(T.face); cudaFree(T.fd);
+    cudaFree(T.posl); cudaFree(T.parent); cudaFree(T.child); cudaFree(T.apron); cudaFree(T.face); cudaFree(T.fd); cudaFree(T.fmap);
     for (int l = 0; l < kMaxLevels; l++) cudaFree(T.map[l]);
     cudaFree(d_perm); cudaFree(d_perm_new); cudaFree(d_sort_keys64[0]); cudaFree(d_sort_keys64[1]); cudaFree(d_sort_tmp64);
     cudaFree(Tf.posl); cudaFree(Tf.parent); cudaFree(Tf.child); cudaFree(Tf.apron);
@@ -271,6 +272,10 @@ struct DCGridSim : dcg_sim {
       map_size[l] = full_blocks[l];
       DCG_CUDA_TRY(cudaMalloc(&T.map[l], map_size[l] * 4));
     }
+    if (M64 > kFmapSlotMask) return fail(DCG_ERR_UNSUPPORTED, "max_num_blocks above 2^28 - 1 (finest-block map packs level and slot into 32 bits)");
+    fmap_size = (size_t)idiv_up(gx, kBW) * idiv_up(gy, kBW) * idiv_up(gz, kBW);
+    DCG_CUDA_TRY(cudaMalloc(&T.fmap, fmap_size * 4));
+    Tf.fmap = T.fmap;  // one table, in the numbering of whichever pool the field kernels see (hot())
     DCG_CUDA_TRY(cudaMalloc(&d_flags, (size_t)M * 4));
     DCG_CUDA_TRY(cudaMalloc(&d_free, (size_t)M * 4));
     DCG_CUDA_TRY(cudaMalloc(&d_touched, (size_t)M * 4 * 2));
@@ -806,7 +811,8 @@ struct DCGridSim : dcg_sim {
   int build_face_descriptors() {
     cudaMemsetAsync(d_counters + 1, 0, 4, stream);
     k_dc_build_fdesc<<<blocks_for((size_t)M * 8, 256), 256, 0, stream>>>(hot(), d_counters + 1);
-    launches++;
+    k_dc_build_fmap<<<blocks_for(fmap_size, 256), 256, 0, stream>>>(hot(), kp);
+    launches += 2;
     return rebuild_order();
   }
   // ---- field order (dcgrid_kernels.cuh, "field order") ----------------------------------------------------

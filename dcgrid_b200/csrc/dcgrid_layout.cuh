@@ -41,6 +41,7 @@ struct Pool {
   uint32_t *fd;                     // [12*slot]: 6 face-neighbour slots + 6 face codes (dcgrid_stencil.cuh)
   uint32_t *face;                   // [96*slot + 16*f + 4*a + b], f = -x,+x,-y,+y,-z,+z; irregular blocks only
   uint32_t *map[kMaxLevels];        // dense block-coordinate -> slot map of each sparse level
+  uint32_t *fmap;                   // finest-block map (k_dc_build_fmap): level-0 block coordinate -> level << 28 | slot
 };
 
 // Work partition of the slab-decomposed solver (dcgrid.cu, "sharding"): the tiles (kTile consecutive slots) one

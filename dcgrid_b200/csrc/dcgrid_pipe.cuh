@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(kJ8Threads, 5) k_dc_jacobi_pipe8(Pool T, KPara
 // stages and the only latency a thread waits for is that of its own gathers.
 //
 // Samples that leave their block (69 % of the warps hold at least one in the developed flow) resolve the
-// covering block with all sparse-level map probes issued at once (the reference walks them one dependent
+// covering block with one load from the finest-block map (the reference walks the level maps one dependent
 // load at a time, dcgrid_utils.cuh:201-233) and derive the block origin from the sample position (block
 // origins are multiples of 4 cells of their level) instead of loading it.
 constexpr int kAStages = 4;
@@ -367,24 +367,27 @@ struct alignas(128) AdvectStage {
 };
 constexpr size_t kAdvectPipeSmem = kAStages * sizeof(AdvectStage) + 2 * kAStages * sizeof(uint64_t);
 
-// getBlockIndexDeep(position, 0) with independent probes; returns the slot and sets (level, origin)
-__device__ __forceinline__ uint32_t block_index_deep_par(const Pool &T, const KParams &P, int ix, int iy, int iz, int4 &bp) {
-  uint32_t cand[4];
-  const int ns = T.sparse_levels < 4 ? T.sparse_levels : 4;
-#pragma unroll
-  for (int l = 0; l < 4; l++) cand[l] = l < ns ? map_lookup(T, P, ix >> l, iy >> l, iz >> l, l) : kNone;
+// getBlockIndexDeep(position, 0) as ONE load.  The finest block covering a level-0 cell is the same for all cells of a
+// level-0 block footprint (every block origin is a multiple of 4 cells of its level), so the walk over the level maps
+// (dcgrid_utils.cuh:201-233: one dependent probe per sparse level) is tabulated per level-0 block coordinate whenever
+// the topology changes: fmap[(bx * ry + by) * rz + bz] = level << 28 | slot (k_dc_build_fmap evaluates the walk
+// itself, so the table cannot disagree with it).  8 MiB at 512^3.
+constexpr uint32_t kFmapSlotMask = 0x0FFFFFFFu;
+__global__ void __launch_bounds__(256) k_dc_build_fmap(Pool T, KParams P) {
+  const int3 r = level_dims(P, 0);
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= (size_t)r.x * r.y * r.z) return;
+  const int bz = (int)(i % r.z), by = (int)((i / r.z) % r.y), bx = (int)(i / ((size_t)r.z * r.y));
   int level = 0;
-  uint32_t b = kNone;
-#pragma unroll
-  for (int l = 3; l >= 0; l--)
-    if (cand[l] != kNone) { b = cand[l]; level = l; }
-  if (b == kNone) {
-    level = ns;
-    int x = ix >> ns, y = iy >> ns, z = iz >> ns;
-    b = block_index_deep(T, P, x, y, z, level);  // remaining sparse levels (if > 4), then the ordered one
-  }
+  const uint32_t b = block_index_deep(T, P, bx * kBW, by * kBW, bz * kBW, level);
+  T.fmap[i] = b == kNone ? kNone : ((uint32_t)level << 28 | b);
+}
+__device__ __forceinline__ uint32_t block_index_finest(const Pool &T, const KParams &P, int ix, int iy, int iz, int4 &bp) {
+  const int ry = idiv_up(P.gy, kBW), rz = idiv_up(P.gz, kBW);
+  const uint32_t e = __ldg(T.fmap + ((size_t)(ix >> 2) * ry + (iy >> 2)) * rz + (iz >> 2));
+  const int level = (int)(e >> 28);
   bp = make_int4((ix >> level) & ~(kBW - 1), (iy >> level) & ~(kBW - 1), (iz >> level) & ~(kBW - 1), level);
-  return b;
+  return e & kFmapSlotMask;
 }
 
 __device__ __forceinline__ DSample d_sample_pipe(const Pool &T, const KParams &P, const uint32_t *own_apron, const uint32_t *own_child,
@@ -395,7 +398,7 @@ __device__ __forceinline__ DSample d_sample_pipe(const Pool &T, const KParams &P
       own_child[((lx >> 1) << 2) | ((ly >> 1) << 1) | (lz >> 1)] == kNone)
     return d_sample_in(own_apron, pl, px, py, pz);
   int4 bp;
-  const uint32_t b = block_index_deep_par(T, P, ix, iy, iz, bp);
+  const uint32_t b = block_index_finest(T, P, ix, iy, iz, bp);
   return d_sample_in(T.apron + (size_t)b * kAV, bp, px, py, pz);
 }
 
