@@ -153,6 +153,7 @@ struct DCGridSim : dcg_sim {
   bool coarse_in_smem = true;
   static constexpr size_t kCoarseSmemMax = 200 * 1024;
   bool skip_dead_zeroing = true;  // k_dc_divergence4: no pressure clears that project() never reads
+  int experiment = 0;  // dcg_options.experiment
   int advect_min_blocks = 3;  // __launch_bounds__ variant of the advection kernels (3 or 4 CTAs per SM)
   bool use_pipe = true, snake = true;
   bool jacobi8 = true;  // k_dc_jacobi_pipe8 (8 cells per thread) instead of k_dc_jacobi_pipe (4)
@@ -253,6 +254,7 @@ struct DCGridSim : dcg_sim {
     DCG_TRY(setup_sharding());
     DCG_CUDA_TRY(cudaMalloc(&d_perm, (size_t)M * 4));
     use_pdl = !opt.no_pdl;
+    experiment = opt.experiment;
     use_resort = !opt.no_resort;
     if (opt.resort_every != 0) resort_every = std::max(0, opt.resort_every);  // -1: only at the fixed point
     DCG_CUDA_TRY(cudaMalloc(&d_pcount, (kMaxLevels + 1) * 4));

@@ -185,6 +185,13 @@ __global__ void __launch_bounds__(kCTA4, 4) k_dc_jacobi_pipe(Pool T, KParams P, 
 // 128 threads per 16-block tile: the x/y/z neighbours inside the subblock are the thread's own registers, only
 // one 2x2 face per axis crosses lanes (12 shuffles per 8 cells), and the per-thread overhead is paid once per
 // 8 cells.  Ring, barriers, ghost prefetch, arithmetic and its order are those of k_dc_jacobi_pipe.
+// (Measured and rejected, profiles/README.md r2l: one range test for the eight div6 of a thread instead of eight, the
+// tile loop unrolled over three named ghost sets instead of the rotating copies, one merged branch for three
+// same-level faces, a single-run shortcut for the tile index — each removes instructions, ptxas then allocates 79-80
+// registers instead of 94 and schedules the ghost prefetch later: 39 -> 44-47 us per level-0 sweep, and the same
+// happens to THIS code under __launch_bounds__(128, 6): 79 registers, 47 us at 6 CTAs per SM, 55 us at 5.  The kernel
+// is bound by how long its ghost loads stay in flight, not by instruction count; with the 79-register schedule it
+// scales 62 / 52 / 45 us at 4 / 5 / 6 resident CTAs per SM.)
 constexpr int kJ8Threads = kB4 * 8;
 struct Ghost12 {
   float gx[4];  // [cy*2+cz]: the subblock's x face (-x if sx = 0, +x if sx = 1)

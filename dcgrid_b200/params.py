@@ -84,7 +84,7 @@ class Options(ctypes.Structure):
         "jacobi", "jacobi_ctas_per_sm", "no_snake", "advect", "advect_slot_order", "advect_no_fuse", "advect_min_blocks",
         "advect_ctas_per_sm", "stencil", "stencil_ctas_per_sm", "apply_min_blocks", "coarse_in_gmem", "zero_all", "no_resort",
         "resort_every")] + [("shard_unit", ctypes.c_uint32), ("no_pdl", ctypes.c_int32), ("host_selection", ctypes.c_int32),
-                            ("jacobi_max_ctas", ctypes.c_int32), ("reserved", ctypes.c_int32 * 13)]
+                            ("jacobi_max_ctas", ctypes.c_int32), ("experiment", ctypes.c_int32), ("reserved", ctypes.c_int32 * 12)]
 
 
 def make_options(options=None) -> Options:

@@ -99,7 +99,8 @@ typedef struct dcg_options {
                                   (std::nth_element / std::sort on scores copied D2H)                    */
   int32_t jacobi_max_ctas;     /* > 0: cap on the resident CTAs of the ring kernel (tests: few CTAs walk many
                                   tiles each, the regime of the big scenes, on a small one)               */
-  int32_t reserved[13];
+  int32_t experiment;          /* kernel-variant bits for A/B measurements (tools/); 0 = the shipped kernels      */
+  int32_t reserved[12];
 } dcg_options;
 DCG_API int dcg_default_options(dcg_options *out);
 
