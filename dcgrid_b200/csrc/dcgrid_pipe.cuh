@@ -191,7 +191,8 @@ __global__ void __launch_bounds__(kCTA4, 4) k_dc_jacobi_pipe(Pool T, KParams P, 
 // registers instead of 94 and schedules the ghost prefetch later: 39 -> 44-47 us per level-0 sweep, and the same
 // happens to THIS code under __launch_bounds__(128, 6): 79 registers, 47 us at 6 CTAs per SM, 55 us at 5.  The kernel
 // is bound by how long its ghost loads stay in flight, not by instruction count; with the 79-register schedule it
-// scales 62 / 52 / 45 us at 4 / 5 / 6 resident CTAs per SM.)
+// scales 62 / 52 / 45 us at 4 / 5 / 6 resident CTAs per SM.  Ghosts one tile ahead instead of two: 71 registers,
+// 43 us at 6 CTAs per SM.)
 constexpr int kJ8Threads = kB4 * 8;
 struct Ghost12 {
   float gx[4];  // [cy*2+cz]: the subblock's x face (-x if sx = 0, +x if sx = 1)
