@@ -1500,7 +1500,11 @@ struct DCGridSim : dcg_sim {
     each_rank([&](int, RankWork &w) {
       const TileRuns &R = w.level[l];
       if (run_total(R) == 0) return;
-      if (prolong_staged) launch_pdl(k_dc_prolongate_staged, dim3(run_total(R)), dim3(kCTA4), 0, hot(), R, l, p);
+      // one GPU, a level that fills it: by parent block (every block of the level is a child of a listed block)
+      if (prolong_staged && world == 1 && l + 1 < levels - 1 && run_total(R) >= pipe_min_tiles && w.pcount[l + 1] > 0 && !(experiment & 1))
+        launch_pdl(k_dc_prolongate_parents, dim3(std::min<unsigned>(w.pcount[l + 1], 8u * (unsigned)sm_count)), dim3(kPPThreads), 0, hot(),
+                   (const uint32_t *)(w.d_plist + offsets[l + 1]), w.pcount[l + 1], p);
+      else if (prolong_staged) launch_pdl(k_dc_prolongate_staged, dim3(run_total(R)), dim3(kCTA4), 0, hot(), R, l, p);
       else launch_pdl(k_dc_prolongate4, dim3(blocks_for(loads[l], kB4)), dim3(kCTA4), 0, hot(), l, p);
       launches++;
     });

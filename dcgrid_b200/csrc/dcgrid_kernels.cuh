@@ -650,6 +650,82 @@ __global__ void __launch_bounds__(kCTA4) k_dc_prolongate_staged(Pool T, TileRuns
   *reinterpret_cast<float4 *>(p + (size_t)b * kBV + 4 * t) = o4;
 }
 
+// Prolongation by PARENT block, persistent and software-pipelined (levels that fill the GPU, one GPU).
+// The eight children of a refined block interpolate from the same 6^3 apron of that block, and the apron map of
+// a block is one contiguous 864-byte range: a CTA walks the list of blocks with children (k_dc_list_parents),
+// gathers the parent's 216 apron'ed pressures ONCE (the per-child kernel gathers 64 per child: 512 for eight) and
+// writes all its child blocks from shared memory.  The three dependent load rounds (list entry -> apron ids ->
+// pressures) of parent k + 3 / k + 2 / k + 1 are in flight while parent k is computed.  Same values, same
+// prolong_one expression as k_dc_prolongate4: every block with a parent is the child of exactly one listed block.
+constexpr int kPPThreads = 256;
+__global__ void __launch_bounds__(kPPThreads) k_dc_prolongate_parents(Pool T, const uint32_t *__restrict__ list, uint32_t n, float *p) {
+  pdl_enter();
+  __shared__ float sc[2][kAV + 8];
+  __shared__ uint32_t sch[2][kSV];
+  const int i = threadIdx.x;
+  const bool gath = i < kAV;
+  const bool link = i >= 224 && i < 224 + kSV;
+  const uint32_t stride = gridDim.x;
+  uint32_t j = blockIdx.x;
+  auto entry = [&](uint32_t jj) -> uint32_t { return jj < n ? __ldg(list + jj) : kNone; };
+  // pipeline registers: P = parent slot, id = apron id, ch = child link, v = pressure
+  uint32_t P1 = entry(j + stride), P2 = entry(j + 2 * stride), P3;
+  uint32_t id0 = 0, id1 = 0, id2 = 0, ch0 = kNone, ch1 = kNone, ch2 = kNone;
+  float v0 = 0.f, v1 = 0.f;
+  {
+    const uint32_t P0 = entry(j);
+    if (P0 != kNone) {
+      if (gath) id0 = T.apron[(size_t)P0 * kAV + i];
+      if (link) ch0 = T.child[(size_t)P0 * kSV + (i - 224)];
+    }
+    if (P1 != kNone) {
+      if (gath) id1 = T.apron[(size_t)P1 * kAV + i];
+      if (link) ch1 = T.child[(size_t)P1 * kSV + (i - 224)];
+    }
+    if (P0 != kNone && gath) v0 = p[id0];
+  }
+  for (uint32_t k = 0; j < n; k++, j += stride) {
+    // issue the rounds of the following parents
+    if (P1 != kNone && gath) v1 = p[id1];
+    if (P2 != kNone) {
+      if (gath) id2 = T.apron[(size_t)P2 * kAV + i];
+      if (link) ch2 = T.child[(size_t)P2 * kSV + (i - 224)];
+    }
+    P3 = entry(j + 3 * stride);
+    // this parent
+    const int buf = (int)(k & 1u);
+    if (gath) sc[buf][i] = v0;
+    if (link) sch[buf][i - 224] = ch0;
+    __syncthreads();
+    if (i < 128) {
+      const int s = i >> 4, t = i & 15;
+      const uint32_t cb = sch[buf][s];
+      if (cb != kNone) {
+        int X, Y0, Z0;
+        quad_coords(t, X, Y0, Z0);
+        // the child covers subblock s of the parent: parent cell = 2 * subblock bit + (child cell >> 1)
+        const int base = kAA * (1 + ((s >> 2) & 1) * 2 + (X >> 1)) + kAW * (1 + ((s >> 1) & 1) * 2 + (Y0 >> 1)) + (1 + (s & 1) * 2 + (Z0 >> 1));
+        const int di = (X & 1) ? kAA : -kAA;
+        float c[2][3][3];
+#pragma unroll
+        for (int a = 0; a < 2; a++)
+#pragma unroll
+          for (int dj = -1; dj <= 1; dj++)
+#pragma unroll
+            for (int dk = -1; dk <= 1; dk++) c[a][dj + 1][dk + 1] = sc[buf][base + a * di + kAW * dj + dk];
+        float4 o4;
+        o4.x = prolong_one(c, -1, -1);
+        o4.y = prolong_one(c, -1, 1);
+        o4.z = prolong_one(c, 1, -1);
+        o4.w = prolong_one(c, 1, 1);
+        *reinterpret_cast<float4 *>(p + (size_t)cb * kBV + 4 * t) = o4;
+      }
+    }
+    // rotate (one barrier per parent: the buffers alternate, and nobody gets two parents ahead of the barrier)
+    v0 = v1; id1 = id2; ch0 = ch1; ch1 = ch2; P1 = P2; P2 = P3;
+  }
+}
+
 // k_dcgrid_debug_stats, dcgrid_structure.cu:224-251: one thread per block, sequential i,j,k order
 __global__ void __launch_bounds__(256) k_dc_debug_stats(Pool T, KParams P, const float *__restrict__ p, const float *__restrict__ div,
                                                         float *__restrict__ stats) {
