@@ -364,7 +364,12 @@ __global__ void __launch_bounds__(kJ8Threads, 5) k_dc_jacobi_pipe8(Pool T, KPara
 // covering block with one load from the finest-block map (the reference walks the level maps one dependent
 // load at a time, dcgrid_utils.cuh:201-233) and derive the block origin from the sample position (block
 // origins are multiples of 4 cells of their level) instead of loading it.
-constexpr int kAStages = 4;
+// Ring depth 2: the consumers release a slot before their gathers, so two tiles in flight cover the copy latency, and
+// every KiB of shared memory not used is L1 for the gathers (4 stages: 853 us, 2 stages: 840 us at dcgrid512).
+// (Measured and rejected, profiles/README.md r2n: one private ring per warp, no producer warp, 4-warp CTAs at 80 / 95
+// registers = 6 / 5 CTAs per SM: 901 / 971 us.  The kernel is bound by the L1 data pipe and its hit rate — twice as
+// many blocks in flight per SM, each at half speed, only widen the gather footprint that has to stay in L1.)
+constexpr int kAStages = 2;
 constexpr int kAdvectThreads = kCTA + 32;  // 8 consumer warps (4 blocks) + 1 producer warp
 struct alignas(128) AdvectStage {
   uint32_t apron[kBPC * kAV];  // 3456 B
