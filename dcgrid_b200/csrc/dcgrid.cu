@@ -131,7 +131,15 @@ struct DCGridSim : dcg_sim {
     uint32_t n_order = 0;
     uint32_t *d_plist = nullptr;    // blocks with children, per level at [offsets[l] ...)
     uint32_t pcount[kMaxLevels] = {0};
+    uint32_t *d_tstarts = nullptr;  // k_dc_restrict_tree: the blocks its 8-lane groups start from
+    uint32_t n_tstarts = 0;
   };
+  // one-launch restriction (k_dc_restrict_tree): per-block expected counts | level, completion counters, top level of the walk
+  uint8_t *d_texpect = nullptr;
+  uint32_t *d_tcount = nullptr;
+  int tree_top = 0;
+  bool use_tree = true;
+  bool spec_restricted = false;  // the speculative velocity (advect_both) has been restricted together with the density
   std::vector<RankWork> work;
   std::vector<char> level_single;  // the active blocks of the level all belong to one rank: its sweeps need no barrier between them
   // cross-process state (vmm)
@@ -179,7 +187,8 @@ struct DCGridSim : dcg_sim {
     cudaFree(d_new_posl); cudaFree(d_sub_scores); cudaFree(d_block_scores);
     cudaFree(d_pcount);
     if (h_pcount) cudaFreeHost(h_pcount);
-    for (auto &w : work) { cudaFree(w.d_order); cudaFree(w.d_plist); }
+    for (auto &w : work) { cudaFree(w.d_order); cudaFree(w.d_plist); cudaFree(w.d_tstarts); }
+    cudaFree(d_texpect); cudaFree(d_tcount);
     cudaFree(d_unit_owner); cudaFree(d_epoch); cudaFree(d_barrier_err);
     cudaFree(d_order_keys[0]); cudaFree(d_order_keys[1]); cudaFree(d_order_vals); cudaFree(d_sort_tmp);
     if (vmm) {
@@ -402,10 +411,15 @@ struct DCGridSim : dcg_sim {
     DCG_CUDA_TRY(cudaMalloc(&d_unit_owner, nunits));
     DCG_CUDA_TRY(cudaMemcpyAsync(d_unit_owner, unit_owner.data(), nunits, cudaMemcpyHostToDevice, stream));
     DCG_CUDA_TRY(cudaStreamSynchronize(stream));
+    DCG_CUDA_TRY(cudaMalloc(&d_texpect, (size_t)M));
+    DCG_CUDA_TRY(cudaMalloc(&d_tcount, (size_t)M * 4));
+    DCG_CUDA_TRY(cudaMemsetAsync(d_tcount, 0, (size_t)M * 4, stream));
+    use_tree = !(experiment & 8);
     work.resize(nlocal);
     for (auto &w : work) {
       DCG_CUDA_TRY(cudaMalloc(&w.d_order, ((size_t)M + kBPC) * 4));
       DCG_CUDA_TRY(cudaMalloc(&w.d_plist, (size_t)M * 4));
+      DCG_CUDA_TRY(cudaMalloc(&w.d_tstarts, (size_t)M * 4));
       w.level.assign(levels, TileRuns{});
     }
     return DCG_OK;
@@ -906,6 +920,10 @@ struct DCGridSim : dcg_sim {
   // its active blocks, the lists of its blocks with children, and the tile runs of every level
   int rebuild_order() {
     runs_overflow = false;
+    // restriction tree: one GPU walks to the top; sharded ranks own the subtrees below the small levels (k_dc_accumulate_coarse above)
+    tree_top = world > 1 ? small_levels_from(512) - 1 : levels - 1;
+    k_dc_tree_expect<<<blocks_for(M, 256), 256, 0, stream>>>(hot(), d_texpect);
+    launches++;
     for (int lr = 0; lr < nlocal; lr++) {
       RankWork &w = work[lr];
       const int rank = rank0 + lr;
@@ -919,6 +937,12 @@ struct DCGridSim : dcg_sim {
       cudaStreamSynchronize(stream);
       for (int l = 0; l < kMaxLevels; l++) w.pcount[l] = h_pcount[l];
       const uint32_t n = h_pcount[kMaxLevels];
+      cudaMemsetAsync(d_pcount, 0, 4, stream);
+      k_dc_tree_starts<<<blocks_for(M, 256), 256, 0, stream>>>(hot(), tree_top, own, unit, rank, d_texpect, w.d_tstarts, d_pcount);
+      cudaMemcpyAsync(h_pcount, d_pcount, 4, cudaMemcpyDeviceToHost, stream);
+      cudaStreamSynchronize(stream);
+      w.n_tstarts = h_pcount[0];
+      launches++;
       w.n_order = (n + kBPC - 1) / kBPC * kBPC;
       if (w.n_order > n) k_dc_order_pad<<<1, 256, 0, stream>>>(w.d_order, n, w.n_order);
       launches += 4;
@@ -1339,7 +1363,32 @@ struct DCGridSim : dcg_sim {
   }
   // `fused`: the kernel that produced the field restricted every block without children itself, so level 0
   // (never refined) needs no pass at all and the other levels only push up blocks that have children.
+  template <bool kV, bool kS>
+  void launch_restrict_tree(float4 *v, float *ch) {
+    each_rank([&](int, RankWork &w) {
+      if (w.n_tstarts == 0) return;
+      launch_pdl(k_dc_restrict_tree<kV, kS>, dim3(blocks_for(8 * (size_t)w.n_tstarts, 256)), dim3(256), 0, hot(), (const uint32_t *)w.d_tstarts, w.n_tstarts,
+                 (const uint8_t *)d_texpect, d_tcount, tree_top, v, ch);
+      launches++;
+    });
+  }
   void accumulate(float4 *v, float *ch, bool fused) {  // :496-515, fine -> coarse
+    if (fused && use_tree) {  // blocks with children: one launch walks up the block tree (k_dc_restrict_tree)
+      if (v && ch) launch_restrict_tree<true, true>(v, ch);
+      else if (v) launch_restrict_tree<true, false>(v, nullptr);
+      else launch_restrict_tree<false, true>(nullptr, ch);
+      if (world > 1) {  // the levels above the ranks' subtrees
+        barrier();
+        if (tree_top + 1 < levels - 1) {
+          if (has_rank0()) {
+            if (v) { launch_pdl(k_dc_accumulate_coarse, dim3(kAccClusterCTAs), dim3(kAccClusterThreads), 0, hot(), tree_top + 1, v, (float *)nullptr); launches++; }
+            if (ch) { launch_pdl(k_dc_accumulate_coarse, dim3(kAccClusterCTAs), dim3(kAccClusterThreads), 0, hot(), tree_top + 1, (float4 *)nullptr, ch); launches++; }
+          }
+          barrier();
+        }
+      }
+      return;
+    }
     const int tail = small_levels_from(512);
     for (int l = fused ? 1 : 0; l < levels - 1 && l < tail; l++) {
       if (loads[l] == 0) continue;
@@ -1422,7 +1471,8 @@ struct DCGridSim : dcg_sim {
       // vw[cur_v ^ 1] already holds this step's advected velocity (written by the previous advect_density())
       spec_velocity = false;
       cur_v ^= 1;
-      accumulate_velocity(true);
+      if (!spec_restricted) accumulate_velocity(true);
+      spec_restricted = false;
     } else if (use_advect_pipe) {
       launch_advect_pipe(0, vw[cur_v], vw[cur_v ^ 1], nullptr, nullptr);
       cur_v ^= 1;
@@ -1457,7 +1507,10 @@ struct DCGridSim : dcg_sim {
       launch_advect_pipe(fuse_advect ? 2 : 1, vw[cur_v], vw[cur_v ^ 1], q[cur_q], q[cur_q ^ 1]);
       spec_velocity = fuse_advect;
       cur_q ^= 1;
-      accumulate_scalar(q[cur_q], true);
+      // one GPU: the speculative velocity is restricted in the same launch as the density (advect_velocity() then only flips)
+      spec_restricted = fuse_advect && use_tree && world == 1;
+      if (spec_restricted) accumulate(vw[cur_v ^ 1], q[cur_q], true);
+      else accumulate_scalar(q[cur_q], true);
     } else {
       k_dc_advect_density<<<blocks_for(M, kBPC), kCTA, 0, stream>>>(hot(), kp, vw[cur_v], fl, q[cur_q], q[cur_q ^ 1]);
       launches++;

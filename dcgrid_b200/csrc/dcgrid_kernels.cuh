@@ -224,6 +224,92 @@ __global__ void __launch_bounds__(256) k_dc_accumulate_scalar_list(Pool T, const
   ch[(size_t)kSV * ps + (sb % 8)] = a * .125f;
 }
 
+// ---- restriction of the blocks WITH children in one launch: a counter-driven walk up the block tree ----------------
+// The list passes above need one launch (sharded: one barrier) per level because a block with children can only be
+// restricted after its children have been.  Here every block carries `expect` = the number of its children that have
+// children themselves (k_dc_tree_expect, rebuilt with the topology) and a completion counter: a group of 8 lanes
+// (one per subblock, as in the list passes: same sums, same order) starts at a block whose children are all
+// childless — the producing kernel has already restricted those — pushes it into its parent, counts itself at the
+// parent, and the group that completes the parent's count carries on with the parent.  Values written by other SMs
+// in the same launch are read through L2 (__ldcg).  The walk stops above `top_level` (sharded: the ranks own whole
+// subtrees below that level; the levels above it are the single-CTA-cluster pass k_dc_accumulate_coarse).
+__global__ void __launch_bounds__(256) k_dc_tree_expect(Pool T, uint8_t *__restrict__ expect) {
+  const uint32_t b = blockIdx.x * 256 + threadIdx.x;
+  if (b >= T.M) return;
+  const int level = T.posl[b].w;
+  uint32_t n = 0;
+  if (level != kFree) {
+    for (int s = 0; s < kSV; s++) {
+      const uint32_t cb = T.child[(size_t)b * kSV + s];
+      if (cb != kNone && block_has_children(T, cb)) n++;
+    }
+  }
+  expect[b] = (uint8_t)(n | ((uint32_t)(level & 15) << 4));
+}
+// start list: blocks of level <= top_level with children, a parent and no child that has children; owner != nullptr:
+// only those whose ancestor of level top_level (or the block itself) lies in a unit owned by `rank`
+__global__ void __launch_bounds__(256) k_dc_tree_starts(Pool T, int top_level, const uint8_t *__restrict__ owner, uint32_t unit, int rank,
+                                                        const uint8_t *__restrict__ expect, uint32_t *__restrict__ starts, uint32_t *__restrict__ count) {
+  const uint32_t b = blockIdx.x * 256 + threadIdx.x;
+  if (b >= T.M) return;
+  const int level = T.posl[b].w;
+  if (level == kFree || level > top_level || (expect[b] & 15u) != 0 || T.parent[b] == kNone || !block_has_children(T, b)) return;
+  if (owner) {
+    uint32_t a = b;
+    for (int l = level; l < top_level; l++) {
+      const uint32_t ps = T.parent[a];
+      if (ps == kNone) break;
+      a = ps >> 3;
+    }
+    if (owner[a / unit] != rank) return;
+  }
+  starts[atomicAdd(count, 1u)] = b;
+}
+template <bool kV, bool kS>
+__global__ void __launch_bounds__(256) k_dc_restrict_tree(Pool T, const uint32_t *__restrict__ starts, uint32_t nstarts, const uint8_t *__restrict__ expect,
+                                                          uint32_t *cnt, int top_level, float4 *vw, float *ch) {
+  pdl_enter();
+  const uint32_t gid = blockIdx.x * 256 + threadIdx.x;
+  const uint32_t task = gid >> 3, s = gid & 7u;
+  if (task >= nstarts) return;  // whole groups leave together
+  const unsigned lane0 = threadIdx.x & 24u, gmask = 0xFFu << lane0;
+  uint32_t b = starts[task];
+  for (;;) {
+    const uint32_t ps = T.parent[b];
+    if (ps == kNone) break;
+    const size_t sb = (size_t)kSV * b + s;
+    if (kV) {
+      const float4 *c = vw + kSV * sb;
+      float4 v[kSV];
+#pragma unroll
+      for (int i = 0; i < kSV; i++) v[i] = __ldcg(c + i);
+      float ax = 0.f, ay = 0.f, az = 0.f;
+#pragma unroll
+      for (int i = 0; i < kSV; i++) { ax += v[i].x; ay += v[i].y; az += v[i].z; }
+      float *dst = reinterpret_cast<float *>(vw + ((size_t)kSV * ps + s));
+      dst[0] = ax * .125f; dst[1] = ay * .125f; dst[2] = az * .125f;  // .w (fluidity) untouched
+    }
+    if (kS) {
+      const float4 lo = __ldcg(reinterpret_cast<const float4 *>(ch + kSV * sb)), hi = __ldcg(reinterpret_cast<const float4 *>(ch + kSV * sb + 4));
+      float a = 0.f;
+      a += lo.x; a += lo.y; a += lo.z; a += lo.w; a += hi.x; a += hi.y; a += hi.z; a += hi.w;
+      ch[(size_t)kSV * ps + s] = a * .125f;
+    }
+    const uint32_t pb = ps >> 3;
+    const uint32_t e = expect[pb];
+    if ((int)(e >> 4) > top_level) break;
+    __threadfence();  // this lane's stores, before the group is counted at the parent
+    __syncwarp(gmask);
+    uint32_t old = 0;
+    if (s == 0) old = atomicAdd(cnt + pb, 1u);
+    old = __shfl_sync(gmask, old, lane0);
+    if (old + 1u != (e & 15u)) break;  // another group completes the parent
+    if (s == 0) cnt[pb] = 0;           // ready for the next launch
+    __threadfence();                   // the other children's stores, before this group reads them
+    b = pb;
+  }
+}
+
 // ======================================================================================
 // adaptation (dcgrid_adaptation.cu)
 // ======================================================================================
