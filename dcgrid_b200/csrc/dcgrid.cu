@@ -260,6 +260,7 @@ struct DCGridSim : dcg_sim {
     for (int l = 0; l < levels; l++) { T.offsets[l] = (uint32_t)offsets[l]; T.max_blocks[l] = (uint32_t)max_blocks[l]; }
     DCG_CUDA_TRY(cudaMalloc(&T.posl, (size_t)M * sizeof(int4)));
     DCG_CUDA_TRY(cudaMalloc(&T.parent, ((size_t)M + kB4) * 4));  // padded: the stencil rings stream kB4 entries per tile
+    experiment = opt.experiment;
     DCG_TRY(setup_sharding());
     DCG_CUDA_TRY(cudaMalloc(&d_perm, (size_t)M * 4));
     use_pdl = !opt.no_pdl;
@@ -414,7 +415,9 @@ struct DCGridSim : dcg_sim {
     DCG_CUDA_TRY(cudaMalloc(&d_texpect, (size_t)M));
     DCG_CUDA_TRY(cudaMalloc(&d_tcount, (size_t)M * 4));
     DCG_CUDA_TRY(cudaMemsetAsync(d_tcount, 0, (size_t)M * 4, stream));
-    use_tree = !(experiment & 8);
+    // one GPU: per-level list passes (2.50 against 2.54 ms per step at dcgrid512: the walk's chain of dependent rounds is longer than
+    // four short launches); sharded: the tree walk (one barrier per pass instead of one per level: 2.88 against 2.94 ms on 2 B200)
+    use_tree = (world > 1) != ((experiment & 8) != 0);
     work.resize(nlocal);
     for (auto &w : work) {
       DCG_CUDA_TRY(cudaMalloc(&w.d_order, ((size_t)M + kBPC) * 4));
@@ -938,7 +941,7 @@ struct DCGridSim : dcg_sim {
       for (int l = 0; l < kMaxLevels; l++) w.pcount[l] = h_pcount[l];
       const uint32_t n = h_pcount[kMaxLevels];
       cudaMemsetAsync(d_pcount, 0, 4, stream);
-      k_dc_tree_starts<<<blocks_for(M, 256), 256, 0, stream>>>(hot(), tree_top, own, unit, rank, d_texpect, w.d_tstarts, d_pcount);
+      k_dc_tree_starts<<<blocks_for(M, 256), 256, 0, stream>>>(hot(), kp, tree_top, world, slab_axis, rank, d_texpect, w.d_tstarts, d_pcount);
       cudaMemcpyAsync(h_pcount, d_pcount, 4, cudaMemcpyDeviceToHost, stream);
       cudaStreamSynchronize(stream);
       w.n_tstarts = h_pcount[0];
@@ -1381,8 +1384,8 @@ struct DCGridSim : dcg_sim {
         barrier();
         if (tree_top + 1 < levels - 1) {
           if (has_rank0()) {
-            if (v) { launch_pdl(k_dc_accumulate_coarse, dim3(kAccClusterCTAs), dim3(kAccClusterThreads), 0, hot(), tree_top + 1, v, (float *)nullptr); launches++; }
-            if (ch) { launch_pdl(k_dc_accumulate_coarse, dim3(kAccClusterCTAs), dim3(kAccClusterThreads), 0, hot(), tree_top + 1, (float4 *)nullptr, ch); launches++; }
+            launch_pdl(k_dc_accumulate_coarse, dim3(kAccClusterCTAs), dim3(kAccClusterThreads), 0, hot(), tree_top + 1, v, ch);
+            launches++;
           }
           barrier();
         }
@@ -1396,8 +1399,11 @@ struct DCGridSim : dcg_sim {
         each_rank([&](int, RankWork &w) {
           const uint32_t n = w.pcount[l];
           if (n == 0) return;
-          if (v) launch_pdl(k_dc_accumulate_velocity_list, dim3(blocks_for(8 * (size_t)n, 256)), dim3(256), 0, hot(), w.d_plist + offsets[l], n, v);
-          else launch_pdl(k_dc_accumulate_scalar_list, dim3(blocks_for(8 * (size_t)n, 256)), dim3(256), 0, hot(), w.d_plist + offsets[l], n, ch);
+          const dim3 grid(blocks_for(8 * (size_t)n, 256));
+          const uint32_t *list = w.d_plist + offsets[l];
+          if (v && ch) launch_pdl(k_dc_accumulate_list<true, true>, grid, dim3(256), 0, hot(), list, n, v, ch);
+          else if (v) launch_pdl(k_dc_accumulate_list<true, false>, grid, dim3(256), 0, hot(), list, n, v, (float *)nullptr);
+          else launch_pdl(k_dc_accumulate_list<false, true>, grid, dim3(256), 0, hot(), list, n, (float4 *)nullptr, ch);
           launches++;
         });
         barrier();
@@ -1507,8 +1513,8 @@ struct DCGridSim : dcg_sim {
       launch_advect_pipe(fuse_advect ? 2 : 1, vw[cur_v], vw[cur_v ^ 1], q[cur_q], q[cur_q ^ 1]);
       spec_velocity = fuse_advect;
       cur_q ^= 1;
-      // one GPU: the speculative velocity is restricted in the same launch as the density (advect_velocity() then only flips)
-      spec_restricted = fuse_advect && use_tree && world == 1;
+      // the speculative velocity is restricted in the same launch as the density (advect_velocity() then only flips)
+      spec_restricted = fuse_advect;
       if (spec_restricted) accumulate(vw[cur_v ^ 1], q[cur_q], true);
       else accumulate_scalar(q[cur_q], true);
     } else {
@@ -1521,6 +1527,9 @@ struct DCGridSim : dcg_sim {
     return DCG_OK;
   }
   // one sweep of a level; persistent TMA-ring kernel for levels with enough tiles to fill the machine
+  // (Measured and rejected, profiles/README.md r2q: the barrier between two sweeps of a shared level folded into the ring
+  // kernels — last CTA of a sweep raises the epoch at the peers, every CTA of the next sweep waits for the peers' before its
+  // first ghost load — is slower than the stand-alone barrier kernel: 3.07 against 2.98 ms per step on 2 B200.)
   void jacobi_sweep(int l, const float *in, float *out) {
     if (snake) sweep_parity ^= 1;
     each_rank([&](int, RankWork &w) {
@@ -1550,18 +1559,26 @@ struct DCGridSim : dcg_sim {
     jacobi_sweep(l, tp, p);
   }
   void launch_prolongate(int l) {
+    // a level that fills the GPU(s): by parent block (every block of the level is a child of exactly one listed block; sharded:
+    // a rank writes the children of ITS parents wherever they live, so every rank must take the same path — the test uses the
+    // level's global size — and the ranks meet afterwards even if the level itself has one owner)
+    // (one GPU: the per-child kernel; the by-parent kernel is faster alone, 36 against 48 us, and slower inside the step, +15 us)
+    const bool by_parent = prolong_staged && l + 1 < levels - 1 && (loads[l] + kB4 - 1) / kB4 >= (uint64_t)pipe_min_tiles * (uint64_t)world &&
+                           (world > 1) != ((experiment & 1) != 0);
     each_rank([&](int, RankWork &w) {
       const TileRuns &R = w.level[l];
-      if (run_total(R) == 0) return;
-      // one GPU, a level that fills it: by parent block (every block of the level is a child of a listed block)
-      if (prolong_staged && world == 1 && l + 1 < levels - 1 && run_total(R) >= pipe_min_tiles && w.pcount[l + 1] > 0 && !(experiment & 1))
+      if (by_parent) {
+        if (w.pcount[l + 1] == 0) return;
         launch_pdl(k_dc_prolongate_parents, dim3(std::min<unsigned>(w.pcount[l + 1], 8u * (unsigned)sm_count)), dim3(kPPThreads), 0, hot(),
                    (const uint32_t *)(w.d_plist + offsets[l + 1]), w.pcount[l + 1], p);
-      else if (prolong_staged) launch_pdl(k_dc_prolongate_staged, dim3(run_total(R)), dim3(kCTA4), 0, hot(), R, l, p);
-      else launch_pdl(k_dc_prolongate4, dim3(blocks_for(loads[l], kB4)), dim3(kCTA4), 0, hot(), l, p);
+      } else {
+        if (run_total(R) == 0) return;
+        if (prolong_staged) launch_pdl(k_dc_prolongate_staged, dim3(run_total(R)), dim3(kCTA4), 0, hot(), R, l, p);
+        else launch_pdl(k_dc_prolongate4, dim3(blocks_for(loads[l], kB4)), dim3(kCTA4), 0, hot(), l, p);
+      }
       launches++;
     });
-    if (!level_single[l]) barrier();  // single-owner level: the same rank sweeps it next
+    if (!level_single[l] || (by_parent && world > 1)) barrier();  // single-owner level written by its owner: the same rank sweeps it next
   }
   void launch_divergence(int zero_from) {
     each_rank([&](int, RankWork &w) {

@@ -195,33 +195,33 @@ __global__ void __launch_bounds__(256) k_dc_list_parents(Pool T, const uint8_t *
   if (level == kFree || T.parent[b] == kNone || !block_has_children(T, b)) return;
   plist[T.offsets[level] + atomicAdd(&pcount[level], 1u)] = b;
 }
-__global__ void __launch_bounds__(256) k_dc_accumulate_velocity_list(Pool T, const uint32_t *__restrict__ list, uint32_t n, float4 *__restrict__ vw) {
+// one pass over the listed blocks of a level; kV / kS: the packed velocity and / or one scalar channel (after the fused
+// advection the density and the speculative velocity are restricted together)
+template <bool kV, bool kS>
+__global__ void __launch_bounds__(256) k_dc_accumulate_list(Pool T, const uint32_t *__restrict__ list, uint32_t n, float4 *__restrict__ vw, float *__restrict__ ch) {
   pdl_enter();
   const uint32_t t = blockIdx.x * 256 + threadIdx.x;
   if (t >= 8 * n) return;
   const uint32_t b = list[t >> 3], sb = 8 * b + (t & 7u);
   const uint32_t ps = T.parent[b];
-  const float4 *c = vw + (size_t)kSV * sb;
-  float4 v[kSV];
+  if (kV) {
+    const float4 *c = vw + (size_t)kSV * sb;
+    float4 v[kSV];
 #pragma unroll
-  for (int i = 0; i < kSV; i++) v[i] = c[i];
-  float ax = 0.f, ay = 0.f, az = 0.f;
+    for (int i = 0; i < kSV; i++) v[i] = c[i];
+    float ax = 0.f, ay = 0.f, az = 0.f;
 #pragma unroll
-  for (int i = 0; i < kSV; i++) { ax += v[i].x; ay += v[i].y; az += v[i].z; }
-  float *dst = reinterpret_cast<float *>(vw + ((size_t)kSV * ps + (sb % 8)));
-  dst[0] = ax * .125f; dst[1] = ay * .125f; dst[2] = az * .125f;
-}
-__global__ void __launch_bounds__(256) k_dc_accumulate_scalar_list(Pool T, const uint32_t *__restrict__ list, uint32_t n, float *__restrict__ ch) {
-  pdl_enter();
-  const uint32_t t = blockIdx.x * 256 + threadIdx.x;
-  if (t >= 8 * n) return;
-  const uint32_t b = list[t >> 3], sb = 8 * b + (t & 7u);
-  const uint32_t ps = T.parent[b];
-  const float4 lo = *reinterpret_cast<const float4 *>(ch + (size_t)kSV * sb);
-  const float4 hi = *reinterpret_cast<const float4 *>(ch + (size_t)kSV * sb + 4);
-  float a = 0.f;
-  a += lo.x; a += lo.y; a += lo.z; a += lo.w; a += hi.x; a += hi.y; a += hi.z; a += hi.w;
-  ch[(size_t)kSV * ps + (sb % 8)] = a * .125f;
+    for (int i = 0; i < kSV; i++) { ax += v[i].x; ay += v[i].y; az += v[i].z; }
+    float *dst = reinterpret_cast<float *>(vw + ((size_t)kSV * ps + (sb % 8)));
+    dst[0] = ax * .125f; dst[1] = ay * .125f; dst[2] = az * .125f;
+  }
+  if (kS) {
+    const float4 lo = *reinterpret_cast<const float4 *>(ch + (size_t)kSV * sb);
+    const float4 hi = *reinterpret_cast<const float4 *>(ch + (size_t)kSV * sb + 4);
+    float a = 0.f;
+    a += lo.x; a += lo.y; a += lo.z; a += lo.w; a += hi.x; a += hi.y; a += hi.z; a += hi.w;
+    ch[(size_t)kSV * ps + (sb % 8)] = a * .125f;
+  }
 }
 
 // ---- restriction of the blocks WITH children in one launch: a counter-driven walk up the block tree ----------------
@@ -246,22 +246,28 @@ __global__ void __launch_bounds__(256) k_dc_tree_expect(Pool T, uint8_t *__restr
   }
   expect[b] = (uint8_t)(n | ((uint32_t)(level & 15) << 4));
 }
-// start list: blocks of level <= top_level with children, a parent and no child that has children; owner != nullptr:
-// only those whose ancestor of level top_level (or the block itself) lies in a unit owned by `rank`
-__global__ void __launch_bounds__(256) k_dc_tree_starts(Pool T, int top_level, const uint8_t *__restrict__ owner, uint32_t unit, int rank,
+// start list: blocks of level <= top_level with children, a parent and no child that has children; world > 1: only
+// those whose ancestor of level top_level (or the block itself, if the chain ends below) lies in this rank's share
+// of the domain along `axis` (equal slabs of space: the small levels' slots all sit in one ownership unit, so unit
+// ownership would hand every subtree to one rank; a subtree is walked by ONE rank because its counters are per rank)
+__global__ void __launch_bounds__(256) k_dc_tree_starts(Pool T, KParams P, int top_level, int world, int axis, int rank,
                                                         const uint8_t *__restrict__ expect, uint32_t *__restrict__ starts, uint32_t *__restrict__ count) {
   const uint32_t b = blockIdx.x * 256 + threadIdx.x;
   if (b >= T.M) return;
   const int level = T.posl[b].w;
   if (level == kFree || level > top_level || (expect[b] & 15u) != 0 || T.parent[b] == kNone || !block_has_children(T, b)) return;
-  if (owner) {
+  if (world > 1) {
     uint32_t a = b;
     for (int l = level; l < top_level; l++) {
       const uint32_t ps = T.parent[a];
       if (ps == kNone) break;
       a = ps >> 3;
     }
-    if (owner[a / unit] != rank) return;
+    const int4 pa = T.posl[a];
+    const long long pos = (long long)(axis == 0 ? pa.x : (axis == 1 ? pa.y : pa.z)) << pa.w;  // level-0 cell coordinate of the root's origin
+    const int extent = axis == 0 ? P.gx : (axis == 1 ? P.gy : P.gz);
+    const int owner = (int)min((long long)(world - 1), pos * world / extent);
+    if (owner != rank) return;
   }
   starts[atomicAdd(count, 1u)] = b;
 }

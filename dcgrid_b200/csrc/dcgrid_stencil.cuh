@@ -646,7 +646,8 @@ __global__ void __cluster_dims__(kAccClusterCTAs, 1, 1) __launch_bounds__(kAccCl
         for (int k = 0; k < kSV; k++) { ax += v[k].x; ay += v[k].y; az += v[k].z; }
         float *dst = reinterpret_cast<float *>(vw + ((size_t)kSV * ps + (sb % 8)));
         dst[0] = ax * .125f; dst[1] = ay * .125f; dst[2] = az * .125f;
-      } else {
+      }
+      if (ch) {
         const float4 lo = *reinterpret_cast<const float4 *>(ch + (size_t)kSV * sb), hi = *reinterpret_cast<const float4 *>(ch + (size_t)kSV * sb + 4);
         float a = 0.f;
         a += lo.x; a += lo.y; a += lo.z; a += lo.w; a += hi.x; a += hi.y; a += hi.z; a += hi.w;
