@@ -426,13 +426,14 @@ def main():
             ach = b / (ms * 1e-3) / 1e9
             # DRAM traffic of the dominant kernel from the committed ncu --set full capture — only if that capture was
             # taken on exactly these sources (csrc_digest recorded beside it), else null
-            traffic, traffic_src = None, None
+            traffic, traffic_src, hot_traffic = None, None, None
             tpath = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
             if os.path.exists(tpath) and args.workload == "dcgrid512":
                 with open(tpath) as f:
                     tj = json.load(f)
                 if tj.get("csrc_digest") == csrc_digest():
                     traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
+                    hot_traffic = tj.get("all_hot_kernels")
                 else:
                     traffic_src = f"stale: {tj.get('source')} was captured on csrc {tj.get('csrc_digest')}, this is {csrc_digest()}"
             sweeps_big = 0  # sweeps per step that run this kernel on a level of this size (levels 0 and 1 at dcgrid512)
@@ -445,7 +446,8 @@ def main():
                     "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src,
                     "peak_source": peak_src, "ms_per_launch": ms, "alg_bytes_per_launch": b,
                     "share_of_step": sweeps_big * ms / ms_per_step,
-                    "share_of_step_what": f"{sweeps_big} launches of this size per step x ms_per_launch / ms_per_step (the kernel family with the largest share)"}
+                    "share_of_step_what": f"{sweeps_big} launches of this size per step x ms_per_launch / ms_per_step (the kernel family with the largest share)",
+                    "traffic_hot_kernels": hot_traffic}
             for st in (("advect_both",) if grid == "dcgrid" else ()) + ("advect_velocity", "divergence", "apply_pressure", "advect_density"):
                 sim.benchStage(st, 0, 2)
                 ms_s, b_s = sim.benchStage(st, 0, 6)
