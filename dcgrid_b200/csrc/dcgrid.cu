@@ -92,6 +92,13 @@ struct DCGridSim : dcg_sim {
 
   // host wall time spent in the phases of adaptTopology() (incl. their stream synchronisations): dcg_get_info "adapt_*_ms"
   double t_move_ms = 0, t_refine_ms = 0, t_apron_ms = 0, t_layout_ms = 0, t_propagate_ms = 0;
+  // early scores: the geometric scores the NEXT adaptTopology() needs depend on the topology only, so they are computed as
+  // soon as this call has settled it and copied to the host on a side stream while the step's field kernels run
+  bool early_ready = false, early_copy_pending = false, use_early_scores = true;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_scores = nullptr, ev_scores_copied = nullptr;
+  ScoreSummary *h_summary_init = nullptr;
+  uint64_t n_early_scores = 0;
   double t_sel_scores_ms = 0, t_sel_d2h_ms = 0, t_sel_host_ms = 0;  // inside moveBlocks: score kernels + summary, score slices D2H, host selection
   static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
   bool timing_sync = false;  // diagnostics: synchronise between the phases so that the split above is exact
@@ -184,6 +191,10 @@ struct DCGridSim : dcg_sim {
     for (int l = 0; l < kMaxLevels; l++) cudaFree(Tf.map[l]);
     cudaFree(d_flags); cudaFree(d_free); cudaFree(d_touched); cudaFree(d_to_move); cudaFree(d_dest); cudaFree(d_counters); cudaFree(d_flag_bits); cudaFree(d_summary);
     if (h_summary) cudaFreeHost(h_summary);
+    if (h_summary_init) cudaFreeHost(h_summary_init);
+    if (copy_stream) { cudaStreamSynchronize(copy_stream); cudaStreamDestroy(copy_stream); }
+    if (ev_scores) cudaEventDestroy(ev_scores);
+    if (ev_scores_copied) cudaEventDestroy(ev_scores_copied);
     cudaFree(d_new_posl); cudaFree(d_sub_scores); cudaFree(d_block_scores);
     cudaFree(d_pcount);
     if (h_pcount) cudaFreeHost(h_pcount);
@@ -267,8 +278,8 @@ struct DCGridSim : dcg_sim {
     experiment = opt.experiment;
     use_resort = !opt.no_resort;
     if (opt.resort_every != 0) resort_every = std::max(0, opt.resort_every);  // -1: only at the fixed point
-    DCG_CUDA_TRY(cudaMalloc(&d_pcount, (kMaxLevels + 1) * 4));
-    DCG_CUDA_TRY(cudaMallocHost(&h_pcount, (kMaxLevels + 1) * 4));
+    DCG_CUDA_TRY(cudaMalloc(&d_pcount, (kMaxLevels + 2) * 4));
+    DCG_CUDA_TRY(cudaMallocHost(&h_pcount, (kMaxLevels + 2) * 4));
     DCG_CUDA_TRY(cudaMalloc(&d_order_keys[0], (size_t)M * 4));
     DCG_CUDA_TRY(cudaMalloc(&d_order_keys[1], (size_t)M * 4));
     DCG_CUDA_TRY(cudaMalloc(&d_order_vals, (size_t)M * 4));
@@ -297,6 +308,12 @@ struct DCGridSim : dcg_sim {
     DCG_CUDA_TRY(cudaMalloc(&d_counters, 2 * 4));
     DCG_CUDA_TRY(cudaMalloc(&d_summary, sizeof(ScoreSummary)));
     DCG_CUDA_TRY(cudaMallocHost(&h_summary, sizeof(ScoreSummary)));
+    DCG_CUDA_TRY(cudaMallocHost(&h_summary_init, sizeof(ScoreSummary)));
+    for (int l = 0; l < kMaxLevels; l++) { h_summary_init->max_ss[l] = -1; h_summary_init->min_bs[l] = 0xFFFFFFFFu; h_summary_init->n_refine[l] = 0; }
+    DCG_CUDA_TRY(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+    DCG_CUDA_TRY(cudaEventCreateWithFlags(&ev_scores, cudaEventDisableTiming));
+    DCG_CUDA_TRY(cudaEventCreateWithFlags(&ev_scores_copied, cudaEventDisableTiming));
+    use_early_scores = !(experiment & 32);
     DCG_CUDA_TRY(cudaMalloc(&d_new_posl, (size_t)M * sizeof(int4)));
     DCG_CUDA_TRY(cudaMalloc(&d_sub_scores, ((size_t)M * 8 + 1) * 4));
     DCG_CUDA_TRY(cudaMalloc(&d_block_scores, (size_t)M * 4));
@@ -634,6 +651,7 @@ struct DCGridSim : dcg_sim {
     if (params.gx != gx || params.gy != gy || params.gz != gz)
       return fail(DCG_ERR_INVALID, "grid size is fixed at construction (the reference sizes its pool in the ctor)");
     steady = false;  // scores depend on SimParams: the fixed-point proof no longer holds
+    early_ready = false;
     spec_velocity = false;
     drop_graphs();
     return DCG_OK;
@@ -645,6 +663,7 @@ struct DCGridSim : dcg_sim {
     DCG_CUDA_TRY(cudaSetDevice(device));
     DCG_TRY(ensure_ext_storage());
     steady = false;
+    early_ready = false;
     spec_velocity = false;
     drop_graphs();
     return DCG_OK;
@@ -745,6 +764,7 @@ struct DCGridSim : dcg_sim {
     DCG_TRY(enter());
     drop_graphs();
     steady = false;
+    early_ready = false;
     spec_velocity = false;
     k_fill_posl<<<blocks_for(M, 256), 256, 0, stream>>>(T.posl, M);
     DCG_CUDA_TRY(cudaMemsetAsync(d_flags, 0, (size_t)M * 4, stream));
@@ -925,27 +945,28 @@ struct DCGridSim : dcg_sim {
     runs_overflow = false;
     // restriction tree: one GPU walks to the top; sharded ranks own the subtrees below the small levels (k_dc_accumulate_coarse above)
     tree_top = world > 1 ? small_levels_from(512) - 1 : levels - 1;
-    k_dc_tree_expect<<<blocks_for(M, 256), 256, 0, stream>>>(hot(), d_texpect);
-    launches++;
+    if (use_tree) {
+      k_dc_tree_expect<<<blocks_for(M, 256), 256, 0, stream>>>(hot(), d_texpect);
+      launches++;
+    }
     for (int lr = 0; lr < nlocal; lr++) {
       RankWork &w = work[lr];
       const int rank = rank0 + lr;
       const uint8_t *own = world > 1 ? d_unit_owner : nullptr;
-      cudaMemsetAsync(d_pcount, 0, (kMaxLevels + 1) * 4, stream);
+      cudaMemsetAsync(d_pcount, 0, (kMaxLevels + 2) * 4, stream);
       k_dc_order_keys<<<blocks_for(M, 256), 256, 0, stream>>>(hot(), order_mode, own, unit, rank, d_order_keys[0], d_order_vals, d_pcount + kMaxLevels);
       size_t bytes = sort_tmp_bytes;
       cub::DeviceRadixSort::SortPairs(d_sort_tmp, bytes, d_order_keys[0], d_order_keys[1], d_order_vals, w.d_order, (int)M, 0, 32, stream);
       k_dc_list_parents<<<blocks_for(M, 256), 256, 0, stream>>>(hot(), own, unit, rank, w.d_plist, d_pcount);
-      cudaMemcpyAsync(h_pcount, d_pcount, (kMaxLevels + 1) * 4, cudaMemcpyDeviceToHost, stream);
+      if (use_tree) {
+        k_dc_tree_starts<<<blocks_for(M, 256), 256, 0, stream>>>(hot(), kp, tree_top, world, slab_axis, rank, d_texpect, w.d_tstarts, d_pcount + kMaxLevels + 1);
+        launches++;
+      }
+      cudaMemcpyAsync(h_pcount, d_pcount, (kMaxLevels + 2) * 4, cudaMemcpyDeviceToHost, stream);
       cudaStreamSynchronize(stream);
       for (int l = 0; l < kMaxLevels; l++) w.pcount[l] = h_pcount[l];
       const uint32_t n = h_pcount[kMaxLevels];
-      cudaMemsetAsync(d_pcount, 0, 4, stream);
-      k_dc_tree_starts<<<blocks_for(M, 256), 256, 0, stream>>>(hot(), kp, tree_top, world, slab_axis, rank, d_texpect, w.d_tstarts, d_pcount);
-      cudaMemcpyAsync(h_pcount, d_pcount, 4, cudaMemcpyDeviceToHost, stream);
-      cudaStreamSynchronize(stream);
-      w.n_tstarts = h_pcount[0];
-      launches++;
+      w.n_tstarts = use_tree ? h_pcount[kMaxLevels + 1] : 0;
       w.n_order = (n + kBPC - 1) / kBPC * kBPC;
       if (w.n_order > n) k_dc_order_pad<<<1, 256, 0, stream>>>(w.d_order, n, w.n_order);
       launches += 4;
@@ -972,12 +993,13 @@ struct DCGridSim : dcg_sim {
   }
 
   // Scores stay on the device; only the 192-byte per-level summary comes back.
-  int compute_scores(bool with_block_scores) {
+  int launch_scores(bool with_block_scores) {
     const uint32_t mask = finer_full_mask();
-    ScoreSummary init;
-    for (int l = 0; l < kMaxLevels; l++) { init.max_ss[l] = -1; init.min_bs[l] = 0xFFFFFFFFu; init.n_refine[l] = 0; }
-    *h_summary = init;
-    DCG_CUDA_TRY(cudaMemcpyAsync(d_summary, h_summary, sizeof(ScoreSummary), cudaMemcpyHostToDevice, stream));
+    if (early_copy_pending) {  // the side stream may still be reading the score buffers of the previous pass
+      DCG_CUDA_TRY(cudaStreamWaitEvent(stream, ev_scores_copied, 0));
+      early_copy_pending = false;
+    }
+    DCG_CUDA_TRY(cudaMemcpyAsync(d_summary, h_summary_init, sizeof(ScoreSummary), cudaMemcpyHostToDevice, stream));
     k_dc_subblock_scores<<<blocks_for((size_t)M * 8, 256), 256, 0, stream>>>(T, kp, mask, d_sub_scores, d_summary, ext.score_mode == 1 ? vort : nullptr,
                                                                              d_perm);
     launches++;
@@ -985,8 +1007,49 @@ struct DCGridSim : dcg_sim {
       k_dc_block_scores<<<blocks_for(M, 256), 256, 0, stream>>>(T, mask, d_sub_scores, d_block_scores, d_summary);
       launches++;
     }
+    return DCG_OK;
+  }
+  int compute_scores(bool with_block_scores) {
+    DCG_TRY(launch_scores(with_block_scores));
     DCG_CUDA_TRY(cudaMemcpyAsync(h_summary, d_summary, sizeof(ScoreSummary), cudaMemcpyDeviceToHost, stream));
     DCG_CUDA_TRY(cudaStreamSynchronize(stream));
+    return DCG_OK;
+  }
+  // the score slices the host selection of `level` reads, device -> pinned host, on stream `st`
+  int copy_score_slices(const std::vector<char> &need, cudaStream_t st) {
+    std::vector<char> got_bs(levels, 0), got_ss(levels, 0);
+    for (int level = 0; level < levels - 1; level++) {
+      if (!need[level]) continue;
+      // block scores of level l and l+1 (the protect-next-parent write, :417, lands in level l+1), subblock scores of level l+1
+      for (int l2 = level; l2 <= level + 1; l2++)
+        if (!got_bs[l2]) {
+          got_bs[l2] = 1;
+          DCG_CUDA_TRY(cudaMemcpyAsync(h_block_scores + offsets[l2], d_block_scores + offsets[l2], max_blocks[l2] * 4, cudaMemcpyDeviceToHost, st));
+        }
+      if (!got_ss[level + 1]) {
+        got_ss[level + 1] = 1;
+        // +1 float: dc[matches] may index one past the level's last subblock (App. B-3)
+        DCG_CUDA_TRY(cudaMemcpyAsync(h_sub_scores + 8 * offsets[level + 1], d_sub_scores + 8 * offsets[level + 1],
+                                     (8 * max_blocks[level + 1] + 1) * 4, cudaMemcpyDeviceToHost, st));
+      }
+    }
+    return DCG_OK;
+  }
+  // called at the end of an adaptTopology() that leaves the transient running: scores + summary of the settled topology,
+  // summary and the slices of every level that has move candidates copied on the side stream (the host selection of the
+  // next call then finds them in pinned memory while the GPU is still busy with this step's field kernels)
+  int early_scores() {
+    if (!use_early_scores || ext.score_mode != 0 || ext.selection == 1) return DCG_OK;
+    DCG_TRY(launch_scores(true));
+    DCG_CUDA_TRY(cudaEventRecord(ev_scores, stream));
+    DCG_CUDA_TRY(cudaStreamWaitEvent(copy_stream, ev_scores, 0));
+    DCG_CUDA_TRY(cudaMemcpyAsync(h_summary, d_summary, sizeof(ScoreSummary), cudaMemcpyDeviceToHost, copy_stream));
+    std::vector<char> cand(levels, 0);
+    for (int level = 0; level < levels - 1; level++) cand[level] = move_candidates(level) > 0 ? 1 : 0;
+    DCG_TRY(copy_score_slices(cand, copy_stream));
+    DCG_CUDA_TRY(cudaEventRecord(ev_scores_copied, copy_stream));
+    early_ready = early_copy_pending = true;
+    n_early_scores++;
     return DCG_OK;
   }
 
@@ -1012,7 +1075,10 @@ struct DCGridSim : dcg_sim {
   // level's slice of the scores.
   int move_blocks(uint32_t &num_touched) {
     double tm0 = now_ms();
-    DCG_TRY(compute_scores(true));
+    const bool early = early_ready;  // scores, summary and slices of this topology are already on their way to the host
+    early_ready = false;
+    if (early) DCG_CUDA_TRY(cudaEventSynchronize(ev_scores_copied));
+    else DCG_TRY(compute_scores(true));
     t_sel_scores_ms += now_ms() - tm0;
     DCG_CUDA_TRY(cudaMemsetAsync(d_flags, 0, (size_t)M * 4, stream));  // :369
     std::vector<char> need(levels, 0);
@@ -1034,25 +1100,11 @@ struct DCGridSim : dcg_sim {
       return DCG_OK;
     }
     if (ext.selection == 1) return move_blocks_device(need, num_touched);
-    // slices the host selection reads: block scores of level l and l+1 (the protect-next-parent write,
-    // :417, lands in level l+1), subblock scores of level l+1
-    std::vector<char> got_bs(levels, 0), got_ss(levels, 0);
-    for (int level = 0; level < levels - 1; level++) {
-      if (!need[level]) continue;
-      for (int l2 = level; l2 <= level + 1; l2++)
-        if (!got_bs[l2]) {
-          got_bs[l2] = 1;
-          DCG_CUDA_TRY(cudaMemcpyAsync(h_block_scores + offsets[l2], d_block_scores + offsets[l2], max_blocks[l2] * 4, cudaMemcpyDeviceToHost, stream));
-        }
-      if (!got_ss[level + 1]) {
-        got_ss[level + 1] = 1;
-        // +1 float: dc[matches] may index one past the level's last subblock (App. B-3)
-        DCG_CUDA_TRY(cudaMemcpyAsync(h_sub_scores + 8 * offsets[level + 1], d_sub_scores + 8 * offsets[level + 1],
-                                     (8 * max_blocks[level + 1] + 1) * 4, cudaMemcpyDeviceToHost, stream));
-      }
-    }
     tm0 = now_ms();
-    DCG_CUDA_TRY(cudaStreamSynchronize(stream));
+    if (!early) {
+      DCG_TRY(copy_score_slices(need, stream));
+      DCG_CUDA_TRY(cudaStreamSynchronize(stream));
+    }
     t_sel_d2h_ms += now_ms() - tm0;
     tm0 = now_ms();
     const float *bs = h_block_scores, *ss = h_sub_scores;
@@ -1346,12 +1398,15 @@ struct DCGridSim : dcg_sim {
       n_failed = h_cnt[0];
       n_irregular = h_cnt[1];
       t_propagate_ms += now_ms() - t0;
+      DCG_TRY(early_scores());
     } else if (move_limit == limit_before && ext.score_mode == 0) {  // (flow-driven scores change with the fields: never a fixed point)
       steady = true;  // nothing changed and the selection state is unchanged: fixed point
       if (use_resort && changes_since_resort > 0) {  // the layout the steady state will run on, for good
         DCG_TRY(resort());
         DCG_TRY(build_face_descriptors());
       }
+    } else {
+      DCG_TRY(early_scores());  // nothing moved, the move limits did: the transient goes on
     }
     DCG_CUDA_TRY(cudaGetLastError());
     return DCG_OK;
@@ -1994,6 +2049,7 @@ struct DCGridSim : dcg_sim {
     mirrored = false;
     changes_since_resort = 1;
     steady = false;
+    early_ready = false;
     spec_velocity = false;
     cur_v = cur_q = cur_s = 0;
     k_iota_u32<<<blocks_for(M, 256), 256, 0, stream>>>(d_perm, M);
@@ -2117,6 +2173,7 @@ struct DCGridSim : dcg_sim {
     else if (k == "adapt_apron_ms") *out = t_apron_ms;
     else if (k == "adapt_layout_ms") *out = t_layout_ms;
     else if (k == "adapt_propagate_ms") *out = t_propagate_ms;
+    else if (k == "early_scores") *out = (double)n_early_scores;
     else if (k == "select_scores_ms") *out = t_sel_scores_ms;
     else if (k == "select_d2h_ms") *out = t_sel_d2h_ms;
     else if (k == "select_host_ms") *out = t_sel_host_ms;

@@ -193,7 +193,13 @@ __global__ void __launch_bounds__(256) k_dc_list_parents(Pool T, const uint8_t *
   if (owner && owner[b / unit] != rank) return;
   const int level = T.posl[b].w;
   if (level == kFree || T.parent[b] == kNone || !block_has_children(T, b)) return;
-  plist[T.offsets[level] + atomicAdd(&pcount[level], 1u)] = b;
+  // one atomic per warp and level (the lanes of a warp are consecutive slots: almost always one level)
+  const unsigned peers = __match_any_sync(__activemask(), level);
+  const int leader = __ffs(peers) - 1, lane = threadIdx.x & 31;
+  uint32_t base = 0;
+  if (lane == leader) base = atomicAdd(&pcount[level], (uint32_t)__popc(peers));
+  base = __shfl_sync(peers, base, leader);
+  plist[T.offsets[level] + base + __popc(peers & ((1u << lane) - 1u))] = b;
 }
 // one pass over the listed blocks of a level; kV / kS: the packed velocity and / or one scalar channel (after the fused
 // advection the density and the speculative velocity are restricted together)
@@ -361,7 +367,12 @@ __global__ void __launch_bounds__(256) k_dc_subblock_scores(Pool T, KParams P, u
     }
     sub_scores[sb] = score;
   }
-  // summary: warp-shuffle reduction, one atomic per warp when the warp sits inside one level
+  // summary: warp-shuffle reduction when the warp sits inside one level, then per CTA in shared memory: one global
+  // atomic per CTA and level (131 k warps hammering two addresses per level cost 180 us at 512^3, profiles/README.md r2v)
+  __shared__ int s_max[kMaxLevels];
+  __shared__ uint32_t s_cnt[kMaxLevels];
+  if (threadIdx.x < kMaxLevels) { s_max[threadIdx.x] = -1; s_cnt[threadIdx.x] = 0; }
+  __syncthreads();
   int mx = score >= 0.f ? __float_as_int(score) : -1;
   uint32_t cnt = score > 1e-4f ? 1u : 0u;
   if (warp_uniform(level)) {
@@ -371,12 +382,17 @@ __global__ void __launch_bounds__(256) k_dc_subblock_scores(Pool T, KParams P, u
       cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
     }
     if ((threadIdx.x & 31) == 0 && level != kFree) {
-      if (mx >= 0) atomicMax(&sum->max_ss[level], mx);
-      if (cnt) atomicAdd(&sum->n_refine[level], cnt);
+      if (mx >= 0) atomicMax(&s_max[level], mx);
+      if (cnt) atomicAdd(&s_cnt[level], cnt);
     }
   } else if (level != kFree) {
-    if (mx >= 0) atomicMax(&sum->max_ss[level], mx);
-    if (cnt) atomicAdd(&sum->n_refine[level], cnt);
+    if (mx >= 0) atomicMax(&s_max[level], mx);
+    if (cnt) atomicAdd(&s_cnt[level], cnt);
+  }
+  __syncthreads();
+  if (threadIdx.x < kMaxLevels) {
+    if (s_max[threadIdx.x] >= 0) atomicMax(&sum->max_ss[threadIdx.x], s_max[threadIdx.x]);
+    if (s_cnt[threadIdx.x]) atomicAdd(&sum->n_refine[threadIdx.x], s_cnt[threadIdx.x]);
   }
 }
 
