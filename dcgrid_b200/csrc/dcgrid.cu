@@ -1582,9 +1582,12 @@ struct DCGridSim : dcg_sim {
     return DCG_OK;
   }
   // one sweep of a level; persistent TMA-ring kernel for levels with enough tiles to fill the machine
-  // (Measured and rejected, profiles/README.md r2q: the barrier between two sweeps of a shared level folded into the ring
-  // kernels — last CTA of a sweep raises the epoch at the peers, every CTA of the next sweep waits for the peers' before its
-  // first ghost load — is slower than the stand-alone barrier kernel: 3.07 against 2.98 ms per step on 2 B200.)
+  // (Measured and rejected, profiles/README.md r2q / r2z: the barrier between two sweeps of a shared level moved into the ring
+  // kernels.  Whole barrier folded (last CTA of a sweep raises the epoch at the peers, every CTA of the next sweep waits before
+  // its first ghost load): 3.07 against 2.98 ms per step on 2 B200.  Halo overlap (tile lists with the tiles that touch another
+  // rank first, epoch raised once those are done, interior tiles afterwards): 2.885 against 2.874 ms on 2 B200, 3.24-3.27 against
+  // 3.26 on 4 — the 18 barrier launches it removes are paid back by the sweep kernel itself (list indirection, boundary-first
+  // order against the L2-friendly snake order).  The stand-alone barrier kernel stays.)
   void jacobi_sweep(int l, const float *in, float *out) {
     if (snake) sweep_parity ^= 1;
     each_rank([&](int, RankWork &w) {
