@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdcgrid_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-SOURCES = ["api.cu", "uniform.cu", "dcgrid.cu", "uniform_sharded.cu"]
+SOURCES = ["api.cu", "uniform.cu", "dcgrid.cu"]
 FLAGS = [
     "-O3", "-std=c++17", "-fmad=false", "-lineinfo",
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -17,12 +17,17 @@
 #include <string>
 #include <vector>
 
+#include "shard_vmm.h"
 #include "sim.h"
 
 namespace dcg {
 namespace {
 
 constexpr int BX = 32, BY = 4, BZ = 2;  // 256 threads, x-contiguous 128-byte rows
+// planes [zb, ze) of the level a launch covers: everything on one GPU, a rank's slab in the sharded solver (blockIdx.z counts from zb)
+struct ZRange {
+  int zb, ze;
+};
 
 struct UGrid {
   int gx, gy, gz;
@@ -36,10 +41,10 @@ __device__ __forceinline__ int clampi(int v, int lo, int hi) { return max(lo, mi
 
 // k_uniform_set_solidity_ratio, uniformgrid_structure.cu:23-31
 __global__ void __launch_bounds__(256) k_u_fluidity(KParams P, float *__restrict__ fluidity, uint64_t off, int level,
-                                                    float4 *__restrict__ vw0, float4 *__restrict__ vw1) {
-  const int x = blockIdx.x * BX + threadIdx.x, y = blockIdx.y * BY + threadIdx.y, z = blockIdx.z * BZ + threadIdx.z;
+                                                    float4 *__restrict__ vw0, float4 *__restrict__ vw1, ZRange Z) {
+  const int x = blockIdx.x * BX + threadIdx.x, y = blockIdx.y * BY + threadIdx.y, z = Z.zb + blockIdx.z * BZ + threadIdx.z;
   const int w = P.gx >> level, h = P.gy >> level, d = P.gz >> level;
-  if (x >= w || y >= h || z >= d) return;
+  if (x >= w || y >= h || z >= min(d, Z.ze)) return;
   const int scale = 1 << level;
   const float f = cell_fluidity(P, x, y, z, scale);
   const uint64_t i = ((uint64_t)z * (P.gy / scale) + y) * (P.gx / scale) + x;
@@ -81,9 +86,9 @@ __device__ __forceinline__ bool u_inside(const KParams &P, const USample &s) {
 }
 
 // k_uniform_advect_velocity, uniformgrid_fluid.cu:50-67,88-95
-__global__ void __launch_bounds__(256) k_u_advect_velocity(KParams P, const float4 *__restrict__ vin, float4 *__restrict__ vout) {
-  const int x = blockIdx.x * BX + threadIdx.x, y = blockIdx.y * BY + threadIdx.y, z = blockIdx.z * BZ + threadIdx.z;
-  if (x >= P.gx || y >= P.gy || z >= P.gz) return;
+__global__ void __launch_bounds__(256) k_u_advect_velocity(KParams P, const float4 *__restrict__ vin, float4 *__restrict__ vout, ZRange Z) {
+  const int x = blockIdx.x * BX + threadIdx.x, y = blockIdx.y * BY + threadIdx.y, z = Z.zb + blockIdx.z * BZ + threadIdx.z;
+  if (x >= P.gx || y >= P.gy || z >= min(P.gz, Z.ze)) return;
   const uint64_t i = lidx(P, x, y, z);
   const float4 me = vin[i];
   const float bx = ((float)x + .5f) - me.x * P.dt * P.rdx;
@@ -115,9 +120,9 @@ __global__ void __launch_bounds__(256) k_u_advect_velocity(KParams P, const floa
 
 // k_uniform_advect_density, uniformgrid_fluid.cu:69-86,97-105
 __global__ void __launch_bounds__(256) k_u_advect_density(KParams P, const float4 *__restrict__ vw, const float *__restrict__ qin,
-                                                          float *__restrict__ qout) {
-  const int x = blockIdx.x * BX + threadIdx.x, y = blockIdx.y * BY + threadIdx.y, z = blockIdx.z * BZ + threadIdx.z;
-  if (x >= P.gx || y >= P.gy || z >= P.gz) return;
+                                                          float *__restrict__ qout, ZRange Z) {
+  const int x = blockIdx.x * BX + threadIdx.x, y = blockIdx.y * BY + threadIdx.y, z = Z.zb + blockIdx.z * BZ + threadIdx.z;
+  if (x >= P.gx || y >= P.gy || z >= min(P.gz, Z.ze)) return;
   const uint64_t i = lidx(P, x, y, z);
   const float4 me = vw[i];
   const float bx = ((float)x + .5f) - me.x * P.dt * P.rdx;
@@ -148,9 +153,9 @@ __global__ void __launch_bounds__(256) k_u_advect_density(KParams P, const float
 // clamped ids and the fluidity-weighted weights.  The advected velocity goes to the idle ping-pong buffer; the
 // host uses it in the next advect_velocity() if nothing touched the state in between (`spec_velocity`).
 __global__ void __launch_bounds__(256) k_u_advect_both(KParams P, const float4 *__restrict__ vin, float4 *__restrict__ vout,
-                                                       const float *__restrict__ qin, float *__restrict__ qout) {
-  const int x = blockIdx.x * BX + threadIdx.x, y = blockIdx.y * BY + threadIdx.y, z = blockIdx.z * BZ + threadIdx.z;
-  if (x >= P.gx || y >= P.gy || z >= P.gz) return;
+                                                       const float *__restrict__ qin, float *__restrict__ qout, ZRange Z) {
+  const int x = blockIdx.x * BX + threadIdx.x, y = blockIdx.y * BY + threadIdx.y, z = Z.zb + blockIdx.z * BZ + threadIdx.z;
+  if (x >= P.gx || y >= P.gy || z >= min(P.gz, Z.ze)) return;
   const uint64_t i = lidx(P, x, y, z);
   const float4 me = vin[i];
   const float bx = ((float)x + .5f) - me.x * P.dt * P.rdx;
@@ -192,9 +197,9 @@ __global__ void __launch_bounds__(256) k_u_advect_both(KParams P, const float4 *
 // fetched one plane ahead, so that only the corner loads are on a thread's critical path, and the index set-up is paid
 // once per column.
 __global__ void __launch_bounds__(256) k_u_advect_both_zm(KParams P, const float4 *__restrict__ vin, float4 *__restrict__ vout,
-                                                          const float *__restrict__ qin, float *__restrict__ qout, int zc) {
+                                                          const float *__restrict__ qin, float *__restrict__ qout, int zc, ZRange Z) {
   const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
-  const int z0 = blockIdx.z * zc, z1 = min(z0 + zc, P.gz);
+  const int z0 = Z.zb + blockIdx.z * zc, z1 = min(z0 + zc, min(P.gz, Z.ze));
   if (x >= P.gx || y >= P.gy) return;
   const uint64_t sz = (uint64_t)P.gx * P.gy;
   const uint64_t col = (uint64_t)y * P.gx + x;
@@ -245,9 +250,9 @@ __global__ void __launch_bounds__(256) k_u_advect_both_zm(KParams P, const float
 // zero: bit 0 = clear p, bit 1 = clear t_p like the reference does here; project() skips the level-0 clears it provably
 // never reads (the prolongation rewrites every p of the level, the first sweep every t_p, before either is read)
 __global__ void __launch_bounds__(256) k_u_divergence(KParams P, const float4 *__restrict__ vw, float *__restrict__ div,
-                                                      float *__restrict__ p, float *__restrict__ tp, int zero) {
-  const int x = blockIdx.x * BX + threadIdx.x, y = blockIdx.y * BY + threadIdx.y, z = blockIdx.z * BZ + threadIdx.z;
-  if (x >= P.gx || y >= P.gy || z >= P.gz) return;
+                                                      float *__restrict__ p, float *__restrict__ tp, int zero, ZRange Z) {
+  const int x = blockIdx.x * BX + threadIdx.x, y = blockIdx.y * BY + threadIdx.y, z = Z.zb + blockIdx.z * BZ + threadIdx.z;
+  if (x >= P.gx || y >= P.gy || z >= min(P.gz, Z.ze)) return;
   const uint64_t i = lidx(P, x, y, z);
   const uint64_t sx = 1, sy = P.gx, sz = (uint64_t)P.gx * P.gy;
   const float4 l = vw[x > 0 ? i - sx : i], r = vw[x < P.gx - 1 ? i + sx : i];
@@ -266,10 +271,10 @@ __global__ void __launch_bounds__(256) k_u_divergence(KParams P, const float4 *_
 
 // k_uniform_restrict, uniformgrid_fluid.cu:134-160.  `off`/`coff` = pyramid offsets of this/child level.
 __global__ void __launch_bounds__(256) k_u_restrict(KParams P, int level, uint64_t off, uint64_t coff, float *__restrict__ div,
-                                                    float *__restrict__ p, float *__restrict__ tp) {
-  const int x = blockIdx.x * BX + threadIdx.x, y = blockIdx.y * BY + threadIdx.y, z = blockIdx.z * BZ + threadIdx.z;
+                                                    float *__restrict__ p, float *__restrict__ tp, ZRange Z) {
+  const int x = blockIdx.x * BX + threadIdx.x, y = blockIdx.y * BY + threadIdx.y, z = Z.zb + blockIdx.z * BZ + threadIdx.z;
   const int W = P.gx >> level, H = P.gy >> level, D = P.gz >> level;
-  if (x >= W || y >= H || z >= D) return;
+  if (x >= W || y >= H || z >= min(D, Z.ze)) return;
   const uint64_t cw = (uint64_t)(P.gx >> (level - 1)), ch = (uint64_t)(P.gy >> (level - 1));
   const uint64_t i = off + ((uint64_t)z * H + y) * W + x;
   const float *c = div + coff + ((uint64_t)(2 * z) * ch + 2 * y) * cw + 2 * x;
@@ -280,10 +285,10 @@ __global__ void __launch_bounds__(256) k_u_restrict(KParams P, int level, uint64
 
 // calcPressure<in,out>, uniformgrid_fluid.cu:162-192 (k_uniform_jacobi / k_uniform_jacobi_inv :194-204)
 __global__ void __launch_bounds__(256) k_u_jacobi(KParams P, int level, uint64_t off, const float *__restrict__ in,
-                                                  float *__restrict__ out, const float *__restrict__ div) {
-  const int x = blockIdx.x * BX + threadIdx.x, y = blockIdx.y * BY + threadIdx.y, z = blockIdx.z * BZ + threadIdx.z;
+                                                  float *__restrict__ out, const float *__restrict__ div, ZRange Z) {
+  const int x = blockIdx.x * BX + threadIdx.x, y = blockIdx.y * BY + threadIdx.y, z = Z.zb + blockIdx.z * BZ + threadIdx.z;
   const int w = P.gx >> level, h = P.gy >> level, d = P.gz >> level;
-  if (x >= w || y >= h || z >= d) return;
+  if (x >= w || y >= h || z >= min(d, Z.ze)) return;
   const int scale = 1 << level;
   const float alpha = P.dx * P.dx * scale * scale;
   const uint64_t i = off + ((uint64_t)z * h + y) * w + x;
@@ -305,10 +310,10 @@ __global__ void __launch_bounds__(256) k_u_jacobi(KParams P, int level, uint64_t
 constexpr int ZTX = 32, ZTY = 8;  // 256 threads: a warp covers one x row of the tile
 
 __global__ void __launch_bounds__(ZTX * ZTY) k_u_jacobi_zm(KParams P, int level, uint64_t off, const float *__restrict__ in, float *__restrict__ out,
-                                                           const float *__restrict__ div, int zc) {
+                                                           const float *__restrict__ div, int zc, ZRange Z) {
   const int w = P.gx >> level, h = P.gy >> level, d = P.gz >> level;
   const int x = 4 * (blockIdx.x * ZTX + threadIdx.x), y = blockIdx.y * ZTY + threadIdx.y;
-  const int z0 = blockIdx.z * zc, z1 = min(z0 + zc, d);
+  const int z0 = Z.zb + blockIdx.z * zc, z1 = min(z0 + zc, min(d, Z.ze));
   const int scale = 1 << level;
   const float alpha = P.dx * P.dx * scale * scale;
   const size_t sy = (size_t)w, sz = (size_t)w * h;
@@ -339,9 +344,9 @@ __global__ void __launch_bounds__(ZTX * ZTY) k_u_jacobi_zm(KParams P, int level,
 }
 
 __global__ void __launch_bounds__(ZTX * ZTY) k_u_divergence_zm(KParams P, const float4 *__restrict__ vw, float *__restrict__ div, float *__restrict__ p,
-                                                               float *__restrict__ tp, int zc, int zero) {
+                                                               float *__restrict__ tp, int zc, int zero, ZRange Z) {
   const int x = blockIdx.x * ZTX + threadIdx.x, y = blockIdx.y * ZTY + threadIdx.y;
-  const int z0 = blockIdx.z * zc, z1 = min(z0 + zc, P.gz);
+  const int z0 = Z.zb + blockIdx.z * zc, z1 = min(z0 + zc, min(P.gz, Z.ze));
   const size_t sy = (size_t)P.gx, sz = (size_t)P.gx * P.gy;
   const size_t col = (size_t)y * P.gx + x;
   const size_t dnrow = y > 0 ? col - sy : col, uprow = y < P.gy - 1 ? col + sy : col;
@@ -380,10 +385,10 @@ __global__ void __launch_bounds__(ZTX * ZTY) k_u_divergence_zm(KParams P, const 
 }
 
 // k_uniform_prolongate, uniformgrid_fluid.cu:206-237
-__global__ void __launch_bounds__(256) k_u_prolongate(KParams P, int level, uint64_t off, uint64_t poff, float *__restrict__ p) {
-  const int x = blockIdx.x * BX + threadIdx.x, y = blockIdx.y * BY + threadIdx.y, z = blockIdx.z * BZ + threadIdx.z;
+__global__ void __launch_bounds__(256) k_u_prolongate(KParams P, int level, uint64_t off, uint64_t poff, float *__restrict__ p, ZRange Z) {
+  const int x = blockIdx.x * BX + threadIdx.x, y = blockIdx.y * BY + threadIdx.y, z = Z.zb + blockIdx.z * BZ + threadIdx.z;
   const int w = P.gx >> level, h = P.gy >> level, d = P.gz >> level;
-  if (x >= w || y >= h || z >= d) return;
+  if (x >= w || y >= h || z >= min(d, Z.ze)) return;
   const uint64_t i = off + ((uint64_t)z * h + y) * w + x;
   const int64_t pw = w / 2, ph = h / 2;
   const int64_t i000 = (int64_t)poff + ((int64_t)(z / 2) * ph + y / 2) * pw + x / 2;
@@ -399,10 +404,10 @@ __global__ void __launch_bounds__(256) k_u_prolongate(KParams P, int level, uint
 // z-marching prolongation: 4 fine cells (one float4 store) per thread and plane.  The one-thread-per-cell kernel above
 // took 4.5 ms at 1024^3 for 4.8 GB of traffic (8 coarse loads and a page of 64-bit index arithmetic per cell); here the
 // four cells x = 4k .. 4k+3 share the coarse cells 2k-1 .. 2k+2 of four coarse rows.  Same expression per cell.
-__global__ void __launch_bounds__(ZTX * ZTY) k_u_prolongate_zm(KParams P, int level, uint64_t off, uint64_t poff, float *__restrict__ p, int zc) {
+__global__ void __launch_bounds__(ZTX * ZTY) k_u_prolongate_zm(KParams P, int level, uint64_t off, uint64_t poff, float *__restrict__ p, int zc, ZRange Z) {
   const int w = P.gx >> level, h = P.gy >> level, d = P.gz >> level;
   const int x = 4 * (blockIdx.x * ZTX + threadIdx.x), y = blockIdx.y * ZTY + threadIdx.y;
-  const int z0 = blockIdx.z * zc, z1 = min(z0 + zc, d);
+  const int z0 = Z.zb + blockIdx.z * zc, z1 = min(z0 + zc, min(d, Z.ze));
   const int pw = w / 2, ph = h / 2;
   const int sy = (y == 0 || y == h - 1) ? 0 : 2 * (y % 2) - 1;
   const float *c = p + poff;
@@ -440,9 +445,9 @@ __global__ void __launch_bounds__(ZTX * ZTY) k_u_prolongate_zm(KParams P, int le
 
 // k_uniform_apply_pressure, uniformgrid_fluid.cu:239-260
 __global__ void __launch_bounds__(256) k_u_apply_pressure(KParams P, const float *__restrict__ p, const float *__restrict__ fl,
-                                                          float4 *__restrict__ vw) {
-  const int x = blockIdx.x * BX + threadIdx.x, y = blockIdx.y * BY + threadIdx.y, z = blockIdx.z * BZ + threadIdx.z;
-  if (x >= P.gx || y >= P.gy || z >= P.gz) return;
+                                                          float4 *__restrict__ vw, ZRange Z) {
+  const int x = blockIdx.x * BX + threadIdx.x, y = blockIdx.y * BY + threadIdx.y, z = Z.zb + blockIdx.z * BZ + threadIdx.z;
+  if (x >= P.gx || y >= P.gy || z >= min(P.gz, Z.ze)) return;
   const uint64_t i = lidx(P, x, y, z);
   const uint64_t sy = P.gx, sz = (uint64_t)P.gx * P.gy;
   const uint64_t il = x > 0 ? i - 1 : i, ir = x < P.gx - 1 ? i + 1 : i;
@@ -462,9 +467,9 @@ __global__ void __launch_bounds__(256) k_u_apply_pressure(KParams P, const float
 
 // z-marching pressure gradient: the column's pressure and fluidity planes in registers, x neighbours by shuffle
 __global__ void __launch_bounds__(ZTX * ZTY) k_u_apply_zm(KParams P, const float *__restrict__ p, const float *__restrict__ fl, float4 *__restrict__ vw,
-                                                          int zc) {
+                                                          int zc, ZRange Z) {
   const int x = blockIdx.x * ZTX + threadIdx.x, y = blockIdx.y * ZTY + threadIdx.y;
-  const int z0 = blockIdx.z * zc, z1 = min(z0 + zc, P.gz);
+  const int z0 = Z.zb + blockIdx.z * zc, z1 = min(z0 + zc, min(P.gz, Z.ze));
   const size_t sy = (size_t)P.gx, sz = (size_t)P.gx * P.gy;
   const size_t col = (size_t)y * P.gx + x;
   const size_t dnrow = y > 0 ? col - sy : col, uprow = y < P.gy - 1 ? col + sy : col;
@@ -535,6 +540,42 @@ uint64_t pyramid_offset(uint64_t w, uint64_t h, uint64_t d, uint64_t scale) {  /
   return off;
 }
 
+// ---- slab decomposition ------------------------------------------------------------------------------
+// The dense solver sharded over `world` ranks by contiguous z-slabs runs THE SAME kernels: every field lives in one
+// virtual address range that looks the same on every GPU (one process per GPU: stitched from physical pieces the ranks
+// allocate on their own devices, shard_vmm.h; all ranks in one process: plain allocations), a launch covers the planes
+// [zb, ze) of its rank (ZRange), and a neighbour plane, a backtraced gather corner (CFL ~ 23-46 cells: no fixed-width
+// halo would do) or a coarse parent cell that another rank owns is read in place over NVLink.  A coarse plane belongs
+// to the owner of its first fine plane.  Ranks meet at a flag barrier over peer memory before every stage.
+constexpr int kMaxShardRanks = 8;
+struct ShardFlags {
+  volatile uint32_t *flags[kMaxShardRanks];  // flags[r][j] = the last epoch rank j announced to rank r
+};
+__device__ __forceinline__ unsigned long long shard_global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// epoch in device memory: the launch is identical every time (graph-capturable)
+__global__ void __launch_bounds__(32) k_u_barrier(ShardFlags B, int rank, int world, uint32_t *epoch_counter, uint32_t *err) {
+  const int t = threadIdx.x;
+  uint32_t epoch = 0;
+  if (t == 0) epoch = ++(*epoch_counter);
+  epoch = __shfl_sync(0xFFFFFFFFu, epoch, 0);
+  if (t < world && t != rank) {
+    __threadfence_system();       // everything this rank wrote before the barrier is visible system-wide
+    B.flags[t][rank] = epoch;     // 4-byte store into the peer's control block over NVLink
+    const unsigned long long t0 = shard_global_ns();
+    while ((int32_t)(B.flags[rank][t] - epoch) < 0) {
+      if (shard_global_ns() - t0 > 10000000000ull) {  // 10 s: a rank that never arrives trips *err instead of hanging the GPU
+        *err = 1;
+        break;
+      }
+    }
+    __threadfence_system();
+  }
+}
+
 struct UniformSim : dcg_sim {
   int gx = 0, gy = 0, gz = 0, mip_levels = 1;
   uint64_t N = 0, pyr = 0;
@@ -551,15 +592,35 @@ struct UniformSim : dcg_sim {
   bool fuse_advect = true, spec_velocity = false;
   std::vector<uint64_t> level_off;
 
+  // slab decomposition: ranks [rank0, rank0 + nlocal) of `world`; world == 1: the plain single-GPU solver
+  int world = 1, rank0 = 0, nlocal = 1, slab = 0;
+  bool vmm = false, ready = true;  // vmm: one rank per process, fields stitched from every rank's physical pieces
+  vmm::Driver drv;
+  vmm::FdServer fd_server;
+  static constexpr int kFields = 8;  // vw0 vw1 q0 q1 fluidity p tp div
+  size_t gran = 0, field_bytes[kFields] = {0}, field_va_bytes[kFields] = {0};
+  CUdeviceptr field_va[kFields] = {0}, ctrl_va = 0;
+  std::vector<std::vector<CUmemGenericAllocationHandle>> pieces;  // [rank]: control block, then its non-empty field pieces in field order
+  ShardFlags peers{};
+  uint32_t *d_epoch = nullptr, *d_barrier_err = nullptr;
+  uint64_t n_barriers = 0;
+
   // CUDA graph of one full step (advectVelocity, adaptTopology, project, advectDensity)
   cudaGraphExec_t step_graph[4] = {nullptr, nullptr, nullptr, nullptr};  // one per (cur_v, cur_q) start state
-  uint64_t step_graph_launches = 0;
+  uint64_t step_graph_launches = 0, step_graph_barriers = 0;
 
   ~UniformSim() override {
     cudaSetDevice(device);
+    if (stream) cudaStreamSynchronize(stream);
     drop_graphs();
-    for (int i = 0; i < 2; i++) { cudaFree(vw[i]); cudaFree(q[i]); }
-    cudaFree(fluidity); cudaFree(p); cudaFree(tp); cudaFree(div); cudaFree(scratch); cudaFree(d_partial);
+    if (vmm) {
+      fd_server.finish();
+      release_vmm();
+    } else {
+      for (int i = 0; i < 2; i++) { cudaFree(vw[i]); cudaFree(q[i]); }
+      cudaFree(fluidity); cudaFree(p); cudaFree(tp); cudaFree(div);
+    }
+    cudaFree(scratch); cudaFree(d_partial); cudaFree(d_epoch); cudaFree(d_barrier_err);
     if (h_partial) cudaFreeHost(h_partial);
     base_teardown();
   }
@@ -572,11 +633,23 @@ struct UniformSim : dcg_sim {
 
   void invalidate_graphs() override { drop_graphs(); }
 
-  int construct(const dcg_sim_params *prm, int dev) override {
+  int construct(const dcg_sim_params *prm, int dev) override { return construct_sharded(prm, dev, 0, 1, 1); }
+
+  // rank / wsize / nloc: this instance holds ranks [rank, rank + nloc) of a wsize-way z-slab decomposition
+  // (nloc == wsize: all of them, on one device, in stream order; nloc == 1 < wsize: one rank per process)
+  int construct_sharded(const dcg_sim_params *prm, int dev, int rank, int wsize, int nloc) {
     DCG_TRY(base_setup(prm, dev));
     project_coarsest_pairs = 2; project_level_pairs = 1; local_pairs = 5;  // fluid_simulation_uniform.cu:103,116,129
     gx = prm->gx; gy = prm->gy; gz = prm->gz;
+    world = wsize; rank0 = rank; nlocal = nloc;
     if (gx <= 0 || gy <= 0 || gz <= 0) return fail(DCG_ERR_INVALID, "grid size must be positive");
+    if (world < 1 || world > kMaxShardRanks) return fail(DCG_ERR_INVALID, "world size must be in [1, %d]", kMaxShardRanks);
+    if (nlocal != 1 && nlocal != world) return fail(DCG_ERR_INVALID, "nlocal must be 1 (one rank per process) or world (all ranks in this process)");
+    if (rank0 < 0 || rank0 + nlocal > world) return fail(DCG_ERR_INVALID, "rank out of range");
+    if (gz % world != 0) return fail(DCG_ERR_INVALID, "gz (%d) must be a multiple of the world size (%d): slabs are whole z-planes of equal count", gz, world);
+    if (((uint64_t)gx * gy) % 256 != 0 && world > 1) return fail(DCG_ERR_INVALID, "gx*gy must be a multiple of 256 (debugStats bins must not straddle slabs)");
+    slab = gz / world;
+    vmm = nlocal != world;
     N = (uint64_t)gx * gy * gz;
     // mipmapLevels rule, fluid_simulation_uniform.cu:8-17
     uint64_t min_dim = (gx < gy && gx < gz) ? gx : (gy < gz ? gy : gz);
@@ -589,24 +662,203 @@ struct UniformSim : dcg_sim {
     pyr = pyramid_cells(gx, gy, gz);
     level_off.resize(mip_levels);
     for (int l = 0; l < mip_levels; l++) level_off[l] = pyramid_offset(gx, gy, gz, 1ull << l);
-    for (int i = 0; i < 2; i++) {
-      DCG_CUDA_TRY(cudaMalloc(&vw[i], N * sizeof(float4)));
-      DCG_CUDA_TRY(cudaMalloc(&q[i], N * sizeof(float)));
-    }
-    DCG_CUDA_TRY(cudaMalloc(&fluidity, pyr * sizeof(float)));
-    DCG_CUDA_TRY(cudaMalloc(&p, pyr * sizeof(float)));
-    DCG_CUDA_TRY(cudaMalloc(&tp, pyr * sizeof(float)));
-    DCG_CUDA_TRY(cudaMalloc(&div, pyr * sizeof(float)));
-    DCG_CUDA_TRY(cudaMalloc(&scratch, 3 * N * sizeof(float)));
+    for (int f = 0; f < kFields; f++) field_bytes[f] = f < 2 ? N * sizeof(float4) : (f < 4 ? N * sizeof(float) : pyr * sizeof(float));
+    DCG_CUDA_TRY(cudaMalloc(&scratch, 3 * local_cells() * sizeof(float)));
     DCG_CUDA_TRY(cudaMalloc(&d_partial, 1024 * sizeof(double)));
     DCG_CUDA_TRY(cudaMallocHost(&h_partial, 1024 * sizeof(double)));
     fuse_advect = !opt.advect_no_fuse;
+    if (vmm) return create_arena();  // the caller exchanges handles, then import_handles() maps the peers and resets
+    for (int i = 0; i < 2; i++) {
+      DCG_CUDA_TRY(cudaMalloc(&vw[i], field_bytes[i]));
+      DCG_CUDA_TRY(cudaMalloc(&q[i], field_bytes[2 + i]));
+    }
+    DCG_CUDA_TRY(cudaMalloc(&fluidity, field_bytes[4]));
+    DCG_CUDA_TRY(cudaMalloc(&p, field_bytes[5]));
+    DCG_CUDA_TRY(cudaMalloc(&tp, field_bytes[6]));
+    DCG_CUDA_TRY(cudaMalloc(&div, field_bytes[7]));
     return reset();
   }
 
-  dim3 grid_for(int level) const {
-    return dim3(idiv_up(gx >> level, BX), idiv_up(gy >> level, BY), idiv_up(gz >> level, BZ));
+  // ---- one rank per process: the fields as one virtual range per field, stitched from every rank's pieces ----
+  // Who holds a byte decides where it lives, not who computes it — but a remote byte costs ~8x a local one, so the physical
+  // pieces follow the ownership of the cells: every allocation granule (2 MiB) of a field's byte range belongs to the rank that
+  // owns the cell in its middle (level-0 arrays: its z-slab; pyramids: the slab of whichever level the granule lies in), and a
+  // rank allocates one piece per maximal run of its granules.
+  struct PieceRun { size_t b0, b1; int owner; };
+  std::vector<PieceRun> piece_runs[kFields];
+  int owner_of_byte(int f, size_t byte) const {
+    if (f < 4) {
+      const uint64_t cell = std::min<uint64_t>(N - 1, byte / (f < 2 ? sizeof(float4) : sizeof(float)));
+      return (int)std::min<uint64_t>(world - 1, cell / ((uint64_t)gx * gy) / slab);
+    }
+    const uint64_t cell = std::min<uint64_t>(pyr - 1, byte / sizeof(float));
+    int l = 0;
+    while (l + 1 < mip_levels && cell >= level_off[l + 1]) l++;
+    if (cell >= level_off[l] + (uint64_t)(gx >> l) * (gy >> l) * (gz >> l)) return world - 1;  // levels beyond mip_levels (never touched)
+    const uint64_t z = (cell - level_off[l]) / ((uint64_t)(gx >> l) * (gy >> l));
+    return (int)std::min<uint64_t>(world - 1, (z << l) / slab);
   }
+  void build_piece_runs() {
+    for (int f = 0; f < kFields; f++) {
+      piece_runs[f].clear();
+      const size_t ngran = (field_bytes[f] + gran - 1) / gran;
+      for (size_t g = 0; g < ngran; g++) {
+        const int o = owner_of_byte(f, g * gran + gran / 2);
+        if (!piece_runs[f].empty() && piece_runs[f].back().owner == o) piece_runs[f].back().b1 = (g + 1) * gran;
+        else piece_runs[f].push_back({g * gran, (g + 1) * gran, o});
+      }
+    }
+  }
+  CUmemAccessDesc access_desc() const {
+    CUmemAccessDesc acc;
+    std::memset(&acc, 0, sizeof acc);
+    acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    acc.location.id = device;
+    acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+    return acc;
+  }
+  int map_piece(CUdeviceptr va, size_t bytes, CUmemGenericAllocationHandle h) {
+    if (drv.memMap(va, bytes, 0, h, 0) != CUDA_SUCCESS) return fail(DCG_ERR_CUDA, "cuMemMap failed (%zu bytes)", bytes);
+    CUmemAccessDesc acc = access_desc();
+    if (drv.memSetAccess(va, bytes, &acc, 1) != CUDA_SUCCESS) return fail(DCG_ERR_CUDA, "cuMemSetAccess failed: peer access between the GPUs is required");
+    return DCG_OK;
+  }
+  int create_arena() {
+    if (!drv.load()) return fail(DCG_ERR_CUDA, "CUDA virtual memory management entry points are not available");
+    CUmemAllocationProp prop = vmm::device_prop(device);
+    if (drv.memGranularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_MINIMUM) != CUDA_SUCCESS || gran == 0) return fail(DCG_ERR_CUDA, "cuMemGetAllocationGranularity failed");
+    pieces.assign(world, {});
+    std::vector<int> fds;
+    auto create = [&](size_t bytes) -> int {
+      CUmemGenericAllocationHandle h;
+      if (drv.memCreate(&h, bytes, &prop, 0) != CUDA_SUCCESS) return fail(DCG_ERR_CUDA, "cuMemCreate(%zu bytes) failed", bytes);
+      pieces[rank0].push_back(h);
+      int fd = -1;
+      if (drv.memExport(&fd, h, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0) != CUDA_SUCCESS) return fail(DCG_ERR_CUDA, "cuMemExportToShareableHandle failed");
+      fds.push_back(fd);
+      return DCG_OK;
+    };
+    auto prepare = [&]() -> int {
+      DCG_TRY(create(gran));  // control block (barrier flags)
+      build_piece_runs();
+      for (int f = 0; f < kFields; f++)
+        for (const PieceRun &r : piece_runs[f])
+          if (r.owner == rank0) DCG_TRY(create(r.b1 - r.b0));
+      // this rank's control block is mapped and cleared BEFORE the pieces are published: a peer may announce its
+      // first barrier epoch as soon as it has imported them
+      if (drv.memReserve(&ctrl_va, (size_t)world * gran, gran, 0, 0) != CUDA_SUCCESS) return fail(DCG_ERR_CUDA, "cuMemAddressReserve failed");
+      DCG_TRY(map_piece(ctrl_va + (size_t)rank0 * gran, gran, pieces[rank0][0]));
+      DCG_CUDA_TRY(cudaMemset(reinterpret_cast<void *>(ctrl_va + (size_t)rank0 * gran), 0, 4096));
+      DCG_CUDA_TRY(cudaDeviceSynchronize());
+      return DCG_OK;
+    };
+    const int rc = prepare();
+    if (rc != DCG_OK) {
+      for (int fd : fds) close(fd);
+      return rc;
+    }
+    if (!fd_server.start(fds, world - 1)) return fail(DCG_ERR_CUDA, "cannot open the descriptor socket");
+    ready = false;
+    return DCG_OK;
+  }
+  int export_handle(void *out, uint64_t cap) override {
+    if (!vmm) return fail(DCG_ERR_INVALID, "not a one-rank-per-process instance");
+    if (cap < vmm::kHandleBytes) return fail(DCG_ERR_INVALID, "handle buffer too small");
+    std::memcpy(out, fd_server.name, vmm::kHandleBytes);
+    return DCG_OK;
+  }
+  int import_handles(const void *handles, int count) override {
+    if (!vmm) return fail(DCG_ERR_INVALID, "all ranks are local: nothing to import");
+    if (count != world) return fail(DCG_ERR_INVALID, "expected %d handles, got %d", world, count);
+    DCG_CUDA_TRY(cudaSetDevice(device));
+    for (int r = 0; r < world; r++) {
+      if (r == rank0) continue;
+      int npieces = 1;
+      for (int f = 0; f < kFields; f++)
+        for (const PieceRun &pr : piece_runs[f]) npieces += pr.owner == r ? 1 : 0;
+      char name[vmm::kHandleBytes + 1] = {0};
+      std::memcpy(name, static_cast<const char *>(handles) + (size_t)r * vmm::kHandleBytes, vmm::kHandleBytes);
+      std::vector<int> fds;
+      if (!vmm::fetch_fds(name, npieces, fds)) return fail(DCG_ERR_CUDA, "could not fetch the memory descriptors of rank %d", r);
+      for (int fd : fds) {
+        CUmemGenericAllocationHandle h;
+        const CUresult rc = drv.memImport(&h, (void *)(uintptr_t)fd, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR);
+        close(fd);
+        if (rc != CUDA_SUCCESS) return fail(DCG_ERR_CUDA, "cuMemImportFromShareableHandle failed for rank %d", r);
+        pieces[r].push_back(h);
+      }
+    }
+    fd_server.finish_after_serving(world - 1, 120000);
+    if (fd_server.served.load() != world - 1) return fail(DCG_ERR_CUDA, "only %d of %d peers fetched this rank's memory", fd_server.served.load(), world - 1);
+    for (int r = 0; r < world; r++) {
+      if (r != rank0) DCG_TRY(map_piece(ctrl_va + (size_t)r * gran, gran, pieces[r][0]));
+      peers.flags[r] = reinterpret_cast<volatile uint32_t *>(ctrl_va + (size_t)r * gran);
+    }
+    std::vector<size_t> next(world, 1);  // pieces[r][0] = control block, then the rank's runs in (field, run) order
+    for (int f = 0; f < kFields; f++) {
+      field_va_bytes[f] = (field_bytes[f] + gran - 1) / gran * gran;
+      if (drv.memReserve(&field_va[f], field_va_bytes[f], gran, 0, 0) != CUDA_SUCCESS) return fail(DCG_ERR_CUDA, "cuMemAddressReserve failed");
+      for (const PieceRun &pr : piece_runs[f]) DCG_TRY(map_piece(field_va[f] + pr.b0, pr.b1 - pr.b0, pieces[pr.owner][next[pr.owner]++]));
+    }
+    vw[0] = reinterpret_cast<float4 *>(field_va[0]); vw[1] = reinterpret_cast<float4 *>(field_va[1]);
+    q[0] = reinterpret_cast<float *>(field_va[2]); q[1] = reinterpret_cast<float *>(field_va[3]);
+    fluidity = reinterpret_cast<float *>(field_va[4]); p = reinterpret_cast<float *>(field_va[5]);
+    tp = reinterpret_cast<float *>(field_va[6]); div = reinterpret_cast<float *>(field_va[7]);
+    DCG_CUDA_TRY(cudaMalloc(&d_epoch, 4));
+    DCG_CUDA_TRY(cudaMalloc(&d_barrier_err, 4));
+    DCG_CUDA_TRY(cudaMemset(d_epoch, 0, 4));
+    DCG_CUDA_TRY(cudaMemset(d_barrier_err, 0, 4));
+    DCG_CUDA_TRY(cudaDeviceSynchronize());
+    ready = true;
+    DCG_TRY(reset());  // starts with a barrier: every rank has mapped every piece before any field is touched
+    return check_barrier_error();
+  }
+  void release_vmm() {
+    if (ctrl_va) { drv.memUnmap(ctrl_va, (size_t)world * gran); drv.memFree(ctrl_va, (size_t)world * gran); }
+    for (int f = 0; f < kFields; f++)
+      if (field_va[f]) { drv.memUnmap(field_va[f], field_va_bytes[f]); drv.memFree(field_va[f], field_va_bytes[f]); }
+    for (auto &v : pieces)
+      for (auto h : v) drv.memRelease(h);
+  }
+  int enter() {
+    DCG_CUDA_TRY(cudaSetDevice(device));
+    return ready ? DCG_OK : fail(DCG_ERR_INVALID, "sharded instance not finalized: call dcg_shard_import_handles first");
+  }
+  int check_barrier_error() {
+    if (!vmm || !d_barrier_err) return DCG_OK;  // (before import_handles there is no barrier yet)
+    uint32_t e = 0;
+    DCG_CUDA_TRY(cudaMemcpyAsync(&e, d_barrier_err, 4, cudaMemcpyDeviceToHost, stream));
+    DCG_CUDA_TRY(cudaStreamSynchronize(stream));
+    if (e) return fail(DCG_ERR_CUDA, "shard barrier timed out: a peer rank never arrived (ranks must issue identical call sequences)");
+    return DCG_OK;
+  }
+  int health_check() override { return check_barrier_error(); }
+
+  // ---- the planes of a rank, stages ----
+  uint64_t local_cells() const { return (uint64_t)gx * gy * (uint64_t)(gz / world) * nlocal; }
+  uint64_t local_first() const { return (uint64_t)gx * gy * (uint64_t)(gz / world) * rank0; }
+  // first plane of mip level `level` owned by rank r: a coarse plane belongs to the owner of its first fine plane
+  int zfirst(int level, int r) const { return std::min(gz >> level, (r * slab + (1 << level) - 1) >> level); }
+  // every rank has finished everything it launched so far, and its writes are visible to all
+  void barrier() {
+    if (!vmm) return;  // all ranks share this stream: program order is the barrier
+    k_u_barrier<<<1, 32, 0, stream>>>(peers, rank0, world, d_epoch, d_barrier_err);
+    launches++;
+    n_barriers++;
+  }
+  // one lock-step stage: [barrier,] launch(Z, planes) for every local rank that owns planes of `level`
+  template <typename F>
+  void stage(int level, F &&launch) {
+    for (int lr = 0; lr < nlocal; lr++) {
+      barrier();
+      const ZRange Z{zfirst(level, rank0 + lr), zfirst(level, rank0 + lr + 1)};
+      if (Z.ze > Z.zb) {
+        launch(Z, Z.ze - Z.zb);
+        launches++;
+      }
+    }
+  }
+  dim3 grid_for(int level, int planes) const { return dim3(idiv_up(gx >> level, BX), idiv_up(gy >> level, BY), idiv_up(planes, BZ)); }
   static dim3 block() { return dim3(BX, BY, BZ); }
 
   int on_params_changed() override {
@@ -618,21 +870,35 @@ struct UniformSim : dcg_sim {
     return DCG_OK;
   }
 
+  // clears this instance's planes of a field (level 0 of `bytes_per_cell`-sized cells, or the whole pyramid share)
+  int clear_level0(void *base, size_t bytes_per_cell) {
+    DCG_CUDA_TRY(cudaMemsetAsync(static_cast<char *>(base) + local_first() * bytes_per_cell, 0, local_cells() * bytes_per_cell, stream));
+    return DCG_OK;
+  }
+  int clear_pyramid(float *base) {
+    for (int l = 0; l < mip_levels; l++) {
+      const uint64_t plane = (uint64_t)(gx >> l) * (gy >> l);
+      const int z0 = zfirst(l, rank0), z1 = zfirst(l, rank0 + nlocal);
+      if (z1 > z0) DCG_CUDA_TRY(cudaMemsetAsync(base + level_off[l] + (uint64_t)z0 * plane, 0, (uint64_t)(z1 - z0) * plane * sizeof(float), stream));
+    }
+    return DCG_OK;
+  }
   int reset() override {  // fluid_simulation_uniform.cu:81-88
-    DCG_CUDA_TRY(cudaSetDevice(device));
-    DCG_CUDA_TRY(cudaMemsetAsync(p, 0, pyr * sizeof(float), stream));
-    DCG_CUDA_TRY(cudaMemsetAsync(tp, 0, pyr * sizeof(float), stream));
-    DCG_CUDA_TRY(cudaMemsetAsync(div, 0, pyr * sizeof(float), stream));
-    DCG_CUDA_TRY(cudaMemsetAsync(fluidity, 0, pyr * sizeof(float), stream));
+    DCG_TRY(enter());
+    barrier();  // nobody is still reading the fields we are about to clear
+    DCG_TRY(clear_pyramid(p));
+    DCG_TRY(clear_pyramid(tp));
+    DCG_TRY(clear_pyramid(div));
+    DCG_TRY(clear_pyramid(fluidity));
     cur_v = cur_q = 0;
     spec_velocity = false;
     return init();
   }
   int init() override {  // fluid_simulation_uniform.cu:76-79: adaptTopology + k_uniform_init (zero density, velocity)
-    DCG_CUDA_TRY(cudaSetDevice(device));
+    DCG_TRY(enter());
     for (int i = 0; i < 2; i++) {
-      DCG_CUDA_TRY(cudaMemsetAsync(vw[i], 0, N * sizeof(float4), stream));
-      DCG_CUDA_TRY(cudaMemsetAsync(q[i], 0, N * sizeof(float), stream));
+      DCG_TRY(clear_level0(vw[i], sizeof(float4)));
+      DCG_TRY(clear_level0(q[i], sizeof(float)));
     }
     fluidity_dirty = true;  // the memset cleared the packed .w lanes
     spec_velocity = false;
@@ -640,40 +906,41 @@ struct UniformSim : dcg_sim {
   }
 
   int adapt_topology() override {  // fluid_simulation_uniform.cu:143-147
+    DCG_TRY(enter());
     if (!fluidity_dirty) return DCG_OK;  // static field: identical values every step in the reference
-    for (int l = 0; l < mip_levels; l++) {
-      k_u_fluidity<<<grid_for(l), block(), 0, stream>>>(kp, fluidity, level_off[l], l, vw[0], vw[1]);
-      launches++;
-    }
+    for (int l = 0; l < mip_levels; l++)
+      stage(l, [&](ZRange Z, int planes) { k_u_fluidity<<<grid_for(l, planes), block(), 0, stream>>>(kp, fluidity, level_off[l], l, vw[0], vw[1], Z); });
     DCG_CUDA_TRY(cudaGetLastError());
     fluidity_dirty = false;
     return DCG_OK;
   }
 
   int advect_velocity() override {  // fluid_simulation_uniform.cu:90-94
+    DCG_TRY(enter());
     if (spec_velocity) {
       spec_velocity = false;  // vw[cur_v ^ 1] already holds this step's advected velocity (k_u_advect_both)
     } else {
-      k_u_advect_velocity<<<grid_for(0), block(), 0, stream>>>(kp, vw[cur_v], vw[cur_v ^ 1]);
-      launches++;
+      stage(0, [&](ZRange Z, int planes) { k_u_advect_velocity<<<grid_for(0, planes), block(), 0, stream>>>(kp, vw[cur_v], vw[cur_v ^ 1], Z); });
     }
     cur_v ^= 1;
     DCG_CUDA_TRY(cudaGetLastError());
     return DCG_OK;
   }
   int advect_density() override {  // fluid_simulation_uniform.cu:137-141
+    DCG_TRY(enter());
     if (fuse_advect && !opt.advect && gz >= 64) {
       const int zc = opt.advect_ctas_per_sm > 0 ? opt.advect_ctas_per_sm : 16;  // (option reused: planes per thread)
-      k_u_advect_both_zm<<<dim3(idiv_up(gx, 32), idiv_up(gy, 8), idiv_up(gz, zc)), dim3(32, 8), 0, stream>>>(kp, vw[cur_v], vw[cur_v ^ 1], q[cur_q],
-                                                                                                           q[cur_q ^ 1], zc);
+      stage(0, [&](ZRange Z, int planes) {
+        k_u_advect_both_zm<<<dim3(idiv_up(gx, 32), idiv_up(gy, 8), idiv_up(planes, zc)), dim3(32, 8), 0, stream>>>(kp, vw[cur_v], vw[cur_v ^ 1], q[cur_q],
+                                                                                                                     q[cur_q ^ 1], zc, Z);
+      });
       spec_velocity = true;
     } else if (fuse_advect) {
-      k_u_advect_both<<<grid_for(0), block(), 0, stream>>>(kp, vw[cur_v], vw[cur_v ^ 1], q[cur_q], q[cur_q ^ 1]);
+      stage(0, [&](ZRange Z, int planes) { k_u_advect_both<<<grid_for(0, planes), block(), 0, stream>>>(kp, vw[cur_v], vw[cur_v ^ 1], q[cur_q], q[cur_q ^ 1], Z); });
       spec_velocity = true;
     } else {
-      k_u_advect_density<<<grid_for(0), block(), 0, stream>>>(kp, vw[cur_v], q[cur_q], q[cur_q ^ 1]);
+      stage(0, [&](ZRange Z, int planes) { k_u_advect_density<<<grid_for(0, planes), block(), 0, stream>>>(kp, vw[cur_v], q[cur_q], q[cur_q ^ 1], Z); });
     }
-    launches++;
     cur_q ^= 1;
     DCG_CUDA_TRY(cudaGetLastError());
     return DCG_OK;
@@ -686,12 +953,13 @@ struct UniformSim : dcg_sim {
   static int zm_chunk(int d) { return d >= 256 ? 32 : (d >= 32 ? 16 : d); }
   void jacobi_sweep(int l, const float *in, float *out) {
     if (zm_ok(l)) {
-      const int d = gz >> l, zc = zm_chunk(d);
-      k_u_jacobi_zm<<<dim3((gx >> l) / (4 * ZTX), (gy >> l) / ZTY, idiv_up(d, zc)), dim3(ZTX, ZTY), 0, stream>>>(kp, l, level_off[l], in, out, div, zc);
+      const int zc = zm_chunk(gz >> l);
+      stage(l, [&](ZRange Z, int planes) {
+        k_u_jacobi_zm<<<dim3((gx >> l) / (4 * ZTX), (gy >> l) / ZTY, idiv_up(planes, zc)), dim3(ZTX, ZTY), 0, stream>>>(kp, l, level_off[l], in, out, div, zc, Z);
+      });
     } else {
-      k_u_jacobi<<<grid_for(l), block(), 0, stream>>>(kp, l, level_off[l], in, out, div);
+      stage(l, [&](ZRange Z, int planes) { k_u_jacobi<<<grid_for(l, planes), block(), 0, stream>>>(kp, l, level_off[l], in, out, div, Z); });
     }
-    launches++;
   }
   void jacobi_pair(int l) {
     jacobi_sweep(l, p, tp);
@@ -700,38 +968,40 @@ struct UniformSim : dcg_sim {
   void launch_apply() {
     if (!opt.stencil && gx % ZTX == 0 && gy % ZTY == 0) {
       const int zc = zm_chunk(gz);
-      k_u_apply_zm<<<dim3(gx / ZTX, gy / ZTY, idiv_up(gz, zc)), dim3(ZTX, ZTY), 0, stream>>>(kp, p, fluidity, vw[cur_v], zc);
+      stage(0, [&](ZRange Z, int planes) {
+        k_u_apply_zm<<<dim3(gx / ZTX, gy / ZTY, idiv_up(planes, zc)), dim3(ZTX, ZTY), 0, stream>>>(kp, p, fluidity, vw[cur_v], zc, Z);
+      });
     } else {
-      k_u_apply_pressure<<<grid_for(0), block(), 0, stream>>>(kp, p, fluidity, vw[cur_v]);
+      stage(0, [&](ZRange Z, int planes) { k_u_apply_pressure<<<grid_for(0, planes), block(), 0, stream>>>(kp, p, fluidity, vw[cur_v], Z); });
     }
-    launches++;
   }
   void launch_divergence(int zero = 3) {
     if (opt.zero_all) zero = 3;
     if (!opt.stencil && gx % ZTX == 0 && gy % ZTY == 0) {
       const int zc = zm_chunk(gz);
-      k_u_divergence_zm<<<dim3(gx / ZTX, gy / ZTY, idiv_up(gz, zc)), dim3(ZTX, ZTY), 0, stream>>>(kp, vw[cur_v], div, p, tp, zc, zero);
+      stage(0, [&](ZRange Z, int planes) {
+        k_u_divergence_zm<<<dim3(gx / ZTX, gy / ZTY, idiv_up(planes, zc)), dim3(ZTX, ZTY), 0, stream>>>(kp, vw[cur_v], div, p, tp, zc, zero, Z);
+      });
     } else {
-      k_u_divergence<<<grid_for(0), block(), 0, stream>>>(kp, vw[cur_v], div, p, tp, zero);
+      stage(0, [&](ZRange Z, int planes) { k_u_divergence<<<grid_for(0, planes), block(), 0, stream>>>(kp, vw[cur_v], div, p, tp, zero, Z); });
     }
-    launches++;
   }
   int project() override {  // fluid_simulation_uniform.cu:96-124
+    DCG_TRY(enter());
     spec_velocity = false;
     launch_divergence(mip_levels > 1 && project_level_pairs >= 1 ? 0 : 3);
-    for (int l = 1; l < mip_levels; l++) {
-      k_u_restrict<<<grid_for(l), block(), 0, stream>>>(kp, l, level_off[l], level_off[l - 1], div, p, tp);
-      launches++;
-    }
+    for (int l = 1; l < mip_levels; l++)
+      stage(l, [&](ZRange Z, int planes) { k_u_restrict<<<grid_for(l, planes), block(), 0, stream>>>(kp, l, level_off[l], level_off[l - 1], div, p, tp, Z); });
     for (int i = 0; i < project_coarsest_pairs; i++) jacobi_pair(mip_levels - 1);
     for (int l = mip_levels - 2; l >= 0; l--) {
       if (zm_ok(l) && level_off[l + 1] % 2 == 0) {
-        const int d = gz >> l, zc = zm_chunk(d);
-        k_u_prolongate_zm<<<dim3((gx >> l) / (4 * ZTX), (gy >> l) / ZTY, idiv_up(d, zc)), dim3(ZTX, ZTY), 0, stream>>>(kp, l, level_off[l], level_off[l + 1], p, zc);
+        const int zc = zm_chunk(gz >> l);
+        stage(l, [&](ZRange Z, int planes) {
+          k_u_prolongate_zm<<<dim3((gx >> l) / (4 * ZTX), (gy >> l) / ZTY, idiv_up(planes, zc)), dim3(ZTX, ZTY), 0, stream>>>(kp, l, level_off[l], level_off[l + 1], p, zc, Z);
+        });
       } else {
-        k_u_prolongate<<<grid_for(l), block(), 0, stream>>>(kp, l, level_off[l], level_off[l + 1], p);
+        stage(l, [&](ZRange Z, int planes) { k_u_prolongate<<<grid_for(l, planes), block(), 0, stream>>>(kp, l, level_off[l], level_off[l + 1], p, Z); });
       }
-      launches++;
       for (int i = 0; i < project_level_pairs; i++) jacobi_pair(l);
     }
     launch_apply();
@@ -739,6 +1009,7 @@ struct UniformSim : dcg_sim {
     return DCG_OK;
   }
   int project_local() override {  // fluid_simulation_uniform.cu:126-135
+    DCG_TRY(enter());
     spec_velocity = false;
     launch_divergence();
     for (int i = 0; i < local_pairs; i++) jacobi_pair(0);
@@ -750,7 +1021,7 @@ struct UniformSim : dcg_sim {
   // One full step = src/simulation.cpp:104-111, captured once per ping-pong parity as a CUDA graph
   // (29 launches at 64^3 become one graph launch) and replayed.
   int step(int n) override {
-    DCG_CUDA_TRY(cudaSetDevice(device));
+    DCG_TRY(enter());
     DCG_TRY(adapt_topology());  // flush a pending fluidity rebuild outside the graph
     DCG_CUDA_TRY(cudaEventRecord(ev_begin, stream));
     for (int done = 0; done < n; done++) {
@@ -760,7 +1031,7 @@ struct UniformSim : dcg_sim {
       }
       cudaGraphExec_t &ge = step_graph[cur_v * 2 + cur_q];
       if (!ge) {
-        const uint64_t before = launches;
+        const uint64_t before = launches, barriers_before = n_barriers;
         const int sv = cur_v, sq = cur_q;
         const bool sspec = spec_velocity;
         cudaGraph_t g = nullptr;
@@ -769,7 +1040,9 @@ struct UniformSim : dcg_sim {
         const cudaError_t ce = cudaStreamEndCapture(stream, &g);
         cur_v = sv; cur_q = sq; spec_velocity = sspec;  // capture records, it does not execute
         step_graph_launches = launches - before;
+        step_graph_barriers = n_barriers - barriers_before;
         launches = before;
+        n_barriers = barriers_before;
         if (rc != DCG_OK) return rc;
         DCG_CUDA_TRY(ce);
         DCG_CUDA_TRY(cudaGraphInstantiate(&ge, g, 0));
@@ -777,6 +1050,7 @@ struct UniformSim : dcg_sim {
       }
       DCG_CUDA_TRY(cudaGraphLaunch(ge, stream));
       launches += step_graph_launches;
+      n_barriers += step_graph_barriers;
       cur_v ^= 1;
       cur_q ^= 1;
     }
@@ -785,11 +1059,13 @@ struct UniformSim : dcg_sim {
     return DCG_OK;
   }
 
+  // sharded: local partial results (this instance's slabs); the host side (bench / tests) combines the ranks
   int debug_stats(float *out) override {  // fluid_simulation_uniform.cu:160-176 (host sums the bins in order)
-    DCG_CUDA_TRY(cudaSetDevice(device));
-    const uint64_t bins = N / 256;
+    DCG_TRY(enter());
+    const uint64_t bins = local_cells() / 256, first = local_first();
     if (bins == 0) { *out = 0.f; return DCG_OK; }
-    k_u_debug_stats<<<(unsigned)((bins + 255) / 256), 256, 0, stream>>>(q[cur_q], vw[cur_v], scratch, bins);
+    barrier();
+    k_u_debug_stats<<<(unsigned)((bins + 255) / 256), 256, 0, stream>>>(q[cur_q] + first, vw[cur_v] + first, scratch, bins);
     launches++;
     std::vector<float> h(bins);
     DCG_CUDA_TRY(cudaMemcpyAsync(h.data(), scratch, bins * sizeof(float), cudaMemcpyDeviceToHost, stream));
@@ -797,29 +1073,32 @@ struct UniformSim : dcg_sim {
     float sum = 0.f;
     for (uint64_t i = 0; i < bins; i++) sum += h[i];
     *out = sum;
-    return DCG_OK;
+    return check_barrier_error();
   }
 
   int total_density(double *out) override {
-    DCG_CUDA_TRY(cudaSetDevice(device));
-    const int blocks = (int)std::min<uint64_t>(1024, (N + 255) / 256);
-    k_u_total_density<<<blocks, 256, 0, stream>>>(q[cur_q], vw[cur_v], N, d_partial);
+    DCG_TRY(enter());
+    const uint64_t n = local_cells(), first = local_first();
+    const int blocks = (int)std::min<uint64_t>(1024, (n + 255) / 256);
+    barrier();
+    k_u_total_density<<<blocks, 256, 0, stream>>>(q[cur_q] + first, vw[cur_v] + first, n, d_partial);
     launches++;
     DCG_CUDA_TRY(cudaMemcpyAsync(h_partial, d_partial, blocks * sizeof(double), cudaMemcpyDeviceToHost, stream));
     DCG_TRY(synchronize());
     double s = 0.0;
     for (int i = 0; i < blocks; i++) s += h_partial[i];
     *out = s;
-    return DCG_OK;
+    return check_barrier_error();
   }
 
-  uint64_t num_cells() const override { return N; }
+  uint64_t num_cells() const override { return local_cells(); }  // cells held by this instance
   int num_levels() const override { return mip_levels; }
 
   // one launch of a single stage, `reps` times, CUDA-event timed on the instance's stream
-  int bench_stage(const char *stage, int level, int reps, float *ms_per_launch, double *alg_bytes) override {
-    DCG_CUDA_TRY(cudaSetDevice(device));
-    const std::string st(stage);
+  int bench_stage(const char *stage_name, int level, int reps, float *ms_per_launch, double *alg_bytes) override {
+    DCG_TRY(enter());
+    if (world > 1) return fail(DCG_ERR_UNSUPPORTED, "bench_stage: not available on sharded instances");
+    const std::string st(stage_name);
     if (level < 0 || level >= mip_levels) return fail(DCG_ERR_INVALID, "bench_stage: bad level");
     const double n0 = (double)N, nl = (double)((uint64_t)(gx >> level) * (gy >> level) * (gz >> level));
     double bytes = 0;
@@ -842,7 +1121,7 @@ struct UniformSim : dcg_sim {
       } else if (st == "apply_pressure") {
         launch_apply();
         bytes = 32.0 * n0;
-      } else return fail(DCG_ERR_INVALID, "bench_stage: unknown stage %s", stage);
+      } else return fail(DCG_ERR_INVALID, "bench_stage: unknown stage %s", stage_name);
     }
     DCG_CUDA_TRY(cudaEventRecord(ev_end, stream));
     DCG_CUDA_TRY(cudaStreamSynchronize(stream));
@@ -854,35 +1133,47 @@ struct UniformSim : dcg_sim {
     return DCG_OK;
   }
 
+  // sharded: this instance's slab(s), ranks in order — with nlocal == world the whole field in the reference's memory
+  // order (a z-slab is a contiguous index range).  Pyramid fields return their level-0 part.
   int get_field(int field, int layout, float *dst, uint64_t count) override {
-    DCG_CUDA_TRY(cudaSetDevice(device));
+    DCG_TRY(enter());
     (void)layout;  // NATIVE == DENSE_L0 on the uniform grid
-    const uint64_t need = field == DCG_FIELD_VELOCITY ? 3 * N : N;
+    const uint64_t n = local_cells(), first = local_first();
+    const uint64_t need = field == DCG_FIELD_VELOCITY ? 3 * n : n;
     if (!dst || count < need) return fail(DCG_ERR_INVALID, "get_field: destination too small (%llu < %llu)", (unsigned long long)count, (unsigned long long)need);
     const float *src = nullptr;
+    barrier();
     switch (field) {
-      case DCG_FIELD_DENSITY: src = q[cur_q]; break;
+      case DCG_FIELD_DENSITY: src = q[cur_q] + first; break;
       case DCG_FIELD_VELOCITY:
-        k_unpack_velocity<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(vw[cur_v], scratch, N);
+        k_unpack_velocity<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(vw[cur_v] + first, scratch, n);
         launches++;
         src = scratch;
         break;
-      case DCG_FIELD_FLUIDITY: src = fluidity; break;
-      case DCG_FIELD_PRESSURE: src = p; break;
-      case DCG_FIELD_DIVERGENCE: src = div; break;
-      case DCG_FIELD_T_PRESSURE: src = tp; break;
+      case DCG_FIELD_FLUIDITY: src = fluidity + first; break;
+      case DCG_FIELD_PRESSURE: src = p + first; break;
+      case DCG_FIELD_DIVERGENCE: src = div + first; break;
+      case DCG_FIELD_T_PRESSURE: src = tp + first; break;
       default: return fail(DCG_ERR_INVALID, "get_field: unknown field %d", field);
     }
     DCG_CUDA_TRY(cudaMemcpyAsync(dst, src, need * sizeof(float), cudaMemcpyDeviceToHost, stream));
-    return synchronize();
+    DCG_TRY(synchronize());
+    return check_barrier_error();
   }
 
-  // fields only, fp32, each field read once + written once per stage.
+  int get_counters(uint64_t out[8]) override {
+    for (int i = 0; i < 8; i++) out[i] = 0;
+    out[6] = launches;
+    out[7] = n_barriers;
+    return DCG_OK;
+  }
+
+  // fields only, fp32, each field read once + written once per stage; the cells THIS instance owns.
   int algorithmic_bytes(double *bytes, uint64_t *active_blocks) override {
-    double per_level0 = 28.0 /*advectV*/ + 28.0 /*divergence*/ + 32.0 /*apply*/ + 24.0 /*advectQ*/;
-    double b = per_level0 * (double)N;
+    const double per_level0 = 28.0 /*advectV*/ + 28.0 /*divergence*/ + 32.0 /*apply*/ + 24.0 /*advectQ*/;
+    double b = per_level0 * (double)local_cells();
     for (int l = 0; l < mip_levels; l++) {
-      const double n = (double)((uint64_t)(gx >> l) * (gy >> l) * (gz >> l));
+      const double n = (double)(zfirst(l, rank0 + nlocal) - zfirst(l, rank0)) * (double)(gx >> l) * (double)(gy >> l);
       const int pairs = (l == mip_levels - 1) ? project_coarsest_pairs : project_level_pairs;
       b += n * 12.0 * 2 * pairs;               // Jacobi sweeps
       if (l >= 1) b += n * (8 * 4.0 + 12.0);   // restrict: read 8 children, write div,p,tp
@@ -909,3 +1200,42 @@ int dcg_sim::step(int n) {
 }
 
 dcg_sim *dcg_make_uniform() { return new dcg::UniformSim(); }
+
+extern "C" {
+
+DCG_API int dcg_create_uniform_sharded(const dcg_sim_params *params, int device, int rank, int world, int nlocal, dcg_sim **out) {
+  if (!params || !out) return DCG_ERR_INVALID;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return DCG_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= n) return DCG_ERR_INVALID;
+  auto *s = new dcg::UniformSim();
+  int rc = s->construct_sharded(params, device, rank, world, nlocal);
+  if (rc == DCG_OK) rc = s->synchronize();
+  if (rc != DCG_OK) {
+    dcg_set_create_error(s->err.c_str());
+    delete s;
+    return rc;
+  }
+  *out = s;
+  return DCG_OK;
+}
+
+DCG_API uint64_t dcg_shard_handle_bytes(void) { return dcg::vmm::kHandleBytes; }
+
+DCG_API int dcg_shard_export_handle(dcg_sim *sim, void *out, uint64_t capacity) {
+  if (!sim || !out) return DCG_ERR_INVALID;
+  return sim->export_handle(out, capacity);
+}
+
+DCG_API int dcg_shard_import_handles(dcg_sim *sim, const void *handles, int count) {
+  if (!sim || !handles) return DCG_ERR_INVALID;
+  int rc = sim->import_handles(handles, count);
+  if (rc == DCG_OK) rc = sim->synchronize();
+  return rc;
+}
+
+}  // extern "C"

@@ -1,9 +1,10 @@
 """Host-side logic of the z-slab decomposition (multi-GPU uniform grid).
 
 The reference is single-GPU (src/main.cpp:46-48); this is new design, see DESIGN.md §6.  One process per
-GPU (torchrun); ``torch.distributed`` is only the bootstrap channel (it carries 64-byte CUDA-IPC handles
-once, and scalar reductions of residual / smoke totals).  The data path never goes through it: kernels read
-neighbour slabs directly over NVLink through the peer mappings (dcgrid_b200/csrc/uniform_sharded.cu).
+GPU (torchrun); ``torch.distributed`` is only the bootstrap channel (it carries 64-byte handles once, and
+scalar reductions of residual / smoke totals).  The data path never goes through it: every field is one virtual
+address range stitched from the ranks' physical pieces, the single-GPU kernels run on each rank's planes and read
+neighbour slabs in place over NVLink (dcgrid_b200/csrc/uniform.cu, "slab decomposition").
 
 Everything here is pure host arithmetic + collectives, so it runs (and is tested) on CPU with gloo.
 """
@@ -26,7 +27,7 @@ def slab_range(gz, world, rank):
 
 def first_plane(slab, level, rank):
     """First plane of mip level ``level`` owned by ``rank``: a coarse plane belongs to the owner of its
-    first fine plane (same rule as first_plane() in uniform_sharded.cu)."""
+    first fine plane (same rule as UniformSim::zfirst() in uniform.cu)."""
     return (rank * slab + (1 << level) - 1) >> level
 
 

@@ -1,7 +1,7 @@
 """z-slab decomposition of the uniform solver: an N-rank run must equal the 1-GPU run bit for bit (same
 per-cell arithmetic, only the owner of the memory differs).  Here all ranks live in one process on one
 device (nlocal == world), which exercises every ownership / peer-pointer index path of
-uniform_sharded.cu; the multi-process NVLink path is tests/mgpu_uniform_check.py (torchrun, >= 2 GPUs)."""
+uniform.cu (slab decomposition); the multi-process NVLink path is tests/mgpu_uniform_check.py (torchrun, >= 2 GPUs)."""
 import numpy as np
 import pytest
 
