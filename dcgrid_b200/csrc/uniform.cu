@@ -343,6 +343,8 @@ __global__ void __launch_bounds__(ZTX * ZTY) k_u_jacobi_zm(KParams P, int level,
   }
 }
 
+// (Measured and rejected, profiles/README.md r3c: the y neighbours' (vy, fluidity) exchanged between the warps of the tile through
+// shared memory instead of two 16-byte loads per cell: 6.74 ms at 1024^3 either way — those loads hit L1 / L2.)
 __global__ void __launch_bounds__(ZTX * ZTY) k_u_divergence_zm(KParams P, const float4 *__restrict__ vw, float *__restrict__ div, float *__restrict__ p,
                                                                float *__restrict__ tp, int zc, int zero, ZRange Z) {
   const int x = blockIdx.x * ZTX + threadIdx.x, y = blockIdx.y * ZTY + threadIdx.y;
