@@ -100,6 +100,24 @@ __global__ void __launch_bounds__(256) k_dc_refresh_apron(Pool T, KParams P, con
   if (pl.w == kFree) return;
   const int level = pl.w;
   const bool self_moved = flag_bit(flag_bits, b) && (flags[b] & kFlagMoved) != 0;
+  if (!self_moved) {
+    // Most blocks have no touched neighbour: two coalesced 16-byte loads per lane cover the whole 864-byte map, and a
+    // block none of whose entries points into a flagged block leaves here (the entry-by-entry walk below cost 336 us per
+    // topology change at 512^3, profiles/README.md r2v).  Conservative: interior entries are tested too.
+    const uint4 *m4 = reinterpret_cast<const uint4 *>(T.apron + (size_t)b * kAV);  // 216 entries = 54 uint4, 16-byte aligned (864 = 54 * 16)
+    const int lane = threadIdx.x & 31;
+    bool hit = false;
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+      const int v = lane + 32 * r;
+      if (v < kAV / 4) {
+        const uint4 e = m4[v];
+        auto touched = [&](uint32_t id) { return id / kBV < T.M && flag_bit(flag_bits, id / kBV); };
+        hit = hit || touched(e.x) || touched(e.y) || touched(e.z) || touched(e.w);
+      }
+    }
+    if (!__any_sync(0xFFFFFFFFu, hit)) return;
+  }
   for (int ai = threadIdx.x & 31; ai < kAV; ai += 32) {
     const int i = ai / kAA, j = (ai / kAW) % kAW, k = ai % kAW;
     if (i % (kAW - 1) != 0 && j % (kAW - 1) != 0 && k % (kAW - 1) != 0) continue;
