@@ -106,7 +106,7 @@ struct DCGridSim : dcg_sim {
   uint64_t n_adapt = 0, n_changed = 0, n_moved = 0, n_refined = 0, n_skipped = 0, n_failed = 0;
 
   // persistent TMA-ring kernels (dcgrid_pipe.cuh): resident CTAs per device, sweep direction toggle
-  int sm_count = 0, jacobi_pipe_ctas = 0, advect_per_sm[3] = {0, 0, 0};
+  int sm_count = 0, jacobi_pipe_ctas = 0, advect_per_sm[3] = {0, 0, 0}, advect_ext_per_sm[3] = {0, 0, 0};
   bool use_advect_pipe = true;
   // k_dc_advect_pipe<2>: advect_density() also produces the NEXT step's advected velocity in vw[cur_v ^ 1];
   // spec_velocity = that buffer is valid, i.e. nothing has touched velocity, topology or parameters since
@@ -373,6 +373,13 @@ struct DCGridSim : dcg_sim {
         DCG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&advect_per_sm[mode], fn, kAdvectThreads, kAdvectPipeSmem));
         if (advect_per_sm[mode] < 1) return fail(DCG_ERR_CUDA, "k_dc_advect_pipe does not fit on an SM");
         if (opt.advect_ctas_per_sm > 0) advect_per_sm[mode] = opt.advect_ctas_per_sm;
+        if (mode >= 1) {
+          const void *fx = advect_fn(mode, true);
+          DCG_CUDA_TRY(cudaFuncSetAttribute(fx, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAdvectPipeSmem));
+          DCG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&advect_ext_per_sm[mode], fx, kAdvectThreads, kAdvectPipeSmem));
+          if (advect_ext_per_sm[mode] < 1) return fail(DCG_ERR_CUDA, "k_dc_advect_pipe (with scalars) does not fit on an SM");
+          if (opt.advect_ctas_per_sm > 0) advect_ext_per_sm[mode] = opt.advect_ctas_per_sm;
+        }
       }
       pipe_min_tiles = 2u * (unsigned)sm_count;  // refined below once the resident CTA count of the ring kernel is known
       {
@@ -715,10 +722,9 @@ struct DCGridSim : dcg_sim {
     launch_vorticity();
     ext::k_dc_ext_sources<<<blocks_for(M, kBPC), kCTA, 0, stream>>>(hot(), kp, ext, vw[cur_v], q[cur_q], th[cur_s], qvp[cur_s], vort);
     launches++;
-    accumulate(vw[cur_v], nullptr, false);
-    accumulate(nullptr, q[cur_q], false);
-    accumulate(nullptr, th[cur_s], false);
-    accumulate(nullptr, qvp[cur_s], false);
+    accumulate(vw[cur_v], q[cur_q], true);  // the kernel restricted the childless blocks: only the blocks with children are left
+    accumulate(nullptr, th[cur_s], true);
+    accumulate(nullptr, qvp[cur_s], true);
     DCG_CUDA_TRY(cudaGetLastError());
     return DCG_OK;
   }
@@ -1480,30 +1486,37 @@ struct DCGridSim : dcg_sim {
   }
   void accumulate_velocity(bool fused) { accumulate(vw[cur_v], nullptr, fused); }
   void accumulate_scalar(float *ch, bool fused) { accumulate(nullptr, ch, fused); }
-  const void *advect_fn(int mode) const {
+  const void *advect_fn(int mode, bool with_scalars = false) const {
+    if (with_scalars) {  // extension scalars ride along (modes 1 and 2, the default register budget)
+      if (mode == 1) return (const void *)k_dc_advect_pipe<1, 3, true>;
+      return (const void *)k_dc_advect_pipe<2, 3, true>;
+    }
     if (advect_min_blocks == 2) {
-      if (mode == 0) return (const void *)k_dc_advect_pipe<0, 2>;
-      if (mode == 1) return (const void *)k_dc_advect_pipe<1, 2>;
-      return (const void *)k_dc_advect_pipe<2, 2>;
+      if (mode == 0) return (const void *)k_dc_advect_pipe<0, 2, false>;
+      if (mode == 1) return (const void *)k_dc_advect_pipe<1, 2, false>;
+      return (const void *)k_dc_advect_pipe<2, 2, false>;
     }
     if (advect_min_blocks == 3) {
-      if (mode == 0) return (const void *)k_dc_advect_pipe<0, 3>;
-      if (mode == 1) return (const void *)k_dc_advect_pipe<1, 3>;
-      return (const void *)k_dc_advect_pipe<2, 3>;
+      if (mode == 0) return (const void *)k_dc_advect_pipe<0, 3, false>;
+      if (mode == 1) return (const void *)k_dc_advect_pipe<1, 3, false>;
+      return (const void *)k_dc_advect_pipe<2, 3, false>;
     }
-    if (mode == 0) return (const void *)k_dc_advect_pipe<0, 4>;
-    if (mode == 1) return (const void *)k_dc_advect_pipe<1, 4>;
-    return (const void *)k_dc_advect_pipe<2, 4>;
+    if (mode == 0) return (const void *)k_dc_advect_pipe<0, 4, false>;
+    if (mode == 1) return (const void *)k_dc_advect_pipe<1, 4, false>;
+    return (const void *)k_dc_advect_pipe<2, 4, false>;
   }
   // mode 0: vout <- advected velocity; 1: qout <- advected density; 2: both (k_dc_advect_pipe)
-  void launch_advect_pipe(int mode, const float4 *vin, float4 *vout, const float *qi, float *qo) {
+  // scalars != nullptr: temperature and vapor advected in the same pass (modes 1 and 2)
+  void launch_advect_pipe(int mode, const float4 *vin, float4 *vout, const float *qi, float *qo, const AdvectScalars *scalars = nullptr) {
     each_rank([&](int, RankWork &w) {
       if (w.n_order == 0) return;
-      const unsigned grid = std::min<unsigned>(w.n_order / kBPC, (unsigned)(advect_per_sm[mode] * sm_count));
+      const unsigned grid = std::min<unsigned>(w.n_order / kBPC, (unsigned)((scalars ? advect_ext_per_sm[mode] : advect_per_sm[mode]) * sm_count));
       const float *flp = fl;
       const uint32_t *ord = w.d_order;
       Pool hp = hot();
-      void *args[] = {&hp, &kp, &ord, &w.n_order, &vin, &vout, &flp, &qi, &qo};
+      AdvectScalars xs{};
+      if (scalars) xs = *scalars;
+      void *args[] = {&hp, &kp, &ord, &w.n_order, &vin, &vout, &flp, &qi, &qo, &xs};
       cudaLaunchConfig_t cfg{};
       cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kAdvectThreads); cfg.dynamicSmemBytes = kAdvectPipeSmem; cfg.stream = stream;
       cudaLaunchAttribute at{};
@@ -1511,7 +1524,7 @@ struct DCGridSim : dcg_sim {
       at.val.programmaticStreamSerializationAllowed = 1;
       cfg.attrs = &at;
       cfg.numAttrs = use_pdl ? 1 : 0;
-      cudaLaunchKernelExC(&cfg, advect_fn(mode), args);
+      cudaLaunchKernelExC(&cfg, advect_fn(mode, scalars != nullptr), args);
       launches++;
     });
     barrier();
@@ -1559,13 +1572,21 @@ struct DCGridSim : dcg_sim {
       DCG_CUDA_TRY(cudaGetLastError());
       return DCG_OK;
     }
-    if (ext.sources) {  // extension: temperature and vapor ride along (same trajectories; before the velocity buffer flips)
+    const bool ride = ext.sources && use_advect_pipe;  // temperature and vapor in the density's own gather pass
+    if (ext.sources && !ride) {  // extension: temperature and vapor ride along (same trajectories; before the velocity buffer flips)
       sl_scalar(1, th[cur_s], th[cur_s ^ 1]);
       sl_scalar(2, qvp[cur_s], qvp[cur_s ^ 1]);
       cur_s ^= 1;
     }
     if (use_advect_pipe) {
-      launch_advect_pipe(fuse_advect ? 2 : 1, vw[cur_v], vw[cur_v ^ 1], q[cur_q], q[cur_q ^ 1]);
+      AdvectScalars xs{};
+      if (ride) { xs.th_in = th[cur_s]; xs.qv_in = qvp[cur_s]; xs.th_out = th[cur_s ^ 1]; xs.qv_out = qvp[cur_s ^ 1]; xs.E = ext; }
+      launch_advect_pipe(fuse_advect ? 2 : 1, vw[cur_v], vw[cur_v ^ 1], q[cur_q], q[cur_q ^ 1], ride ? &xs : nullptr);
+      if (ride) {
+        cur_s ^= 1;
+        accumulate(nullptr, th[cur_s], true);
+        accumulate(nullptr, qvp[cur_s], true);
+      }
       spec_velocity = fuse_advect;
       cur_q ^= 1;
       // the speculative velocity is restricted in the same launch as the density (advect_velocity() then only flips)

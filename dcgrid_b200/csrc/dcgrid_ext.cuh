@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(kCTA) k_dc_ext_vorticity(Pool T, KParams P, co
   if (b >= T.M) return;
   const int4 pl = T.posl[b];
   if (pl.w == kFree) return;
-  const uint32_t *a = T.apron + (size_t)b * kAV;
+  const uint32_t *a = T.apron + (size_t)b * kAV;  // (staging the map in shared memory first: 351 -> 443 us, profiles/README.md r3e)
   const int ai = apron_of(t);
   const float4 l = vw[a[ai - kAA]], r = vw[a[ai + kAA]], d = vw[a[ai - kAW]], u = vw[a[ai + kAW]], bk = vw[a[ai - 1]], f = vw[a[ai + 1]];
   const int scale = 1 << pl.w;
@@ -53,7 +53,8 @@ __global__ void __launch_bounds__(kCTA) k_dc_ext_vorticity(Pool T, KParams P, co
   vort[(size_t)b * kBV + t] = o;
 }
 
-// the fused source pass (oracle apply_sources): leaf cells only, in place; reads neighbours' |omega| only
+// the fused source pass (oracle apply_sources): leaf cells only, in place; reads neighbours' |omega| only; blocks without
+// children restrict what they wrote themselves
 __global__ void __launch_bounds__(kCTA) k_dc_ext_sources(Pool T, KParams P, dcg_ext_params E, float4 *__restrict__ vw, float *__restrict__ q,
                                                          float *__restrict__ th, float *__restrict__ qv, const float4 *__restrict__ vort) {
   const uint32_t g = threadIdx.x >> 6, t = threadIdx.x & 63;
@@ -61,7 +62,20 @@ __global__ void __launch_bounds__(kCTA) k_dc_ext_sources(Pool T, KParams P, dcg_
   if (b >= T.M) return;
   const int4 pl = T.posl[b];
   if (pl.w == kFree) return;
-  if (T.child[(size_t)b * kSV + (t >> 3)] != kNone) return;
+  // fused restriction (accumulate<T>, dcgrid_structure.cu:188-222) of blocks without children, as in the field kernels: the 8 cells
+  // of a subblock are 8 consecutive lanes, summed in cell order from 0.f; blocks WITH children are left to the list passes
+  const uint4 *cl = reinterpret_cast<const uint4 *>(T.child + (size_t)b * kSV);
+  const uint4 c0 = cl[0], c1 = cl[1];
+  const uint32_t ps = T.parent[b];
+  const bool push = (c0.x & c0.y & c0.z & c0.w & c1.x & c1.y & c1.z & c1.w) == kNone && ps != kNone;  // uniform over the block
+  auto sub_sum = [&](float v) {
+    const unsigned base = threadIdx.x & 24u;
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; k++) acc += __shfl_sync(0xFFFFFFFFu, v, base + k);
+    return acc;
+  };
+  if (!push && T.child[(size_t)b * kSV + (t >> 3)] != kNone) return;  // (a block that pushes has no refined subblock)
   const size_t c = (size_t)b * kBV + t;
   const uint32_t *a = T.apron + (size_t)b * kAV;
   const int scale = 1 << pl.w;
@@ -102,6 +116,17 @@ __global__ void __launch_bounds__(kCTA) k_dc_ext_sources(Pool T, KParams P, dcg_
   th[c] = tc;
   qv[c] = vc;
   q[c] = qc;
+  if (push) {
+    const float ax = sub_sum(v.x), ay = sub_sum(v.y), az = sub_sum(v.z), at = sub_sum(tc), av = sub_sum(vc), aq = sub_sum(qc);
+    if ((t & 7u) == 7u) {
+      const size_t pc = (size_t)kSV * ps + (t >> 3);
+      float *dst = reinterpret_cast<float *>(vw + pc);
+      dst[0] = ax * .125f; dst[1] = ay * .125f; dst[2] = az * .125f;  // .w (fluidity) untouched
+      th[pc] = at * .125f;
+      qv[pc] = av * .125f;
+      q[pc] = aq * .125f;
+    }
+  }
 }
 
 // initial temperature / vapor of every active block (oracle activate_level): the ambient profile

@@ -447,11 +447,19 @@ __device__ __forceinline__ float subblock_sum(float v) {
 // the 8 consumer warps never meet at a CTA barrier: each waits for the `full` mbarrier of its tile, resolves
 // its samples, releases the slot (`empty` mbarrier, one arrival per warp) and goes on to its gathers, so the
 // warps of a CTA drift apart by up to kAStages tiles and their load rounds overlap.
-template <int kMode, int kMinBlocks>
+// kExt (extension, dcg_ext_params.sources): potential temperature and vapor ride along with the density — same sample,
+// same weights, their own boundary values (ext::scalar_bc), the ambient value where a sample has no fluid weight
+// (oracle advect_scalar; k_dc_ext_advect_scalar is the stand-alone kernel) — instead of two more gather passes.
+struct AdvectScalars {
+  const float *th_in, *qv_in;
+  float *th_out, *qv_out;
+  dcg_ext_params E;
+};
+template <int kMode, int kMinBlocks, bool kExt>
 __global__ void __launch_bounds__(kAdvectThreads, kMinBlocks) k_dc_advect_pipe(Pool T, KParams P, const uint32_t *__restrict__ order, uint32_t norder,
                                                                                const float4 *__restrict__ vin, float4 *__restrict__ vout,
                                                                                const float *__restrict__ fl, const float *__restrict__ qin,
-                                                                               float *__restrict__ qout) {
+                                                                               float *__restrict__ qout, AdvectScalars X) {
   pdl_enter();
   extern __shared__ __align__(128) unsigned char smem_raw[];
   AdvectStage *st = reinterpret_cast<AdvectStage *>(smem_raw);
@@ -533,19 +541,39 @@ __global__ void __launch_bounds__(kAdvectThreads, kMinBlocks) k_dc_advect_pipe(P
     if (!live) continue;
     const uint32_t c = b * kBV + t;
     float3 vo = make_float3(0.f, 0.f, 0.f);
-    float qo = 0.f;
+    float qo = 0.f, to = 0.f, wo = 0.f;
     if (leaf) {
       float4 cv[8];
-      float qv[8], f[8];
+      float qv[8], f[8], tv[8], wv[8];
 #pragma unroll
       for (int k = 0; k < 8; k++) {
         if (kMode != 1) cv[k] = vin[smp.id[k]];
         if (kMode != 0) qv[k] = qin[smp.id[k]];
+        if (kExt) {
+          tv[k] = X.th_in[smp.id[k]];
+          wv[k] = X.qv_in[smp.id[k]];
+        }
         f[k] = kMode == 1 ? fl[smp.id[k]] : cv[k].w;
+      }
+      if (kExt) {  // a sample without fluid weight takes the ambient values
+        to = ext::ambient_theta(X.E, ext::cell_height(P, pl.y | cell_y(t), 1 << pl.w));
+        wo = X.E.ambient_vapor;
       }
       const Weights8 W = corner_weights(f, smp.fx, smp.fy, smp.fz);
       if (!(W.acc < 1e-6f)) {
         const bool inside = sample_inside(P, smp);
+        if (kExt) {
+          if (!inside) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+              const int cx = smp.x0 + ((k >> 2) & 1), cy = smp.y0 + ((k >> 1) & 1), cz = smp.z0 + (k & 1);
+              tv[k] = ext::scalar_bc<1>(P, X.E, tv[k], cx, cy, cz, smp.scale);
+              wv[k] = ext::scalar_bc<2>(P, X.E, wv[k], cx, cy, cz, smp.scale);
+            }
+          }
+          to = blend8(tv, W.w);
+          wo = blend8(wv, W.w);
+        }
         if (kMode != 1) {
           float vx[8], vy[8], vz[8];
 #pragma unroll
@@ -583,6 +611,19 @@ __global__ void __launch_bounds__(kAdvectThreads, kMinBlocks) k_dc_advect_pipe(P
       if (push) {
         const float a = subblock_sum(qo);
         if ((t & 7u) == 7u) qout[(size_t)kSV * ps + (t >> 3)] = a * .125f;
+      }
+    }
+    if (kExt) {
+      if (leaf) {
+        X.th_out[c] = to;
+        X.qv_out[c] = wo;
+      }
+      if (push) {
+        const float a = subblock_sum(to), b2 = subblock_sum(wo);
+        if ((t & 7u) == 7u) {
+          X.th_out[(size_t)kSV * ps + (t >> 3)] = a * .125f;
+          X.qv_out[(size_t)kSV * ps + (t >> 3)] = b2 * .125f;
+        }
       }
     }
   }
