@@ -32,7 +32,7 @@ static int run_rank(int rank, int name_pipe_in, int name_pipe_out) {
   if (read(name_pipe_in, peer, vmm::kHandleBytes) != (ssize_t)vmm::kHandleBytes) return 14;
   std::vector<int> got;
   if (!vmm::fetch_fds(peer, 3, got)) return 15;
-  server.finish();
+  server.finish_after_serving(1, 30000);  // (the peer may not have connected yet: finish() alone would cancel the server under it)
   if (server.served.load() != 1) return 16;
   for (int i = 0; i < 3; i++) {
     char buf[32] = {0}, want[32];
