@@ -99,7 +99,10 @@ typedef struct dcg_options {
                                   (std::nth_element / std::sort on scores copied D2H)                    */
   int32_t jacobi_max_ctas;     /* > 0: cap on the resident CTAs of the ring kernel (tests: few CTAs walk many
                                   tiles each, the regime of the big scenes, on a small one)               */
-  int32_t experiment;          /* kernel-variant bits for A/B measurements (tools/); 0 = the shipped kernels      */
+  int32_t experiment;          /* variant bits for A/B measurements and tests; 0 = the shipped choice.  1: the other
+                                  prolongation kernel (by parent block on one GPU, per child block sharded); 8: the
+                                  other restriction schedule (one walk up the block tree on one GPU, per-level list
+                                  passes sharded); 32: no early scores (adaptTopology computes its scores on entry) */
   int32_t reserved[12];
 } dcg_options;
 DCG_API int dcg_default_options(dcg_options *out);
