@@ -95,6 +95,7 @@ def test_dcgrid_bit_exact_vs_oracle(gpu, d, M, solids, steps, schedule):
     {"advect_min_blocks": 3, "stencil": 1},                # 3-CTA/SM advection build; one-CTA-per-tile divergence / gradient
     {"no_pdl": 1, "host_selection": 1},                    # plain stream order; the reference's host selection on every level
     {"coarse_in_gmem": 1, "zero_all": 1, "apply_min_blocks": 3, "advect_min_blocks": 4},
+    {"experiment": 32},                                    # adaptTopology computes its scores on entry (no early scores on the side stream)
     {"jacobi": 2, "experiment": 9},                        # the sharded defaults on one GPU: restriction as ONE walk up the block tree
                                                            # (k_dc_restrict_tree), prolongation by parent block (k_dc_prolongate_parents)
 ], ids=lambda o: ",".join(f"{k}={v}" for k, v in o.items()))
