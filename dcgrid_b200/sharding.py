@@ -49,6 +49,51 @@ def halo_bytes_per_sweep(gx, gy, gz, world, rank, level=0):
     return faces * (gx >> level) * (gy >> level) * 4
 
 
+def uniform_piece_runs(gx, gy, gz, world, gran, field):
+    """Physical placement of one field of the sharded dense solver (same arithmetic as UniformSim::build_piece_runs in
+    csrc/uniform.cu): the field's byte range in allocation granules of ``gran`` bytes, each granule on the rank that owns
+    the cell in its middle; returns the maximal runs [(byte0, byte1, owner), ...].  ``field``: "vw" (float4 per level-0
+    cell), "q" (float per level-0 cell) or "pyramid" (float per cell of every mip level, levels concatenated)."""
+    slab = gz // world
+    n0 = gx * gy * gz
+    if field == "pyramid":
+        offs, s, cells = [], 1, 0
+        while gx % s == 0 and gy % s == 0 and gz % s == 0:   # grid_math.cuh:24-30 (mipmapCells)
+            offs.append(cells)
+            cells += n0 // (s * s * s)
+            s *= 2
+        min_dim, levels, cell = min(gx, gy, gz), 1, 2
+        while gx % cell == 0 and gy % cell == 0 and gz % cell == 0 and cell * 4 <= min_dim:   # fluid_simulation_uniform.cu:8-17
+            levels += 1
+            cell *= 2
+        item, total_cells = 4, cells
+    else:
+        item, total_cells = (16 if field == "vw" else 4), n0
+
+    def owner(byte):
+        c = min(total_cells - 1, byte // item)
+        if field != "pyramid":
+            return min(world - 1, c // (gx * gy) // slab)
+        l = 0
+        while l + 1 < levels and c >= offs[l + 1]:
+            l += 1
+        w, h, d = gx >> l, gy >> l, gz >> l
+        if c >= offs[l] + w * h * d:
+            return world - 1
+        z = (c - offs[l]) // (w * h)
+        return min(world - 1, (z << l) // slab)
+
+    runs = []
+    ngran = (total_cells * item + gran - 1) // gran
+    for g in range(ngran):
+        o = owner(g * gran + gran // 2)
+        if runs and runs[-1][2] == o:
+            runs[-1] = (runs[-1][0], (g + 1) * gran, o)
+        else:
+            runs.append((g * gran, (g + 1) * gran, o))
+    return runs
+
+
 def all_gather_bytes(blob: bytes, dist=None):
     """All-gathers one fixed-size byte blob per rank, in rank order.  ``dist`` = torch.distributed (any
     backend; gloo on CPU in the tests, nccl on the GPU box) or None for a single process."""

@@ -44,6 +44,37 @@ def test_halo_traffic_is_two_planes_for_interior_ranks():
     assert sharding.halo_bytes_per_sweep(64, 64, 64, 1, 0) == 0
 
 
+def test_uniform_pieces_follow_cell_ownership():
+    """Placement of the sharded dense solver's fields (uniform_piece_runs mirrors UniformSim::build_piece_runs): a rank's
+    level-0 slab lies in its own physical pieces, and so do its planes of every pyramid level big enough for a granule —
+    with equal byte shares 14 % of a rank's level-0 pressure cells were remote (2 GPUs ran at 1.36x one)."""
+    gran = 2 << 20
+    for (gx, gy, gz), world in (((1024, 1024, 1024), 2), ((1024, 1024, 1024), 8), ((512, 512, 512), 4), ((256, 128, 512), 4)):
+        slab = gz // world
+        for field, item in (("vw", 16), ("q", 4)):
+            runs = sharding.uniform_piece_runs(gx, gy, gz, world, gran, field)
+            assert runs[0][0] == 0 and all(a[1] == b[0] for a, b in zip(runs, runs[1:]))     # contiguous cover
+            assert [r[2] for r in runs] == sorted(r[2] for r in runs)                          # one run per rank, in order
+            slab_bytes = gx * gy * slab * item
+            if slab_bytes % gran == 0:
+                assert [(r[0], r[1]) for r in runs] == [(k * slab_bytes, (k + 1) * slab_bytes) for k in range(world)]
+        runs = sharding.uniform_piece_runs(gx, gy, gz, world, gran, "pyramid")
+        assert runs[0][0] == 0 and all(a[1] == b[0] for a, b in zip(runs, runs[1:]))
+        # level 0 of the pyramid: every rank's slab in its own pieces (slab bytes are granule multiples at these sizes)
+        n0 = gx * gy * gz
+        for k in range(world):
+            lo, hi = k * gx * gy * slab * 4, (k + 1) * gx * gy * slab * 4
+            if (gx * gy * slab * 4) % gran:
+                continue
+            covered = sum(min(hi, r[1]) - max(lo, r[0]) for r in runs if r[2] == k and r[1] > lo and r[0] < hi)
+            assert covered == hi - lo, ((gx, gy, gz), world, k)
+        # level 1 starts a new round of owners right after level 0
+        after_l0 = [r for r in runs if r[0] >= n0 * 4]
+        if after_l0 and (gx * gy * slab * 4 // 8) % gran == 0:
+            assert after_l0[0][2] == 0
+    assert sharding.uniform_piece_runs(64, 64, 64, 1, gran, "pyramid") == [(0, gran * ((sum((64 >> l) ** 3 for l in range(7)) * 4 + gran - 1) // gran), 0)]
+
+
 def _worker(rank, world, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
