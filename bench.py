@@ -47,14 +47,18 @@ METRIC = "effective cell-updates/s per full step"
 UNIT = "cell-updates/s"
 
 
-def csrc_digest():
-    """SHA-256 over the product sources (dcgrid_b200/csrc + include): ties a committed ncu figure to the code it was taken on."""
+def csrc_digest(tu=None):
+    """SHA-256 over the product sources (dcgrid_b200/csrc + include): ties a committed ncu figure to the code it was taken on.
+    tu = "dcgrid" / "uniform": only the translation unit that holds that solver's kernels (its .cu + every header) — the two
+    solvers are separate translation units of the library, so a change to one cannot alter the other's machine code."""
     import hashlib
 
     h = hashlib.sha256()
     for d in (os.path.join(ROOT, "dcgrid_b200", "csrc"), os.path.join(ROOT, "include")):
         for f in sorted(os.listdir(d)):
             if f.endswith((".cu", ".cuh", ".h")):
+                if tu is not None and f.endswith(".cu") and f != tu + ".cu":
+                    continue
                 with open(os.path.join(d, f), "rb") as fh:
                     h.update(f.encode() + b"\0" + fh.read())
     return h.hexdigest()[:16]
@@ -425,17 +429,17 @@ def main():
             ms, b = sim.benchStage("jacobi", lvl, 40)
             ach = b / (ms * 1e-3) / 1e9
             # DRAM traffic of the dominant kernel from the committed ncu --set full capture — only if that capture was
-            # taken on exactly these sources (csrc_digest recorded beside it), else null
+            # taken on exactly these kernel sources (digest of the DCGrid translation unit recorded beside it), else null
             traffic, traffic_src, hot_traffic = None, None, None
             tpath = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
             if os.path.exists(tpath) and args.workload == "dcgrid512":
                 with open(tpath) as f:
                     tj = json.load(f)
-                if tj.get("csrc_digest") == csrc_digest():
+                if tj.get("tu_digest") == csrc_digest("dcgrid"):
                     traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
                     hot_traffic = tj.get("all_hot_kernels")
                 else:
-                    traffic_src = f"stale: {tj.get('source')} was captured on csrc {tj.get('csrc_digest')}, this is {csrc_digest()}"
+                    traffic_src = f"stale: {tj.get('source')} was captured on dcgrid.cu + headers {tj.get('tu_digest')}, this is {csrc_digest('dcgrid')}"
             sweeps_big = 0  # sweeps per step that run this kernel on a level of this size (levels 0 and 1 at dcgrid512)
             if grid == "dcgrid":
                 big = int(tab["loads"][lvl])

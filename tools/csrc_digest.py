@@ -6,4 +6,4 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench  # noqa: E402
 
-print(bench.csrc_digest())
+print(bench.csrc_digest(sys.argv[1] if len(sys.argv) > 1 else None))
