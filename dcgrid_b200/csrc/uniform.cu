@@ -196,7 +196,10 @@ __global__ void __launch_bounds__(256) k_u_advect_both(KParams P, const float4 *
 // The same, marching along z: the cell's own velocity — the first of the two dependent load rounds of a gather — is
 // fetched one plane ahead, so that only the corner loads are on a thread's critical path, and the index set-up is paid
 // once per column.
-__global__ void __launch_bounds__(256) k_u_advect_both_zm(KParams P, const float4 *__restrict__ vin, float4 *__restrict__ vout,
+// 4 CTAs per SM (64 registers, 16 bytes of spill) instead of the 3 ptxas picks on its own (79 registers): the kernel waits on
+// its gathers, a fourth CTA's warps are worth more than the registers — 14.5 -> 13.75 ms at 1024^3; 5 CTAs (48 registers,
+// 160 bytes of spill): 34 ms (profiles/README.md r4b-r4d).
+__global__ void __launch_bounds__(256, 4) k_u_advect_both_zm(KParams P, const float4 *__restrict__ vin, float4 *__restrict__ vout,
                                                           const float *__restrict__ qin, float *__restrict__ qout, int zc, ZRange Z) {
   const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
   const int z0 = Z.zb + blockIdx.z * zc, z1 = min(z0 + zc, min(P.gz, Z.ze));
@@ -386,6 +389,102 @@ __global__ void __launch_bounds__(ZTX * ZTY) k_u_divergence_zm(KParams P, const 
   }
 }
 
+// Two rows per thread.  ncu of the kernel above at 1024^3 (profiles/README.md r4a): 5.92 ms, DRAM traffic at its minimum
+// (22.5 GB) but only 3.8 TB/s — long-scoreboard stalls, ~124 executed instructions per 32 cells at 63 % of the issue slots,
+// the L1 data pipe at 63 % (three 16-byte row loads per cell; ptxas splits the y neighbours into 4-byte loads at a 16-byte
+// stride).  Here a thread owns the cells (x, 2j) and (x, 2j + 1) of a plane: each is the other's y neighbour (4 row loads per
+// 2 cells instead of 6) and pointer arithmetic, chunk bounds and the loop are paid once per 2 cells.  Same expression per
+// cell.  What the A/B runs say (r4b-r4d, ms per divergence stage at 1024^3; one row 6.71): the kernel lives on resident
+// warps — four rows at 79 registers / 3 CTAs per SM 6.34; with the column fetched two planes ahead 7.77 (108 registers,
+// 2 CTAs); two rows fetched two planes ahead 5.96 (64 registers, 4 CTAs); two rows, the plane ahead fetched in the iteration
+// that uses it, 48 registers / 5 CTAs: 5.86 (shipped); capped at 40 registers / 6 CTAs (48 bytes of spill) 7.1.  Fetching two
+// planes ahead changed nothing for the one-row kernel either.
+//
+// kRestrict (one GPU, even extents, chunks of an even number of planes): the level-1 divergence — the reference's sequential
+// sum over a coarse cell's 2x2x2 children (k_uniform_restrict, uniformgrid_fluid.cu:134-160: x fastest, then y, then z) — is
+// accumulated on the way: the children are the lane pair (2i, 2i + 1), the thread's two rows and two consecutive iterations.
+// Saves the pass that re-reads the level-0 divergence (0.83 ms for 4.8 GB at 1024^3; 0.1-0.5 ms of it arrive in the step).
+constexpr int ZRY = 2;
+template <bool kRestrict>
+__global__ void __launch_bounds__(ZTX * ZTY, 5) k_u_divergence_zm2(KParams P, const float4 *__restrict__ vw, float *__restrict__ div, float *__restrict__ p,
+                                                                   float *__restrict__ tp, int zc, int zero, ZRange Z, uint64_t off1) {
+  const int x = blockIdx.x * ZTX + threadIdx.x, y0 = (blockIdx.y * ZTY + threadIdx.y) * ZRY;
+  const int z0 = Z.zb + blockIdx.z * zc, z1 = min(z0 + zc, min(P.gz, Z.ze));
+  const ptrdiff_t sy = P.gx, sz = (ptrdiff_t)P.gx * P.gy;
+  // y neighbours outside the thread's rows, relative to its first row (clamped at the walls like the reference's indices)
+  const ptrdiff_t dno = y0 > 0 ? -sy : 0, upo = y0 + ZRY < P.gy ? ZRY * sy : (ZRY - 1) * sy;
+  const bool left_edge = threadIdx.x == 0, right_edge = threadIdx.x == ZTX - 1;
+  // boundary conditions only substitute values of neighbours OUTSIDE the domain (sim_utils.cu:24-39)
+  const bool x_inner = x > 0 && x < P.gx - 1;
+  const size_t first = (size_t)z0 * sz + (size_t)y0 * P.gx + x;
+  const float4 *pc = vw + first;  // (x, y0) of plane z
+  float *pd = div + first;
+  float4 cur[ZRY];
+  float pz[ZRY], pw[ZRY];  // plane z - 1: only (vz, fluidity) are used
+#pragma unroll
+  for (int k = 0; k < ZRY; k++) {
+    cur[k] = __ldg(pc + k * sy);
+    const float4 b = z0 > 0 ? __ldg(pc + k * sy - sz) : cur[k];
+    pz[k] = b.z; pw[k] = b.w;
+  }
+  float carry = 0.f;  // kRestrict: the sum over the coarse cell's four children of the even plane
+  for (int z = z0; z < z1; z++, pc += sz, pd += sz) {
+    float4 next[ZRY];
+#pragma unroll
+    for (int k = 0; k < ZRY; k++) next[k] = z < P.gz - 1 ? __ldg(pc + k * sy + sz) : cur[k];
+    const float4 dn = __ldg(pc + dno), up = __ldg(pc + upo);
+    const bool z_inner = z > 0 && z < P.gz - 1;
+    float dv[ZRY];
+#pragma unroll
+    for (int k = 0; k < ZRY; k++) {
+      const int y = y0 + k;
+      const float4 c = cur[k];
+      const float4 d = k == 0 ? dn : cur[0], u = k == ZRY - 1 ? up : cur[ZRY - 1];
+      float4 l, r;
+      l.x = __shfl_up_sync(0xFFFFFFFFu, c.x, 1); l.w = __shfl_up_sync(0xFFFFFFFFu, c.w, 1);
+      r.x = __shfl_down_sync(0xFFFFFFFFu, c.x, 1); r.w = __shfl_down_sync(0xFFFFFFFFu, c.w, 1);
+      l.y = l.z = r.y = r.z = 0.f;
+      if (left_edge) l = x > 0 ? pc[k * sy - 1] : c;
+      if (right_edge) r = x < P.gx - 1 ? pc[k * sy + 1] : c;
+      float lx = l.x, rx = r.x, dy = d.y, uy = u.y, bz = pz[k], fz = next[k].z;
+      if (!(x_inner && z_inner && y > 0 && y < P.gy - 1)) {
+        lx = velocity_bc(P, make_float3(l.x, l.y, l.z), x - 1, y, z, 1).x;
+        rx = velocity_bc(P, make_float3(r.x, r.y, r.z), x + 1, y, z, 1).x;
+        dy = velocity_bc(P, make_float3(d.x, d.y, d.z), x, y - 1, z, 1).y;
+        uy = velocity_bc(P, make_float3(u.x, u.y, u.z), x, y + 1, z, 1).y;
+        bz = velocity_bc(P, make_float3(0.f, 0.f, pz[k]), x, y, z - 1, 1).z;
+        fz = velocity_bc(P, make_float3(next[k].x, next[k].y, next[k].z), x, y, z + 1, 1).z;
+      }
+      if (zero) {
+        const size_t i = (size_t)(pd - div) + k * sy;
+        if (zero & 1) p[i] = 0.f;
+        if (zero & 2) tp[i] = 0.f;
+      }
+      dv[k] = .5f * P.rdx * (r.w * rx - l.w * lx + u.w * uy - d.w * dy + next[k].w * fz - pw[k] * bz);
+      pd[k * sy] = dv[k];
+    }
+    if (kRestrict) {
+      const float o0 = __shfl_down_sync(0xFFFFFFFFu, dv[0], 1), o1 = __shfl_down_sync(0xFFFFFFFFu, dv[1], 1);
+      if (z & 1) {
+        const float s = carry + dv[0] + o0 + dv[1] + o1;
+        if (!(threadIdx.x & 1)) {
+          const size_t ci = off1 + ((size_t)(z >> 1) * (P.gy >> 1) + (y0 >> 1)) * (P.gx >> 1) + (x >> 1);
+          p[ci] = 0.f;
+          tp[ci] = 0.f;
+          div[ci] = .125f * s;
+        }
+      } else {
+        carry = dv[0] + o0 + dv[1] + o1;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < ZRY; k++) {
+      pz[k] = cur[k].z; pw[k] = cur[k].w;
+      cur[k] = next[k];
+    }
+  }
+}
+
 // k_uniform_prolongate, uniformgrid_fluid.cu:206-237
 __global__ void __launch_bounds__(256) k_u_prolongate(KParams P, int level, uint64_t off, uint64_t poff, float *__restrict__ p, ZRange Z) {
   const int x = blockIdx.x * BX + threadIdx.x, y = blockIdx.y * BY + threadIdx.y, z = Z.zb + blockIdx.z * BZ + threadIdx.z;
@@ -467,7 +566,10 @@ __global__ void __launch_bounds__(256) k_u_apply_pressure(KParams P, const float
   vw[i] = v;
 }
 
-// z-marching pressure gradient: the column's pressure and fluidity planes in registers, x neighbours by shuffle
+// z-marching pressure gradient: the column's pressure and fluidity planes in registers, x neighbours by shuffle.
+// ncu (profiles/README.md r4a): 7.60 ms at 1024^3 = 5.7 TB/s of DRAM traffic, 87 % of the measured peak for the 40 B/cell it moves.
+// (Measured and rejected, r4b: the front plane's fluidity taken from `.w` of that plane's packed velocity, fetched two planes
+// ahead by the thread that updates it — 36 B/cell, but 59 registers instead of 40 and 9.7 ms instead of 7.7.)
 __global__ void __launch_bounds__(ZTX * ZTY) k_u_apply_zm(KParams P, const float *__restrict__ p, const float *__restrict__ fl, float4 *__restrict__ vw,
                                                           int zc, ZRange Z) {
   const int x = blockIdx.x * ZTX + threadIdx.x, y = blockIdx.y * ZTY + threadIdx.y;
@@ -933,8 +1035,8 @@ struct UniformSim : dcg_sim {
     if (fuse_advect && !opt.advect && gz >= 64) {
       const int zc = opt.advect_ctas_per_sm > 0 ? opt.advect_ctas_per_sm : 16;  // (option reused: planes per thread)
       stage(0, [&](ZRange Z, int planes) {
-        k_u_advect_both_zm<<<dim3(idiv_up(gx, 32), idiv_up(gy, 8), idiv_up(planes, zc)), dim3(32, 8), 0, stream>>>(kp, vw[cur_v], vw[cur_v ^ 1], q[cur_q],
-                                                                                                                     q[cur_q ^ 1], zc, Z);
+        const dim3 g(idiv_up(gx, 32), idiv_up(gy, 8), idiv_up(planes, zc));
+        k_u_advect_both_zm<<<g, dim3(32, 8), 0, stream>>>(kp, vw[cur_v], vw[cur_v ^ 1], q[cur_q], q[cur_q ^ 1], zc, Z);
       });
       spec_velocity = true;
     } else if (fuse_advect) {
@@ -977,12 +1079,25 @@ struct UniformSim : dcg_sim {
       stage(0, [&](ZRange Z, int planes) { k_u_apply_pressure<<<grid_for(0, planes), block(), 0, stream>>>(kp, p, fluidity, vw[cur_v], Z); });
     }
   }
-  void launch_divergence(int zero = 3) {
+  bool fused_restrict1 = false;  // set by launch_divergence when the level-1 divergence has been written along the way
+  void launch_divergence(int zero = 3, bool restrict1 = false) {
+    fused_restrict1 = false;
     if (opt.zero_all) zero = 3;
     if (!opt.stencil && gx % ZTX == 0 && gy % ZTY == 0) {
       const int zc = zm_chunk(gz);
       stage(0, [&](ZRange Z, int planes) {
-        k_u_divergence_zm<<<dim3(gx / ZTX, gy / ZTY, idiv_up(planes, zc)), dim3(ZTX, ZTY), 0, stream>>>(kp, vw[cur_v], div, p, tp, zc, zero, Z);
+        const dim3 g2(gx / ZTX, gy / (ZTY * ZRY), idiv_up(planes, zc)), b(ZTX, ZTY);
+        const int e = opt.experiment;  // tests / A/B: 64 = the one-row kernel, 1024 = no fused level-1 restriction
+        if (gy % (ZTY * ZRY) == 0 && !(e & 64)) {
+          // the level-1 restriction rides along on one GPU (coarse cells never straddle a chunk: even chunk sizes, even extents)
+          if (restrict1 && world == 1 && !(e & 1024) && gx % 2 == 0 && gz % 2 == 0 && zc % 2 == 0) {
+            k_u_divergence_zm2<true><<<g2, b, 0, stream>>>(kp, vw[cur_v], div, p, tp, zc, zero, Z, level_off[1]);
+            fused_restrict1 = true;
+          } else {
+            k_u_divergence_zm2<false><<<g2, b, 0, stream>>>(kp, vw[cur_v], div, p, tp, zc, zero, Z, 0);
+          }
+        } else
+          k_u_divergence_zm<<<dim3(gx / ZTX, gy / ZTY, idiv_up(planes, zc)), dim3(ZTX, ZTY), 0, stream>>>(kp, vw[cur_v], div, p, tp, zc, zero, Z);
       });
     } else {
       stage(0, [&](ZRange Z, int planes) { k_u_divergence<<<grid_for(0, planes), block(), 0, stream>>>(kp, vw[cur_v], div, p, tp, zero, Z); });
@@ -991,8 +1106,8 @@ struct UniformSim : dcg_sim {
   int project() override {  // fluid_simulation_uniform.cu:96-124
     DCG_TRY(enter());
     spec_velocity = false;
-    launch_divergence(mip_levels > 1 && project_level_pairs >= 1 ? 0 : 3);
-    for (int l = 1; l < mip_levels; l++)
+    launch_divergence(mip_levels > 1 && project_level_pairs >= 1 ? 0 : 3, mip_levels > 1);
+    for (int l = fused_restrict1 ? 2 : 1; l < mip_levels; l++)
       stage(l, [&](ZRange Z, int planes) { k_u_restrict<<<grid_for(l, planes), block(), 0, stream>>>(kp, l, level_off[l], level_off[l - 1], div, p, tp, Z); });
     for (int i = 0; i < project_coarsest_pairs; i++) jacobi_pair(mip_levels - 1);
     for (int l = mip_levels - 2; l >= 0; l--) {

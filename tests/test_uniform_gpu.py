@@ -63,9 +63,13 @@ def test_uniform_non_cubic(gpu):
     ((256, 16, 32), False, "project", None),    # levels 0 and 1 take the z-marching kernels (x extent in whole warps of float4)
     ((128, 64, 72), True, "local", None),       # z extent not a multiple of the chunk; solids; projectLocal's 5 pairs
     ((256, 16, 32), False, "project", {"stencil": 1}),  # the one-thread-per-cell kernels at the same size
+    ((128, 64, 72), True, "project", {"experiment": 64}),       # the one-row divergence kernel (sizes with gy % 16 != 0 take it)
+    ((128, 64, 72), True, "project", {"experiment": 1024}),     # two-row divergence without the fused level-1 restriction
+    ((128, 64, 72), True, "project", None),                     # ... and with it (the shipped choice on one GPU)
 ])
 def test_uniform_z_marching_kernels(gpu, size, solids, schedule, options):
-    """k_u_jacobi_zm / k_u_divergence_zm only engage from 128 cells in x: sizes the other cases never reach."""
+    """The z-marching kernels only engage from 128 cells in x (two-row divergence: gy % 16 == 0; its fused level-1 restriction:
+    project() on one GPU): sizes the other cases never reach."""
     p = scene_params(*size, solids=solids)
     sim = FluidSimulationUniform(size, p, options=options)
     orc = Oracle(p)
